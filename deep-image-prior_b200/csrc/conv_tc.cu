@@ -1,0 +1,389 @@
+// tcgen05 / TMA implicit-GEMM convolution kernels for sm_100a (hand-written, no CUTLASS).
+//
+// Replaces what torch.nn.Conv2d forward/backward computes for the skip network
+// (reference call site: models/common.py:120 via models/skip.py:58,64,68,83,89; backward = autograd of same).
+//
+//   tc_conv_kernel  : fprop and dgrad.  Persistent, warp-specialised:
+//                       warp 0     TMA producer (im2col folded into the tensor-map coordinates: one 5-D box per tap)
+//                       warp 1     single-thread tcgen05.mma issuer, fp32 accumulators in TMEM (double-buffered)
+//                       warp 2     TMEM allocator
+//                       warps 4-7  epilogue: tcgen05.ld -> +bias -> swizzled smem -> per-channel BN statistics
+//                                  -> TMA store
+//   tc_wgrad_kernel : weight gradient, both operands MN-major straight from NHWC activations, split-K over CTAs.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace dip {
+
+static constexpr int kTileM = 128;            // output pixels per tile (UMMA M)
+static constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 32 fp32
+static constexpr int kChunkBytes = kTileM * 128;
+static constexpr int kNumThreads = 256;
+
+struct SmemCtl {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float bias[160];
+};
+
+__device__ __forceinline__ uint32_t tmem_cols_pow2(uint32_t n) {
+  uint32_t c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------ fprop / dgrad
+__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.n_mma * 128;
+  const int stage_bytes = kABytes + ((b_bytes + 1023) & ~1023);
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + p.stages * stage_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(staging + p.n_chunks * kChunkBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_x * p.tiles_y;
+  const int kb_per_tile = p.kh * p.kw * p.kblocks;
+  const uint32_t acc_cols = (p.n_mma + 31) & ~31;  // column stride between the two accumulators
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->tmem_full[i], 1);
+      mbar_init(&ctl->tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctl->tmem_base, tmem_cols_pow2(2 * acc_cols));
+    tmem_relinquish();
+  }
+  if (warp == 3) {
+    for (int i = lane; i < 160; i += 32) ctl->bias[i] = (p.bias != nullptr && i < p.n_mma) ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const int x0 = tx * p.bw, y0 = ty * p.bh;
+        for (int r = 0; r < p.kh; ++r) {
+          for (int s = 0; s < p.kw; ++s) {
+            const int ix = p.offx + s, iy = p.offy + r;  // tap offset in input coordinates
+            int cpx, cx, cpy, cy;
+            if (p.stride == 1) {
+              cpx = 0; cx = x0 + ix; cpy = 0; cy = y0 + iy;
+            } else {
+              // input coordinate = 2*out + i  ->  (parity, half) = (i & 1, out + (i >> 1)); offsets are >= 0 here
+              cpx = ix & 1; cx = x0 + (ix >> 1); cpy = iy & 1; cy = y0 + (iy >> 1);
+            }
+            const int tap = r * p.kw + s;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(&ctl->empty[stage], phase ^ 1);
+              uint8_t* sa = stage_base + stage * stage_bytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_expect_tx(&ctl->full[stage], kABytes + b_bytes);
+              tma_load_5d(sa, &p.tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
+              tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_mma, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * acc_cols;
+        for (int kbt = 0; kbt < kb_per_tile; ++kbt) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const bool last_kb = ((kbt % p.kblocks) == p.kblocks - 1);
+          const int nmma = last_kb ? p.tail_mmas : 4;
+          for (int k = 0; k < nmma; ++k) {
+            // K-major SW128: 8-row groups are 1024 B apart; advancing K by 8 fp32 = +32 B inside the swizzle atom
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (kbt > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&ctl->empty[stage]);  // frees this smem stage once the MMAs above have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&ctl->tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (128 threads)
+    const int ew = warp - 4;             // TMEM lane quarter = warp % 4
+    const int et = threadIdx.x - 128;    // 0..127
+    const int row = ew * 32 + lane;      // tile row (pixel) owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+      const int x0 = tx * p.bw, y0 = ty * p.bh;
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      // staging buffer must be free (previous tile's TMA store has finished reading it)
+      if (et == 0) tma_store_wait_read0();
+      named_bar_sync(1, 128);
+      const uint32_t taddr = tmem_base + acc * acc_cols + (static_cast<uint32_t>(ew * 32) << 16);
+      for (int j = 0; j < p.n_chunks; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + j * 32, v);
+        tmem_ld_wait();
+        uint8_t* rowp = staging + j * kChunkBytes + row * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          o.x = __uint_as_float(v[q * 4 + 0]) + ctl->bias[j * 32 + q * 4 + 0];
+          o.y = __uint_as_float(v[q * 4 + 1]) + ctl->bias[j * 32 + q * 4 + 1];
+          o.z = __uint_as_float(v[q * 4 + 2]) + ctl->bias[j * 32 + q * 4 + 2];
+          o.w = __uint_as_float(v[q * 4 + 3]) + ctl->bias[j * 32 + q * 4 + 3];
+          *reinterpret_cast<float4*>(rowp + ((q ^ (row & 7)) << 4)) = o;  // 128B swizzle (matches the TMA map)
+        }
+      }
+      // accumulator drained -> hand TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, j * 32, x0, y0);
+        tma_store_commit();
+      }
+      if (p.stats != nullptr) {
+        // per-channel sum / sum-of-squares over the valid rows of this tile (feeds the following BatchNorm)
+        for (int c = et; c < p.n_chunks * 32; c += 128) {
+          const int j = c >> 5, q = (c & 31) >> 2, e = c & 3;
+          const uint8_t* cb = staging + j * kChunkBytes + e * 4;
+          float s1 = 0.f, s2 = 0.f;
+          for (int m = 0; m < kTileM; ++m) {
+            const int px = m % p.bw, py = m / p.bw;
+            if (x0 + px < p.out_w && y0 + py < p.out_h) {
+              const float x = *reinterpret_cast<const float*>(cb + m * 128 + ((q ^ (m & 7)) << 4));
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+          }
+          if (c < p.stats_ld) {
+            atomicAdd(&p.stats[c], static_cast<double>(s1));
+            atomicAdd(&p.stats[p.stats_ld + c], static_cast<double>(s2));
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (et == 0) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols_pow2(2 * acc_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct SmemCtlW {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int chunk_bytes = p.kp * 128;                          // kp pixel rows x 32 channels
+  const int y_bytes = 4 * chunk_bytes;                         // dY: 128 channels
+  const int x_bytes = p.c_chunks * chunk_bytes;                // X : c_pad channels, per tap column
+  const int stage_bytes = y_bytes + p.kw * x_bytes;            // multiple of 2048
+  SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(smem + p.stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x / p.ksplits;   // filter row handled by this CTA
+  const int ks = blockIdx.x % p.ksplits;  // split-K index
+  const int c_pad = p.c_chunks * 32;
+  const uint32_t ncols = tmem_cols_pow2(p.kw * c_pad);
+  const int blk0 = static_cast<int>((static_cast<long long>(p.px_blocks) * ks) / p.ksplits);
+  const int blk1 = static_cast<int>((static_cast<long long>(p.px_blocks) * (ks + 1)) / p.ksplits);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmY);
+    tma_prefetch_desc(&p.tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+    }
+    mbar_init(&ctl->tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctl->tmem_base, ncols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int blk = blk0; blk < blk1; ++blk) {
+        const int y = blk / p.px_blocks_x;
+        const int x0 = (blk % p.px_blocks_x) * p.kp;
+        mbar_wait(&ctl->empty[stage], phase ^ 1);
+        uint8_t* sy = smem + stage * stage_bytes;
+        mbar_expect_tx(&ctl->full[stage], stage_bytes);
+        for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * chunk_bytes, &p.tmY, &ctl->full[stage], j * 32, x0, y);
+        for (int s = 0; s < p.kw; ++s) {
+          const int ix = p.offx + s, iy = p.offy + r;
+          int cpx, cx, cpy, cy;
+          if (p.stride == 1) {
+            cpx = 0; cx = x0 + ix; cpy = 0; cy = y + iy;
+          } else {
+            cpx = ix & 1; cx = x0 + (ix >> 1); cpy = iy & 1; cy = y + (iy >> 1);
+          }
+          uint8_t* sx = sy + y_bytes + s * x_bytes;
+          for (int j = 0; j < p.c_chunks; ++j)
+            tma_load_5d(sx + j * chunk_bytes, &p.tmX, &ctl->full[stage], j * 32, cpx, cx, cpy, cy);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A = dY (M = 128 output channels), B = X (N = c_pad input channels); both MN-major, K = pixels.
+      const uint32_t idesc = make_idesc_tf32(128, c_pad, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int blk = blk0; blk < blk1; ++blk) {
+        mbar_wait(&ctl->full[stage], phase);
+        tc_fence_after();
+        const uint32_t sy = smem_u32(smem + stage * stage_bytes);
+        for (int s = 0; s < p.kw; ++s) {
+          const uint32_t sx = sy + y_bytes + s * x_bytes;
+          for (int k = 0; k < p.kp / 8; ++k) {
+            // MN-major SW128: 32-channel chunks are LBO = chunk_bytes apart; 8-pixel K groups are 1024 B apart
+            const uint64_t adesc = make_smem_desc_sw128(sy + k * 1024, chunk_bytes, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sx + k * 1024, chunk_bytes, 1024);
+            mma_tf32_ss(tmem_base + s * c_pad, adesc, bdesc, idesc, (blk > blk0 || k > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(&ctl->empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&ctl->tmem_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int n = ew * 32 + lane;  // output channel (TMEM lane)
+    if (blk1 > blk0) {
+      mbar_wait(&ctl->tmem_full, 0);
+      tc_fence_after();
+    }
+    for (int s = 0; s < p.kw; ++s) {
+      const int tap = r * p.kw + s;
+      float* dst = p.partial + ((static_cast<size_t>(ks) * (p.kh * p.kw) + tap) * 128 + n) * c_pad;
+      for (int j = 0; j < p.c_chunks; ++j) {
+        uint32_t v[32];
+        if (blk1 > blk0) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * c_pad + j * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                 __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+          *reinterpret_cast<float4*>(dst + j * 32 + q * 4) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static constexpr size_t kMaxSmem = 232448;  // 227 KB
+
+size_t tc_conv_smem_bytes(const TcConvParams& p) {
+  const size_t b_bytes = (static_cast<size_t>(p.n_mma) * 128 + 1023) & ~size_t(1023);
+  return 1024 + p.stages * (kABytes + b_bytes) + static_cast<size_t>(p.n_chunks) * kChunkBytes + sizeof(SmemCtl);
+}
+size_t tc_wgrad_smem_bytes(const TcWgradParams& p) {
+  const size_t chunk = static_cast<size_t>(p.kp) * 128;
+  return 1024 + p.stages * (4 * chunk + static_cast<size_t>(p.kw) * p.c_chunks * chunk) + sizeof(SmemCtlW);
+}
+
+cudaError_t tc_kernels_init() {
+  cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+}
+
+cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  const size_t smem = tc_conv_smem_bytes(p);
+  if (smem > kMaxSmem) return cudaErrorInvalidValue;
+  tc_conv_kernel<<<grid, kNumThreads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_wgrad_launch(const TcWgradParams& p, cudaStream_t s) {
+  const size_t smem = tc_wgrad_smem_bytes(p);
+  if (smem > kMaxSmem) return cudaErrorInvalidValue;
+  tc_wgrad_kernel<<<p.kh * p.ksplits, kNumThreads, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace dip

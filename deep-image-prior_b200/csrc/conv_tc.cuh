@@ -1,0 +1,57 @@
+// Host-side descriptors for the tcgen05 implicit-GEMM convolution kernels (conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dip {
+
+// Implicit-GEMM forward/dgrad conv:  D[pixel][n] = sum_{tap, c} A[pixel (+) tap][c] * Wp[tap][n][c]  (+ bias[n])
+//   A  : NHWC fp32 activation seen through a 5-D tensor map (C, px, X, py, Y)   (parity dims px/py have extent 1
+//        for stride-1 convs and 2 for stride-2 convs; out-of-bounds coordinates read as zero)
+//   Wp : packed weights [tap][n_rows][c_pad] fp32, K-major, through a 2-D map (c_pad, taps*n_rows)
+//   D  : NHWC fp32 output through a 3-D map (C_out, W_out, H_out); partial tiles are clipped by TMA.
+struct TcConvParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  CUtensorMap tmD;
+  int tiles_x, tiles_y;    // output tile grid
+  int bw, bh;              // tile = bw x bh output pixels, bw*bh == 128
+  int out_w, out_h;        // valid output extent (for masked statistics)
+  int kh, kw;              // filter taps
+  int stride;              // 1 or 2 (spatial stride of A reads)
+  int offx, offy;          // input coordinate of tap (0,0) for output pixel (0,0)
+  int kblocks;             // 32-channel K blocks per tap
+  int tail_mmas;           // number of K=8 MMAs issued for the last K block of a tap (1..4)
+  int n_mma;               // UMMA N (multiple of 16, <= 160)
+  int n_chunks;            // output 32-channel chunks written (ceil(n_mma/32))
+  int stages;              // smem pipeline depth
+  const float* bias;       // [n_mma] or nullptr
+  double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
+  int stats_ld;
+};
+
+// Weight-gradient GEMM:  dW[tap][n][c] = sum_{pixels} dY[pixel][n] * X[pixel (+) tap][c]
+//   dY : NHWC fp32 [H][W][128] through a 3-D map (128, W, H)
+//   X  : conv input through the same 5-D view as in TcConvParams
+//   out: fp32 partials [ksplit][tap][128][c_pad]  (deterministic split-K; reduced by a follow-up kernel)
+struct TcWgradParams {
+  CUtensorMap tmY;
+  CUtensorMap tmX;
+  float* partial;          // [ksplits][kh*kw][128][c_pad]
+  int kh, kw, stride, offx, offy;
+  int px_blocks_x;         // W / kp
+  int px_blocks;           // total pixel blocks = H * px_blocks_x
+  int kp;                  // pixels per K block (box width): 16 or 32
+  int c_chunks;            // 32-channel chunks of X (c_pad = 32*c_chunks)
+  int ksplits;             // CTAs per tap row
+  int stages;
+};
+
+size_t tc_conv_smem_bytes(const TcConvParams& p);
+size_t tc_wgrad_smem_bytes(const TcWgradParams& p);
+cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s);
+cudaError_t tc_wgrad_launch(const TcWgradParams& p, cudaStream_t s);
+cudaError_t tc_kernels_init();
+
+}  // namespace dip

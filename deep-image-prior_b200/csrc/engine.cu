@@ -1,0 +1,1012 @@
+// dip-b200 engine: plan builder (shapes -> HBM buffers, TMA tensor maps, kernel schedule) and the C ABI of
+// libdip.so (include/dip.h).  Replaces the execution of the reference's skip network
+// (models/skip.py:41-100, module tree interpreted by torch.nn.Sequential) + autograd backward + Adam.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <initializer_list>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dip.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace dip {
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+#define DIP_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+  } while (0)
+#define DIP_CHECK(expr)        \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int g_num_sms = 0;
+static bool g_inited = false;
+
+static int engine_init() {
+  if (g_inited) return 0;
+  int dev = 0;
+  DIP_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DIP_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail("dip-b200 requires an sm_100 (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+  g_num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  DIP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (fn == nullptr || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  DIP_CUDA(tc_kernels_init());
+  g_inited = true;
+  return 0;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0],
+             box[1], rank > 2 ? box[2] : 0);
+    return fail(buf);
+  }
+  return 0;
+}
+// activation [rows][cols][ld] (c valid channels) as the 5-D view (C, px, X, py, Y) used by the conv kernels
+static int map_act5(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int stride, int bw, int bh) {
+  const cuuint64_t e = sizeof(float);
+  cuuint64_t dims[5], str[4];
+  if (stride == 1) {
+    dims[0] = c; dims[1] = 1; dims[2] = cols; dims[3] = 1; dims[4] = rows;
+    str[0] = ld * e; str[1] = ld * e; str[2] = (cuuint64_t)cols * ld * e; str[3] = (cuuint64_t)cols * ld * e;
+  } else {
+    dims[0] = c; dims[1] = 2; dims[2] = cols / 2; dims[3] = 2; dims[4] = rows / 2;
+    str[0] = ld * e; str[1] = 2 * ld * e; str[2] = (cuuint64_t)cols * ld * e; str[3] = 2 * (cuuint64_t)cols * ld * e;
+  }
+  cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)bh};
+  return encode_map(m, base, 5, dims, str, box);
+}
+static int map_act3(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int bw, int bh) {
+  const cuuint64_t e = sizeof(float);
+  cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t str[2] = {ld * e, (cuuint64_t)cols * ld * e};
+  cuuint32_t box[3] = {32, (cuuint32_t)bw, (cuuint32_t)bh};
+  return encode_map(m, base, 3, dims, str, box);
+}
+static int map_w2(CUtensorMap* m, const float* base, int rows_total, int kcols, int box_rows) {
+  const cuuint64_t e = sizeof(float);
+  cuuint64_t dims[2] = {(cuuint64_t)kcols, (cuuint64_t)rows_total};
+  cuuint64_t str[1] = {kcols * e};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  return encode_map(m, base, 2, dims, str, box);
+}
+
+static void pick_tile(int w, int h, int* bw, int* bh) {
+  const int cand[5][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}, {8, 16}};
+  long long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const long long cw = (w + cand[i][0] - 1) / cand[i][0] * cand[i][0];
+    const long long ch = (h + cand[i][1] - 1) / cand[i][1] * cand[i][1];
+    // prefer square-ish tiles on ties (smaller halo re-reads for 3x3 taps)
+    const long long cost = cw * ch * 64 + (cand[i][0] + cand[i][1]);
+    if (best < 0 || cost < best) { best = cost; *bw = cand[i][0]; *bh = cand[i][1]; }
+  }
+}
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ conv op
+struct ConvOp {
+  int N = 128, C = 0, k = 1, stride = 1, rot = 0;
+  int c_pad = 0;   // fprop K extent per tap (multiple of 32)
+  int crows = 0;   // dgrad UMMA N (input channels rounded to 16)
+  // forward
+  const float* in = nullptr; int in_rows = 0, in_cols = 0, in_ld = 0; int offx = 0, offy = 0;
+  float* out = nullptr; int out_h = 0, out_w = 0;
+  double* stats = nullptr;
+  float* wp_f = nullptr; float* wp_d = nullptr;
+  // dgrad: dg_in [dg_in_h][dg_in_w][128] -> dg_out [dg_out_h][dg_out_w][C]
+  bool has_dgrad = false;
+  const float* dg_in = nullptr; int dg_in_h = 0, dg_in_w = 0;
+  float* dg_out = nullptr; int dg_out_h = 0, dg_out_w = 0; int dg_off = 0;
+  // wgrad: dY [wg_h][wg_w][128]
+  const float* wg_dy = nullptr; int wg_h = 0, wg_w = 0;
+  // param slots
+  int p_w = -1, p_b = -1;
+  TcConvParams fp{}, dg{};
+  TcWgradParams wg{};
+  int simt_ksplits = 1;
+
+  void set_shapes() {
+    c_pad = round_up(C, 32);
+    crows = round_up(C, 16);
+  }
+  size_t wp_f_elems() const { return (size_t)k * k * N * c_pad; }
+  size_t wp_d_elems() const { return (size_t)k * k * crows * 128; }
+  int tc_ksplits() const {
+    const int kp = (wg_w % 32 == 0) ? 32 : 16;
+    const int blocks = wg_h * ((wg_w + kp - 1) / kp);
+    int ks = 148 / k;
+    if (ks > blocks) ks = blocks;
+    return ks < 1 ? 1 : ks;
+  }
+  size_t partial_elems(int prec) const {
+    const int ks = prec == DIP_PRECISION_TF32 ? tc_ksplits() : simt_ksplits;
+    return (size_t)ks * k * k * 128 * c_pad;
+  }
+
+  int build_tc(float* partial) {
+    // ---- fprop
+    int bw, bh;
+    pick_tile(out_w, out_h, &bw, &bh);
+    fp = TcConvParams{};
+    DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N));
+    DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
+    fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
+    fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
+    fp.kh = fp.kw = k; fp.stride = stride; fp.offx = offx; fp.offy = offy;
+    fp.kblocks = c_pad / 32;
+    fp.tail_mmas = (C % 32 == 0) ? 4 : (C % 32 + 7) / 8;
+    fp.n_mma = N; fp.n_chunks = N / 32;
+    fp.bias = nullptr; fp.stats = stats; fp.stats_ld = N;
+    fp.stages = 6;
+    while (tc_conv_smem_bytes(fp) > 232448 && fp.stages > 2) fp.stages--;
+    // ---- dgrad
+    if (has_dgrad) {
+      pick_tile(dg_out_w, dg_out_h, &bw, &bh);
+      dg = TcConvParams{};
+      DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows));
+      DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, C, C, bw, bh));
+      dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
+      dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
+      dg.kh = dg.kw = k; dg.stride = 1; dg.offx = dg.offy = dg_off;
+      dg.kblocks = 4; dg.tail_mmas = 4;
+      dg.n_mma = crows; dg.n_chunks = (crows + 31) / 32;
+      dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
+      dg.stages = 6;
+      while (tc_conv_smem_bytes(dg) > 232448 && dg.stages > 2) dg.stages--;
+    }
+    // ---- wgrad
+    wg = TcWgradParams{};
+    wg.kp = (wg_w % 32 == 0) ? 32 : 16;
+    DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1));
+    DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.kp, 1));
+    wg.partial = partial;
+    wg.kh = wg.kw = k; wg.stride = stride; wg.offx = offx; wg.offy = offy;
+    wg.px_blocks_x = (wg_w + wg.kp - 1) / wg.kp;
+    wg.px_blocks = wg_h * wg.px_blocks_x;
+    wg.c_chunks = c_pad / 32;
+    wg.ksplits = tc_ksplits();
+    wg.stages = 6;
+    while (tc_wgrad_smem_bytes(wg) > 232448 && wg.stages > 1) wg.stages--;
+    if (tc_wgrad_smem_bytes(wg) > 232448) return fail("wgrad stage does not fit in shared memory");
+    return 0;
+  }
+
+  int run_fprop(int prec, const float* bias, cudaStream_t s) {
+    if (prec == DIP_PRECISION_TF32) {
+      TcConvParams p = fp;
+      p.bias = bias;
+      DIP_CUDA(tc_conv_launch(p, g_num_sms, s));
+    } else {
+      SimtConvArgs a{};
+      a.A = in; a.a_h = in_rows; a.a_w = in_cols; a.a_ld = in_ld; a.a_c = C;
+      a.Wp = wp_f; a.n_rows = N; a.c_pad = c_pad;
+      a.D = out; a.d_h = out_h; a.d_w = out_w; a.d_ld = N; a.d_c = N;
+      a.kh = a.kw = k; a.stride = stride; a.offx = offx; a.offy = offy; a.bias = bias;
+      launch_simt_conv(a, s);
+      if (stats != nullptr) launch_channel_stats(out, N, N, out_h * out_w, stats, s);
+      DIP_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
+  int run_dgrad(int prec, cudaStream_t s) {
+    if (prec == DIP_PRECISION_TF32) {
+      DIP_CUDA(tc_conv_launch(dg, g_num_sms, s));
+    } else {
+      SimtConvArgs a{};
+      a.A = dg_in; a.a_h = dg_in_h; a.a_w = dg_in_w; a.a_ld = 128; a.a_c = 128;
+      a.Wp = wp_d; a.n_rows = crows; a.c_pad = 128;
+      a.D = dg_out; a.d_h = dg_out_h; a.d_w = dg_out_w; a.d_ld = C; a.d_c = C;
+      a.kh = a.kw = k; a.stride = 1; a.offx = a.offy = dg_off; a.bias = nullptr;
+      launch_simt_conv(a, s);
+      DIP_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
+  int run_wgrad(int prec, float* partial, float* dw, cudaStream_t s) {
+    int ks;
+    if (prec == DIP_PRECISION_TF32) {
+      TcWgradParams p = wg;
+      p.partial = partial;
+      ks = p.ksplits;
+      DIP_CUDA(tc_wgrad_launch(p, s));
+    } else {
+      SimtWgradArgs a{};
+      a.dY = wg_dy; a.h = wg_h; a.w = wg_w;
+      a.X = in; a.x_h = in_rows; a.x_w = in_cols; a.x_ld = in_ld; a.x_c = C;
+      a.kh = a.kw = k; a.stride = stride; a.offx = offx; a.offy = offy;
+      a.partial = partial; a.c_pad = c_pad; a.ksplits = ks = simt_ksplits;
+      launch_simt_wgrad(a, s);
+    }
+    launch_wgrad_reduce(partial, ks, N, C, k, k, rot, c_pad, dw, s);
+    DIP_CUDA(cudaGetLastError());
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ table kernels
+struct PackEntry {
+  const float* w; float* dst_f; float* dst_d;
+  int N, C, k, rot, n_rows, c_pad, c_rows;
+};
+__global__ void k_pack_table(const PackEntry* __restrict__ tab) {
+  const PackEntry e = tab[blockIdx.y];
+  const int taps = e.k * e.k;
+  const long long nf = (long long)taps * e.n_rows * e.c_pad;
+  const long long nd = e.dst_d != nullptr ? (long long)taps * e.c_rows * 128 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (long long)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int c = (int)(i % e.c_pad), n = (int)((i / e.c_pad) % e.n_rows), tap = (int)(i / ((long long)e.c_pad * e.n_rows));
+      float v = 0.f;
+      if (n < e.N && c < e.C) v = e.w[((long long)n * e.C + (c + e.rot) % e.C) * taps + tap];
+      e.dst_f[i] = v;
+    } else {
+      const long long j = i - nf;
+      const int n = (int)(j % 128), c = (int)((j / 128) % e.c_rows), tapf = (int)(j / (128LL * e.c_rows));
+      const int tap = taps - 1 - tapf;
+      float v = 0.f;
+      if (n < e.N && c < e.C) v = e.w[((long long)n * e.C + (c + e.rot) % e.C) * taps + tap];
+      e.dst_d[j] = v;
+    }
+  }
+}
+struct CvtEntry {
+  const double* src; float* dst; int n, rot;
+};
+__global__ void k_cvt_table(const CvtEntry* __restrict__ tab) {
+  const CvtEntry e = tab[blockIdx.x];
+  for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)e.src[i];
+}
+struct RunEntry {
+  const double* fwd; float* rm; float* rv; long long* nb; int C, rot; float n;
+};
+__global__ void k_running_table(const RunEntry* __restrict__ tab) {
+  const RunEntry e = tab[blockIdx.x];
+  if (e.rm == nullptr) return;
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    const int ct = (c + e.rot) % e.C;
+    const double m = e.fwd[c] / e.n;
+    double var = e.fwd[e.C + c] / e.n - m * m;
+    if (var < 0) var = 0;
+    const double unb = e.n > 1.f ? var * e.n / (e.n - 1.0) : var;
+    e.rm[ct] = 0.9f * e.rm[ct] + 0.1f * (float)m;
+    e.rv[ct] = 0.9f * e.rv[ct] + 0.1f * (float)unb;
+  }
+  if (threadIdx.x == 0 && e.nb != nullptr) *e.nb += 1;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct Arena {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* get(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+struct BufInfo {
+  void* ptr; int rows, cols, ld, c;
+};
+struct BnLayer {
+  int C = 0, rot = 0; float n = 1.f;
+  double* fwd = nullptr; double* bwd = nullptr; double* dbias = nullptr;
+  int p_gamma = -1, p_beta = -1, p_bias = -1, idx = -1;
+};
+struct Level {
+  int H, W, h, w, Cin;
+  float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
+  float *dRaw_v, *dA_u, *dRaw_u, *dP_cat, *dCat, *dRaw_s, *G_sdx, *dRaw_d2, *dP_d1, *dRaw_d1, *ZS, *dPin;
+  BnLayer bn_s, bn_d1, bn_d2, bn_cat, bn_u, bn_v;
+  int p_skip_w, p_skip_b;
+  double* dw_s;
+  ConvOp d1, d2, up, c11;
+};
+
+}  // namespace dip
+
+using namespace dip;
+
+struct dip_plan {
+  dip_net_desc desc;
+  int H, W;
+  bool dry = false;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<Level> lv;
+  std::vector<long long> numel;
+  std::vector<float*> params, grads;
+  std::vector<void*> running;
+  std::vector<BnLayer*> bns;
+  std::vector<ConvOp*> convs;
+  std::map<std::string, BufInfo> bufs;
+  // head
+  int p_head_w = -1, p_head_b = -1;
+  double* dw_head = nullptr; double* db_head = nullptr; double* db_scratch = nullptr;
+  float* dU0 = nullptr;
+  float* out_saved = nullptr;  // [C_out][H][W] (sigmoid output, needed by backward)
+  // accumulators
+  double* acc_fwd = nullptr; size_t acc_fwd_n = 0;
+  double* acc_bwd = nullptr; size_t acc_bwd_n = 0;
+  float* partial = nullptr;
+  // runner scratch
+  float* zbuf = nullptr; float* dout = nullptr; double* loss = nullptr;
+  // tables
+  PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
+  int n_pack = 0, n_cvt = 0, n_run = 0;
+  long long pack_max = 0;
+  bool bound = false;
+  int launches_fwd = 0, launches_bwd = 0;
+};
+
+namespace dip {
+
+static BnRef bn_ref(const dip_plan* P, const BnLayer& b) {
+  BnRef r;
+  r.fwd = b.fwd; r.gamma = P->params[b.p_gamma]; r.beta = P->params[b.p_beta];
+  r.C = b.C; r.rot = b.rot; r.inv_n = 1.f / b.n;
+  return r;
+}
+
+static int build_plan(dip_plan* P, Arena& A) {
+  const dip_net_desc& d = P->desc;
+  const int L = d.num_scales, CH = d.channels, CS = d.skip_channels;
+  if (CH != 128) return fail("dip-b200: only num_channels_down == num_channels_up == 128 is supported by the engine");
+  if (CS != 4) return fail("dip-b200: only num_channels_skip == 4 is supported by the engine (round 1)");
+  if (d.in_channels % 4 != 0 || d.in_channels < 4 || d.in_channels > 128 || (d.in_channels & (d.in_channels - 1)))
+    return fail("dip-b200: input depth must be a power of two in [4,128]");
+  if (d.out_channels < 1 || d.out_channels > 4) return fail("dip-b200: num_output_channels must be <= 4");
+  if (L < 1 || L > 8) return fail("dip-b200: 1..8 scales supported");
+  if (P->H % (1 << L) || P->W % (1 << L)) return fail("dip-b200: H and W must be divisible by 2^num_scales");
+  if (!d.need_sigmoid) return fail("dip-b200: need_sigmoid=False is not supported by the engine (round 1)");
+  const int prec = d.precision;
+  P->lv.resize(L);
+  int pidx = 0;
+  // parameter slots in net.parameters() order: assigned recursively (pre-order part, then post-order part)
+  std::vector<int> pre(L), post(L);
+  {
+    int idx = 0;
+    for (int l = 0; l < L; ++l) { pre[l] = idx; idx += 12; }
+    for (int l = L - 1; l >= 0; --l) { post[l] = idx; idx += 10; }
+    P->p_head_w = idx; P->p_head_b = idx + 1;
+    pidx = idx + 2;
+  }
+  P->numel.assign(pidx, 0);
+  P->bns.clear(); P->convs.clear();
+  size_t acc_f = 0, acc_b = 0;
+  auto bn_init = [&](BnLayer& b, int C, int rot, int n, int pg, int pbias) {
+    b.C = C; b.rot = rot; b.n = (float)n; b.p_gamma = pg; b.p_beta = pg + 1; b.p_bias = pbias;
+    P->numel[pg] = C; P->numel[pg + 1] = C;
+    acc_f += 2 * C; acc_b += 3 * C;
+  };
+  for (int l = 0; l < L; ++l) {
+    Level& v = P->lv[l];
+    v.H = P->H >> l; v.W = P->W >> l; v.h = v.H / 2; v.w = v.W / 2;
+    v.Cin = l == 0 ? d.in_channels : CH;
+    const int b0 = pre[l], b1 = post[l];
+    // skip conv 1x1 Cin -> CS
+    v.p_skip_w = b0; v.p_skip_b = b0 + 1;
+    P->numel[b0] = (long long)CS * v.Cin; P->numel[b0 + 1] = CS;
+    bn_init(v.bn_s, CS, 0, v.H * v.W, b0 + 2, b0 + 1);
+    // down1 3x3 s2
+    v.d1.C = v.Cin; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + 4; v.d1.p_b = b0 + 5;
+    P->numel[b0 + 4] = 128LL * v.Cin * 9; P->numel[b0 + 5] = 128;
+    bn_init(v.bn_d1, 128, 0, v.h * v.w, b0 + 6, b0 + 5);
+    // down2 3x3
+    v.d2.C = 128; v.d2.k = 3; v.d2.stride = 1; v.d2.p_w = b0 + 8; v.d2.p_b = b0 + 9;
+    P->numel[b0 + 8] = 128LL * 128 * 9; P->numel[b0 + 9] = 128;
+    bn_init(v.bn_d2, 128, 0, v.h * v.w, b0 + 10, b0 + 9);
+    // concat BN (torch channel order [skip | up], engine order [up | skip])
+    bn_init(v.bn_cat, 128 + CS, CS, v.H * v.W, b1 + 0, -1);
+    // up 3x3 (128+CS) -> 128
+    v.up.C = 128 + CS; v.up.k = 3; v.up.stride = 1; v.up.rot = CS; v.up.p_w = b1 + 2; v.up.p_b = b1 + 3;
+    P->numel[b1 + 2] = 128LL * (128 + CS) * 9; P->numel[b1 + 3] = 128;
+    bn_init(v.bn_u, 128, 0, v.H * v.W, b1 + 4, b1 + 3);
+    // 1x1 128 -> 128
+    v.c11.C = 128; v.c11.k = 1; v.c11.stride = 1; v.c11.p_w = b1 + 6; v.c11.p_b = b1 + 7;
+    P->numel[b1 + 6] = 128LL * 128; P->numel[b1 + 7] = 128;
+    bn_init(v.bn_v, 128, 0, v.H * v.W, b1 + 8, b1 + 7);
+  }
+  P->numel[P->p_head_w] = (long long)d.out_channels * 128;
+  P->numel[P->p_head_b] = d.out_channels;
+  // BN order (running-stat table) follows state_dict order: skip, d1, d2, <deeper>, cat, up, 1x1
+  {
+    std::vector<BnLayer*> a, b;
+    for (int l = 0; l < L; ++l) { a.push_back(&P->lv[l].bn_s); a.push_back(&P->lv[l].bn_d1); a.push_back(&P->lv[l].bn_d2); }
+    for (int l = L - 1; l >= 0; --l) { a.push_back(&P->lv[l].bn_cat); a.push_back(&P->lv[l].bn_u); a.push_back(&P->lv[l].bn_v); }
+    P->bns = a;
+    for (size_t i = 0; i < P->bns.size(); ++i) P->bns[i]->idx = (int)i;
+  }
+  // ---- accumulators
+  size_t skinny_acc = 0;
+  for (int l = 0; l < L; ++l) skinny_acc += (size_t)CS * P->lv[l].Cin;
+  skinny_acc += (size_t)d.out_channels * 128 + 8;
+  P->acc_fwd_n = acc_f;
+  P->acc_bwd_n = acc_b + skinny_acc;
+  P->acc_fwd = A.get<double>(P->acc_fwd_n);
+  P->acc_bwd = A.get<double>(P->acc_bwd_n);
+  {
+    double* f = P->acc_fwd; double* b = P->acc_bwd;
+    for (BnLayer* bn : P->bns) {
+      bn->fwd = f; f = f ? f + 2 * bn->C : nullptr;
+      bn->bwd = b; bn->dbias = b ? b + 2 * bn->C : nullptr; b = b ? b + 3 * bn->C : nullptr;
+    }
+    for (int l = 0; l < L; ++l) { P->lv[l].dw_s = b; b = b ? b + (size_t)CS * P->lv[l].Cin : nullptr; }
+    P->dw_head = b; b = b ? b + (size_t)d.out_channels * 128 : nullptr;
+    P->db_head = b;
+    P->db_scratch = b ? b + 4 : nullptr;
+  }
+  // ---- activations
+  auto reg = [&](const std::string& name, void* p, int rows, int cols, int ld, int c) { P->bufs[name] = BufInfo{p, rows, cols, ld, c}; };
+  for (int l = 0; l < L; ++l) {
+    Level& v = P->lv[l];
+    const std::string pf = "L" + std::to_string(l) + ".";
+    const size_t HW = (size_t)v.H * v.W, hw = (size_t)v.h * v.w;
+    const size_t HWp = (size_t)(v.H + 2) * (v.W + 2), hwp = (size_t)(v.h + 2) * (v.w + 2);
+    const bool last = l == L - 1;
+    if (l == 0) v.Pin = A.get<float>(HWp * v.Cin); else v.Pin = P->lv[l - 1].P_d2;
+    v.raw_s = A.get<float>(HW * CS);
+    v.raw_d1 = A.get<float>(hw * 128);
+    v.P_d1 = A.get<float>(hwp * 128);
+    v.raw_d2 = A.get<float>(hw * 128);
+    v.P_d2 = A.get<float>(last ? hw * 128 : hwp * 128);
+    v.P_cat = A.get<float>(HWp * (128 + CS));
+    v.raw_u = A.get<float>(HW * 128);
+    v.A_u = A.get<float>(HW * 128);
+    v.raw_v = A.get<float>(HW * 128);
+    v.U = A.get<float>(HW * 128);
+    v.dRaw_v = A.get<float>(HW * 128);
+    v.dA_u = A.get<float>(HW * 128);
+    v.dRaw_u = A.get<float>(HW * 128);
+    v.dP_cat = A.get<float>(HWp * (128 + CS));
+    v.dCat = A.get<float>(HW * (128 + CS));
+    v.dRaw_s = A.get<float>(HW * CS);
+    v.G_sdx = l > 0 ? A.get<float>(HW * v.Cin) : nullptr;
+    v.dRaw_d2 = A.get<float>(hw * 128);
+    v.dP_d1 = A.get<float>(hwp * 128);
+    v.dRaw_d1 = A.get<float>(hw * 128);
+    v.ZS = l > 0 ? A.get<float>(HW * 128) : nullptr;
+    v.dPin = l > 0 ? A.get<float>(HWp * 128) : nullptr;
+    reg(pf + "Pin", v.Pin, v.H + 2, v.W + 2, v.Cin, v.Cin);
+    reg(pf + "raw_s", v.raw_s, v.H, v.W, CS, CS);
+    reg(pf + "raw_d1", v.raw_d1, v.h, v.w, 128, 128);
+    reg(pf + "P_d1", v.P_d1, v.h + 2, v.w + 2, 128, 128);
+    reg(pf + "raw_d2", v.raw_d2, v.h, v.w, 128, 128);
+    if (last) reg(pf + "P_d2", v.P_d2, v.h, v.w, 128, 128); else reg(pf + "P_d2", v.P_d2, v.h + 2, v.w + 2, 128, 128);
+    reg(pf + "P_cat", v.P_cat, v.H + 2, v.W + 2, 128 + CS, 128 + CS);
+    reg(pf + "raw_u", v.raw_u, v.H, v.W, 128, 128);
+    reg(pf + "A_u", v.A_u, v.H, v.W, 128, 128);
+    reg(pf + "raw_v", v.raw_v, v.H, v.W, 128, 128);
+    reg(pf + "U", v.U, v.H, v.W, 128, 128);
+    reg(pf + "dRaw_v", v.dRaw_v, v.H, v.W, 128, 128);
+    reg(pf + "dA_u", v.dA_u, v.H, v.W, 128, 128);
+    reg(pf + "dRaw_u", v.dRaw_u, v.H, v.W, 128, 128);
+    reg(pf + "dP_cat", v.dP_cat, v.H + 2, v.W + 2, 128 + CS, 128 + CS);
+    reg(pf + "dCat", v.dCat, v.H, v.W, 128 + CS, 128 + CS);
+    reg(pf + "dRaw_s", v.dRaw_s, v.H, v.W, CS, CS);
+    reg(pf + "dRaw_d2", v.dRaw_d2, v.h, v.w, 128, 128);
+    reg(pf + "dP_d1", v.dP_d1, v.h + 2, v.w + 2, 128, 128);
+    reg(pf + "dRaw_d1", v.dRaw_d1, v.h, v.w, 128, 128);
+    if (l > 0) {
+      reg(pf + "G_sdx", v.G_sdx, v.H, v.W, v.Cin, v.Cin);
+      reg(pf + "ZS", v.ZS, v.H, v.W, 128, 128);
+      reg(pf + "dPin", v.dPin, v.H + 2, v.W + 2, 128, 128);
+    }
+  }
+  P->dU0 = A.get<float>((size_t)P->H * P->W * 128);
+  P->out_saved = A.get<float>((size_t)P->H * P->W * d.out_channels);
+  P->zbuf = A.get<float>((size_t)P->H * P->W * d.in_channels);
+  P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
+  P->loss = A.get<double>(4);
+  reg("dU0", P->dU0, P->H, P->W, 128, 128);
+  // ---- conv ops
+  size_t partial_max = 0;
+  for (int l = 0; l < L; ++l) {
+    Level& v = P->lv[l];
+    // down1: Pin (padded, stride 2) -> raw_d1
+    ConvOp& a = v.d1;
+    a.set_shapes();
+    a.in = v.Pin; a.in_rows = v.H + 2; a.in_cols = v.W + 2; a.in_ld = v.Cin; a.offx = a.offy = 0;
+    a.out = v.raw_d1; a.out_h = v.h; a.out_w = v.w; a.stats = v.bn_d1.fwd;
+    a.has_dgrad = l > 0;
+    a.dg_in = v.ZS; a.dg_in_h = v.H; a.dg_in_w = v.W; a.dg_out = v.dPin; a.dg_out_h = v.H + 2; a.dg_out_w = v.W + 2; a.dg_off = -2;
+    a.wg_dy = v.dRaw_d1; a.wg_h = v.h; a.wg_w = v.w;
+    // down2: P_d1 -> raw_d2
+    ConvOp& b = v.d2;
+    b.set_shapes();
+    b.in = v.P_d1; b.in_rows = v.h + 2; b.in_cols = v.w + 2; b.in_ld = 128; b.offx = b.offy = 0;
+    b.out = v.raw_d2; b.out_h = v.h; b.out_w = v.w; b.stats = v.bn_d2.fwd;
+    b.has_dgrad = true;
+    b.dg_in = v.dRaw_d2; b.dg_in_h = v.h; b.dg_in_w = v.w; b.dg_out = v.dP_d1; b.dg_out_h = v.h + 2; b.dg_out_w = v.w + 2; b.dg_off = -2;
+    b.wg_dy = v.dRaw_d2; b.wg_h = v.h; b.wg_w = v.w;
+    // up: P_cat -> raw_u
+    ConvOp& c = v.up;
+    c.set_shapes();
+    c.in = v.P_cat; c.in_rows = v.H + 2; c.in_cols = v.W + 2; c.in_ld = 128 + CS; c.offx = c.offy = 0;
+    c.out = v.raw_u; c.out_h = v.H; c.out_w = v.W; c.stats = v.bn_u.fwd;
+    c.has_dgrad = true;
+    c.dg_in = v.dRaw_u; c.dg_in_h = v.H; c.dg_in_w = v.W; c.dg_out = v.dP_cat; c.dg_out_h = v.H + 2; c.dg_out_w = v.W + 2; c.dg_off = -2;
+    c.wg_dy = v.dRaw_u; c.wg_h = v.H; c.wg_w = v.W;
+    // 1x1: A_u -> raw_v
+    ConvOp& e = v.c11;
+    e.set_shapes();
+    e.in = v.A_u; e.in_rows = v.H; e.in_cols = v.W; e.in_ld = 128; e.offx = e.offy = 0;
+    e.out = v.raw_v; e.out_h = v.H; e.out_w = v.W; e.stats = v.bn_v.fwd;
+    e.has_dgrad = true;
+    e.dg_in = v.dRaw_v; e.dg_in_h = v.H; e.dg_in_w = v.W; e.dg_out = v.dA_u; e.dg_out_h = v.H; e.dg_out_w = v.W; e.dg_off = 0;
+    e.wg_dy = v.dRaw_v; e.wg_h = v.H; e.wg_w = v.W;
+    for (ConvOp* op : {&a, &b, &c, &e}) {
+      op->wp_f = A.get<float>(op->wp_f_elems());
+      op->wp_d = op->has_dgrad ? A.get<float>(op->wp_d_elems()) : nullptr;
+      op->simt_ksplits = op->wg_h < 64 ? op->wg_h : 64;
+      const size_t pe = op->partial_elems(prec);
+      if (pe > partial_max) partial_max = pe;
+      P->convs.push_back(op);
+    }
+  }
+  P->partial = A.get<float>(partial_max);
+  P->n_pack = (int)P->convs.size();
+  P->n_cvt = (int)P->bns.size() * 3 + L + 2;
+  P->n_run = (int)P->bns.size();
+  P->d_pack = A.get<PackEntry>(P->n_pack);
+  P->d_cvt = A.get<CvtEntry>(P->n_cvt);
+  P->d_run = A.get<RunEntry>(P->n_run);
+  if (P->dry) return 0;
+  // ---- device-side setup
+  // The zero-stuffed buffers are written at even positions only: clear them once.
+  for (int l = 1; l < L; ++l) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
+  if (prec == DIP_PRECISION_TF32)
+    for (ConvOp* op : P->convs) DIP_CHECK(op->build_tc(P->partial));
+  P->pack_max = 0;
+  for (ConvOp* op : P->convs) {
+    const long long n = (long long)op->wp_f_elems() + (op->has_dgrad ? (long long)op->wp_d_elems() : 0);
+    if (n > P->pack_max) P->pack_max = n;
+  }
+  return 0;
+}
+
+static int upload_tables(dip_plan* P) {
+  std::vector<PackEntry> pk;
+  for (ConvOp* op : P->convs) {
+    PackEntry e{};
+    e.w = P->params[op->p_w]; e.dst_f = op->wp_f; e.dst_d = op->has_dgrad ? op->wp_d : nullptr;
+    e.N = op->N; e.C = op->C; e.k = op->k; e.rot = op->rot; e.n_rows = op->N; e.c_pad = op->c_pad; e.c_rows = op->crows;
+    pk.push_back(e);
+  }
+  DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
+  std::vector<CvtEntry> cv;
+  for (BnLayer* b : P->bns) {
+    cv.push_back(CvtEntry{b->bwd + b->C, P->grads[b->p_gamma], b->C, b->rot});  // dgamma = sum dz*xhat
+    cv.push_back(CvtEntry{b->bwd, P->grads[b->p_beta], b->C, b->rot});          // dbeta  = sum dz
+    if (b->p_bias >= 0) cv.push_back(CvtEntry{b->dbias, P->grads[b->p_bias], b->C, 0});
+    else cv.push_back(CvtEntry{b->dbias, nullptr, 0, 0});
+  }
+  for (size_t l = 0; l < P->lv.size(); ++l)
+    cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0});
+  cv.push_back(CvtEntry{P->dw_head, P->grads[P->p_head_w], (int)P->numel[P->p_head_w], 0});
+  cv.push_back(CvtEntry{P->db_head, P->grads[P->p_head_b], (int)P->numel[P->p_head_b], 0});
+  if ((int)cv.size() != P->n_cvt) return fail("internal: cvt table size mismatch");
+  DIP_CUDA(cudaMemcpy(P->d_cvt, cv.data(), cv.size() * sizeof(CvtEntry), cudaMemcpyHostToDevice));
+  std::vector<RunEntry> rn;
+  for (BnLayer* b : P->bns) {
+    RunEntry e{};
+    e.fwd = b->fwd; e.C = b->C; e.rot = b->rot; e.n = b->n;
+    if (!P->running.empty()) {
+      e.rm = (float*)P->running[3 * b->idx]; e.rv = (float*)P->running[3 * b->idx + 1]; e.nb = (long long*)P->running[3 * b->idx + 2];
+    }
+    rn.push_back(e);
+  }
+  DIP_CUDA(cudaMemcpy(P->d_run, rn.data(), rn.size() * sizeof(RunEntry), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+static CatArgs cat_args(const dip_plan* P, const Level& v, const float* Usrc) {
+  CatArgs a;
+  a.U = Usrc; a.raw_s = v.raw_s; a.bn_s = bn_ref(P, v.bn_s);
+  a.Cu = 128; a.Cs = P->desc.skip_channels; a.H = v.H; a.W = v.W; a.bilinear = P->desc.upsample_bilinear;
+  return a;
+}
+static const float* level_usrc(const dip_plan* P, int l) {
+  const int L = (int)P->lv.size();
+  return l == L - 1 ? P->lv[l].P_d2 : P->lv[l + 1].U;
+}
+
+static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
+  Level& v = P->lv[l];
+  const int prec = P->desc.precision;
+  const int CS = P->desc.skip_channels;
+  const bool last = l == (int)P->lv.size() - 1;
+  const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
+  // skip branch: 1x1 conv Cin -> CS (+ statistics)
+  launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0, s);
+  launch_channel_stats(v.raw_s, CS, CS, v.H * v.W, v.bn_s.fwd, s);
+  nl += 2;
+  // deeper branch
+  DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
+  launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, v.P_d1, 128, 1, 1, s);
+  DIP_CHECK(v.d2.run_fprop(prec, P->params[v.d2.p_b], s));
+  launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, v.P_d2, 128, last ? 0 : 1, 1, s);
+  nl += 4 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
+  if (!last) DIP_CHECK(fwd_level(P, l + 1, s, nl));
+  // upsample + concat + BN + pad
+  CatArgs ca = cat_args(P, v, level_usrc(P, l));
+  launch_cat_stats(ca, v.bn_cat.fwd, s);
+  launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s);
+  DIP_CHECK(v.up.run_fprop(prec, P->params[v.up.p_b], s));
+  launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, v.A_u, 128, 0, 1, s);
+  DIP_CHECK(v.c11.run_fprop(prec, P->params[v.c11.p_b], s));
+  launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s);
+  nl += 6 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int plan_forward(dip_plan* P, const float* z, const float* noise, float sigma, float* out, cudaStream_t s) {
+  if (!P->bound) return fail("dip_forward: parameters not bound (call dip_plan_bind)");
+  int nl = 0;
+  DIP_CUDA(cudaMemsetAsync(P->acc_fwd, 0, P->acc_fwd_n * sizeof(double), s));
+  {
+    dim3 grid((unsigned)((P->pack_max + 255) / 256 < 64 ? (P->pack_max + 255) / 256 : 64), P->n_pack);
+    k_pack_table<<<grid, 256, 0, s>>>(P->d_pack);
+  }
+  Level& v0 = P->lv[0];
+  launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s);
+  nl += 3;
+  DIP_CHECK(fwd_level(P, 0, s, nl));
+  launch_skinny_fwd(v0.U, 128, v0.W, P->params[P->p_head_w], P->params[P->p_head_b], 128, P->desc.out_channels, v0.H, v0.W,
+                    P->out_saved, 1, s);
+  if (out != nullptr && out != P->out_saved)
+    DIP_CUDA(cudaMemcpyAsync(out, P->out_saved, (size_t)v0.H * v0.W * P->desc.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  k_running_table<<<P->n_run, 160, 0, s>>>(P->d_run);
+  nl += 3;
+  DIP_CUDA(cudaGetLastError());
+  P->launches_fwd = nl;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+static int bn_bwd(dip_plan* P, const float* raw, int ld_raw, BnLayer& b, int act, GradSrc src, int H, int W, float* draw,
+                  float* zs, cudaStream_t s, int& nl) {
+  BnRef r = bn_ref(P, b);
+  launch_bn_bwd_reduce(raw, ld_raw, r, act, src, H, W, b.bwd, s);
+  launch_bn_bwd_apply(raw, ld_raw, r, act, src, H, W, b.bwd, draw, zs, b.dbias, s);
+  nl += 2;
+  return 0;
+}
+static GradSrc src_plain(const float* g, int ld, int coff) { GradSrc s{}; s.kind = 0; s.g = g; s.ld = ld; s.coff = coff; return s; }
+static GradSrc src_fold(const float* gp, int ld, const float* g2, int ld2) { GradSrc s{}; s.kind = 1; s.g = gp; s.ld = ld; s.coff = 0; s.g2 = g2; s.ld2 = ld2; return s; }
+static GradSrc src_upadj(const float* d, int ld, int bilinear) { GradSrc s{}; s.kind = 2; s.g = d; s.ld = ld; s.coff = 0; s.bilinear = bilinear; return s; }
+
+static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl) {
+  Level& v = P->lv[l];
+  const int prec = P->desc.precision;
+  const int CS = P->desc.skip_channels;
+  const int CC = 128 + CS;
+  const bool last = l == (int)P->lv.size() - 1;
+  const int wl = prec == DIP_PRECISION_TF32 ? 2 : 2;
+  // 1x1 conv + BN + LReLU
+  DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl));
+  DIP_CHECK(v.c11.run_wgrad(prec, P->partial, P->grads[v.c11.p_w], s));
+  DIP_CHECK(v.c11.run_dgrad(prec, s));
+  nl += wl + 1;
+  // up conv + BN + LReLU
+  DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl));
+  DIP_CHECK(v.up.run_wgrad(prec, P->partial, P->grads[v.up.p_w], s));
+  DIP_CHECK(v.up.run_dgrad(prec, s));
+  nl += wl + 1;
+  // concat BN
+  CatArgs ca = cat_args(P, v, level_usrc(P, l));
+  BnRef rc = bn_ref(P, v.bn_cat);
+  launch_cat_bwd_reduce(ca, rc, v.dP_cat, CC, v.bn_cat.bwd, s);
+  launch_cat_bwd_apply(ca, rc, v.dP_cat, CC, v.bn_cat.bwd, v.dCat, s);
+  nl += 2;
+  // skip branch
+  DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, s, nl));
+  {
+    const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
+    launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
+                      l > 0 ? v.G_sdx : nullptr, v.dw_s, P->db_scratch /*bias grad comes from the BN backward*/, s);
+    nl += 1;
+  }
+  // deeper branch
+  GradSrc src_d2;
+  if (!last) {
+    DIP_CHECK(bwd_level(P, l + 1, src_upadj(v.dCat, CC, P->desc.upsample_bilinear), s, nl));
+    Level& n = P->lv[l + 1];
+    src_d2 = src_fold(n.dPin, 128, n.G_sdx, 128);
+  } else {
+    src_d2 = src_upadj(v.dCat, CC, P->desc.upsample_bilinear);
+  }
+  DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl));
+  DIP_CHECK(v.d2.run_wgrad(prec, P->partial, P->grads[v.d2.p_w], s));
+  DIP_CHECK(v.d2.run_dgrad(prec, s));
+  nl += wl + 1;
+  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, 0), v.h, v.w, v.dRaw_d1, l > 0 ? v.ZS : nullptr, s, nl));
+  DIP_CHECK(v.d1.run_wgrad(prec, P->partial, P->grads[v.d1.p_w], s));
+  nl += wl;
+  if (l > 0) { DIP_CHECK(v.d1.run_dgrad(prec, s)); nl += 1; }
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
+  if (!P->bound) return fail("dip_backward: parameters not bound");
+  int nl = 0;
+  DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
+  Level& v0 = P->lv[0];
+  launch_skinny_bwd(v0.U, 128, v0.W, P->params[P->p_head_w], 128, P->desc.out_channels, v0.H, v0.W, dout, P->out_saved, 1, P->dU0,
+                    P->dw_head, P->db_head, s);
+  nl += 2;
+  DIP_CHECK(bwd_level(P, 0, src_plain(P->dU0, 128, 0), s, nl));
+  k_cvt_table<<<P->n_cvt, 128, 0, s>>>(P->d_cvt);
+  nl += 1;
+  DIP_CUDA(cudaGetLastError());
+  P->launches_bwd = nl;
+  return 0;
+}
+
+}  // namespace dip
+
+// ================================================================================================ C ABI
+struct dip_adam {
+  int n = 0;
+  std::vector<long long> numel;
+  int nblocks = 0;
+  float** d_p = nullptr; const float** d_g = nullptr; float** d_m = nullptr; float** d_v = nullptr;
+  int* d_blk_tensor = nullptr; int* d_blk_start = nullptr; int* d_numel = nullptr;
+  bool bound = false;
+};
+
+extern "C" {
+
+const char* dip_last_error(void) { return g_err.c_str(); }
+int dip_version(void) { return 100; }
+
+size_t dip_plan_workspace_bytes(const dip_net_desc* desc, int H, int W) {
+  dip_plan P;
+  P.desc = *desc; P.H = H; P.W = W; P.dry = true;
+  Arena A{nullptr};
+  if (build_plan(&P, A) != 0) return 0;
+  return A.off + 4096;
+}
+
+int dip_plan_create(const dip_net_desc* desc, int H, int W, void* workspace, size_t workspace_bytes, dip_plan** out) {
+  DIP_CHECK(engine_init());
+  const size_t need = dip_plan_workspace_bytes(desc, H, W);
+  if (need == 0) return -1;
+  if (workspace == nullptr || workspace_bytes < need) return fail("dip_plan_create: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return fail("dip_plan_create: workspace must be 256-byte aligned");
+  dip_plan* P = new dip_plan();
+  P->desc = *desc; P->H = H; P->W = W; P->ws = (uint8_t*)workspace; P->ws_bytes = workspace_bytes;
+  Arena A{(uint8_t*)workspace};
+  if (build_plan(P, A) != 0) { delete P; return -1; }
+  *out = P;
+  return 0;
+}
+void dip_plan_destroy(dip_plan* plan) { delete plan; }
+int dip_plan_num_params(const dip_plan* plan) { return (int)plan->numel.size(); }
+int dip_plan_num_bn(const dip_plan* plan) { return (int)plan->bns.size(); }
+long long dip_plan_param_numel(const dip_plan* plan, int index) {
+  if (index < 0 || index >= (int)plan->numel.size()) return -1;
+  return plan->numel[index];
+}
+int dip_plan_bind(dip_plan* P, void* const* params, void* const* grads, void* const* bn_running) {
+  const int n = (int)P->numel.size();
+  P->params.resize(n); P->grads.resize(n);
+  for (int i = 0; i < n; ++i) {
+    if (params[i] == nullptr || grads[i] == nullptr) return fail("dip_plan_bind: null parameter/gradient pointer");
+    P->params[i] = (float*)params[i]; P->grads[i] = (float*)grads[i];
+  }
+  P->running.clear();
+  if (bn_running != nullptr) P->running.assign(bn_running, bn_running + 3 * P->bns.size());
+  DIP_CHECK(upload_tables(P));
+  P->bound = true;
+  return 0;
+}
+int dip_forward(dip_plan* P, const void* z, const void* noise, float sigma, void* out, dip_stream_t stream) {
+  return plan_forward(P, (const float*)z, (const float*)noise, sigma, (float*)out, (cudaStream_t)stream);
+}
+int dip_backward(dip_plan* P, const void* dout, dip_stream_t stream) {
+  return plan_backward(P, (const float*)dout, (cudaStream_t)stream);
+}
+int dip_loss_mse(const void* out, const void* target, const void* mask, int channels, int hw, double* loss, void* dout,
+                 dip_stream_t stream) {
+  launch_mse((const float*)out, (const float*)target, (const float*)mask, channels, hw, loss, (float*)dout, (cudaStream_t)stream);
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+int dip_noise_perturb(const void* z0, void* z, float sigma, uint64_t seed, uint64_t offset, size_t n, dip_stream_t stream) {
+  if (n % 4 != 0) return fail("dip_noise_perturb: n must be a multiple of 4");
+  launch_noise((const float*)z0, (float*)z, sigma, seed, offset, n, (cudaStream_t)stream);
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dip_adam_create(int ntensors, const long long* numel, dip_adam** out) {
+  dip_adam* a = new dip_adam();
+  a->n = ntensors;
+  a->numel.assign(numel, numel + ntensors);
+  std::vector<int> bt, bs, ne;
+  const int chunk = adam_chunk();
+  for (int t = 0; t < ntensors; ++t) {
+    ne.push_back((int)numel[t]);
+    for (long long st = 0; st < numel[t]; st += chunk) { bt.push_back(t); bs.push_back((int)st); }
+  }
+  a->nblocks = (int)bt.size();
+  DIP_CUDA(cudaMalloc(&a->d_p, ntensors * sizeof(void*)));
+  DIP_CUDA(cudaMalloc(&a->d_g, ntensors * sizeof(void*)));
+  DIP_CUDA(cudaMalloc(&a->d_m, ntensors * sizeof(void*)));
+  DIP_CUDA(cudaMalloc(&a->d_v, ntensors * sizeof(void*)));
+  DIP_CUDA(cudaMalloc(&a->d_blk_tensor, bt.size() * sizeof(int)));
+  DIP_CUDA(cudaMalloc(&a->d_blk_start, bs.size() * sizeof(int)));
+  DIP_CUDA(cudaMalloc(&a->d_numel, ne.size() * sizeof(int)));
+  DIP_CUDA(cudaMemcpy(a->d_blk_tensor, bt.data(), bt.size() * sizeof(int), cudaMemcpyHostToDevice));
+  DIP_CUDA(cudaMemcpy(a->d_blk_start, bs.data(), bs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  DIP_CUDA(cudaMemcpy(a->d_numel, ne.data(), ne.size() * sizeof(int), cudaMemcpyHostToDevice));
+  *out = a;
+  return 0;
+}
+void dip_adam_destroy(dip_adam* a) {
+  if (!a) return;
+  cudaFree(a->d_p); cudaFree(a->d_g); cudaFree(a->d_m); cudaFree(a->d_v);
+  cudaFree(a->d_blk_tensor); cudaFree(a->d_blk_start); cudaFree(a->d_numel);
+  delete a;
+}
+int dip_adam_bind(dip_adam* a, void* const* p, void* const* g, void* const* m, void* const* v) {
+  DIP_CUDA(cudaMemcpy(a->d_p, p, a->n * sizeof(void*), cudaMemcpyHostToDevice));
+  DIP_CUDA(cudaMemcpy(a->d_g, g, a->n * sizeof(void*), cudaMemcpyHostToDevice));
+  DIP_CUDA(cudaMemcpy(a->d_m, m, a->n * sizeof(void*), cudaMemcpyHostToDevice));
+  DIP_CUDA(cudaMemcpy(a->d_v, v, a->n * sizeof(void*), cudaMemcpyHostToDevice));
+  a->bound = true;
+  return 0;
+}
+int dip_adam_step(dip_adam* a, double lr, double beta1, double beta2, double eps, int step, dip_stream_t stream) {
+  if (!a->bound) return fail("dip_adam_step: not bound");
+  if (step < 1) return fail("dip_adam_step: step must be >= 1");
+  AdamTable t{a->d_p, a->d_g, a->d_m, a->d_v, a->d_blk_tensor, a->d_blk_start, a->d_numel, a->nblocks};
+  launch_adam(t, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* target, const void* mask, float sigma,
+                       uint64_t seed, int step0, int iters, double lr, void* out, double* loss_hist, dip_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nz = (size_t)P->H * P->W * P->desc.in_channels;
+  const int hw = P->H * P->W;
+  for (int i = 0; i < iters; ++i) {
+    const float* zin = (const float*)z0;
+    if (sigma > 0.f) {
+      launch_noise((const float*)z0, P->zbuf, sigma, seed, (uint64_t)(step0 + i), nz, s);
+      zin = P->zbuf;
+    }
+    DIP_CHECK(plan_forward(P, zin, nullptr, 0.f, (float*)out, s));
+    double* lp = loss_hist != nullptr ? loss_hist + i : P->loss;
+    DIP_CUDA(cudaMemsetAsync(lp, 0, sizeof(double), s));
+    launch_mse(P->out_saved, (const float*)target, (const float*)mask, P->desc.out_channels, hw, lp, P->dout, s);
+    DIP_CHECK(plan_backward(P, P->dout, s));
+    DIP_CHECK(dip_adam_step(adam, lr, 0.9, 0.999, 1e-8, step0 + i + 1, stream));
+  }
+  return 0;
+}
+
+int dip_plan_buffer(const dip_plan* plan, const char* name, void** ptr, int* dims4) {
+  auto it = plan->bufs.find(name);
+  if (it == plan->bufs.end()) return fail(std::string("dip_plan_buffer: unknown buffer ") + name);
+  *ptr = it->second.ptr;
+  dims4[0] = it->second.rows; dims4[1] = it->second.cols; dims4[2] = it->second.ld; dims4[3] = it->second.c;
+  return 0;
+}
+int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {
+  *fwd = plan->launches_fwd; *bwd = plan->launches_bwd;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- single-op entry points
+size_t dip_op_scratch_bytes(void) { return (size_t)96 << 20; }
+
+static int op_common(ConvOp& op, int N, int C, int k, int stride, int rot, float* scratch, const float* w, cudaStream_t s) {
+  if (N != 128) return fail("dip_op_conv_*: N must be 128");
+  if (C % 4 != 0 || C > 160) return fail("dip_op_conv_*: C must be a multiple of 4 and <= 160");
+  op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;
+  op.set_shapes();
+  op.wp_f = scratch;
+  op.wp_d = scratch + ((op.wp_f_elems() + 63) & ~size_t(63));
+  launch_pack_fprop(w, N, C, k, k, rot, op.wp_f, N, op.c_pad, s);
+  launch_pack_dgrad(w, N, C, k, k, rot, op.wp_d, op.crows, 128, s);
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+static float* op_partial(ConvOp& op, float* scratch) {
+  return scratch + ((op.wp_f_elems() + 63) & ~size_t(63)) + ((op.wp_d_elems() + 63) & ~size_t(63));
+}
+
+int dip_op_conv_fprop(const void* a, int a_h, int a_w, int a_c, const void* w, const void* bias, int N, int C, int k, int stride,
+                      int offx, int offy, int rot, void* d, int d_h, int d_w, double* stats, int precision, void* scratch,
+                      dip_stream_t stream) {
+  DIP_CHECK(engine_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvOp op;
+  DIP_CHECK(op_common(op, N, C, k, stride, rot, (float*)scratch, (const float*)w, s));
+  op.in = (const float*)a; op.in_rows = a_h; op.in_cols = a_w; op.in_ld = a_c; op.offx = offx; op.offy = offy;
+  op.out = (float*)d; op.out_h = d_h; op.out_w = d_w; op.stats = stats;
+  op.has_dgrad = false;
+  op.wg_dy = (const float*)d; op.wg_h = d_h; op.wg_w = d_w;  // placeholders so that build_tc can encode maps
+  if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
+  return op.run_fprop(precision, (const float*)bias, s);
+}
+int dip_op_conv_dgrad(const void* dy, int dy_h, int dy_w, const void* w, int N, int C, int k, int rot, void* dx, int dx_h, int dx_w,
+                      int precision, void* scratch, dip_stream_t stream) {
+  DIP_CHECK(engine_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvOp op;
+  DIP_CHECK(op_common(op, N, C, k, 1, rot, (float*)scratch, (const float*)w, s));
+  // fprop/wgrad placeholders (valid maps over the same buffers; not launched)
+  op.in = (const float*)dx; op.in_rows = dx_h; op.in_cols = dx_w; op.in_ld = C; op.out = (float*)const_cast<void*>(dy);
+  op.out_h = dy_h; op.out_w = dy_w; op.wg_dy = (const float*)dy; op.wg_h = dy_h; op.wg_w = dy_w;
+  op.has_dgrad = true;
+  op.dg_in = (const float*)dy; op.dg_in_h = dy_h; op.dg_in_w = dy_w;
+  op.dg_out = (float*)dx; op.dg_out_h = dx_h; op.dg_out_w = dx_w; op.dg_off = -(k - 1);
+  if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
+  return op.run_dgrad(precision, s);
+}
+int dip_op_conv_wgrad(const void* dy, int dy_h, int dy_w, const void* a, int a_h, int a_w, int a_c, int N, int C, int k, int stride,
+                      int offx, int offy, int rot, void* dw, int precision, void* scratch, dip_stream_t stream) {
+  DIP_CHECK(engine_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvOp op;
+  // weights are not needed for wgrad; pack from dw is skipped
+  if (N != 128) return fail("dip_op_conv_wgrad: N must be 128");
+  op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;
+  op.set_shapes();
+  op.wp_f = (float*)scratch;
+  op.wp_d = nullptr;
+  op.in = (const float*)a; op.in_rows = a_h; op.in_cols = a_w; op.in_ld = a_c; op.offx = offx; op.offy = offy;
+  op.out = (float*)const_cast<void*>(dy); op.out_h = dy_h; op.out_w = dy_w;
+  op.has_dgrad = false;
+  op.wg_dy = (const float*)dy; op.wg_h = dy_h; op.wg_w = dy_w;
+  op.simt_ksplits = dy_h < 64 ? dy_h : 64;
+  float* partial = (float*)scratch + ((op.wp_f_elems() + 63) & ~size_t(63));
+  if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(partial));
+  return op.run_wgrad(precision, partial, (float*)dw, s);
+}
+
+}  // extern "C"

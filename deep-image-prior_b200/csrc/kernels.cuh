@@ -1,0 +1,139 @@
+// Launch wrappers of the HBM-bound kernels of the dip-b200 engine (kernels_mem.cu, conv_simt.cu).
+// All activations are fp32 NHWC; "ld" is the channel stride of a buffer in floats.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dip {
+
+static constexpr float kBnEps = 1e-5f;
+static constexpr float kLreluSlope = 0.2f;
+
+// Statistics of one BatchNorm layer: fp64 accumulators, zeroed once per iteration.
+//   fwd[0..C)   sum x          fwd[C..2C)   sum x^2
+//   bwd[0..C)   sum dz         bwd[C..2C)   sum dz * xhat          (dz = grad wrt BN output)
+//   dbias[0..C) sum dx         (grad wrt the conv bias that feeds this BN)
+struct BnRef {
+  const double* fwd;   // [2*C]
+  const float* gamma;  // [C] (torch order)
+  const float* beta;   // [C]
+  int C;               // channels
+  int rot;             // torch channel = (c + rot) % C   (4 for the concat BN: [up|skip] here, [skip|up] in torch)
+  float inv_n;         // 1 / (H*W)
+};
+
+// z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
+void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
+                      cudaStream_t s);
+
+// generic per-channel sum / sum^2 of a plain NHWC tensor (SIMT-conv path and skinny convs)
+void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s);
+
+// y = lrelu(bn(x)) written plain [H][W][ld_out] or reflection padded [(H+2)][(W+2)][ld_out]
+void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
+                         int act, cudaStream_t s);
+
+// Concat stage:  cat = [ up2x(U)(Cu ch) | lrelu(bn_s(raw_s))(Cs ch) ] at H x W (U is H/2 x W/2, plain, ld = Cu)
+struct CatArgs {
+  const float* U;      // [H/2][W/2][Cu]
+  const float* raw_s;  // [H][W][Cs]
+  BnRef bn_s;          // BN of the skip branch
+  int Cu, Cs, H, W;
+  int bilinear;        // 1 bilinear (align_corners=False), 0 nearest
+};
+void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s);
+// dst = bn_cat(cat) with reflection pad: [(H+2)][(W+2)][Cu+Cs]
+void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s);
+
+// Gradient sources for the BN backward kernels
+struct GradSrc {
+  int kind;            // 0 plain, 1 fold(padded) (+ optional plain), 2 upsample-adjoint
+  const float* g;      // kind 0: [H][W][ld] (+coff) ; kind 1: padded [(H+2)][(W+2)][ld] ; kind 2: [2H][2W][ld]
+  int ld, coff;
+  const float* g2;     // kind 1: optional plain [H][W][ld2]
+  int ld2;
+  int bilinear;        // kind 2
+};
+
+// BN(+LeakyReLU) backward. reduce: bwd[0..C) += sum dz, bwd[C..2C) += sum dz*xhat.
+// apply: dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)); writes draw plain [H][W][C];
+//        optionally a zero-stuffed copy zs [2H][2W][C] (only even positions written); dbias[c] += sum dx.
+void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
+                          cudaStream_t s);
+void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
+                         const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s);
+
+// Concat-BN backward (no activation). Gradient = fold of the padded dgrad output gp [(H+2)][(W+2)][ld_gp].
+void launch_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, double* bwd, cudaStream_t s);
+void launch_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, const double* bwd, float* dcat,
+                          cudaStream_t s);
+
+// Skinny 1x1 convs (N <= 4 outputs): y[p][n] = b[n] + sum_c x[p][c] w[n][c]
+//   x: pixel (i,j) at x + (i*x_rs + j)*ldx floats (works for padded interiors)
+//   mode 0: y NHWC [H][W][N]; mode 1: y = sigmoid(.) NCHW [N][H][W]; mode 2: NCHW without sigmoid
+void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
+                       int W, float* y, int mode, cudaStream_t s);
+// backward: dy NHWC [H][W][N] (mode 0) or dout NCHW with sigmoid derivative folded in (mode 1: dy = dout*o*(1-o))
+//   dx (optional) plain [H][W][C]; dw[N][C] and db[N] accumulated into fp64 (zeroed by caller)
+void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
+                       const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
+                       cudaStream_t s);
+
+// loss = mean(m^2 (o - t)^2), dout = 2 m^2 (o - t) / n; mask may be null ([H*W], broadcast over C channels)
+void launch_mse(const float* out, const float* target, const float* mask, int C, int HW, double* loss, float* dout,
+                cudaStream_t s);
+
+// z = z0 + sigma * N(0,1)  (Philox4x32-10 + Box-Muller; counter = element index / 4, key = seed, stream = offset)
+void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, size_t n,
+                  cudaStream_t s);
+
+// weight repacking ---------------------------------------------------------------------------------
+// torch OIHW [N][C][kh][kw]  ->  fprop pack [tap][n_rows][c_pad] (K-major), channel rotation c_t = (c + rot) % C
+void launch_pack_fprop(const float* w, int N, int C, int kh, int kw, int rot, float* dst, int n_rows, int c_pad,
+                       cudaStream_t s);
+// -> dgrad pack [tap'][c_rows][n_pad] with tap' = flipped tap, rows = input channel (rotated), cols = out channel
+void launch_pack_dgrad(const float* w, int N, int C, int kh, int kw, int rot, float* dst, int c_rows, int n_pad,
+                       cudaStream_t s);
+// split-K partials [ksplits][tap][128][c_pad] -> OIHW gradient [N][C][kh][kw]
+void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh, int kw, int rot, int c_pad,
+                         float* dw, cudaStream_t s);
+// fp64 accumulators -> fp32 gradient tensors (bias / gamma / beta / skinny weights)
+void launch_cvt_f64_f32(const double* src, float* dst, int n, int rot, cudaStream_t s);
+
+// BN running statistics (momentum 0.1, unbiased variance), one launch per layer table entry
+void launch_bn_running(const double* fwd, int C, int rot, float n, float* running_mean, float* running_var,
+                       long long* num_batches, cudaStream_t s);
+
+// Adam ---------------------------------------------------------------------------------------------
+struct AdamTable {
+  float* const* p;
+  const float* const* g;
+  float* const* m;
+  float* const* v;
+  const int* blk_tensor;   // per block: tensor index
+  const int* blk_start;    // per block: first element
+  const int* numel;        // per tensor
+  int nblocks;
+};
+void launch_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, cudaStream_t s);
+int adam_chunk();
+
+// SIMT fp32 reference convolutions (exact-fp32 mode) ---------------------------------------------------
+struct SimtConvArgs {
+  const float* A; int a_h, a_w, a_ld, a_c;       // input NHWC (rows, cols, stride, valid channels)
+  const float* Wp; int n_rows, c_pad;            // packed weights [tap][n_rows][c_pad]
+  float* D; int d_h, d_w, d_ld, d_c;             // output NHWC
+  int kh, kw, stride, offx, offy;
+  const float* bias;
+};
+void launch_simt_conv(SimtConvArgs a, cudaStream_t s);
+struct SimtWgradArgs {
+  const float* dY; int h, w;                     // [h][w][128]
+  const float* X; int x_h, x_w, x_ld, x_c;
+  int kh, kw, stride, offx, offy;
+  float* partial; int c_pad;                     // [ksplits][tap][128][c_pad]
+  int ksplits;
+};
+void launch_simt_wgrad(SimtWgradArgs a, cudaStream_t s);
+
+}  // namespace dip

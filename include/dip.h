@@ -1,0 +1,111 @@
+/* dip.h -- C ABI of libdip.so, the B200-native deep-image-prior hot-path engine.
+ *
+ * The reference (DmitryUlyanov/deep-image-prior) has no FFI: its hot path sits behind plain Python call sites.
+ * Every entry point below names the reference call site it replaces (file:line into the reference repo).
+ * The Python side (deep-image-prior_b200/dip_engine.py, ctypes) binds exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions: all device buffers are caller-owned (the Python side allocates them with torch so that autograd,
+ * state_dict and the caching allocator keep working); calls are asynchronous on the given stream and never
+ * synchronise; nothing throws across the ABI: 0 = success, negative = error, text via dip_last_error().
+ * Activations inside the engine are fp32 NHWC; tensors crossing the ABI are torch-layout (NCHW / OIHW) fp32.
+ */
+#ifndef DIP_H_
+#define DIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dip_plan dip_plan;
+typedef struct dip_adam dip_adam;
+typedef void* dip_stream_t; /* cudaStream_t */
+
+enum { DIP_PRECISION_TF32 = 0, /* tcgen05 kind::tf32 convolutions, fp32 accumulate (cuDNN's default fp32 mode) */
+       DIP_PRECISION_FP32 = 1  /* exact-fp32 CUDA-core convolutions (parity mode) */ };
+
+/* Arguments of models.skip(...) that the engine supports (reference: models/skip.py:5-11, models/__init__.py:12-17). */
+typedef struct {
+  int in_channels;       /* num_input_channels (multiple of 4; 32 in every BASELINE config)            */
+  int out_channels;      /* num_output_channels (<= 4; 3)                                               */
+  int num_scales;        /* len(num_channels_down)                                                      */
+  int channels;          /* num_channels_down[i] == num_channels_up[i] == 128                           */
+  int skip_channels;     /* num_channels_skip[i] (4)                                                    */
+  int upsample_bilinear; /* upsample_mode: 1 'bilinear', 0 'nearest'                                    */
+  int need_sigmoid;      /* 1                                                                           */
+  int precision;         /* DIP_PRECISION_*                                                             */
+} dip_net_desc;
+
+const char* dip_last_error(void);
+int dip_version(void);
+
+/* ---- plan: shapes -> buffers, TMA tensor maps, kernel schedule (replaces nn.Sequential.__call__ over the module
+ *      tree built by models/skip.py:41-100).  Parameter order = net.parameters() order of the reference
+ *      (depth-first: skip conv/bn, down conv/bn x2, <deeper level>, concat bn, up conv/bn, 1x1 conv/bn; head last). */
+size_t dip_plan_workspace_bytes(const dip_net_desc* desc, int H, int W);
+int dip_plan_create(const dip_net_desc* desc, int H, int W, void* workspace, size_t workspace_bytes,
+                    dip_plan** out);
+void dip_plan_destroy(dip_plan* plan);
+int dip_plan_num_params(const dip_plan* plan);
+int dip_plan_num_bn(const dip_plan* plan);
+long long dip_plan_param_numel(const dip_plan* plan, int index);
+/* params[i], grads[i]: fp32 device buffers in torch layout; bn_running: 3 pointers per BatchNorm
+ * (running_mean, running_var, num_batches_tracked[int64]) or NULL.  May be called again when pointers change. */
+int dip_plan_bind(dip_plan* plan, void* const* params, void* const* grads, void* const* bn_running);
+
+/* out = net(z + sigma * noise)      (reference: `out = net(net_input)`, denoising.ipynb c10:12-15)
+ * z, noise: [C_in][H][W] fp32 (noise may be NULL); out: [C_out][H][W].  Training-mode BatchNorm statistics. */
+int dip_forward(dip_plan* plan, const void* z, const void* noise, float sigma, void* out, dip_stream_t stream);
+/* total_loss.backward() through the network (denoising.ipynb c10:24): dout [C_out][H][W] = dL/d(out).
+ * Fills the bound grads[] (overwrite, not accumulate). */
+int dip_backward(dip_plan* plan, const void* dout, dip_stream_t stream);
+
+/* torch.nn.MSELoss()(out*mask, target*mask) and its gradient (denoising.ipynb c8:50,c10:23; inpainting.ipynb c17:17).
+ * loss: device double (accumulated: zero it first); dout may be NULL; mask [H*W] or NULL. */
+int dip_loss_mse(const void* out, const void* target, const void* mask, int channels, int hw, double* loss,
+                 void* dout, dip_stream_t stream);
+/* net_input = net_input_saved + noise.normal_() * sigma (denoising.ipynb c10:12-13), Philox4x32-10 on device. */
+int dip_noise_perturb(const void* z0, void* z, float sigma, uint64_t seed, uint64_t offset, size_t n,
+                      dip_stream_t stream);
+
+/* ---- torch.optim.Adam(parameters, lr).step() as one multi-tensor launch (utils/common_utils.py:225-230). */
+int dip_adam_create(int ntensors, const long long* numel, dip_adam** out);
+void dip_adam_destroy(dip_adam* a);
+int dip_adam_bind(dip_adam* a, void* const* p, void* const* g, void* const* m, void* const* v);
+int dip_adam_step(dip_adam* a, double lr, double beta1, double beta2, double eps, int step, dip_stream_t stream);
+
+/* ---- closure-free runner: `iters` iterations of  noise -> forward -> MSE -> backward -> Adam  entirely on the
+ *      device (utils/common_utils.py:227-230 with the lean closure of denoising.ipynb c10).  m, v: Adam state
+ *      (ntensors buffers).  Losses (device doubles, one per iteration) are written to loss_hist if non-NULL.
+ *      step0 = number of Adam steps already taken. */
+int dip_run_iterations(dip_plan* plan, dip_adam* adam, const void* z0, const void* target, const void* mask,
+                       float sigma, uint64_t seed, int step0, int iters, double lr, void* out, double* loss_hist,
+                       dip_stream_t stream);
+
+/* ---- test / profiling access to internal NHWC buffers: name e.g. "L0.raw_u"; dims = {rows, cols, ld, channels} */
+int dip_plan_buffer(const dip_plan* plan, const char* name, void** ptr, int* dims4);
+int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd);
+
+/* ---- single-op entry points (same kernels as the plan; used by the per-kernel parity tests).
+ * Convolution of an NHWC fp32 tensor a[a_h][a_w][a_c] with torch OIHW weights w[N][C][k][k]:
+ *   d[y][x][n] = bias[n] + sum a[y*stride+offy+r][x*stride+offx+s][c] * w[n][(c+rot)%C][r][s], out-of-range reads = 0.
+ * scratch: device buffer of at least dip_op_scratch_bytes(). stats (nullable): 2*N doubles (sum, sum^2), accumulated. */
+size_t dip_op_scratch_bytes(void);
+int dip_op_conv_fprop(const void* a, int a_h, int a_w, int a_c, const void* w, const void* bias, int N, int C, int k,
+                      int stride, int offx, int offy, int rot, void* d, int d_h, int d_w, double* stats,
+                      int precision, void* scratch, dip_stream_t stream);
+/* dgrad on the padded domain: dx[u][v][c] = sum dy[u-r+off][v-s+off][n] w[n][(c+rot)%C][r][s]; off = 0 gives the
+ * "full" correlation onto (dy_h + k - 1) x (dy_w + k - 1). */
+int dip_op_conv_dgrad(const void* dy, int dy_h, int dy_w, const void* w, int N, int C, int k, int rot, void* dx,
+                      int dx_h, int dx_w, int precision, void* scratch, dip_stream_t stream);
+/* dw[n][(c+rot)%C][r][s] = sum dy[y][x][n] * a[y*stride+offy+r][x*stride+offx+s][c] */
+int dip_op_conv_wgrad(const void* dy, int dy_h, int dy_w, const void* a, int a_h, int a_w, int a_c, int N, int C,
+                      int k, int stride, int offx, int offy, int rot, void* dw, int precision, void* scratch,
+                      dip_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIP_H_ */

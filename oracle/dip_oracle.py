@@ -1,0 +1,221 @@
+"""CPU oracle for the deep-image-prior hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module;
+the product path (deep-image-prior_b200/) never does.
+
+What it is: a self-contained restatement, on torch-CPU functional ops, of what the reference executes per iteration
+(the reference's arithmetic lives in its third-party dependency PyTorch -- pinned `pytorch=0.4` in environment.yml:13,
+installed here: torch 2.11 -- so the oracle restates the reference's *graph* on the same dependency):
+
+  * skip-network forward            models/skip.py:41-100 + models/common.py:11-124 (Concat, conv, bn, act)
+  * parameter initialisation order  models/skip.py:45-98 (construction order = RNG draw order)
+  * loss                            torch.nn.MSELoss, denoising.ipynb c8:50, c10:23; masked: inpainting.ipynb c17:17
+  * optimiser                       torch.optim.Adam defaults, utils/common_utils.py:225-230
+  * input perturbation              denoising.ipynb c10:12-13
+  * get_noise                       utils/common_utils.py:127-153
+
+Pinning: the reference has NO golden vectors / tests.  The oracle is pinned instead against
+outputs of the reference itself, generated in the build container by tests/golden/make_golden.py (which imports
+/root/reference) and committed as tests/golden/*.npz; tests/test_oracle.py checks oracle == golden, and
+oracle == live reference whenever /root/reference is present.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class SkipConfig:
+    """Arguments of models.skip() that matter for the BASELINE configs (models/skip.py:5-11)."""
+
+    def __init__(self, in_channels=32, out_channels=3, num_scales=5, channels=128, skip_channels=4,
+                 upsample_mode="bilinear", need_sigmoid=True):
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_scales = num_scales
+        self.channels = channels
+        self.skip_channels = skip_channels
+        self.upsample_mode = upsample_mode
+        self.need_sigmoid = need_sigmoid
+
+
+def param_layout(cfg):
+    """[(name, shape)] in net.parameters() order of the reference (depth-first over the module tree)."""
+    L, C, S = cfg.num_scales, cfg.channels, cfg.skip_channels
+    pre, post = [], []
+    for l in range(L):
+        cin = cfg.in_channels if l == 0 else C
+        pre.append([("L%d.skip.w" % l, (S, cin, 1, 1)), ("L%d.skip.b" % l, (S,)),
+                    ("L%d.skip_bn.g" % l, (S,)), ("L%d.skip_bn.b" % l, (S,)),
+                    ("L%d.d1.w" % l, (C, cin, 3, 3)), ("L%d.d1.b" % l, (C,)),
+                    ("L%d.d1_bn.g" % l, (C,)), ("L%d.d1_bn.b" % l, (C,)),
+                    ("L%d.d2.w" % l, (C, C, 3, 3)), ("L%d.d2.b" % l, (C,)),
+                    ("L%d.d2_bn.g" % l, (C,)), ("L%d.d2_bn.b" % l, (C,))])
+        post.append([("L%d.cat_bn.g" % l, (C + S,)), ("L%d.cat_bn.b" % l, (C + S,)),
+                     ("L%d.up.w" % l, (C, C + S, 3, 3)), ("L%d.up.b" % l, (C,)),
+                     ("L%d.up_bn.g" % l, (C,)), ("L%d.up_bn.b" % l, (C,)),
+                     ("L%d.c11.w" % l, (C, C, 1, 1)), ("L%d.c11.b" % l, (C,)),
+                     ("L%d.c11_bn.g" % l, (C,)), ("L%d.c11_bn.b" % l, (C,))])
+    out = []
+    for l in range(L):
+        out += pre[l]
+    for l in reversed(range(L)):
+        out += post[l]
+    out += [("head.w", (cfg.out_channels, C, 1, 1)), ("head.b", (cfg.out_channels,))]
+    return out
+
+
+def init_params(cfg, seed=None, dtype=torch.float32):
+    """Parameters with the reference's initialisation AND RNG draw order (models/skip.py:45-98: per level the convs
+    are constructed skip, down1, down2, up3x3, up1x1; levels top-down; head last; BatchNorm draws nothing)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    L, C, S = cfg.num_scales, cfg.channels, cfg.skip_channels
+    vals = {}
+    for l in range(L):
+        cin = cfg.in_channels if l == 0 else C
+        for name, (o, i, k) in (("skip", (S, cin, 1)), ("d1", (C, cin, 3)), ("d2", (C, C, 3)), ("up", (C, C + S, 3)),
+                                ("c11", (C, C, 1))):
+            m = nn.Conv2d(i, o, k)  # torch default init: kaiming_uniform(a=sqrt(5)) + bias U(+-1/sqrt(fan_in))
+            vals["L%d.%s.w" % (l, name)] = m.weight.detach()
+            vals["L%d.%s.b" % (l, name)] = m.bias.detach()
+    m = nn.Conv2d(C, cfg.out_channels, 1)
+    vals["head.w"], vals["head.b"] = m.weight.detach(), m.bias.detach()
+    params = []
+    for name, shape in param_layout(cfg):
+        if name in vals:
+            t = vals[name]
+        elif name.endswith(".g"):
+            t = torch.ones(shape)
+        else:
+            t = torch.zeros(shape)
+        params.append(t.to(dtype).clone().requires_grad_(True))
+    return params
+
+
+def _conv(x, w, b, stride=1):
+    k = w.shape[-1]
+    if k > 1:
+        x = F.pad(x, (k // 2,) * 4, mode="reflect")  # nn.ReflectionPad2d, models/common.py:116-118
+    return F.conv2d(x, w, b, stride=stride)
+
+
+def _bn(x, g, b):
+    # nn.BatchNorm2d in training mode (nothing in the reference ever calls .eval()): biased batch variance, eps 1e-5
+    return F.batch_norm(x, None, None, g, b, training=True, momentum=0.1, eps=1e-5)
+
+
+def _act(x):
+    return F.leaky_relu(x, 0.2)
+
+
+def skip_forward(params, z, cfg, tape=None):
+    """out = net(z).  params in param_layout() order.  tape (dict) receives named intermediates (for debugging)."""
+    P = {name: p for (name, _), p in zip(param_layout(cfg), params)}
+
+    def rec(l, x):
+        pre = "L%d." % l
+        s = _conv(x, P[pre + "skip.w"], P[pre + "skip.b"])
+        if tape is not None:
+            tape[pre + "raw_s"] = s
+        s = _act(_bn(s, P[pre + "skip_bn.g"], P[pre + "skip_bn.b"]))
+        d = _conv(x, P[pre + "d1.w"], P[pre + "d1.b"], stride=2)
+        if tape is not None:
+            tape[pre + "raw_d1"] = d
+        d = _act(_bn(d, P[pre + "d1_bn.g"], P[pre + "d1_bn.b"]))
+        d = _conv(d, P[pre + "d2.w"], P[pre + "d2.b"])
+        if tape is not None:
+            tape[pre + "raw_d2"] = d
+        d = _act(_bn(d, P[pre + "d2_bn.g"], P[pre + "d2_bn.b"]))
+        if l < cfg.num_scales - 1:
+            d = rec(l + 1, d)
+        if cfg.upsample_mode == "bilinear":
+            d = F.interpolate(d, scale_factor=2, mode="bilinear", align_corners=False)
+        else:
+            d = F.interpolate(d, scale_factor=2, mode="nearest")
+        c = torch.cat([s, d], dim=1)  # Concat: skip channels first (models/common.py:19-39)
+        if tape is not None:
+            tape[pre + "cat"] = c
+        c = _bn(c, P[pre + "cat_bn.g"], P[pre + "cat_bn.b"])
+        u = _conv(c, P[pre + "up.w"], P[pre + "up.b"])
+        if tape is not None:
+            tape[pre + "raw_u"] = u
+        u = _act(_bn(u, P[pre + "up_bn.g"], P[pre + "up_bn.b"]))
+        v = _conv(u, P[pre + "c11.w"], P[pre + "c11.b"])
+        if tape is not None:
+            tape[pre + "raw_v"] = v
+        v = _act(_bn(v, P[pre + "c11_bn.g"], P[pre + "c11_bn.b"]))
+        if tape is not None:
+            tape[pre + "U"] = v
+        return v
+
+    y = rec(0, z)
+    y = F.conv2d(y, P["head.w"], P["head.b"])
+    if cfg.need_sigmoid:
+        y = torch.sigmoid(y)
+    return y
+
+
+def mse_loss(out, target, mask=None):
+    """torch.nn.MSELoss()(out, target) / masked variant mse(out*mask, target*mask) (mean over all C*H*W)."""
+    if mask is not None:
+        return F.mse_loss(out * mask, target * mask)
+    return F.mse_loss(out, target)
+
+
+def get_noise(input_depth, spatial_size, var=0.1, seed=None):
+    """utils/common_utils.py:127-153 with method='noise', noise_type='u'."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    if isinstance(spatial_size, int):
+        spatial_size = (spatial_size, spatial_size)
+    z = torch.zeros([1, input_depth, spatial_size[0], spatial_size[1]])
+    z.uniform_()
+    z *= var
+    return z
+
+
+class Adam:
+    """torch.optim.Adam defaults (beta 0.9/0.999, eps 1e-8), written out in the order of torch/optim/adam.py."""
+
+    def __init__(self, params, lr):
+        self.params, self.lr, self.t = params, lr, 0
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+
+    def step(self, grads):
+        self.t += 1
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        bc1 = 1 - b1 ** self.t
+        bc2 = 1 - b2 ** self.t
+        with torch.no_grad():
+            for p, g, m, v in zip(self.params, grads, self.m, self.v):
+                m.lerp_(g, 1 - b1)
+                v.mul_(b2).addcmul_(g, g, value=1 - b2)
+                denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+                p.addcdiv_(m, denom, value=-self.lr / bc1)
+
+
+def run(cfg, params, z0, target, noises, sigma, lr, mask=None, record=None):
+    """`len(noises)` iterations of the lean closure: z = z0 + noise*sigma; out = net(z); loss; backward; Adam.
+    Returns (losses, last_out).  record(i, out, loss, grads) is called before the Adam step."""
+    opt = Adam(params, lr)
+    losses, out = [], None
+    for i, nz in enumerate(noises):
+        z = z0 + nz * sigma if nz is not None else z0
+        out = skip_forward(params, z, cfg)
+        loss = mse_loss(out, target, mask)
+        grads = torch.autograd.grad(loss, params)
+        if record is not None:
+            record(i, out.detach(), loss.item(), grads)
+        losses.append(loss.item())
+        opt.step(grads)
+    return losses, out.detach()
+
+
+def psnr(a, b):
+    """skimage.measure.compare_psnr for float images in [0,1] (data_range 1)."""
+    mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
+    return 10.0 * math.log10(1.0 / mse)

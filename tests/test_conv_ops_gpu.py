@@ -1,0 +1,94 @@
+"""P1 (kernel tier): the tcgen05 / SIMT convolution kernels behind the C ABI vs torch-CPU fp64.
+
+Tolerances: fp32 mode <= 2e-6 relative Frobenius error; tf32 mode <= 2e-3 (10-bit mantissa operands, fp32 accumulate).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 2e-3, 1: 2e-6}
+
+
+def rel_err(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def nhwc(x_chw):
+    return x_chw.permute(1, 2, 0).contiguous()
+
+
+CASES = [
+    # (C, k, stride, out_h, out_w, rot)
+    (128, 1, 1, 32, 32, 0),
+    (128, 3, 1, 32, 32, 0),
+    (32, 3, 2, 32, 32, 0),
+    (128, 3, 2, 16, 16, 0),
+    (132, 3, 1, 32, 32, 4),
+    (128, 3, 1, 24, 36, 0),
+    (132, 3, 1, 2, 2, 4),
+    (128, 3, 1, 64, 128, 0),
+]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("case", CASES)
+def test_fprop(case, prec):
+    import dip_engine as de
+    C, k, stride, oh, ow, rot = case
+    g = torch.Generator().manual_seed(1)
+    ih, iw = (oh - 1) * stride + k, (ow - 1) * stride + k
+    if stride == 2:  # engine buffers are padded to even extents
+        ih += ih % 2
+        iw += iw % 2
+    a = torch.randn(C, ih, iw, generator=g)
+    w = torch.randn(128, C, k, k, generator=g) / (C * k * k) ** 0.5
+    b = torch.randn(128, generator=g)
+    ref = F.conv2d(torch.roll(a, rot, 0)[None].double(), w.double(), b.double(), stride=stride)[0][:, :oh, :ow]
+    stats = torch.zeros(256, dtype=torch.float64, device="cuda")
+    d = de.op_conv_fprop(nhwc(a).cuda(), w.cuda(), b.cuda(), k, stride, 0, 0, oh, ow, rot=rot, stats=stats,
+                         precision=prec)
+    torch.cuda.synchronize()
+    assert rel_err(d.permute(2, 0, 1), ref) < TOL[prec]
+    s1 = ref.sum((1, 2))
+    s2 = (ref * ref).sum((1, 2))
+    assert rel_err(stats[:128], s1) < 10 * TOL[prec] + 1e-6 or (stats[:128].cpu() - s1).abs().max() < 1e-2
+    assert rel_err(stats[128:], s2) < 10 * TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("case", [(128, 3, 32, 32, 0), (132, 3, 32, 32, 4), (128, 1, 32, 32, 0), (128, 3, 10, 20, 0),
+                                  (132, 3, 2, 2, 4), (128, 3, 64, 128, 0)])
+def test_dgrad(case, prec):
+    import dip_engine as de
+    C, k, h, w_, rot = case
+    g = torch.Generator().manual_seed(2)
+    dy = torch.randn(128, h, w_, generator=g)
+    w = torch.randn(128, C, k, k, generator=g) / (128 * k * k) ** 0.5
+    ref = torch.roll(F.conv_transpose2d(dy[None].double(), w.double())[0], -rot, 0)
+    dx = de.op_conv_dgrad(nhwc(dy).cuda(), w.cuda(), k, h + k - 1, w_ + k - 1, rot=rot, precision=prec)
+    torch.cuda.synchronize()
+    assert rel_err(dx.permute(2, 0, 1), ref) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("case", CASES)
+def test_wgrad(case, prec):
+    import dip_engine as de
+    C, k, stride, oh, ow, rot = case
+    g = torch.Generator().manual_seed(3)
+    ih, iw = (oh - 1) * stride + k, (ow - 1) * stride + k
+    if stride == 2:
+        ih += ih % 2
+        iw += iw % 2
+    a = torch.randn(C, ih, iw, generator=g)
+    dy = torch.randn(128, oh, ow, generator=g)
+    ia, ja = (oh - 1) * stride + k, (ow - 1) * stride + k
+    ref = torch.nn.grad.conv2d_weight(torch.roll(a, rot, 0)[None, :, :ia, :ja].double(), (128, C, k, k),
+                                      dy[None].double(), stride=stride)
+    dw = de.op_conv_wgrad(nhwc(dy).cuda(), nhwc(a).cuda(), C, k, stride, 0, 0, rot=rot, precision=prec)
+    torch.cuda.synchronize()
+    assert rel_err(dw, ref) < TOL[prec]
