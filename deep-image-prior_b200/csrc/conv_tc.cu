@@ -305,9 +305,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         for (int s = 0; s < p.kw; ++s) {
           const uint32_t sx = sy + y_bytes + s * x_bytes;
           for (int k = 0; k < p.kp / 8; ++k) {
-            // MN-major SW128: 32-channel chunks are LBO = chunk_bytes apart; 8-pixel K groups are 1024 B apart
-            const uint64_t adesc = make_smem_desc_sw128(sy + k * 1024, chunk_bytes, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(sx + k * 1024, chunk_bytes, 1024);
+            // MN-major tf32 must use the 32-byte-atom 128B swizzle: 32-channel chunks are LBO = chunk_bytes apart,
+            // 4-pixel K atoms are SBO = 512 B apart; one K=8 MMA consumes 8 pixel rows = 1024 B.
+            const uint64_t adesc = make_smem_desc(sy + k * 1024, chunk_bytes, 512, 1);
+            const uint64_t bdesc = make_smem_desc(sx + k * 1024, chunk_bytes, 512, 1);
             mma_tf32_ss(tmem_base + s * c_pad, adesc, bdesc, idesc, (blk > blk0 || k > 0) ? 1u : 0u);
           }
         }

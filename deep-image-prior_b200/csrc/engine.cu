@@ -61,10 +61,11 @@ static int engine_init() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, bool atom32 = false) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -76,7 +77,8 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   return 0;
 }
 // activation [rows][cols][ld] (c valid channels) as the 5-D view (C, px, X, py, Y) used by the conv kernels
-static int map_act5(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int stride, int bw, int bh) {
+static int map_act5(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int stride, int bw, int bh,
+                    bool atom32 = false) {
   const cuuint64_t e = sizeof(float);
   cuuint64_t dims[5], str[4];
   if (stride == 1) {
@@ -87,14 +89,14 @@ static int map_act5(CUtensorMap* m, const float* base, int rows, int cols, int l
     str[0] = ld * e; str[1] = 2 * ld * e; str[2] = (cuuint64_t)cols * ld * e; str[3] = 2 * (cuuint64_t)cols * ld * e;
   }
   cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)bh};
-  return encode_map(m, base, 5, dims, str, box);
+  return encode_map(m, base, 5, dims, str, box, atom32);
 }
-static int map_act3(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int bw, int bh) {
+static int map_act3(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int bw, int bh, bool atom32 = false) {
   const cuuint64_t e = sizeof(float);
   cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t str[2] = {ld * e, (cuuint64_t)cols * ld * e};
   cuuint32_t box[3] = {32, (cuuint32_t)bw, (cuuint32_t)bh};
-  return encode_map(m, base, 3, dims, str, box);
+  return encode_map(m, base, 3, dims, str, box, atom32);
 }
 static int map_w2(CUtensorMap* m, const float* base, int rows_total, int kcols, int box_rows) {
   const cuuint64_t e = sizeof(float);
@@ -193,8 +195,8 @@ struct ConvOp {
     // ---- wgrad
     wg = TcWgradParams{};
     wg.kp = (wg_w % 32 == 0) ? 32 : 16;
-    DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1));
-    DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.kp, 1));
+    DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1, true));
+    DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.kp, 1, true));
     wg.partial = partial;
     wg.kh = wg.kw = k; wg.stride = stride; wg.offx = offx; wg.offy = offy;
     wg.px_blocks_x = (wg_w + wg.kp - 1) / wg.kp;

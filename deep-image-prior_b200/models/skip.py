@@ -1,0 +1,229 @@
+"""models.skip(): the hourglass "skip" network builder with the reference's signature (reference: models/skip.py:5-100).
+
+The returned object is an nn.Sequential whose children, parameter names, parameter order and initialisation RNG order
+are those of the reference (so state_dict()s are interchangeable and torch.manual_seed(s) gives identical weights), but
+calling it does NOT interpret the module tree: for the configurations of BASELINE.json the whole forward + backward runs
+in the hand-written sm_100a engine (libdip.so) through one autograd node.  There is no silent fallback: unsupported
+configurations or CPU tensors raise unless the caller opts in to stock-torch execution with
+`models.allow_torch_execution(True)` (used by the CPU tests that compare the tree with the reference's).
+"""
+import torch
+import torch.nn as nn
+
+from .common import Concat, act, bn, conv
+
+_ALLOW_TORCH = False
+
+
+def allow_torch_execution(flag=True):
+    """Opt in/out of executing un-accelerated configurations with stock torch modules (default: off)."""
+    global _ALLOW_TORCH
+    _ALLOW_TORCH = bool(flag)
+
+
+def _numbered(*mods):
+    s = nn.Sequential()
+    for m in mods:
+        s.add(m)
+    return s
+
+
+def _as_list(v, n):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
+class _EngineFn(torch.autograd.Function):
+    """One autograd node for the whole network: forward = dip_forward, backward = dip_backward."""
+
+    @staticmethod
+    def forward(ctx, net, z, anchor):
+        ctx.net = net
+        return net._engine_forward(z)
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.net._engine_backward(dout)
+        return None, None, None
+
+
+class SkipNet(nn.Sequential):
+    """nn.Sequential with the reference's layout whose __call__ runs on the dip-b200 engine."""
+
+    def __init__(self):
+        super().__init__()
+        self._dip_spec = None        # dict of engine arguments, or None if the configuration is not accelerated
+        self._dip_why = None         # reason when _dip_spec is None
+        self._dip_plans = {}
+        self._dip_grad_arena = None
+        self._dip_anchor = None
+        self.precision = 'tf32'      # 'tf32' (tcgen05 tensor cores, default) | 'fp32' (exact CUDA-core parity mode)
+
+    # ---- engine plumbing -------------------------------------------------------------------------------------
+    def _engine_state(self, z):
+        import dip_engine as de
+        spec = self._dip_spec
+        H, W = int(z.shape[2]), int(z.shape[3])
+        prec = de.PRECISION_TF32 if self.precision == 'tf32' else de.PRECISION_FP32
+        key = (H, W, str(z.device), prec)
+        plan = self._dip_plans.get(key)
+        if plan is None:
+            plan = de.Plan(spec['in_channels'], spec['out_channels'], spec['num_scales'], spec['channels'],
+                           spec['skip_channels'], spec['bilinear'], H, W, precision=prec, device=z.device)
+            self._dip_plans[key] = plan
+        params = list(self.parameters())
+        for p in params:
+            if p.device != z.device or p.dtype != torch.float32:
+                raise RuntimeError("dip-b200: parameters must be float32 on the input's device "
+                                   "(use net.type(torch.cuda.FloatTensor))")
+        total = sum(p.numel() for p in params)
+        arena = self._dip_grad_arena
+        if arena is None or arena.device != z.device or arena.numel() != total:
+            arena = torch.zeros(total, dtype=torch.float32, device=z.device)
+            self._dip_grad_arena = arena
+            views, o = [], 0
+            for p in params:
+                views.append(arena[o:o + p.numel()].view_as(p))
+                o += p.numel()
+            self._dip_grad_views = views
+        running = []
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                running += [m.running_mean, m.running_var, m.num_batches_tracked]
+        plan.bind([p.data for p in params], self._dip_grad_views, running)
+        return plan, params
+
+    def _engine_forward(self, z):
+        plan, _ = self._engine_state(z)
+        self._dip_active_plan = plan
+        zc = z.detach().contiguous()
+        return plan.forward(zc)
+
+    def _engine_backward(self, dout):
+        plan = self._dip_active_plan
+        params = list(self.parameters())
+        views = self._dip_grad_views
+        # gradients already attached to the arena (no zero_grad() since the last backward) must be accumulated
+        stale = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views)]
+        prev = self._dip_grad_arena.clone() if any(stale) else None
+        plan.backward(dout.contiguous())
+        if prev is not None:
+            self._dip_grad_arena.add_(prev)
+        for p, v, s in zip(params, views, stale):
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = v
+            elif not s:
+                p.grad.add_(v)
+
+    # ---- nn.Module surface -----------------------------------------------------------------------------------
+    def forward(self, x):
+        if self._dip_spec is not None and x.is_cuda:
+            if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != self._dip_spec['in_channels']:
+                raise ValueError("dip-b200: expected input of shape 1 x %d x H x W" % self._dip_spec['in_channels'])
+            if x.requires_grad:
+                raise NotImplementedError("dip-b200: gradients w.r.t. the network input (OPT_OVER='input') are not "
+                                          "computed by the engine (SURVEY.md section 8f)")
+            if not torch.is_grad_enabled():
+                return self._engine_forward(x)
+            if self._dip_anchor is None or self._dip_anchor.device != x.device:
+                self._dip_anchor = torch.zeros(1, device=x.device, requires_grad=True)
+            return _EngineFn.apply(self, x, self._dip_anchor)
+        if _ALLOW_TORCH:
+            return super().forward(x)
+        if self._dip_spec is None:
+            raise NotImplementedError("dip-b200: this skip() configuration is not accelerated by the engine (%s). "
+                                      "Call models.allow_torch_execution(True) to run it with stock torch modules."
+                                      % self._dip_why)
+        raise RuntimeError("dip-b200: the accelerated path needs CUDA tensors (net.type(torch.cuda.FloatTensor)); "
+                           "there is no CPU fallback. models.allow_torch_execution(True) opts in to stock torch.")
+
+
+def skip(num_input_channels=2, num_output_channels=3,
+         num_channels_down=[16, 32, 64, 128, 128], num_channels_up=[16, 32, 64, 128, 128],
+         num_channels_skip=[4, 4, 4, 4, 4],
+         filter_size_down=3, filter_size_up=3, filter_skip_size=1,
+         need_sigmoid=True, need_bias=True,
+         pad='zero', upsample_mode='nearest', downsample_mode='stride', act_fun='LeakyReLU',
+         need1x1_up=True):
+    """Assembles the encoder-decoder with skip connections (same arguments as the reference's models.skip)."""
+    assert len(num_channels_down) == len(num_channels_up) == len(num_channels_skip)
+    n = len(num_channels_down)
+    upsample_mode = _as_list(upsample_mode, n)
+    downsample_mode = _as_list(downsample_mode, n)
+    filter_size_down = _as_list(filter_size_down, n)
+    filter_size_up = _as_list(filter_size_up, n)
+
+    # 1) leaves, created in the reference's construction order (= RNG draw order): per scale skip-conv, down convs,
+    #    up conv, 1x1 conv; the RGB head last (reference: models/skip.py:45-98).
+    leaves = []
+    depth = num_input_channels
+    for i in range(n):
+        k_deeper = num_channels_up[i + 1] if i < n - 1 else num_channels_down[i]
+        lv = {}
+        lv['cat_bn'] = bn(num_channels_skip[i] + k_deeper)
+        if num_channels_skip[i] != 0:
+            lv['skip'] = (conv(depth, num_channels_skip[i], filter_skip_size, bias=need_bias, pad=pad),
+                          bn(num_channels_skip[i]), act(act_fun))
+        lv['down1'] = (conv(depth, num_channels_down[i], filter_size_down[i], 2, bias=need_bias, pad=pad,
+                            downsample_mode=downsample_mode[i]), bn(num_channels_down[i]), act(act_fun))
+        lv['down2'] = (conv(num_channels_down[i], num_channels_down[i], filter_size_down[i], bias=need_bias, pad=pad),
+                       bn(num_channels_down[i]), act(act_fun))
+        lv['upsample'] = nn.Upsample(scale_factor=2, mode=upsample_mode[i])
+        lv['up'] = (conv(num_channels_skip[i] + k_deeper, num_channels_up[i], filter_size_up[i], 1, bias=need_bias,
+                         pad=pad), bn(num_channels_up[i]), act(act_fun))
+        if need1x1_up:
+            lv['up1x1'] = (conv(num_channels_up[i], num_channels_up[i], 1, bias=need_bias, pad=pad),
+                           bn(num_channels_up[i]), act(act_fun))
+        leaves.append(lv)
+        depth = num_channels_down[i]
+    head = conv(num_channels_up[0], num_output_channels, 1, bias=need_bias, pad=pad)
+
+    # 2) tree, assembled bottom-up with the reference's child numbering
+    def level_modules(i):
+        lv = leaves[i]
+        deeper_mods = list(lv['down1']) + list(lv['down2'])
+        if i < n - 1:
+            deeper_mods.append(_numbered(*level_modules(i + 1)))
+        deeper_mods.append(lv['upsample'])
+        deeper = _numbered(*deeper_mods)
+        first = Concat(1, _numbered(*lv['skip']), deeper) if 'skip' in lv else deeper
+        mods = [first, lv['cat_bn']] + list(lv['up'])
+        if need1x1_up:
+            mods += list(lv['up1x1'])
+        return mods
+
+    net = SkipNet()
+    for m in level_modules(0):
+        net.add(m)
+    net.add(head)
+    if need_sigmoid:
+        net.add(nn.Sigmoid())
+
+    # 3) is this one of the configurations the engine executes?
+    why = None
+    chans = set(num_channels_down) | set(num_channels_up)
+    if chans != {128}:
+        why = 'num_channels_down/up must all be 128'
+    elif set(num_channels_skip) != {4}:
+        why = 'num_channels_skip must all be 4'
+    elif set(filter_size_down) != {3} or set(filter_size_up) != {3} or filter_skip_size != 1:
+        why = 'filter sizes must be 3/3/1'
+    elif pad != 'reflection':
+        why = "pad must be 'reflection'"
+    elif set(downsample_mode) != {'stride'}:
+        why = "downsample_mode must be 'stride'"
+    elif act_fun != 'LeakyReLU':
+        why = "act_fun must be 'LeakyReLU'"
+    elif not (need_sigmoid and need_bias and need1x1_up):
+        why = 'need_sigmoid, need_bias and need1x1_up must be True'
+    elif len(set(upsample_mode)) != 1 or upsample_mode[0] not in ('bilinear', 'nearest'):
+        why = "upsample_mode must be uniformly 'bilinear' or 'nearest'"
+    elif num_output_channels > 4 or num_input_channels not in (4, 8, 16, 32, 64, 128):
+        why = 'num_output_channels <= 4 and num_input_channels in {4,...,128} (power of two)'
+    if why is None:
+        net._dip_spec = dict(in_channels=num_input_channels, out_channels=num_output_channels, num_scales=n,
+                             channels=128, skip_channels=4, bilinear=upsample_mode[0] == 'bilinear')
+    else:
+        net._dip_why = why
+    return net

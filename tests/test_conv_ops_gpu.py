@@ -52,7 +52,8 @@ def test_fprop(case, prec):
     d = de.op_conv_fprop(nhwc(a).cuda(), w.cuda(), b.cuda(), k, stride, 0, 0, oh, ow, rot=rot, stats=stats,
                          precision=prec)
     torch.cuda.synchronize()
-    assert rel_err(d.permute(2, 0, 1), ref) < TOL[prec]
+    err = rel_err(d.permute(2, 0, 1), ref)
+    assert err < TOL[prec]
     s1 = ref.sum((1, 2))
     s2 = (ref * ref).sum((1, 2))
     assert rel_err(stats[:128], s1) < 10 * TOL[prec] + 1e-6 or (stats[:128].cpu() - s1).abs().max() < 1e-2
@@ -71,7 +72,8 @@ def test_dgrad(case, prec):
     ref = torch.roll(F.conv_transpose2d(dy[None].double(), w.double())[0], -rot, 0)
     dx = de.op_conv_dgrad(nhwc(dy).cuda(), w.cuda(), k, h + k - 1, w_ + k - 1, rot=rot, precision=prec)
     torch.cuda.synchronize()
-    assert rel_err(dx.permute(2, 0, 1), ref) < TOL[prec]
+    err = rel_err(dx.permute(2, 0, 1), ref)
+    assert err < TOL[prec]
 
 
 @pytest.mark.parametrize("prec", [1, 0])
@@ -91,4 +93,5 @@ def test_wgrad(case, prec):
                                       dy[None].double(), stride=stride)
     dw = de.op_conv_wgrad(nhwc(dy).cuda(), nhwc(a).cuda(), C, k, stride, 0, 0, rot=rot, precision=prec)
     torch.cuda.synchronize()
-    assert rel_err(dw, ref) < TOL[prec]
+    err = rel_err(dw, ref)
+    assert err < TOL[prec]

@@ -1,0 +1,219 @@
+"""P1/P2 tiers on the GPU: the CUDA engine (through the C ABI) vs the CPU oracle and the committed reference goldens.
+
+Tolerances: fp32 mode is compared tightly (no TF32 rounding); tf32 mode = cuDNN's default fp32
+behaviour, compared loosely.  Conv biases in front of a BatchNorm have mathematically-zero gradients (pure rounding
+noise in the reference too) and are excluded from relative comparisons.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dip_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+FWD_TOL = {"fp32": 2e-5, "tf32": 5e-3}     # max abs error of the sigmoid output
+RAW_TOL = {"fp32": 1e-4, "tf32": 1e-2}     # relative Frobenius error of pre-BN activations
+GRAD_TOL = {"fp32": 2e-3, "tf32": 5e-2}    # relative Frobenius error of weight gradients
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def make_problem(H, W, mode, seed=0, masked=False):
+    cfg = O.SkipConfig(upsample_mode=mode)
+    params = O.init_params(cfg, seed=seed)
+    z0 = O.get_noise(32, (H, W), seed=1)
+    g = torch.Generator().manual_seed(2)
+    target = torch.rand(1, 3, H, W, generator=g)
+    mask = (torch.rand(1, 1, H, W, generator=g) > 0.3).float() if masked else None
+    return cfg, params, z0, target, mask
+
+
+def make_engine(cfg, params, H, W, prec):
+    import dip_engine as de
+    plan = de.Plan(32, 3, cfg.num_scales, 128, 4, cfg.upsample_mode == "bilinear", H, W,
+                   precision=de.PRECISION_TF32 if prec == "tf32" else de.PRECISION_FP32)
+    dparams = [p.detach().cuda().contiguous() for p in params]
+    dgrads = [torch.zeros_like(p) for p in dparams]
+    plan.bind(dparams, dgrads)
+    return plan, dparams, dgrads
+
+
+def is_dead_bias(name):
+    # conv bias followed by BatchNorm: gradient is exactly zero in exact arithmetic
+    return name.endswith(".b") and "_bn" not in name and not name.startswith("head")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("shape_mode", [(64, 64, "bilinear"), (96, 64, "nearest"), (64, 128, "bilinear")])
+def test_forward_backward_vs_oracle(shape_mode, prec):
+    H, W, mode = shape_mode
+    cfg, params, z0, target, _ = make_problem(H, W, mode)
+    tape = {}
+    out_ref = O.skip_forward(params, z0, cfg, tape=tape)
+    loss = O.mse_loss(out_ref, target)
+    grads_ref = torch.autograd.grad(loss, params)
+    dout = (2.0 * (out_ref.detach() - target) / out_ref.numel()).contiguous()
+
+    plan, dparams, dgrads = make_engine(cfg, params, H, W, prec)
+    out = plan.forward(z0.cuda())
+    torch.cuda.synchronize()
+    # pre-BN activations, level by level (localises a broken kernel)
+    for l in range(cfg.num_scales):
+        for nm in ("raw_s", "raw_d1", "raw_d2", "raw_u", "raw_v"):
+            ref = tape["L%d.%s" % (l, nm)][0].permute(1, 2, 0)
+            got = plan.buffer("L%d.%s" % (l, nm))
+            e = rel(got, ref)
+            assert e < RAW_TOL[prec], ("L%d.%s" % (l, nm), e)
+    err = (out.cpu() - out_ref.detach()).abs().max().item()
+    assert err < FWD_TOL[prec], err
+
+    plan.backward(dout.cuda())
+    torch.cuda.synchronize()
+    names = [n for n, _ in O.param_layout(cfg)]
+    worst = ("", 0.0)
+    for name, g, gr in zip(names, dgrads, grads_ref):
+        if is_dead_bias(name):
+            assert g.abs().max().item() < 1e-4 * (1 + gr.abs().max().item()) + 1e-6, name
+            continue
+        e = rel(g, gr)
+        if e > worst[1]:
+            worst = (name, e)
+    assert worst[1] < GRAD_TOL[prec], worst
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_against_reference_golden(prec):
+    g = np.load(os.path.join(GOLD, "denoise64_bilinear_fp32.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    cfg, params, z0, target, _ = make_problem(H, W, "bilinear")
+    gn = torch.Generator().manual_seed(123)
+    noise = torch.randn(z0.shape, generator=gn)
+    plan, dparams, dgrads = make_engine(cfg, params, H, W, prec)
+    out = plan.forward(z0.cuda(), noise=noise.cuda(), sigma=float(g["sigma"]))
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - g["out0"]).max() < FWD_TOL[prec]
+    loss = ((out.cpu() - target) ** 2).mean().item()
+    assert abs(loss - float(g["losses"][0])) < (1e-5 if prec == "fp32" else 1e-3)
+    dout = (2.0 * (out - target.cuda()) / out.numel()).contiguous()
+    plan.backward(dout)
+    torch.cuda.synchronize()
+    gnorm = np.array([x.double().norm().item() for x in dgrads])
+    big = g["gnorm0"] > 1e-7
+    assert np.abs(gnorm[big] / g["gnorm0"][big] - 1).max() < GRAD_TOL[prec]
+    assert rel(dgrads[-2].cpu(), torch.from_numpy(g["g_head_w"])) < GRAD_TOL[prec]
+    assert rel(dgrads[-10][:4, :8].cpu(), torch.from_numpy(g["g_up0_w_slice"])) < GRAD_TOL[prec]
+
+
+def test_masked_loss_and_adam_vs_oracle():
+    import dip_engine as de
+    H, W = 96, 64
+    cfg, params, z0, target, mask = make_problem(H, W, "nearest", masked=True)
+    plan, dparams, dgrads = make_engine(cfg, params, H, W, "fp32")
+    # one oracle step
+    out_ref = O.skip_forward(params, z0, cfg)
+    loss_ref = O.mse_loss(out_ref, target, mask)
+    grads_ref = torch.autograd.grad(loss_ref, params)
+    opt = O.Adam(params, 0.01)
+    opt.step(grads_ref)
+    # engine: forward, fused masked MSE, backward, fused Adam
+    out = plan.forward(z0.cuda())
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dout = torch.empty_like(out)
+    de.check(de.lib().dip_loss_mse(out.data_ptr(), target.cuda().data_ptr(), mask.cuda().data_ptr(), 3, H * W,
+                                   loss.data_ptr(), dout.data_ptr(), None))
+    plan.backward(dout)
+    for p, gbuf in zip(dparams, dgrads):
+        p.grad = gbuf
+    adam = de.FusedAdam(dparams, lr=0.01)
+    adam.step()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 1e-6
+    names = [n for n, _ in O.param_layout(cfg)]
+    for name, p, pr in zip(names, dparams, params):
+        if is_dead_bias(name):
+            continue  # sign of rounding noise decides a full +-lr step
+        d = (p.cpu() - pr.detach()).abs()
+        # Adam's first step is +-lr * sign(g): only near-zero gradients may flip
+        frac_bad = (d > 1e-3).float().mean().item()
+        assert frac_bad < 0.02, (name, frac_bad)
+
+
+def test_adam_kernel_matches_torch_bitwise_order():
+    import dip_engine as de
+    g = torch.Generator().manual_seed(0)
+    ps = [torch.randn(n, generator=g) for n in (5, 4096, 7001, 128)]
+    gs = [[torch.randn(p.shape, generator=g) * 0.1 for p in ps] for _ in range(3)]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    topt = torch.optim.Adam(ref, lr=0.01)
+    dev = [p.clone().cuda().requires_grad_(True) for p in ps]
+    fopt = de.FusedAdam(dev, lr=0.01)
+    for step in range(3):
+        for r, d, gg in zip(ref, dev, gs[step]):
+            r.grad = gg.clone()
+            d.grad = gg.cuda()
+        topt.step()
+        fopt.step()
+    torch.cuda.synchronize()
+    for r, d in zip(ref, dev):
+        assert torch.allclose(r.detach(), d.detach().cpu(), rtol=0, atol=2e-7)
+
+
+def test_module_api_and_optimize_closure():
+    """The notebook-facing path: models.get_net(...).type(dtype), closure, optimize('adam', ...)."""
+    import models
+    from utils.common_utils import get_noise, get_params, optimize
+    dtype = torch.cuda.FloatTensor
+    torch.manual_seed(0)
+    net = models.get_net(32, "skip", "reflection", skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                         upsample_mode="bilinear").type(dtype)
+    net.precision = "fp32"
+    torch.manual_seed(1)
+    z0 = get_noise(32, "noise", (64, 64)).type(dtype).detach()
+    gen = torch.Generator().manual_seed(2)
+    target = torch.rand(1, 3, 64, 64, generator=gen).type(dtype)
+    mse = torch.nn.MSELoss().type(dtype)
+    losses = []
+
+    def closure():
+        out = net(z0)
+        loss = mse(out, target)
+        loss.backward()
+        losses.append(loss.item())
+        return loss
+
+    p = get_params("net", net, z0)
+    optimize("adam", p, closure, 0.01, 3)
+    # oracle trajectory with the same seeds (no input perturbation)
+    cfg, params, z0c, targetc, _ = make_problem(64, 64, "bilinear")
+    ref_losses, _ = O.run(cfg, params, z0c, targetc, [None] * 3, 0.0, 0.01)
+    assert abs(losses[0] - ref_losses[0]) < 1e-6
+    assert abs(losses[1] - ref_losses[1]) < 5e-3   # chaotic from the first Adam step on
+    assert all(np.isfinite(losses))
+    # BatchNorm running statistics are maintained like torch does
+    sd = net.state_dict()
+    assert int(sd["4.num_batches_tracked"]) == 3
+    assert float(sd["4.running_var"].mean()) != 1.0
+
+
+def test_run_iterations_decreases_loss():
+    import dip_engine as de
+    H, W = 64, 64
+    cfg, params, z0, target, _ = make_problem(H, W, "bilinear")
+    plan, dparams, dgrads = make_engine(cfg, params, H, W, "tf32")
+    for p, gbuf in zip(dparams, dgrads):
+        p.grad = gbuf
+    adam = de.FusedAdam(dparams, lr=0.01)
+    adam._bind(dgrads)
+    hist = torch.zeros(40, dtype=torch.float64, device="cuda")
+    out = torch.empty(1, 3, H, W, device="cuda")
+    de.run_iterations(plan, adam, z0.cuda(), target.cuda(), None, 1. / 30, 7, 40, 0.01, out=out, loss_hist=hist)
+    torch.cuda.synchronize()
+    h = hist.cpu().numpy()
+    assert np.all(np.isfinite(h)) and h[-5:].mean() < h[:5].mean()

@@ -1,0 +1,105 @@
+"""Host-side mirror of the reference interface: module tree, state_dict names, init RNG order, no silent fallback."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import models
+from oracle import dip_oracle as O
+from oracle import ref_harness
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def build(mode="bilinear", seed=0):
+    torch.manual_seed(seed)
+    return models.get_net(32, "skip", "reflection", skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                          upsample_mode=mode)
+
+
+def test_state_dict_keys_match_reference():
+    g = np.load(os.path.join(GOLD, "denoise64_bilinear_fp32.npz"))
+    net = build()
+    assert list(net.state_dict().keys()) == [str(k) for k in g["state_keys"]]
+    assert sum(p.numel() for p in net.parameters()) == 2217831
+    assert len(list(net.parameters())) == 112
+
+
+def test_init_matches_oracle_order():
+    net = build(seed=5)
+    params = O.init_params(O.SkipConfig(), seed=5)
+    for a, b in zip(net.parameters(), params):
+        assert a.shape == b.shape and torch.equal(a.detach(), b.detach())
+
+
+def test_no_silent_cpu_fallback():
+    net = build()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 32, 64, 64))
+    from utils.common_utils import optimize
+    with pytest.raises(RuntimeError):
+        optimize("adam", list(net.parameters()), lambda: None, 0.01, 1)
+
+
+def test_unsupported_config_raises_not_falls_back():
+    net = models.skip(3, 3, num_channels_down=[8, 16], num_channels_up=[8, 16], num_channels_skip=[0, 4],
+                      upsample_mode="bilinear", pad="reflection")
+    assert net._dip_spec is None
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 32, 32))
+
+
+def test_tree_forward_equals_oracle_when_opted_in():
+    net = build(seed=3)
+    z = torch.rand(1, 32, 64, 96) * 0.1
+    models.allow_torch_execution(True)
+    try:
+        out = net(z).detach()
+    finally:
+        models.allow_torch_execution(False)
+    params = O.init_params(O.SkipConfig(), seed=3)
+    ref = O.skip_forward(params, z, O.SkipConfig()).detach()
+    assert torch.allclose(out, ref, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference checkout not present")
+def test_tree_equals_live_reference():
+    with ref_harness.reference_modules() as ref:
+        torch.manual_seed(11)
+        rnet = ref.models.skip(32, 3, num_channels_down=[128] * 3, num_channels_up=[128] * 3,
+                               num_channels_skip=[4] * 3, upsample_mode="nearest", pad="reflection")
+        rsd = {k: v.clone() for k, v in rnet.state_dict().items()}
+        z = torch.rand(1, 32, 32, 32)
+        rout = rnet(z).detach()
+    torch.manual_seed(11)
+    net = models.skip(32, 3, num_channels_down=[128] * 3, num_channels_up=[128] * 3, num_channels_skip=[4] * 3,
+                      upsample_mode="nearest", pad="reflection")
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(rsd.keys())
+    for k in sd:
+        assert torch.equal(sd[k], rsd[k]), k
+    models.allow_torch_execution(True)
+    try:
+        out = net(z).detach()
+    finally:
+        models.allow_torch_execution(False)
+    assert torch.allclose(out, rout, atol=1e-6)
+
+
+def test_get_noise_and_converters():
+    from utils.common_utils import get_noise, np_to_torch, torch_to_np
+    torch.manual_seed(1)
+    a = get_noise(32, "noise", (16, 24))
+    b = O.get_noise(32, (16, 24), seed=1)
+    assert a.shape == (1, 32, 16, 24) and torch.equal(a, b)
+    x = np.random.rand(3, 4, 5).astype(np.float32)
+    assert np.array_equal(torch_to_np(np_to_torch(x)), x)
+
+
+def test_downsampler_kernel_matches_reference_values():
+    # 1-D taps of Lanczos-2, factor 4, phase 1/2 (probed from the reference)
+    k = models.get_kernel(4, "lanczos", 0.5, 17, support=2)
+    taps = k.sum(0)
+    want = [-0.001065, -0.009752, -0.020384, -0.014878, 0.024594, 0.098658, 0.183115, 0.239711]
+    assert k.shape == (16, 16) and np.allclose(taps[:8], want, atol=1e-6) and np.allclose(taps[8:], want[::-1], atol=1e-6)
