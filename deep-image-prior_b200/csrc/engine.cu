@@ -119,8 +119,33 @@ static void pick_tile(int w, int h, int* bw, int* bh) {
 }
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// ------------------------------------------------------------------------------------------------ kernel timing
+// Optional CUDA-event brackets around every tensor-core launch (bench.py roofline: algorithmic FLOPs / device time).
+struct Timer {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cls; double flops; size_t e0, e1; };
+  std::vector<Rec> recs;
+  size_t get(cudaStream_t s) {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    cudaEventRecord(pool[used], s);
+    return used++;
+  }
+  void reset() { used = 0; recs.clear(); }
+};
+struct TimeScope {
+  Timer* t; int cls; double flops; size_t e0 = 0; cudaStream_t s;
+  TimeScope(Timer* t_, int cls_, double flops_, cudaStream_t s_) : t(t_ && t_->on ? t_ : nullptr), cls(cls_), flops(flops_), s(s_) {
+    if (t) e0 = t->get(s);
+  }
+  ~TimeScope() { if (t) { size_t e1 = t->get(s); t->recs.push_back({cls, flops, e0, e1}); } }
+};
+
 // ------------------------------------------------------------------------------------------------ conv op
 struct ConvOp {
+  Timer* timer = nullptr;
+  double alg_flops() const { return 2.0 * out_h * out_w * 128.0 * C * k * k; }
   int N = 128, C = 0, k = 1, stride = 1, rot = 0;
   int c_pad = 0;   // fprop K extent per tap (multiple of 32)
   int crows = 0;   // dgrad UMMA N (input channels rounded to 16)
@@ -213,6 +238,7 @@ struct ConvOp {
     if (prec == DIP_PRECISION_TF32) {
       TcConvParams p = fp;
       p.bias = bias;
+      TimeScope ts(timer, 0, alg_flops(), s);
       DIP_CUDA(tc_conv_launch(p, g_num_sms, s));
     } else {
       SimtConvArgs a{};
@@ -228,6 +254,7 @@ struct ConvOp {
   }
   int run_dgrad(int prec, cudaStream_t s) {
     if (prec == DIP_PRECISION_TF32) {
+      TimeScope ts(timer, 1, alg_flops(), s);
       DIP_CUDA(tc_conv_launch(dg, g_num_sms, s));
     } else {
       SimtConvArgs a{};
@@ -246,6 +273,7 @@ struct ConvOp {
       TcWgradParams p = wg;
       p.partial = partial;
       ks = p.ksplits;
+      TimeScope ts(timer, 2, alg_flops(), s);
       DIP_CUDA(tc_wgrad_launch(p, s));
     } else {
       SimtWgradArgs a{};
@@ -295,7 +323,7 @@ __global__ void k_cvt_table(const CvtEntry* __restrict__ tab) {
   for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)e.src[i];
 }
 struct RunEntry {
-  const double* fwd; float* rm; float* rv; long long* nb; int C, rot; float n;
+  const double* fwd; float* rm; float* rv; void* nb; int C, rot; float n; int nb_is_float;
 };
 __global__ void k_running_table(const RunEntry* __restrict__ tab) {
   const RunEntry e = tab[blockIdx.x];
@@ -309,7 +337,10 @@ __global__ void k_running_table(const RunEntry* __restrict__ tab) {
     e.rm[ct] = 0.9f * e.rm[ct] + 0.1f * (float)m;
     e.rv[ct] = 0.9f * e.rv[ct] + 0.1f * (float)unb;
   }
-  if (threadIdx.x == 0 && e.nb != nullptr) *e.nb += 1;
+  if (threadIdx.x == 0 && e.nb != nullptr) {
+    // Module.type(torch.cuda.FloatTensor) (every notebook does this) also casts num_batches_tracked to float32
+    if (e.nb_is_float) *reinterpret_cast<float*>(e.nb) += 1.f; else *reinterpret_cast<long long*>(e.nb) += 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ plan
@@ -375,7 +406,9 @@ struct dip_plan {
   int n_pack = 0, n_cvt = 0, n_run = 0;
   long long pack_max = 0;
   bool bound = false;
+  int nbt_is_float = 0;
   int launches_fwd = 0, launches_bwd = 0;
+  Timer timer;
 };
 
 namespace dip {
@@ -578,6 +611,7 @@ static int build_plan(dip_plan* P, Arena& A) {
       op->wp_f = A.get<float>(op->wp_f_elems());
       op->wp_d = op->has_dgrad ? A.get<float>(op->wp_d_elems()) : nullptr;
       op->simt_ksplits = op->wg_h < 64 ? op->wg_h : 64;
+      op->timer = &P->timer;
       const size_t pe = op->partial_elems(prec);
       if (pe > partial_max) partial_max = pe;
       P->convs.push_back(op);
@@ -631,7 +665,8 @@ static int upload_tables(dip_plan* P) {
     RunEntry e{};
     e.fwd = b->fwd; e.C = b->C; e.rot = b->rot; e.n = b->n;
     if (!P->running.empty()) {
-      e.rm = (float*)P->running[3 * b->idx]; e.rv = (float*)P->running[3 * b->idx + 1]; e.nb = (long long*)P->running[3 * b->idx + 2];
+      e.rm = (float*)P->running[3 * b->idx]; e.rv = (float*)P->running[3 * b->idx + 1]; e.nb = P->running[3 * b->idx + 2];
+      e.nb_is_float = P->nbt_is_float;
     }
     rn.push_back(e);
   }
@@ -830,7 +865,8 @@ long long dip_plan_param_numel(const dip_plan* plan, int index) {
   if (index < 0 || index >= (int)plan->numel.size()) return -1;
   return plan->numel[index];
 }
-int dip_plan_bind(dip_plan* P, void* const* params, void* const* grads, void* const* bn_running) {
+int dip_plan_bind(dip_plan* P, void* const* params, void* const* grads, void* const* bn_running, int nbt_is_float) {
+  P->nbt_is_float = nbt_is_float;
   const int n = (int)P->numel.size();
   P->params.resize(n); P->grads.resize(n);
   for (int i = 0; i < n; ++i) {
@@ -935,6 +971,22 @@ int dip_plan_buffer(const dip_plan* plan, const char* name, void** ptr, int* dim
   if (it == plan->bufs.end()) return fail(std::string("dip_plan_buffer: unknown buffer ") + name);
   *ptr = it->second.ptr;
   dims4[0] = it->second.rows; dims4[1] = it->second.cols; dims4[2] = it->second.ld; dims4[3] = it->second.c;
+  return 0;
+}
+int dip_plan_set_timing(dip_plan* plan, int enable) {
+  plan->timer.on = enable != 0;
+  plan->timer.reset();
+  return 0;
+}
+int dip_plan_get_timing(dip_plan* plan, double* ms3, double* flops3, int* launches3) {
+  for (int i = 0; i < 3; ++i) { ms3[i] = 0; flops3[i] = 0; launches3[i] = 0; }
+  for (const Timer::Rec& r : plan->timer.recs) {
+    DIP_CUDA(cudaEventSynchronize(plan->timer.pool[r.e1]));
+    float ms = 0.f;
+    DIP_CUDA(cudaEventElapsedTime(&ms, plan->timer.pool[r.e0], plan->timer.pool[r.e1]));
+    ms3[r.cls] += ms; flops3[r.cls] += r.flops; launches3[r.cls] += 1;
+  }
+  plan->timer.reset();
   return 0;
 }
 int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {

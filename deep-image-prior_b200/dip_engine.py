@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "dip_last_error", "dip_version", "dip_plan_workspace_bytes", "dip_plan_create", "dip_plan_destroy",
     "dip_plan_num_params", "dip_plan_num_bn", "dip_plan_param_numel", "dip_plan_bind", "dip_forward", "dip_backward",
     "dip_loss_mse", "dip_noise_perturb", "dip_adam_create", "dip_adam_destroy", "dip_adam_bind", "dip_adam_step",
-    "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_op_scratch_bytes", "dip_op_conv_fprop",
+    "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_plan_set_timing", "dip_plan_get_timing", "dip_op_scratch_bytes", "dip_op_conv_fprop",
     "dip_op_conv_dgrad", "dip_op_conv_wgrad",
 ]
 
@@ -77,7 +77,7 @@ def lib():
     L.dip_plan_num_bn.argtypes = [vp]
     L.dip_plan_param_numel.argtypes = [vp, i32]
     L.dip_plan_param_numel.restype = i64
-    L.dip_plan_bind.argtypes = [vp, pvp, pvp, pvp]
+    L.dip_plan_bind.argtypes = [vp, pvp, pvp, pvp, i32]
     L.dip_forward.argtypes = [vp, vp, vp, f32, vp, vp]
     L.dip_backward.argtypes = [vp, vp, vp]
     L.dip_loss_mse.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
@@ -90,6 +90,8 @@ def lib():
     L.dip_run_iterations.argtypes = [vp, vp, vp, vp, vp, f32, u64, i32, i32, f64, vp, vp, vp]
     L.dip_plan_buffer.argtypes = [vp, ctypes.c_char_p, pvp, ctypes.POINTER(i32)]
     L.dip_plan_num_launches.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.dip_plan_set_timing.argtypes = [vp, i32]
+    L.dip_plan_get_timing.argtypes = [vp, ctypes.POINTER(f64), ctypes.POINTER(f64), ctypes.POINTER(i32)]
     L.dip_op_scratch_bytes.restype = sz
     L.dip_op_conv_fprop.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32,
                                     vp, vp]
@@ -163,12 +165,15 @@ class Plan:
         for p, n in zip(params, self.numel):
             assert p.numel() == n and p.dtype == torch.float32 and p.is_contiguous(), "parameter shape mismatch"
         pa, ga = _ptr_array(params), _ptr_array(grads)
-        ra = None
+        ra, nbt_float = None, 0
         if running is not None:
             assert len(running) == 3 * self.n_bn
             ra = _ptr_array(running)
+            kinds = set(r.dtype for r in running[2::3])
+            assert kinds in ({torch.int64}, {torch.float32}), kinds
+            nbt_float = int(kinds == {torch.float32})
         with torch.cuda.device(self.device):
-            check(lib().dip_plan_bind(self.h, pa, ga, ra))
+            check(lib().dip_plan_bind(self.h, pa, ga, ra, nbt_float))
         self._bound_key = key
         self._keep = (params, grads, running)
 
@@ -192,6 +197,15 @@ class Plan:
         off = p.value - self.workspace.data_ptr()
         flat = self.workspace[off:off + rows * cols * ld * 4].view(torch.float32)
         return flat.view(rows, cols, ld)[:, :, :c].clone()
+
+    def set_timing(self, enable):
+        check(lib().dip_plan_set_timing(self.h, int(bool(enable))))
+
+    def get_timing(self):
+        """{'fprop'|'dgrad'|'wgrad': (ms, algorithmic flops, launches)} since the last call (syncs on the events)."""
+        ms, fl, n = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int * 3)()
+        check(lib().dip_plan_get_timing(self.h, ms, fl, n))
+        return {k: (ms[i], fl[i], n[i]) for i, k in enumerate(("fprop", "dgrad", "wgrad"))}
 
     def num_launches(self):
         a, b = ctypes.c_int(), ctypes.c_int()

@@ -52,8 +52,10 @@ int dip_plan_num_params(const dip_plan* plan);
 int dip_plan_num_bn(const dip_plan* plan);
 long long dip_plan_param_numel(const dip_plan* plan, int index);
 /* params[i], grads[i]: fp32 device buffers in torch layout; bn_running: 3 pointers per BatchNorm
- * (running_mean, running_var, num_batches_tracked[int64]) or NULL.  May be called again when pointers change. */
-int dip_plan_bind(dip_plan* plan, void* const* params, void* const* grads, void* const* bn_running);
+ * (running_mean, running_var, num_batches_tracked) or NULL; nbt_is_float = 1 when num_batches_tracked is float32
+ * (after Module.type(torch.cuda.FloatTensor)), 0 for torch's native int64.  May be called again when pointers change. */
+int dip_plan_bind(dip_plan* plan, void* const* params, void* const* grads, void* const* bn_running,
+                  int nbt_is_float);
 
 /* out = net(z + sigma * noise)      (reference: `out = net(net_input)`, denoising.ipynb c10:12-15)
  * z, noise: [C_in][H][W] fp32 (noise may be NULL); out: [C_out][H][W].  Training-mode BatchNorm statistics. */
@@ -87,6 +89,10 @@ int dip_run_iterations(dip_plan* plan, dip_adam* adam, const void* z0, const voi
 /* ---- test / profiling access to internal NHWC buffers: name e.g. "L0.raw_u"; dims = {rows, cols, ld, channels} */
 int dip_plan_buffer(const dip_plan* plan, const char* name, void** ptr, int* dims4);
 int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd);
+/* CUDA-event brackets around every tensor-core launch (for bench.py's roofline). get_timing drains the records:
+ * index 0 = fprop, 1 = dgrad (both tc_conv_kernel), 2 = wgrad (tc_wgrad_kernel); flops are algorithmic (2*M*N*K). */
+int dip_plan_set_timing(dip_plan* plan, int enable);
+int dip_plan_get_timing(dip_plan* plan, double* ms3, double* flops3, int* launches3);
 
 /* ---- single-op entry points (same kernels as the plan; used by the per-kernel parity tests).
  * Convolution of an NHWC fp32 tensor a[a_h][a_w][a_c] with torch OIHW weights w[N][C][k][k]:
