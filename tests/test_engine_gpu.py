@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FWD_TOL = {"fp32": 1e-4, "tf32": 2e-2}     # max abs error of the sigmoid output
-RAW_TOL = {"fp32": 2e-4, "tf32": 1e-2}     # relative Frobenius error of pre-BN activations
+RAW_TOL = {"fp32": 2e-4, "tf32": 3e-2}     # relative Frobenius error of pre-BN activations
 # Gradients: a forward difference of relative size e flips the LeakyReLU branch of a fraction ~e of the elements, each
 # changing its gradient by 80% -> relative Frobenius error ~0.8*sqrt(e) (5e-3 for e = 5e-5 measured in fp32 mode; the
 # reference shows the same spread between thread counts).
