@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           const int nmma = last_kb ? p.tail_mmas : 4;
           for (int k = 0; k < nmma; ++k) {
             // K-major SW128: 8-row groups are 1024 B apart; advancing K by 8 fp32 = +32 B inside the swizzle atom
-            const uint64_t adesc = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            uint64_t adesc = make_smem_desc_sw128(sa + p.dbg_shift * 128 + k * 32, 16, 1024);
+            if (p.dbg_bo) adesc |= static_cast<uint64_t>(((sa + p.dbg_shift * 128) >> 7) & 7) << 49;
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
             mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (kbt > 0 || k > 0) ? 1u : 0u);
           }

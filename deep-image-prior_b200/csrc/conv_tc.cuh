@@ -29,6 +29,8 @@ struct TcConvParams {
   const float* bias;       // [n_mma] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
   int stats_ld;
+  int dbg_shift;           // experiment: start the A descriptor `dbg_shift` 128-byte rows into the stage
+  int dbg_bo;              // experiment: set the descriptor's base_offset field to ((addr >> 7) & 7)
 };
 
 // Weight-gradient GEMM:  dW[tap][n][c] = sum_{pixels} dY[pixel][n] * X[pixel (+) tap][c]

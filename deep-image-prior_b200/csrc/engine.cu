@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <initializer_list>
@@ -238,6 +239,8 @@ struct ConvOp {
     if (prec == DIP_PRECISION_TF32) {
       TcConvParams p = fp;
       p.bias = bias;
+      if (const char* e = getenv("DIP_DBG_SHIFT")) p.dbg_shift = atoi(e);
+      if (const char* e = getenv("DIP_DBG_BO")) p.dbg_bo = atoi(e);
       TimeScope ts(timer, 0, alg_flops(), s);
       DIP_CUDA(tc_conv_launch(p, g_num_sms, s));
     } else {
@@ -366,7 +369,7 @@ struct BnLayer {
 struct Level {
   int H, W, h, w, Cin;
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
-  float *dRaw_v, *dA_u, *dRaw_u, *dP_cat, *dCat, *dRaw_s, *G_sdx, *dRaw_d2, *dP_d1, *dRaw_d1, *ZS, *dPin;
+  float *dRaw_v, *dA_u, *dRaw_u, *dP_cat, *dCat, *dRaw_s, *dRaw_d2, *dP_d1, *dRaw_d1, *ZS, *dPin;
   BnLayer bn_s, bn_d1, bn_d2, bn_cat, bn_u, bn_v;
   int p_skip_w, p_skip_b;
   double* dw_s;
@@ -393,14 +396,21 @@ struct dip_plan {
   // head
   int p_head_w = -1, p_head_b = -1;
   double* dw_head = nullptr; double* db_head = nullptr; double* db_scratch = nullptr;
-  float* dU0 = nullptr;
   float* out_saved = nullptr;  // [C_out][H][W] (sigmoid output, needed by backward)
   // accumulators
   double* acc_fwd = nullptr; size_t acc_fwd_n = 0;
   double* acc_bwd = nullptr; size_t acc_bwd_n = 0;
   float* partial = nullptr;
   // runner scratch
-  float* zbuf = nullptr; float* dout = nullptr; double* loss = nullptr;
+  float* zbuf = nullptr; float* dout = nullptr;
+  static constexpr int kLossRing = 65536;
+  double* loss_ring = nullptr;   // [kLossRing] loss slots of the runner when the caller passes no history buffer
+  int* it_dev = nullptr;         // [2] device counters: {global Adam step, iteration index of this call}
+  struct GraphKey { const void *z0, *target, *mask, *out, *slots, *adam; float sigma; uint64_t seed; double lr; };
+  GraphKey gkey{};
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   // tables
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
   int n_pack = 0, n_cvt = 0, n_run = 0;
@@ -526,14 +536,13 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.raw_u = A.get<float>(HW * 128);
     v.A_u = A.get<float>(HW * 128);
     v.raw_v = A.get<float>(HW * 128);
-    v.U = A.get<float>(HW * 128);
+    v.U = l > 0 ? A.get<float>(HW * 128) : nullptr;  // level 0 feeds the fused RGB head instead
     v.dRaw_v = A.get<float>(HW * 128);
     v.dA_u = A.get<float>(HW * 128);
     v.dRaw_u = A.get<float>(HW * 128);
     v.dP_cat = A.get<float>(HWp * (128 + CS));
     v.dCat = A.get<float>(HW * (128 + CS));
     v.dRaw_s = A.get<float>(HW * CS);
-    v.G_sdx = l > 0 ? A.get<float>(HW * v.Cin) : nullptr;
     v.dRaw_d2 = A.get<float>(hw * 128);
     v.dP_d1 = A.get<float>(hwp * 128);
     v.dRaw_d1 = A.get<float>(hw * 128);
@@ -549,7 +558,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     reg(pf + "raw_u", v.raw_u, v.H, v.W, 128, 128);
     reg(pf + "A_u", v.A_u, v.H, v.W, 128, 128);
     reg(pf + "raw_v", v.raw_v, v.H, v.W, 128, 128);
-    reg(pf + "U", v.U, v.H, v.W, 128, 128);
+    if (l > 0) reg(pf + "U", v.U, v.H, v.W, 128, 128);
     reg(pf + "dRaw_v", v.dRaw_v, v.H, v.W, 128, 128);
     reg(pf + "dA_u", v.dA_u, v.H, v.W, 128, 128);
     reg(pf + "dRaw_u", v.dRaw_u, v.H, v.W, 128, 128);
@@ -560,17 +569,15 @@ static int build_plan(dip_plan* P, Arena& A) {
     reg(pf + "dP_d1", v.dP_d1, v.h + 2, v.w + 2, 128, 128);
     reg(pf + "dRaw_d1", v.dRaw_d1, v.h, v.w, 128, 128);
     if (l > 0) {
-      reg(pf + "G_sdx", v.G_sdx, v.H, v.W, v.Cin, v.Cin);
       reg(pf + "ZS", v.ZS, v.H, v.W, 128, 128);
       reg(pf + "dPin", v.dPin, v.H + 2, v.W + 2, 128, 128);
     }
   }
-  P->dU0 = A.get<float>((size_t)P->H * P->W * 128);
   P->out_saved = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->zbuf = A.get<float>((size_t)P->H * P->W * d.in_channels);
   P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
-  P->loss = A.get<double>(4);
-  reg("dU0", P->dU0, P->H, P->W, 128, 128);
+  P->loss_ring = A.get<double>(dip_plan::kLossRing);
+  P->it_dev = A.get<int>(4);
   // ---- conv ops
   size_t partial_max = 0;
   for (int l = 0; l < L; ++l) {
@@ -693,9 +700,9 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   const bool last = l == (int)P->lv.size() - 1;
   const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
   // skip branch: 1x1 conv Cin -> CS (+ statistics)
-  launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0, s);
-  launch_channel_stats(v.raw_s, CS, CS, v.H * v.W, v.bn_s.fwd, s);
-  nl += 2;
+  launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
+                    v.bn_s.fwd, s);
+  nl += 1;
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
   launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, v.P_d1, 128, 1, 1, s);
@@ -710,7 +717,13 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   DIP_CHECK(v.up.run_fprop(prec, P->params[v.up.p_b], s));
   launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, v.A_u, 128, 0, 1, s);
   DIP_CHECK(v.c11.run_fprop(prec, P->params[v.c11.p_b], s));
-  launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s);
+  if (l > 0) {
+    launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s);
+  } else {
+    // top level: BN + LeakyReLU + RGB head + sigmoid in one pass; the 128-channel activation is never materialised
+    HeadRef hd{P->params[P->p_head_w], P->params[P->p_head_b], P->desc.out_channels, P->out_saved};
+    launch_bn_act_head(v.raw_v, bn_ref(P, v.bn_v), v.H, v.W, hd, s);
+  }
   nl += 6 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
   DIP_CUDA(cudaGetLastError());
   return 0;
@@ -728,8 +741,6 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
   launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s);
   nl += 3;
   DIP_CHECK(fwd_level(P, 0, s, nl));
-  launch_skinny_fwd(v0.U, 128, v0.W, P->params[P->p_head_w], P->params[P->p_head_b], 128, P->desc.out_channels, v0.H, v0.W,
-                    P->out_saved, 1, s);
   if (out != nullptr && out != P->out_saved)
     DIP_CUDA(cudaMemcpyAsync(out, P->out_saved, (size_t)v0.H * v0.W * P->desc.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
   k_running_table<<<P->n_run, 160, 0, s>>>(P->d_run);
@@ -749,7 +760,10 @@ static int bn_bwd(dip_plan* P, const float* raw, int ld_raw, BnLayer& b, int act
   return 0;
 }
 static GradSrc src_plain(const float* g, int ld, int coff) { GradSrc s{}; s.kind = 0; s.g = g; s.ld = ld; s.coff = coff; return s; }
-static GradSrc src_fold(const float* gp, int ld, const float* g2, int ld2) { GradSrc s{}; s.kind = 1; s.g = gp; s.ld = ld; s.coff = 0; s.g2 = g2; s.ld2 = ld2; return s; }
+// fold of a padded dgrad output; optionally + the dgrad of the next level's 1x1 skip conv computed on the fly
+static GradSrc src_fold(const float* gp, int ld, const float* ds, const float* w2, int n2) {
+  GradSrc s{}; s.kind = 1; s.g = gp; s.ld = ld; s.coff = 0; s.ds = ds; s.w2 = w2; s.n2 = n2; return s;
+}
 static GradSrc src_upadj(const float* d, int ld, int bilinear) { GradSrc s{}; s.kind = 2; s.g = d; s.ld = ld; s.coff = 0; s.bilinear = bilinear; return s; }
 
 static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl) {
@@ -779,8 +793,9 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, s, nl));
   {
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
+    // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
     launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
-                      l > 0 ? v.G_sdx : nullptr, v.dw_s, P->db_scratch /*bias grad comes from the BN backward*/, s);
+                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, s);
     nl += 1;
   }
   // deeper branch
@@ -788,7 +803,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   if (!last) {
     DIP_CHECK(bwd_level(P, l + 1, src_upadj(v.dCat, CC, P->desc.upsample_bilinear), s, nl));
     Level& n = P->lv[l + 1];
-    src_d2 = src_fold(n.dPin, 128, n.G_sdx, 128);
+    src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
   } else {
     src_d2 = src_upadj(v.dCat, CC, P->desc.upsample_bilinear);
   }
@@ -796,7 +811,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(v.d2.run_wgrad(prec, P->partial, P->grads[v.d2.p_w], s));
   DIP_CHECK(v.d2.run_dgrad(prec, s));
   nl += wl + 1;
-  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, 0), v.h, v.w, v.dRaw_d1, l > 0 ? v.ZS : nullptr, s, nl));
+  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, l > 0 ? v.ZS : nullptr, s, nl));
   DIP_CHECK(v.d1.run_wgrad(prec, P->partial, P->grads[v.d1.p_w], s));
   nl += wl;
   if (l > 0) { DIP_CHECK(v.d1.run_dgrad(prec, s)); nl += 1; }
@@ -809,10 +824,12 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
   Level& v0 = P->lv[0];
-  launch_skinny_bwd(v0.U, 128, v0.W, P->params[P->p_head_w], 128, P->desc.out_channels, v0.H, v0.W, dout, P->out_saved, 1, P->dU0,
-                    P->dw_head, P->db_head, s);
-  nl += 2;
-  DIP_CHECK(bwd_level(P, 0, src_plain(P->dU0, 128, 0), s, nl));
+  // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
+  GradSrc sh{};
+  sh.kind = 3; sh.dout = dout; sh.outv = P->out_saved; sh.wh = P->params[P->p_head_w]; sh.nh = P->desc.out_channels;
+  sh.dwh = P->dw_head; sh.dbh = P->db_head;
+  nl += 1;
+  DIP_CHECK(bwd_level(P, 0, sh, s, nl));
   k_cvt_table<<<P->n_cvt, 128, 0, s>>>(P->d_cvt);
   nl += 1;
   DIP_CUDA(cudaGetLastError());
@@ -858,7 +875,15 @@ int dip_plan_create(const dip_net_desc* desc, int H, int W, void* workspace, siz
   *out = P;
   return 0;
 }
-void dip_plan_destroy(dip_plan* plan) { delete plan; }
+void dip_plan_destroy(dip_plan* plan) {
+  if (plan == nullptr) return;
+  if (plan->gexec) cudaGraphExecDestroy(plan->gexec);
+  if (plan->gstream) cudaStreamDestroy(plan->gstream);
+  if (plan->gev_in) cudaEventDestroy(plan->gev_in);
+  if (plan->gev_out) cudaEventDestroy(plan->gev_out);
+  for (cudaEvent_t e : plan->timer.pool) cudaEventDestroy(e);
+  delete plan;
+}
 int dip_plan_num_params(const dip_plan* plan) { return (int)plan->numel.size(); }
 int dip_plan_num_bn(const dip_plan* plan) { return (int)plan->bns.size(); }
 long long dip_plan_param_numel(const dip_plan* plan, int index) {
@@ -887,13 +912,13 @@ int dip_backward(dip_plan* P, const void* dout, dip_stream_t stream) {
 }
 int dip_loss_mse(const void* out, const void* target, const void* mask, int channels, int hw, double* loss, void* dout,
                  dip_stream_t stream) {
-  launch_mse((const float*)out, (const float*)target, (const float*)mask, channels, hw, loss, (float*)dout, (cudaStream_t)stream);
+  launch_mse((const float*)out, (const float*)target, (const float*)mask, channels, hw, loss, (float*)dout, nullptr, (cudaStream_t)stream);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }
 int dip_noise_perturb(const void* z0, void* z, float sigma, uint64_t seed, uint64_t offset, size_t n, dip_stream_t stream) {
   if (n % 4 != 0) return fail("dip_noise_perturb: n must be a multiple of 4");
-  launch_noise((const float*)z0, (float*)z, sigma, seed, offset, n, (cudaStream_t)stream);
+  launch_noise((const float*)z0, (float*)z, sigma, seed, offset, nullptr, n, (cudaStream_t)stream);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -940,7 +965,30 @@ int dip_adam_step(dip_adam* a, double lr, double beta1, double beta2, double eps
   if (!a->bound) return fail("dip_adam_step: not bound");
   if (step < 1) return fail("dip_adam_step: step must be >= 1");
   AdamTable t{a->d_p, a->d_g, a->d_m, a->d_v, a->d_blk_tensor, a->d_blk_start, a->d_numel, a->nblocks};
-  launch_adam(t, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+  launch_adam(t, lr, beta1, beta2, eps, step, nullptr, (cudaStream_t)stream);
+  DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// One iteration of the lean closure: noise -> forward -> MSE -> backward -> Adam.  With it_dev != nullptr every
+// per-iteration scalar (Philox stream, loss slot, Adam step) comes from device counters, so the launch sequence is
+// identical for every iteration and can be replayed as a CUDA graph.
+static int run_body(dip_plan* P, dip_adam* adam, const float* z0, const float* target, const float* mask, float sigma,
+                    uint64_t seed, int step_base, double lr, float* out, double* loss_slot, int* it_dev, cudaStream_t s) {
+  const size_t nz = (size_t)P->H * P->W * P->desc.in_channels;
+  const int hw = P->H * P->W;
+  const float* zin = z0;
+  if (sigma > 0.f) {
+    launch_noise(z0, P->zbuf, sigma, seed, (uint64_t)step_base, it_dev, nz, s);
+    zin = P->zbuf;
+  }
+  DIP_CHECK(plan_forward(P, zin, nullptr, 0.f, out, s));
+  launch_mse(P->out_saved, target, mask, P->desc.out_channels, hw, loss_slot, P->dout, it_dev != nullptr ? it_dev + 1 : nullptr, s);
+  DIP_CHECK(plan_backward(P, P->dout, s));
+  if (!adam->bound) return fail("dip_run_iterations: adam not bound");
+  AdamTable t{adam->d_p, adam->d_g, adam->d_m, adam->d_v, adam->d_blk_tensor, adam->d_blk_start, adam->d_numel, adam->nblocks};
+  launch_adam(t, lr, 0.9, 0.999, 1e-8, step_base + 1, it_dev, s);
+  if (it_dev != nullptr) launch_advance(it_dev, s);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -948,21 +996,56 @@ int dip_adam_step(dip_adam* a, double lr, double beta1, double beta2, double eps
 int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* target, const void* mask, float sigma,
                        uint64_t seed, int step0, int iters, double lr, void* out, double* loss_hist, dip_stream_t stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t nz = (size_t)P->H * P->W * P->desc.in_channels;
-  const int hw = P->H * P->W;
-  for (int i = 0; i < iters; ++i) {
-    const float* zin = (const float*)z0;
-    if (sigma > 0.f) {
-      launch_noise((const float*)z0, P->zbuf, sigma, seed, (uint64_t)(step0 + i), nz, s);
-      zin = P->zbuf;
+  if (iters <= 0) return 0;
+  const bool use_graph = !P->timer.on && getenv("DIP_NO_GRAPH") == nullptr;
+  if (!use_graph) {
+    for (int i = 0; i < iters; ++i) {
+      double* lp = loss_hist != nullptr ? loss_hist + i : P->loss_ring;
+      DIP_CUDA(cudaMemsetAsync(lp, 0, sizeof(double), s));
+      DIP_CHECK(run_body(P, adam, (const float*)z0, (const float*)target, (const float*)mask, sigma, seed, step0 + i, lr,
+                         (float*)out, lp, nullptr, s));
     }
-    DIP_CHECK(plan_forward(P, zin, nullptr, 0.f, (float*)out, s));
-    double* lp = loss_hist != nullptr ? loss_hist + i : P->loss;
-    DIP_CUDA(cudaMemsetAsync(lp, 0, sizeof(double), s));
-    launch_mse(P->out_saved, (const float*)target, (const float*)mask, P->desc.out_channels, hw, lp, P->dout, s);
-    DIP_CHECK(plan_backward(P, P->dout, s));
-    DIP_CHECK(dip_adam_step(adam, lr, 0.9, 0.999, 1e-8, step0 + i + 1, stream));
+    return 0;
   }
+  if (loss_hist == nullptr && iters > dip_plan::kLossRing) {
+    // internal ring too small: split the call
+    for (int done = 0; done < iters; done += dip_plan::kLossRing) {
+      const int n = iters - done < dip_plan::kLossRing ? iters - done : dip_plan::kLossRing;
+      DIP_CHECK(dip_run_iterations(P, adam, z0, target, mask, sigma, seed, step0 + done, n, lr, out, nullptr, stream));
+    }
+    return 0;
+  }
+  // the legacy default stream cannot be captured: replay on a private stream, ordered against the caller's stream
+  if (P->gstream == nullptr) {
+    DIP_CUDA(cudaStreamCreateWithFlags(&P->gstream, cudaStreamNonBlocking));
+    DIP_CUDA(cudaEventCreateWithFlags(&P->gev_in, cudaEventDisableTiming));
+    DIP_CUDA(cudaEventCreateWithFlags(&P->gev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t gs = P->gstream;
+  DIP_CUDA(cudaEventRecord(P->gev_in, s));
+  DIP_CUDA(cudaStreamWaitEvent(gs, P->gev_in, 0));
+  double* slots = loss_hist != nullptr ? loss_hist : P->loss_ring;
+  dip_plan::GraphKey key{z0, target, mask, out, slots, adam, sigma, seed, lr};
+  if (P->gexec == nullptr || memcmp(&key, &P->gkey, sizeof key) != 0) {
+    if (P->gexec != nullptr) { cudaGraphExecDestroy(P->gexec); P->gexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    DIP_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_body(P, adam, (const float*)z0, (const float*)target, (const float*)mask, sigma, seed, 0, lr, (float*)out,
+                            slots, P->it_dev, gs);
+    cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&P->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { P->gexec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    P->gkey = key;
+  }
+  const int init[2] = {step0, 0};
+  DIP_CUDA(cudaMemcpyAsync(P->it_dev, init, sizeof init, cudaMemcpyHostToDevice, gs));
+  DIP_CUDA(cudaMemsetAsync(slots, 0, (size_t)iters * sizeof(double), gs));
+  for (int i = 0; i < iters; ++i) DIP_CUDA(cudaGraphLaunch(P->gexec, gs));
+  DIP_CUDA(cudaEventRecord(P->gev_out, gs));
+  DIP_CUDA(cudaStreamWaitEvent(s, P->gev_out, 0));
   return 0;
 }
 

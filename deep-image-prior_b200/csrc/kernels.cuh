@@ -22,6 +22,14 @@ struct BnRef {
   float inv_n;         // 1 / (H*W)
 };
 
+// RGB head fused into the last BN+LeakyReLU stage: out[k][p] = sigmoid(b[k] + sum_c w[k][c] * act(bn(raw))[p][c])
+struct HeadRef {
+  const float* w;      // [K][C] (torch [K][C][1][1])
+  const float* b;      // [K]
+  int K;               // <= 4
+  float* out;          // NCHW [K][H*W]
+};
+
 // z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
                       cudaStream_t s);
@@ -32,6 +40,8 @@ void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, 
 // y = lrelu(bn(x)) written plain [H][W][ld_out] or reflection padded [(H+2)][(W+2)][ld_out]
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
                          int act, cudaStream_t s);
+// y = lrelu(bn(x)) consumed on the fly by the RGB head (C must be 128); y itself is not materialised
+void launch_bn_act_head(const float* raw, BnRef bn, int H, int W, HeadRef head, cudaStream_t s);
 
 // Concat stage:  cat = [ up2x(U)(Cu ch) | lrelu(bn_s(raw_s))(Cs ch) ] at H x W (U is H/2 x W/2, plain, ld = Cu)
 struct CatArgs {
@@ -47,12 +57,21 @@ void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s);
 
 // Gradient sources for the BN backward kernels
 struct GradSrc {
-  int kind;            // 0 plain, 1 fold(padded) (+ optional plain), 2 upsample-adjoint
+  int kind;            // 0 plain, 1 fold(padded) (+ skip-conv dgrad), 2 upsample-adjoint, 3 RGB head
   const float* g;      // kind 0: [H][W][ld] (+coff) ; kind 1: padded [(H+2)][(W+2)][ld] ; kind 2: [2H][2W][ld]
   int ld, coff;
-  const float* g2;     // kind 1: optional plain [H][W][ld2]
-  int ld2;
+  // kind 1: optional second consumer = 1x1 skip conv of the next level: g += sum_n ds[p][n] * w2[n][c]
+  const float* ds;     // [H][W][n2] or null
+  const float* w2;     // [n2][C]
+  int n2;
   int bilinear;        // kind 2
+  // kind 3: g[p][c] = sum_k dout[k][p] * o[k][p] * (1 - o[k][p]) * wh[k][c]; also accumulates the head's own gradients
+  const float* dout;   // NCHW [K][npix]
+  const float* outv;   // NCHW [K][npix] (sigmoid output)
+  const float* wh;     // [K][C]
+  int nh;
+  double* dwh;         // [K][C] fp64 accumulators (reduce pass)
+  double* dbh;         // [K]
 };
 
 // BN(+LeakyReLU) backward. reduce: bwd[0..C) += sum dz, bwd[C..2C) += sum dz*xhat.
@@ -71,21 +90,26 @@ void launch_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, c
 // Skinny 1x1 convs (N <= 4 outputs): y[p][n] = b[n] + sum_c x[p][c] w[n][c]
 //   x: pixel (i,j) at x + (i*x_rs + j)*ldx floats (works for padded interiors)
 //   mode 0: y NHWC [H][W][N]; mode 1: y = sigmoid(.) NCHW [N][H][W]; mode 2: NCHW without sigmoid
+//   stats (nullable, mode 0): fwd[0..N) += sum y, fwd[N..2N) += sum y^2
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
-                       int W, float* y, int mode, cudaStream_t s);
+                       int W, float* y, int mode, double* stats, cudaStream_t s);
 // backward: dy NHWC [H][W][N] (mode 0) or dout NCHW with sigmoid derivative folded in (mode 1: dy = dout*o*(1-o))
 //   dx (optional) plain [H][W][C]; dw[N][C] and db[N] accumulated into fp64 (zeroed by caller)
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
                        cudaStream_t s);
 
-// loss = mean(m^2 (o - t)^2), dout = 2 m^2 (o - t) / n; mask may be null ([H*W], broadcast over C channels)
+// loss[slot] += mean(m^2 (o - t)^2), dout = 2 m^2 (o - t) / n; mask may be null ([H*W], broadcast over C channels);
+// slot = *it_dev if it_dev != null else 0
 void launch_mse(const float* out, const float* target, const float* mask, int C, int HW, double* loss, float* dout,
-                cudaStream_t s);
+                const int* it_dev, cudaStream_t s);
 
-// z = z0 + sigma * N(0,1)  (Philox4x32-10 + Box-Muller; counter = element index / 4, key = seed, stream = offset)
-void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, size_t n,
+// z = z0 + sigma * N(0,1)  (Philox4x32-10 + Box-Muller; counter = element index / 4, key = seed,
+// stream = offset + *it_dev)
+void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, size_t n,
                   cudaStream_t s);
+// *it_dev += 1 (iteration counter of the graph-captured runner)
+void launch_advance(int* it_dev, cudaStream_t s);
 
 // weight repacking ---------------------------------------------------------------------------------
 // torch OIHW [N][C][kh][kw]  ->  fprop pack [tap][n_rows][c_pad] (K-major), channel rotation c_t = (c + rot) % C
@@ -97,12 +121,6 @@ void launch_pack_dgrad(const float* w, int N, int C, int kh, int kw, int rot, fl
 // split-K partials [ksplits][tap][128][c_pad] -> OIHW gradient [N][C][kh][kw]
 void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh, int kw, int rot, int c_pad,
                          float* dw, cudaStream_t s);
-// fp64 accumulators -> fp32 gradient tensors (bias / gamma / beta / skinny weights)
-void launch_cvt_f64_f32(const double* src, float* dst, int n, int rot, cudaStream_t s);
-
-// BN running statistics (momentum 0.1, unbiased variance), one launch per layer table entry
-void launch_bn_running(const double* fwd, int C, int rot, float n, float* running_mean, float* running_var,
-                       long long* num_batches, cudaStream_t s);
 
 // Adam ---------------------------------------------------------------------------------------------
 struct AdamTable {
@@ -115,7 +133,9 @@ struct AdamTable {
   const int* numel;        // per tensor
   int nblocks;
 };
-void launch_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, cudaStream_t s);
+// step (1-based) = step + *it_dev when it_dev != null
+void launch_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, const int* it_dev,
+                 cudaStream_t s);
 int adam_chunk();
 
 // SIMT fp32 reference convolutions (exact-fp32 mode) ---------------------------------------------------

@@ -4,9 +4,11 @@
 // (models/skip.py:41-100 built from models/common.py:76-124):
 //   input_pad        : net_input perturbation + nn.ReflectionPad2d(1)            (denoising.ipynb c10:12-13, common.py:117)
 //   bn_act_write     : nn.BatchNorm2d (training mode) + nn.LeakyReLU(0.2) + nn.ReflectionPad2d(1)   (common.py:96,82,117)
+//   bn_act_head      : last BN + LeakyReLU + 1x1 conv 128->3 + nn.Sigmoid in one pass (skip.py:90-98)
 //   cat_stats/write  : nn.Upsample(x2) + Concat + nn.BatchNorm2d(132) + pad     (skip.py:81,50-55; common.py:19-39)
-//   bn_bwd_*/cat_bwd_*: autograd adjoints of the above
-//   skinny_*         : 1x1 convs with <= 4 outputs (skip branches, RGB head + nn.Sigmoid, skip.py:57-60,96-98)
+//   bn_bwd_*/cat_bwd_*: autograd adjoints of the above, with the producer of the incoming gradient fused in
+//                       (reflection-pad adjoint, upsample adjoint, skip-conv dgrad, RGB-head dgrad+wgrad)
+//   skinny_*         : 1x1 convs with <= 4 outputs (skip branches, skip.py:57-60)
 //   mse / adam / noise: torch.nn.MSELoss, torch.optim.Adam.step, noise.normal_()  (common_utils.py:225-230)
 #include "kernels.cuh"
 
@@ -27,13 +29,21 @@ __device__ __forceinline__ float4 f4fma(float w, float4 a, float4 acc) {
   return make_float4(fmaf(w, a.x, acc.x), fmaf(w, a.y, acc.y), fmaf(w, a.z, acc.z), fmaf(w, a.w, acc.w));
 }
 __device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4mla(float4 a, float4 b, float4 acc) {
+  return make_float4(fmaf(a.x, b.x, acc.x), fmaf(a.y, b.y, acc.y), fmaf(a.z, b.z, acc.z), fmaf(a.w, b.w, acc.w));
+}
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : kLreluSlope * y; }
 __device__ __forceinline__ float4 lrelu4(float4 y) { return make_float4(lrelu(y.x), lrelu(y.y), lrelu(y.z), lrelu(y.w)); }
+__device__ __forceinline__ float4 shfl_xor4(float4 a, int o) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, a.x, o), __shfl_xor_sync(0xffffffffu, a.y, o),
+                     __shfl_xor_sync(0xffffffffu, a.z, o), __shfl_xor_sync(0xffffffffu, a.w, o));
+}
 
 // per-thread BN coefficients for channels 4v..4v+3
 struct Bn4 {
-  float4 mean, rstd, scale, shift, gamma;
+  float4 mean, rstd, scale, shift;
 };
 __device__ __forceinline__ Bn4 bn_coef(const BnRef& bn, int v) {
   float mean[4], rstd[4], g[4], b[4];
@@ -52,8 +62,7 @@ __device__ __forceinline__ Bn4 bn_coef(const BnRef& bn, int v) {
   Bn4 r;
   r.mean = make_float4(mean[0], mean[1], mean[2], mean[3]);
   r.rstd = make_float4(rstd[0], rstd[1], rstd[2], rstd[3]);
-  r.gamma = make_float4(g[0], g[1], g[2], g[3]);
-  r.scale = f4mul(r.gamma, r.rstd);
+  r.scale = make_float4(g[0] * rstd[0], g[1] * rstd[1], g[2] * rstd[2], g[3] * rstd[3]);
   r.shift = make_float4(b[0] - mean[0] * r.scale.x, b[1] - mean[1] * r.scale.y, b[2] - mean[2] * r.scale.z,
                         b[3] - mean[3] * r.scale.w);
   return r;
@@ -67,39 +76,56 @@ __device__ __forceinline__ float4 bn_xhat(const Bn4& c, float4 x) {
                      (x.w - c.mean.w) * c.rstd.w);
 }
 
-// Launch geometry for "vec-lane per 4 channels" kernels: thread = (pixel slot, v); v fixed per thread.
+// Launch geometry for "vec-lane per 4 channels" kernels: thread = (item slot, v); v fixed per thread.
 struct VecGeom {
   int VL, PPB, threads, blocks;
 };
-static VecGeom vec_geom(int C, long long npix) {
+static VecGeom vec_geom(int C, long long nitems) {
   VecGeom g;
   g.VL = C / 4;
   g.PPB = 256 / g.VL;
   if (g.PPB < 1) g.PPB = 1;
   g.threads = g.VL * g.PPB;
-  long long nb = (npix + g.PPB - 1) / g.PPB;
-  const long long cap = 148LL * 8;
+  long long nb = (nitems + g.PPB - 1) / g.PPB;
+  const long long cap = g.VL >= 8 ? 148LL * 8 : 148LL * 2;
   g.blocks = static_cast<int>(nb < cap ? nb : cap);
   if (g.blocks < 1) g.blocks = 1;
   return g;
 }
 
-// Block reduction of K float4 accumulators over the PPB pixel slots, then fp64 atomics: dst[k][4v+e].
+// Block reduction of K float4 accumulators over the item slots of the block, then fp64 atomics: dst[k][4v+e].
+// Threads are laid out tid = slot * VL + v.  For VL in {1,2,4,8,16} the lanes that share v are first folded with
+// warp shuffles (blockDim is then a multiple of 32).
 template <int K>
-__device__ __forceinline__ void block_reduce_atomic(const float4 (&acc)[K], int VL, int PPB, double* const (&dst)[K]) {
+__device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, int PPB, double* const* dst) {
   extern __shared__ float4 red_smem[];
   const int tid = threadIdx.x;
-  const int nthr = blockDim.x;
+  int nparts, part;
+  if (VL < 32 && (VL & (VL - 1)) == 0) {
+    for (int o = 16; o >= VL; o >>= 1) {
 #pragma unroll
-  for (int k = 0; k < K; ++k) red_smem[k * nthr + tid] = acc[k];
+      for (int k = 0; k < K; ++k) acc[k] = f4add(acc[k], shfl_xor4(acc[k], o));
+    }
+    nparts = blockDim.x >> 5;
+    part = tid >> 5;
+    if ((tid & 31) < VL) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) red_smem[(k * nparts + part) * VL + (tid & 31)] = acc[k];
+    }
+  } else {
+    nparts = PPB;
+    part = tid / VL;
+#pragma unroll
+    for (int k = 0; k < K; ++k) red_smem[(k * nparts + part) * VL + (tid % VL)] = acc[k];
+  }
   __syncthreads();
   if (tid < VL) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (dst[k] == nullptr) continue;
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      for (int pp = 0; pp < PPB; ++pp) {
-        const float4 t = red_smem[k * nthr + pp * VL + tid];
+      for (int pp = 0; pp < nparts; ++pp) {
+        const float4 t = red_smem[(k * nparts + pp) * VL + tid];
         s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
       }
       atomicAdd(dst[k] + 4 * tid + 0, s0);
@@ -109,6 +135,7 @@ __device__ __forceinline__ void block_reduce_atomic(const float4 (&acc)[K], int 
     }
   }
 }
+static size_t red_bytes(const VecGeom& g, int K) { return static_cast<size_t>(K) * g.threads * sizeof(float4); }
 
 // ------------------------------------------------------------------------------------------------ input_pad
 __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict__ noise, float sigma,
@@ -147,21 +174,21 @@ void launch_input_pad(const float* z, const float* noise, float sigma, float* ds
 }
 
 // ------------------------------------------------------------------------------------------------ channel_stats
-__global__ void k_channel_stats(const float* __restrict__ x, int ld, int VL, int PPB, long long npix,
+__global__ void k_channel_stats(const float* __restrict__ x, int ld, int VL, int PPB, int npix,
                                 double* __restrict__ fwd, int C) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   float4 acc[2] = {f4zero(), f4zero()};
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const float4 t = ld4(x + p * ld + 4 * v);
+  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+    const float4 t = ld4(x + static_cast<size_t>(p) * ld + 4 * v);
     acc[0] = f4add(acc[0], t);
-    acc[1] = f4fma(1.f, f4mul(t, t), acc[1]);
+    acc[1] = f4mla(t, t, acc[1]);
   }
   double* const dst[2] = {fwd, fwd + C};
   block_reduce_atomic<2>(acc, VL, PPB, dst);
 }
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s) {
   VecGeom g = vec_geom(C, npix);
-  k_channel_stats<<<g.blocks, g.threads, 2 * g.threads * sizeof(float4), s>>>(x, ld, g.VL, g.PPB, npix, fwd, C);
+  k_channel_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(x, ld, g.VL, g.PPB, npix, fwd, C);
 }
 
 // ------------------------------------------------------------------------------------------------ bn_act_write
@@ -170,14 +197,14 @@ __global__ void k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef b
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
-  const long long nout = static_cast<long long>(Ho) * Wo;
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < nout; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int yo = static_cast<int>(p / Wo), xo = static_cast<int>(p % Wo);
+  const int nout = Ho * Wo;
+  for (int p = blockIdx.x * PPB + slot; p < nout; p += gridDim.x * PPB) {
+    const int yo = p / Wo, xo = p - yo * Wo;
     const int yi = pad ? reflect_idx(yo - 1, H) : yo;
     const int xi = pad ? reflect_idx(xo - 1, W) : xo;
-    float4 y = bn_apply(cf, ld4(raw + (static_cast<long long>(yi) * W + xi) * ld_in + 4 * v));
+    float4 y = bn_apply(cf, ld4(raw + (static_cast<size_t>(yi) * W + xi) * ld_in + 4 * v));
     if (act) y = lrelu4(y);
-    st4(dst + p * ld_out + 4 * v, y);
+    st4(dst + static_cast<size_t>(p) * ld_out + 4 * v, y);
   }
 }
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
@@ -186,28 +213,39 @@ void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, fl
   k_bn_act_write<<<g.blocks, g.threads, 0, s>>>(raw, ld_in, bn, H, W, dst, ld_out, pad, act, g.VL, g.PPB);
 }
 
-// ------------------------------------------------------------------------------------------------ concat stage
-// Pre-BN value of the concat tensor at interior pixel (i, j) for vec lane v (v < Cu/4: upsampled, else skip branch).
-__device__ __forceinline__ float4 up2x_value(const float* __restrict__ U, int Cu, int h, int w, int i, int j, int v,
-                                             int bilinear) {
-  if (!bilinear) return ld4(U + (static_cast<long long>(i >> 1) * w + (j >> 1)) * Cu + 4 * v);
-  const int iy = i >> 1, jx = j >> 1;
-  int y0, y1, x0, x1;
-  float wy0, wx0;
-  if (i & 1) { y0 = iy; y1 = min(iy + 1, h - 1); wy0 = 0.75f; } else { y0 = max(iy - 1, 0); y1 = iy; wy0 = 0.25f; }
-  if (j & 1) { x0 = jx; x1 = min(jx + 1, w - 1); wx0 = 0.75f; } else { x0 = max(jx - 1, 0); x1 = jx; wx0 = 0.25f; }
-  const float wy1 = 1.f - wy0, wx1 = 1.f - wx0;
-  const float4 a = ld4(U + (static_cast<long long>(y0) * w + x0) * Cu + 4 * v);
-  const float4 b = ld4(U + (static_cast<long long>(y0) * w + x1) * Cu + 4 * v);
-  const float4 c = ld4(U + (static_cast<long long>(y1) * w + x0) * Cu + 4 * v);
-  const float4 d = ld4(U + (static_cast<long long>(y1) * w + x1) * Cu + 4 * v);
-  float4 r = f4zero();
-  r = f4fma(wy0 * wx0, a, r);
-  r = f4fma(wy0 * wx1, b, r);
-  r = f4fma(wy1 * wx0, c, r);
-  r = f4fma(wy1 * wx1, d, r);
-  return r;
+// BN + LeakyReLU + RGB head + sigmoid: one warp per pixel (C = 128 -> 32 lanes x float4), nothing but out is written.
+__global__ void __launch_bounds__(256) k_bn_act_head(const float* __restrict__ raw, BnRef bn, int npix, HeadRef head) {
+  const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+  const Bn4 cf = bn_coef(bn, lane);
+  float4 w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = k < head.K ? ld4(head.w + k * 128 + 4 * lane) : f4zero();
+  for (int p = blockIdx.x * 8 + wslot; p < npix; p += gridDim.x * 8) {
+    const float4 y = lrelu4(bn_apply(cf, ld4(raw + static_cast<size_t>(p) * 128 + 4 * lane)));
+    float d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = f4dot(y, w[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
+    }
+    if (lane < head.K) {
+      const float t = (lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]) + head.b[lane];
+      head.out[static_cast<size_t>(lane) * npix + p] = 1.f / (1.f + expf(-t));
+    }
+  }
 }
+void launch_bn_act_head(const float* raw, BnRef bn, int H, int W, HeadRef head, cudaStream_t s) {
+  const int npix = H * W;
+  int blocks = (npix + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_bn_act_head<<<blocks, 256, 0, s>>>(raw, bn, npix, head);
+}
+
+// ------------------------------------------------------------------------------------------------ concat stage
+// Work item = one SOURCE pixel (si, sj) of U (h x w) and its 2x2 block of output pixels (2si+a, 2sj+b):
+// 9 loads produce 4 upsampled values (bilinear, align_corners=False: weights 1/4, 3/4, edge clamp).
 struct CatLane {
   int is_up;
   Bn4 bs;  // skip-branch BN (valid when !is_up)
@@ -218,45 +256,98 @@ __device__ __forceinline__ CatLane cat_lane(const CatArgs& a, int v) {
   if (!l.is_up) l.bs = bn_coef(a.bn_s, v - a.Cu / 4);
   return l;
 }
-__device__ __forceinline__ float4 cat_value(const CatArgs& a, const CatLane& l, int i, int j, int v) {
-  if (l.is_up) return up2x_value(a.U, a.Cu, a.H >> 1, a.W >> 1, i, j, v, a.bilinear);
-  const float4 x = ld4(a.raw_s + (static_cast<long long>(i) * a.W + j) * a.Cs + 4 * (v - a.Cu / 4));
-  return lrelu4(bn_apply(l.bs, x));
+// out[0..3] = pre-BN concat values at (2si,2sj), (2si,2sj+1), (2si+1,2sj), (2si+1,2sj+1)
+__device__ __forceinline__ void cat_quad(const CatArgs& a, const CatLane& l, int si, int sj, int v, float4 (&out)[4]) {
+  const int h = a.H >> 1, w = a.W >> 1;
+  if (l.is_up) {
+    const float* base = a.U + 4 * v;
+    if (!a.bilinear) {
+      const float4 c = ld4(base + (static_cast<size_t>(si) * w + sj) * a.Cu);
+      out[0] = out[1] = out[2] = out[3] = c;
+      return;
+    }
+    const int r0 = max(si - 1, 0), r2 = min(si + 1, h - 1);
+    const int c0 = max(sj - 1, 0), c2 = min(sj + 1, w - 1);
+    const int rr[3] = {r0, si, r2};
+    float4 hl[3], hr[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float* rowp = base + static_cast<size_t>(rr[q]) * w * a.Cu;
+      const float4 n0 = ld4(rowp + static_cast<size_t>(c0) * a.Cu);
+      const float4 n1 = ld4(rowp + static_cast<size_t>(sj) * a.Cu);
+      const float4 n2 = ld4(rowp + static_cast<size_t>(c2) * a.Cu);
+      hl[q] = f4fma(0.25f, n0, f4fma(0.75f, n1, f4zero()));
+      hr[q] = f4fma(0.25f, n2, f4fma(0.75f, n1, f4zero()));
+    }
+    out[0] = f4fma(0.25f, hl[0], f4fma(0.75f, hl[1], f4zero()));
+    out[1] = f4fma(0.25f, hr[0], f4fma(0.75f, hr[1], f4zero()));
+    out[2] = f4fma(0.25f, hl[2], f4fma(0.75f, hl[1], f4zero()));
+    out[3] = f4fma(0.25f, hr[2], f4fma(0.75f, hr[1], f4zero()));
+  } else {
+    const float* base = a.raw_s + 4 * (v - a.Cu / 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = 2 * si + (q >> 1), j = 2 * sj + (q & 1);
+      out[q] = lrelu4(bn_apply(l.bs, ld4(base + (static_cast<size_t>(i) * a.W + j) * a.Cs)));
+    }
+  }
 }
 
 __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
-  const long long npix = static_cast<long long>(a.H) * a.W;
+  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   float4 acc[2] = {f4zero(), f4zero()};
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const float4 t = cat_value(a, l, static_cast<int>(p / a.W), static_cast<int>(p % a.W), v);
-    acc[0] = f4add(acc[0], t);
-    acc[1] = f4fma(1.f, f4mul(t, t), acc[1]);
+  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+    const int si = p / w, sj = p - si * w;
+    float4 q[4];
+    cat_quad(a, l, si, sj, v, q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[0] = f4add(acc[0], q[e]);
+      acc[1] = f4mla(q[e], q[e], acc[1]);
+    }
   }
   double* const dst[2] = {fwd, fwd + (a.Cu + a.Cs)};
   block_reduce_atomic<2>(acc, VL, PPB, dst);
 }
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H) * a.W);
-  k_cat_stats<<<g.blocks, g.threads, 2 * g.threads * sizeof(float4), s>>>(a, fwd_cat, g.VL, g.PPB);
+  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+  k_cat_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, fwd_cat, g.VL, g.PPB);
+}
+
+// store the value of interior pixel (i, j) at its padded position and at every halo position that mirrors it
+__device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld, int H, int W, int i, int j, int v, float4 val) {
+  int rows[3], cols[3];
+  int nr = 0, nc = 0;
+  rows[nr++] = i + 1;
+  if (i == 1) rows[nr++] = 0;
+  if (i == H - 2) rows[nr++] = H + 1;
+  cols[nc++] = j + 1;
+  if (j == 1) cols[nc++] = 0;
+  if (j == W - 2) cols[nc++] = W + 1;
+  const int Wp = W + 2;
+  for (int r = 0; r < nr; ++r)
+    for (int c = 0; c < nc; ++c) st4(dst + (static_cast<size_t>(rows[r]) * Wp + cols[c]) * ld + 4 * v, val);
 }
 
 __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const Bn4 cf = bn_coef(bn_cat, v);
-  const int Wo = a.W + 2;
-  const long long nout = static_cast<long long>(a.H + 2) * Wo;
+  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   const int ld = a.Cu + a.Cs;
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < nout; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int yo = static_cast<int>(p / Wo), xo = static_cast<int>(p % Wo);
-    const int i = reflect_idx(yo - 1, a.H), j = reflect_idx(xo - 1, a.W);
-    st4(dst + p * ld + 4 * v, bn_apply(cf, cat_value(a, l, i, j, v)));
+  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+    const int si = p / w, sj = p - si * w;
+    float4 q[4];
+    cat_quad(a, l, si, sj, v, q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]));
   }
 }
 void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H + 2) * (a.W + 2));
+  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   k_cat_write<<<g.blocks, g.threads, 0, s>>>(a, bn_cat, dst, g.VL, g.PPB);
 }
 
@@ -275,7 +366,7 @@ __device__ __forceinline__ float4 fold_read(const float* __restrict__ gp, int ld
   const int Wp = W + 2;
   float4 r = f4zero();
   for (int a = 0; a < nr; ++a)
-    for (int b = 0; b < nc; ++b) r = f4add(r, ld4(gp + (static_cast<long long>(rows[a]) * Wp + cols[b]) * ld + coff + 4 * v));
+    for (int b = 0; b < nc; ++b) r = f4add(r, ld4(gp + (static_cast<size_t>(rows[a]) * Wp + cols[b]) * ld + coff + 4 * v));
   return r;
 }
 // adjoint of x2 upsampling: D is [2H][2W][ld]
@@ -283,33 +374,78 @@ __device__ __forceinline__ float4 upadj_read(const float* __restrict__ D, int ld
                                              int v, int bilinear) {
   const int H2 = 2 * H, W2 = 2 * W;
   float4 r = f4zero();
+  const float* base = D + coff + 4 * v;
   if (!bilinear) {
+#pragma unroll
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b)
-        r = f4add(r, ld4(D + (static_cast<long long>(2 * i + a) * W2 + (2 * j + b)) * ld + coff + 4 * v));
+#pragma unroll
+      for (int b = 0; b < 2; ++b) r = f4add(r, ld4(base + (static_cast<size_t>(2 * i + a) * W2 + (2 * j + b)) * ld));
     return r;
   }
   const float wgt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  float4 t[16];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int y = min(max(2 * i - 1 + a, 0), H2 - 1);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int x = min(max(2 * j - 1 + b, 0), W2 - 1);
-      r = f4fma(wgt[a] * wgt[b], ld4(D + (static_cast<long long>(y) * W2 + x) * ld + coff + 4 * v), r);
+      t[a * 4 + b] = ld4(base + (static_cast<size_t>(y) * W2 + x) * ld);
     }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r = f4fma(wgt[a] * wgt[b], t[a * 4 + b], r);
+  return r;
+}
+// per-thread constants of a gradient source
+struct SrcRegs {
+  float4 w[4];  // kind 1: skip-conv weight rows; kind 3: head weight rows
+};
+template <int KIND>
+__device__ __forceinline__ SrcRegs src_regs(const GradSrc& s, int C, int v) {
+  SrcRegs r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r.w[k] = f4zero();
+  if (KIND == 1 && s.ds != nullptr) {
+    for (int k = 0; k < s.n2 && k < 4; ++k) r.w[k] = ld4(s.w2 + k * C + 4 * v);
+  }
+  if (KIND == 3) {
+    for (int k = 0; k < s.nh && k < 4; ++k) r.w[k] = ld4(s.wh + k * C + 4 * v);
   }
   return r;
 }
+// gradient w.r.t. the BN(+act) output at pixel p = (i, j); dl (kind 3) returns the head's logit gradients
 template <int KIND>
-__device__ __forceinline__ float4 grad_read(const GradSrc& s, int H, int W, int i, int j, int v) {
-  if (KIND == 0) return ld4(s.g + (static_cast<long long>(i) * W + j) * s.ld + s.coff + 4 * v);
+__device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr, int H, int W, int p, int i, int j, int v,
+                                            float (&dl)[4]) {
+  if (KIND == 0) return ld4(s.g + static_cast<size_t>(p) * s.ld + s.coff + 4 * v);
   if (KIND == 1) {
     float4 r = fold_read(s.g, s.ld, s.coff, H, W, i, j, v);
-    if (s.g2 != nullptr) r = f4add(r, ld4(s.g2 + (static_cast<long long>(i) * W + j) * s.ld2 + 4 * v));
+    if (s.ds != nullptr) {
+      const float4 d = ld4(s.ds + static_cast<size_t>(p) * 4);  // n2 == 4
+      r = f4fma(d.x, sr.w[0], r);
+      r = f4fma(d.y, sr.w[1], r);
+      r = f4fma(d.z, sr.w[2], r);
+      r = f4fma(d.w, sr.w[3], r);
+    }
     return r;
   }
-  return upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
+  if (KIND == 2) return upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
+  // KIND == 3
+  const int npix = H * W;
+  float4 r = f4zero();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    dl[k] = 0.f;
+    if (k < s.nh) {
+      const float o = s.outv[static_cast<size_t>(k) * npix + p];
+      dl[k] = s.dout[static_cast<size_t>(k) * npix + p] * o * (1.f - o);
+      r = f4fma(dl[k], sr.w[k], r);
+    }
+  }
+  return r;
 }
 __device__ __forceinline__ float4 lrelu_bwd4(float4 y, float4 g) {
   return make_float4(y.x > 0.f ? g.x : kLreluSlope * g.x, y.y > 0.f ? g.y : kLreluSlope * g.y,
@@ -322,26 +458,59 @@ __global__ void k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef
                                 double* __restrict__ bwd, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
-  const long long npix = static_cast<long long>(H) * W;
-  float4 acc[2] = {f4zero(), f4zero()};
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int i = static_cast<int>(p / W), j = static_cast<int>(p % W);
-    const float4 x = ld4(raw + p * ld_raw + 4 * v);
-    float4 dz = grad_read<KIND>(src, H, W, i, j, v);
-    if (act) dz = lrelu_bwd4(bn_apply(cf, x), dz);
+  const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
+  const int npix = H * W;
+  constexpr int K = KIND == 3 ? 7 : 2;
+  float4 acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = f4zero();
+  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+    const int i = p / W, j = p - i * W;
+    const float4 x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
+    float dl[4];
+    float4 dz = grad_read<KIND>(src, sr, H, W, p, i, j, v, dl);
+    const float4 y = bn_apply(cf, x);
+    if constexpr (KIND == 3) {
+      // the head's own gradients: dW[k][c] += dl[k] * act(y)[c], db[k] += dl[k]
+      const float4 u = act ? lrelu4(y) : y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[2 + k] = f4fma(dl[k], u, acc[2 + k]);
+      if (v == 0) acc[6] = f4add(acc[6], make_float4(dl[0], dl[1], dl[2], dl[3]));
+    }
+    if (act) dz = lrelu_bwd4(y, dz);
     acc[0] = f4add(acc[0], dz);
-    acc[1] = f4add(acc[1], f4mul(dz, bn_xhat(cf, x)));
+    acc[1] = f4mla(dz, bn_xhat(cf, x), acc[1]);
   }
-  double* const dst[2] = {bwd, bwd + bn.C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst);
+  if constexpr (KIND == 3) {
+    // dwh rows are [K][C]: rows k >= nh are not stored
+    double* const dst[K] = {bwd, bwd + bn.C, src.dwh, src.nh > 1 ? src.dwh + bn.C : nullptr,
+                            src.nh > 2 ? src.dwh + 2 * bn.C : nullptr, src.nh > 3 ? src.dwh + 3 * bn.C : nullptr, nullptr};
+    // db: only lane v == 0 carries data -> handled separately below (dst[6] == nullptr skips the generic path)
+    block_reduce_atomic<K>(acc, VL, PPB, dst);
+    // acc[6] of lanes v == 0 was staged in red_smem by block_reduce_atomic: slot layout (k * nparts + part) * VL + v
+    if (threadIdx.x == 0) {
+      extern __shared__ float4 red_smem[];
+      const int nparts = (VL < 32 && (VL & (VL - 1)) == 0) ? (blockDim.x >> 5) : PPB;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      for (int pp = 0; pp < nparts; ++pp) {
+        const float4 t = red_smem[(6 * nparts + pp) * VL];
+        s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
+      }
+      const double sv[4] = {s0, s1, s2, s3};
+      for (int k = 0; k < src.nh; ++k) atomicAdd(src.dbh + k, sv[k]);
+    }
+  } else {
+    double* const dst[2] = {bwd, bwd + bn.C};
+    block_reduce_atomic<K>(acc, VL, PPB, dst);
+  }
 }
 void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
                           cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
-  const size_t sm = 2 * g.threads * sizeof(float4);
-  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else k_bn_bwd_reduce<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, red_bytes(g, 2), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, red_bytes(g, 2), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, red_bytes(g, 2), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else k_bn_bwd_reduce<3><<<g.blocks, g.threads, red_bytes(g, 7), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
 }
 
 template <int KIND>
@@ -350,18 +519,20 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef 
                                double* __restrict__ dbias, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
+  const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
   const int C = bn.C;
   float4 m1, m2;
   m1.x = static_cast<float>(bwd[4 * v + 0] * bn.inv_n); m1.y = static_cast<float>(bwd[4 * v + 1] * bn.inv_n);
   m1.z = static_cast<float>(bwd[4 * v + 2] * bn.inv_n); m1.w = static_cast<float>(bwd[4 * v + 3] * bn.inv_n);
   m2.x = static_cast<float>(bwd[C + 4 * v + 0] * bn.inv_n); m2.y = static_cast<float>(bwd[C + 4 * v + 1] * bn.inv_n);
   m2.z = static_cast<float>(bwd[C + 4 * v + 2] * bn.inv_n); m2.w = static_cast<float>(bwd[C + 4 * v + 3] * bn.inv_n);
-  const long long npix = static_cast<long long>(H) * W;
+  const int npix = H * W;
   float4 acc[1] = {f4zero()};
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int i = static_cast<int>(p / W), j = static_cast<int>(p % W);
-    const float4 x = ld4(raw + p * ld_raw + 4 * v);
-    float4 dz = grad_read<KIND>(src, H, W, i, j, v);
+  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+    const int i = p / W, j = p - i * W;
+    const float4 x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
+    float dl[4];
+    float4 dz = grad_read<KIND>(src, sr, H, W, p, i, j, v, dl);
     if (act) dz = lrelu_bwd4(bn_apply(cf, x), dz);
     const float4 xh = bn_xhat(cf, x);
     float4 dx;
@@ -369,8 +540,8 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef 
     dx.y = cf.scale.y * (dz.y - m1.y - xh.y * m2.y);
     dx.z = cf.scale.z * (dz.z - m1.z - xh.z * m2.z);
     dx.w = cf.scale.w * (dz.w - m1.w - xh.w * m2.w);
-    st4(draw + p * C + 4 * v, dx);
-    if (zs != nullptr) st4(zs + (static_cast<long long>(2 * i) * (2 * W) + 2 * j) * C + 4 * v, dx);
+    st4(draw + static_cast<size_t>(p) * C + 4 * v, dx);
+    if (zs != nullptr) st4(zs + (static_cast<size_t>(2 * i) * (2 * W) + 2 * j) * C + 4 * v, dx);
     acc[0] = f4add(acc[0], dx);
   }
   double* const dst[1] = {dbias};
@@ -379,10 +550,11 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef 
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
                          const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
-  const size_t sm = g.threads * sizeof(float4);
+  const size_t sm = red_bytes(g, 1);
   if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
   else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else k_bn_bwd_apply<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else k_bn_bwd_apply<3><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
@@ -391,21 +563,25 @@ __global__ void k_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* __restric
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const Bn4 cf = bn_coef(bn_cat, v);
-  const long long npix = static_cast<long long>(a.H) * a.W;
+  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   float4 acc[2] = {f4zero(), f4zero()};
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int i = static_cast<int>(p / a.W), j = static_cast<int>(p % a.W);
-    const float4 x = cat_value(a, l, i, j, v);
-    const float4 dz = fold_read(gp, ld_gp, 0, a.H, a.W, i, j, v);
-    acc[0] = f4add(acc[0], dz);
-    acc[1] = f4add(acc[1], f4mul(dz, bn_xhat(cf, x)));
+  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+    const int si = p / w, sj = p - si * w;
+    float4 q[4];
+    cat_quad(a, l, si, sj, v, q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float4 dz = fold_read(gp, ld_gp, 0, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v);
+      acc[0] = f4add(acc[0], dz);
+      acc[1] = f4mla(dz, bn_xhat(cf, q[e]), acc[1]);
+    }
   }
   double* const dst[2] = {bwd, bwd + bn_cat.C};
   block_reduce_atomic<2>(acc, VL, PPB, dst);
 }
 void launch_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, double* bwd, cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H) * a.W);
-  k_cat_bwd_reduce<<<g.blocks, g.threads, 2 * g.threads * sizeof(float4), s>>>(a, bn_cat, gp, ld_gp, bwd, g.VL, g.PPB);
+  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+  k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, bn_cat, gp, ld_gp, bwd, g.VL, g.PPB);
 }
 __global__ void k_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* __restrict__ gp, int ld_gp,
                                 const double* __restrict__ bwd, float* __restrict__ dcat, int VL, int PPB) {
@@ -419,78 +595,130 @@ __global__ void k_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* __restrict
     m1[e] = static_cast<float>(bwd[4 * v + e] * bn_cat.inv_n);
     m2[e] = static_cast<float>(bwd[C + 4 * v + e] * bn_cat.inv_n);
   }
-  const long long npix = static_cast<long long>(a.H) * a.W;
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int i = static_cast<int>(p / a.W), j = static_cast<int>(p % a.W);
-    const float4 xh = bn_xhat(cf, cat_value(a, l, i, j, v));
-    const float4 dz = fold_read(gp, ld_gp, 0, a.H, a.W, i, j, v);
-    float4 dx;
-    dx.x = cf.scale.x * (dz.x - m1[0] - xh.x * m2[0]);
-    dx.y = cf.scale.y * (dz.y - m1[1] - xh.y * m2[1]);
-    dx.z = cf.scale.z * (dz.z - m1[2] - xh.z * m2[2]);
-    dx.w = cf.scale.w * (dz.w - m1[3] - xh.w * m2[3]);
-    st4(dcat + p * C + 4 * v, dx);
+  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
+  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+    const int si = p / w, sj = p - si * w;
+    float4 q[4];
+    cat_quad(a, l, si, sj, v, q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 2 * si + (e >> 1), j = 2 * sj + (e & 1);
+      const float4 xh = bn_xhat(cf, q[e]);
+      const float4 dz = fold_read(gp, ld_gp, 0, a.H, a.W, i, j, v);
+      float4 dx;
+      dx.x = cf.scale.x * (dz.x - m1[0] - xh.x * m2[0]);
+      dx.y = cf.scale.y * (dz.y - m1[1] - xh.y * m2[1]);
+      dx.z = cf.scale.z * (dz.z - m1[2] - xh.z * m2[2]);
+      dx.w = cf.scale.w * (dz.w - m1[3] - xh.w * m2[3]);
+      st4(dcat + (static_cast<size_t>(i) * a.W + j) * C + 4 * v, dx);
+    }
   }
 }
 void launch_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, const double* bwd, float* dcat,
                           cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H) * a.W);
+  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   k_cat_bwd_apply<<<g.blocks, g.threads, 0, s>>>(a, bn_cat, gp, ld_gp, bwd, dcat, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ skinny 1x1 convs
 // VL = C/4 lanes per pixel (power of two <= 32); warp-shuffle reduction over the pixel's lanes.
-__global__ void k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
-                             const float* __restrict__ b, int C, int N, int H, int W, float* __restrict__ y, int mode) {
+__global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
+                                                    const float* __restrict__ b, int C, int N, int H, int W,
+                                                    float* __restrict__ y, int mode, double* __restrict__ stats) {
   const int VL = C / 4;
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long p = gid / VL;
-  const int v = static_cast<int>(gid % VL);
-  const long long npix = static_cast<long long>(H) * W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p < npix) {
-    const int i = static_cast<int>(p / W), j = static_cast<int>(p % W);
-    const float4 xv = ld4(x + (static_cast<long long>(i) * x_rs + j) * ldx + 4 * v);
-    for (int n = 0; n < N; ++n) {
-      const float4 wv = ld4(w + n * C + 4 * v);
-      acc[n] = xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+  const int PPB = 256 / VL;
+  const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
+  const int npix = H * W;
+  float4 wv[4];
+  float bv[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    wv[n] = n < N ? ld4(w + n * C + 4 * v) : f4zero();
+    bv[n] = (n < N && b != nullptr) ? b[n] : 0.f;
+  }
+  float4 s1 = f4zero(), s2 = f4zero();
+  // every thread runs the same number of trips so that the shuffles stay warp-convergent
+  const int trips = (npix + gridDim.x * PPB - 1) / (gridDim.x * PPB);
+  for (int t = 0; t < trips; ++t) {
+    const int p = (t * gridDim.x + blockIdx.x) * PPB + slot;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < npix) {
+      const int i = p / W, j = p - i * W;
+      const float4 xv = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n] = f4dot(xv, wv[n]);
+    }
+    for (int o = VL >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    }
+    if (p < npix && v == 0) {
+      float o4[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) o4[n] = n < N ? acc[n] + bv[n] : 0.f;
+      if (mode == 0) {
+        if (N == 4) st4(y + static_cast<size_t>(p) * 4, make_float4(o4[0], o4[1], o4[2], o4[3]));
+        else for (int n = 0; n < N; ++n) y[static_cast<size_t>(p) * N + n] = o4[n];
+        const float4 ov = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        s1 = f4add(s1, ov);
+        s2 = f4mla(ov, ov, s2);
+      } else {
+        for (int n = 0; n < N; ++n) y[static_cast<size_t>(n) * npix + p] = (mode == 1) ? 1.f / (1.f + expf(-o4[n])) : o4[n];
+      }
     }
   }
-  for (int o = VL >> 1; o > 0; o >>= 1)
-    for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-  if (p < npix && v == 0) {
-    for (int n = 0; n < N; ++n) {
-      float o = acc[n] + (b != nullptr ? b[n] : 0.f);
-      if (mode == 0) y[p * N + n] = o;
-      else y[n * npix + p] = (mode == 1) ? 1.f / (1.f + expf(-o)) : o;
+  if (stats != nullptr) {
+    // only lanes v == 0 hold data; fold across the block
+    __shared__ float4 sm1[8], sm2[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 = f4add(s1, shfl_xor4(s1, o));
+      s2 = f4add(s2, shfl_xor4(s2, o));
+    }
+    if ((threadIdx.x & 31) == 0) { sm1[threadIdx.x >> 5] = s1; sm2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 8; ++k) {
+        a[0] += sm1[k].x; a[1] += sm1[k].y; a[2] += sm1[k].z; a[3] += sm1[k].w;
+        q[0] += sm2[k].x; q[1] += sm2[k].y; q[2] += sm2[k].z; q[3] += sm2[k].w;
+      }
+      for (int n = 0; n < N; ++n) { atomicAdd(stats + n, a[n]); atomicAdd(stats + N + n, q[n]); }
     }
   }
 }
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
-                       int W, float* y, int mode, cudaStream_t s) {
-  const long long total = static_cast<long long>(H) * W * (C / 4);
-  k_skinny_fwd<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(x, ldx, x_rs, w, b, C, N, H, W, y, mode);
+                       int W, float* y, int mode, double* stats, cudaStream_t s) {
+  const int PPB = 256 / (C / 4);
+  long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
+  if (nb > 148 * 8) nb = 148 * 8;
+  k_skinny_fwd<<<static_cast<int>(nb), 256, 0, s>>>(x, ldx, x_rs, w, b, C, N, H, W, y, mode, stats);
 }
 
 __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
                              int H, int W, const float* __restrict__ dy, const float* __restrict__ out_nchw, int mode,
                              float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
-  const long long npix = static_cast<long long>(H) * W;
+  const int npix = H * W;
   float4 wv[4];
   for (int n = 0; n < 4; ++n) wv[n] = n < N ? ld4(w + n * C + 4 * v) : f4zero();
   float4 acc[5] = {f4zero(), f4zero(), f4zero(), f4zero(), f4zero()};  // dw rows 0..3, db (lane v == 0 only)
-  for (long long p = static_cast<long long>(blockIdx.x) * PPB + slot; p < npix; p += static_cast<long long>(gridDim.x) * PPB) {
-    const int i = static_cast<int>(p / W), j = static_cast<int>(p % W);
+  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
+    const int i = p / W, j = p - i * W;
     float g[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int n = 0; n < N; ++n) {
-      if (mode == 0) g[n] = dy[p * N + n];
-      else {
-        const float d = dy[n * npix + p];
-        if (mode == 1) { const float o = out_nchw[n * npix + p]; g[n] = d * o * (1.f - o); } else g[n] = d;
+    if (mode == 0 && N == 4) {
+      const float4 d = ld4(dy + static_cast<size_t>(p) * 4);
+      g[0] = d.x; g[1] = d.y; g[2] = d.z; g[3] = d.w;
+    } else {
+      for (int n = 0; n < N; ++n) {
+        if (mode == 0) g[n] = dy[static_cast<size_t>(p) * N + n];
+        else {
+          const float d = dy[static_cast<size_t>(n) * npix + p];
+          if (mode == 1) { const float o = out_nchw[static_cast<size_t>(n) * npix + p]; g[n] = d * o * (1.f - o); } else g[n] = d;
+        }
       }
     }
-    const float4 xv = ld4(x + (static_cast<long long>(i) * x_rs + j) * ldx + 4 * v);
+    const float4 xv = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
     float4 d = f4zero();
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -498,51 +726,36 @@ __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, con
       d = f4fma(g[n], wv[n], d);
     }
     if (v == 0) acc[4] = f4add(acc[4], make_float4(g[0], g[1], g[2], g[3]));
-    if (dx != nullptr) st4(dx + p * C + 4 * v, d);
+    if (dx != nullptr) st4(dx + static_cast<size_t>(p) * C + 4 * v, d);
   }
-  // dw[n][4v+e]
-  extern __shared__ float4 red_smem[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int k = 0; k < 5; ++k) red_smem[k * nthr + tid] = acc[k];
-  __syncthreads();
-  if (tid < VL) {
-    for (int n = 0; n < N; ++n) {
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      for (int pp = 0; pp < PPB; ++pp) {
-        const float4 t = red_smem[n * nthr + pp * VL + tid];
-        s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
-      }
-      atomicAdd(dw + n * C + 4 * tid + 0, s0);
-      atomicAdd(dw + n * C + 4 * tid + 1, s1);
-      atomicAdd(dw + n * C + 4 * tid + 2, s2);
-      atomicAdd(dw + n * C + 4 * tid + 3, s3);
+  double* const dst[5] = {dw, N > 1 ? dw + C : nullptr, N > 2 ? dw + 2 * C : nullptr, N > 3 ? dw + 3 * C : nullptr, nullptr};
+  block_reduce_atomic<5>(acc, VL, PPB, dst);
+  if (threadIdx.x == 0 && db != nullptr) {
+    extern __shared__ float4 red_smem[];
+    const int nparts = (VL < 32 && (VL & (VL - 1)) == 0) ? (blockDim.x >> 5) : PPB;
+    double sv[4] = {0, 0, 0, 0};
+    for (int pp = 0; pp < nparts; ++pp) {
+      const float4 t = red_smem[(4 * nparts + pp) * VL];
+      sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
     }
-    if (tid == 0) {
-      double s[4] = {0, 0, 0, 0};
-      for (int pp = 0; pp < PPB; ++pp) {
-        const float4 t = red_smem[4 * nthr + pp * VL];
-        s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
-      }
-      for (int n = 0; n < N; ++n) atomicAdd(db + n, s[n]);
-    }
+    for (int n = 0; n < N; ++n) atomicAdd(db + n, sv[n]);
   }
 }
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
                        cudaStream_t s) {
   VecGeom g = vec_geom(C, static_cast<long long>(H) * W);
-  k_skinny_bwd<<<g.blocks, g.threads, 5 * g.threads * sizeof(float4), s>>>(x, ldx, x_rs, w, C, N, H, W, dy, out_nchw,
-                                                                          mode, dx, dw, db, g.VL, g.PPB);
+  k_skinny_bwd<<<g.blocks, g.threads, red_bytes(g, 5), s>>>(x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
+                                                             g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ MSE loss
 __global__ void k_mse(const float* __restrict__ out, const float* __restrict__ target, const float* __restrict__ mask,
-                      int C, int HW, double* __restrict__ loss, float* __restrict__ dout) {
-  const long long n = static_cast<long long>(C) * HW;
+                      int C, int HW, double* __restrict__ loss, float* __restrict__ dout, const int* __restrict__ it_dev) {
+  const int n = C * HW;
   const float inv_n = 1.f / static_cast<float>(n);
   float acc = 0.f;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float m = mask != nullptr ? mask[i % HW] : 1.f;
     const float d = m * (out[i] - target[i]);
     acc = fmaf(d, d, acc);
@@ -555,15 +768,15 @@ __global__ void k_mse(const float* __restrict__ out, const float* __restrict__ t
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (threadIdx.x == 0) atomicAdd(loss, static_cast<double>(t) * static_cast<double>(inv_n));
+    if (threadIdx.x == 0) atomicAdd(loss + (it_dev != nullptr ? *it_dev : 0), static_cast<double>(t) * static_cast<double>(inv_n));
   }
 }
 void launch_mse(const float* out, const float* target, const float* mask, int C, int HW, double* loss, float* dout,
-                cudaStream_t s) {
+                const int* it_dev, cudaStream_t s) {
   const long long n = static_cast<long long>(C) * HW;
   int blocks = static_cast<int>((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_mse<<<blocks, 256, 0, s>>>(out, target, mask, C, HW, loss, dout);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_mse<<<blocks, 256, 0, s>>>(out, target, mask, C, HW, loss, dout, it_dev);
 }
 
 // ------------------------------------------------------------------------------------------------ Philox noise
@@ -574,7 +787,8 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 __global__ void k_noise(const float* __restrict__ z0, float* __restrict__ z, float sigma, uint64_t seed,
-                        uint64_t offset, size_t n4) {
+                        uint64_t offset, const int* __restrict__ it_dev, size_t n4) {
+  if (it_dev != nullptr) offset += static_cast<uint64_t>(*it_dev);
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     uint32_t c[4] = {static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(offset),
@@ -603,12 +817,15 @@ __global__ void k_noise(const float* __restrict__ z0, float* __restrict__ z, flo
     st4(z + 4 * i, zv);
   }
 }
-void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, size_t n, cudaStream_t s) {
+void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, size_t n,
+                  cudaStream_t s) {
   const size_t n4 = n / 4;
   int blocks = static_cast<int>((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_noise<<<blocks, 256, 0, s>>>(z0, z, sigma, seed, offset, n4);
+  k_noise<<<blocks, 256, 0, s>>>(z0, z, sigma, seed, offset, it_dev, n4);
 }
+__global__ void k_advance(int* it) { *it += 1; }
+void launch_advance(int* it_dev, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(it_dev); }
 
 // ------------------------------------------------------------------------------------------------ weight packing
 __global__ void k_pack_fprop(const float* __restrict__ w, int N, int C, int kh, int kw, int rot, float* __restrict__ dst,
@@ -648,57 +865,67 @@ void launch_pack_dgrad(const float* w, int N, int C, int kh, int kw, int rot, fl
   const long long total = static_cast<long long>(kh) * kw * c_rows * n_pad;
   k_pack_dgrad<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(w, N, C, kh, kw, rot, dst, c_rows, n_pad);
 }
-__global__ void k_wgrad_reduce(const float* __restrict__ partial, int ksplits, int N, int C, int kh, int kw, int rot,
-                               int c_pad, float* __restrict__ dw) {
-  const int taps = kh * kw;
-  const long long total = static_cast<long long>(taps) * N * C;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const int n = static_cast<int>((i / C) % N);
-    const int tap = static_cast<int>(i / (static_cast<long long>(C) * N));
-    double s = 0.0;
-    for (int k = 0; k < ksplits; ++k)
-      s += partial[((static_cast<long long>(k) * taps + tap) * 128 + n) * c_pad + c];
-    dw[(static_cast<long long>(n) * C + (c + rot) % C) * taps + tap] = static_cast<float>(s);
+
+// Split-K reduction.  Block = 32 float4 columns x 8 split-parts: a warp reads 512 contiguous bytes of one split;
+// the 8 parts are folded through shared memory (deterministic order), then scattered to the OIHW gradient.
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int ksplits, int N, int C, int taps,
+                                                      int rot, int c_pad, float* __restrict__ dw) {
+  __shared__ float4 sm[8][32];
+  const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int c4n = c_pad / 4;
+  const int total4 = taps * 128 * c4n;
+  const int idx = blockIdx.x * 32 + e;  // (tap, n, c4)
+  float4 s = f4zero();
+  if (idx < total4) {
+    const size_t split_stride = static_cast<size_t>(taps) * 128 * c_pad;
+    const float* src = partial + static_cast<size_t>(idx) * 4;
+    int k = part;
+    for (; k + 8 < ksplits; k += 16) {
+      const float4 a = ld4(src + k * split_stride);
+      const float4 b = ld4(src + (k + 8) * split_stride);
+      s = f4add(s, f4add(a, b));
+    }
+    for (; k < ksplits; k += 8) s = f4add(s, ld4(src + k * split_stride));
+  }
+  sm[part][e] = s;
+  __syncthreads();
+  if (part == 0 && idx < total4) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s = f4add(s, sm[q][e]);
+    const int c4 = idx % c4n, n = (idx / c4n) % 128, tap = idx / (c4n * 128);
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+    if (n < N) {
+      for (int q = 0; q < 4; ++q) {
+        const int c = 4 * c4 + q;
+        if (c < C) dw[(static_cast<size_t>(n) * C + (c + rot) % C) * taps + tap] = sv[q];
+      }
+    }
   }
 }
 void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh, int kw, int rot, int c_pad,
                          float* dw, cudaStream_t s) {
-  const long long total = static_cast<long long>(kh) * kw * N * C;
-  k_wgrad_reduce<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(partial, ksplits, N, C, kh, kw, rot, c_pad, dw);
-}
-__global__ void k_cvt_f64_f32(const double* __restrict__ src, float* __restrict__ dst, int n, int rot) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[(i + rot) % n] = static_cast<float>(src[i]);
-}
-void launch_cvt_f64_f32(const double* src, float* dst, int n, int rot, cudaStream_t s) {
-  k_cvt_f64_f32<<<(n + 127) / 128, 128, 0, s>>>(src, dst, n, rot);
-}
-__global__ void k_bn_running(const double* __restrict__ fwd, int C, int rot, float n, float* __restrict__ rm,
-                             float* __restrict__ rv, long long* __restrict__ nb) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    const int ct = (c + rot) % C;
-    const double m = fwd[c] / n;
-    double var = fwd[C + c] / n - m * m;
-    if (var < 0) var = 0;
-    const double unb = n > 1.f ? var * n / (n - 1.0) : var;
-    rm[ct] = 0.9f * rm[ct] + 0.1f * static_cast<float>(m);
-    rv[ct] = 0.9f * rv[ct] + 0.1f * static_cast<float>(unb);
-  }
-  if (c == 0 && nb != nullptr) *nb += 1;
-}
-void launch_bn_running(const double* fwd, int C, int rot, float n, float* running_mean, float* running_var,
-                       long long* num_batches, cudaStream_t s) {
-  k_bn_running<<<(C + 127) / 128, 128, 0, s>>>(fwd, C, rot, n, running_mean, running_var, num_batches);
+  const int total4 = kh * kw * 128 * (c_pad / 4);
+  k_wgrad_reduce<<<(total4 + 31) / 32, 256, 0, s>>>(partial, ksplits, N, C, kh * kw, rot, c_pad, dw);
 }
 
 // ------------------------------------------------------------------------------------------------ Adam
 // Arithmetic order follows torch.optim.Adam (single-tensor path): m = lerp(m, g, 1-b1); v = v*b2 + (1-b2) g^2;
-// p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).
+// p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).  Bias corrections are evaluated in fp64 on the device so that the
+// step number can come from a device counter (CUDA-graph replay).
 static constexpr int kAdamChunk = 2048;
-__global__ void k_adam(AdamTable t, float step_size, float w1, float b2, float w2, float bc2_sqrt, float eps) {
+__global__ void k_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, const int* __restrict__ it_dev) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const int st = step + (it_dev != nullptr ? *it_dev : 0);
+    const double bc1 = 1.0 - pow(b1, static_cast<double>(st));
+    const double bc2 = 1.0 - pow(b2, static_cast<double>(st));
+    s_step_size = static_cast<float>(lr / bc1);
+    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float w1 = static_cast<float>(1.0 - b1), fb2 = static_cast<float>(b2), w2 = static_cast<float>(1.0 - b2);
+  const float feps = static_cast<float>(eps);
   const int ti = t.blk_tensor[blockIdx.x];
   const int start = t.blk_start[blockIdx.x];
   const int n = t.numel[ti];
@@ -711,19 +938,15 @@ __global__ void k_adam(AdamTable t, float step_size, float w1, float b2, float w
     const float gi = g[i];
     float mi = m[i];
     mi = mi + (gi - mi) * w1;
-    const float vi = v[i] * b2 + w2 * gi * gi;
+    const float vi = v[i] * fb2 + w2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float denom = sqrtf(vi) / bc2_sqrt + feps;
     p[i] = p[i] - step_size * (mi / denom);
   }
 }
-void launch_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, cudaStream_t s) {
-  const double bc1 = 1.0 - pow(b1, step);
-  const double bc2 = 1.0 - pow(b2, step);
-  k_adam<<<t.nblocks, 256, 0, s>>>(t, static_cast<float>(lr / bc1), static_cast<float>(1.0 - b1),
-                                   static_cast<float>(b2), static_cast<float>(1.0 - b2),
-                                   static_cast<float>(sqrt(bc2)), static_cast<float>(eps));
+void launch_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, const int* it_dev, cudaStream_t s) {
+  k_adam<<<t.nblocks, 256, 0, s>>>(t, lr, b1, b2, eps, step, it_dev);
 }
 int adam_chunk() { return kAdamChunk; }
 
