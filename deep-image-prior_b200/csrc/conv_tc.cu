@@ -25,6 +25,8 @@ struct SmemCtl {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t a_full[2];    // patch mode: input patch buffers
+  uint64_t a_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
   float bias[160];
@@ -42,15 +44,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   // 1024-byte alignment is required by the 128B swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.n_mma * 128;
-  const int stage_bytes = kABytes + ((b_bytes + 1023) & ~1023);
-  uint8_t* stage_base = smem;
-  uint8_t* staging = smem + p.stages * stage_bytes;
+  // per-tap mode: stage = [A tile 16 KB][B tile]; patch mode: two input patches up front, stages hold B tiles only
+  const int patch_bytes = p.patch ? p.pw * p.ph * 128 : 0;
+  const int patch_alloc = (patch_bytes + 1023) & ~1023;
+  const int stage_bytes = (p.patch ? 0 : kABytes) + ((b_bytes + 1023) & ~1023);
+  uint8_t* patch_base = smem;
+  uint8_t* stage_base = smem + 2 * patch_alloc;
+  uint8_t* staging = stage_base + p.stages * stage_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(staging + p.n_chunks * kChunkBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_x * p.tiles_y;
   const int kb_per_tile = p.kh * p.kw * p.kblocks;
+  // Cluster of `csize` CTAs: every CTA works on its own tile, all of them walk the identical (tap, k-block) sequence, and
+  // each CTA fetches 1/csize of the weight tile and multicasts it to the whole cluster (weights are the same for all
+  // tiles) -> L2->SM traffic per k-block drops from 16+16 KB to 16+16/csize KB.  Tiles past the end are harmless
+  // dummies (TMA zero-fills out-of-range reads and clips out-of-range stores; statistics are masked).
+  const int csize = p.csize;
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  const int n_iters = (num_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile0 = (blockIdx.x / csize) * csize + crank;  // first tile of this CTA; stride gridDim.x
   const uint32_t acc_cols = (p.n_mma + 31) & ~31;  // column stride between the two accumulators
 
   if (warp == 0 && lane == 0) {
@@ -61,11 +76,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&ctl->full[i], 1);
-      mbar_init(&ctl->empty[i], 1);
+      mbar_init(&ctl->empty[i], csize);  // released by the MMA warp of every CTA that multicasts into this stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
       mbar_init(&ctl->tmem_empty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&ctl->a_full[i], 1);
+      mbar_init(&ctl->a_empty[i], 1);
     }
     fence_mbar_init();
   }
@@ -78,6 +95,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -86,9 +104,34 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b_rows = p.n_mma / csize;
+      int ab = 0;
+      uint32_t aphase = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        const int tile = tile0 + it * gridDim.x;
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int x0 = tx * p.bw, y0 = ty * p.bh;
+        if (p.patch) {
+          // 3x3 stride-1: ONE (bw+2) x (bh+2) input patch per 32-channel block serves all nine taps (the MMA warp
+          // addresses tap (r,s) as the same patch shifted by r*pw+s rows); only the weight tiles stream per tap.
+          const int taps = p.kh * p.kw;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&ctl->a_empty[ab], aphase ^ 1);
+            mbar_expect_tx(&ctl->a_full[ab], patch_bytes);
+            tma_load_5d(patch_base + ab * patch_alloc, &p.tmA, &ctl->a_full[ab], kb * 32, 0, x0 + p.offx, 0, y0 + p.offy);
+            if (++ab == 2) { ab = 0; aphase ^= 1; }
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&ctl->empty[stage], phase ^ 1);
+              uint8_t* sb = stage_base + stage * stage_bytes;
+              mbar_expect_tx(&ctl->full[stage], b_bytes);
+              if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+              else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                                  tap * p.n_mma + crank * b_rows, cmask);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int r = 0; r < p.kh; ++r) {
           for (int s = 0; s < p.kw; ++s) {
             const int ix = p.offx + s, iy = p.offy + r;  // tap offset in input coordinates
@@ -106,7 +149,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
               uint8_t* sb = sa + kABytes;
               mbar_expect_tx(&ctl->full[stage], kABytes + b_bytes);
               tma_load_5d(sa, &p.tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
-              tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+              if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+              else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                                  tap * p.n_mma + crank * b_rows, cmask);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -121,10 +166,42 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ab = 0;
+      uint32_t aphase = 0;
+      for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
+        if (p.patch) {
+          const int taps = p.kh * p.kw;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(&ctl->a_full[ab], aphase);
+            tc_fence_after();
+            const uint32_t pa = smem_u32(patch_base + ab * patch_alloc);
+            const int nmma = (kb == p.kblocks - 1) ? p.tail_mmas : 4;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&ctl->full[stage], phase);
+              tc_fence_after();
+              const uint32_t sb = smem_u32(stage_base + stage * stage_bytes);
+              const int r = tap / p.kw, sx = tap - r * p.kw;
+              // tile row ty = 8 consecutive patch pixels starting at ((ty + r) * pw + sx): 8-row groups pw*128 B apart.
+              // The group starts are not 1024 B aligned; UMMA and TMA both swizzle on absolute smem address bits.
+              const uint32_t a0 = pa + (r * p.pw + sx) * 128;
+              for (int k = 0; k < nmma; ++k) {
+                const uint64_t adesc = make_smem_desc_sw128(a0 + k * 32, 16, p.pw * 128);
+                const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+              if (csize == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], cmask);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(&ctl->a_empty[ab]);
+            if (++ab == 2) { ab = 0; aphase ^= 1; }
+          }
+          tc_commit(&ctl->tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         for (int kbt = 0; kbt < kb_per_tile; ++kbt) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
@@ -139,7 +216,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
             mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (kbt > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&ctl->empty[stage]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in every CTA that multicasts into it) once the MMAs above have read it
+          if (csize == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], cmask);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&ctl->tmem_full[acc]);
@@ -153,7 +231,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     const int row = ew * 32 + lane;      // tile row (pixel) owned by this thread
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile = tile0 + it * gridDim.x;
       const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
       const int x0 = tx * p.bw, y0 = ty * p.bh;
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
@@ -214,6 +293,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols_pow2(2 * acc_cols));
@@ -359,7 +439,9 @@ static constexpr size_t kMaxSmem = 232448;  // 227 KB
 
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
   const size_t b_bytes = (static_cast<size_t>(p.n_mma) * 128 + 1023) & ~size_t(1023);
-  return 1024 + p.stages * (kABytes + b_bytes) + static_cast<size_t>(p.n_chunks) * kChunkBytes + sizeof(SmemCtl);
+  const size_t patch = p.patch ? ((static_cast<size_t>(p.pw) * p.ph * 128 + 1023) & ~size_t(1023)) : 0;
+  return 1024 + 2 * patch + p.stages * ((p.patch ? 0 : kABytes) + b_bytes) + static_cast<size_t>(p.n_chunks) * kChunkBytes +
+         sizeof(SmemCtl);
 }
 size_t tc_wgrad_smem_bytes(const TcWgradParams& p) {
   const size_t chunk = static_cast<size_t>(p.kp) * 128;
@@ -374,11 +456,29 @@ cudaError_t tc_kernels_init() {
 
 cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
   const int tiles = p.tiles_x * p.tiles_y;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int cs = p.csize < 1 ? 1 : p.csize;
+  int grid = (tiles + cs - 1) / cs * cs;
+  const int cap = num_sms / cs * cs;
+  if (grid > cap) grid = cap;
   const size_t smem = tc_conv_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
-  tc_conv_kernel<<<grid, kNumThreads, smem, s>>>(p);
-  return cudaGetLastError();
+  if (cs == 1) {
+    tc_conv_kernel<<<grid, kNumThreads, smem, s>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc_conv_kernel, p);
 }
 
 cudaError_t tc_wgrad_launch(const TcWgradParams& p, cudaStream_t s) {

@@ -26,6 +26,9 @@ struct TcConvParams {
   int n_mma;               // UMMA N (multiple of 16, <= 160)
   int n_chunks;            // output 32-channel chunks written (ceil(n_mma/32))
   int stages;              // smem pipeline depth
+  int patch;               // 1: 3x3 stride-1 patch mode (tile 8 x 16; one (bw+2) x (bh+2) input patch serves all taps)
+  int pw, ph;              // patch extent in pixels
+  int csize;               // thread-block cluster size (1, 2, 4): the weight tile is multicast across the cluster
   const float* bias;       // [n_mma] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
   int stats_ld;

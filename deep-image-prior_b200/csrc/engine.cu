@@ -119,6 +119,15 @@ static void pick_tile(int w, int h, int* bw, int* bh) {
   }
 }
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// cluster size for the weight multicast: only when there is at least a full wave of tiles; the weight-tile slice of each
+// CTA must be a whole number of 8-row swizzle atoms
+static int pick_csize(int tiles, int n_rows) {
+  int want = 1;  // measured: multicast does not pay at cluster sizes <= 4 (per-SM ingest, not L2 reads, is the limit)
+  if (const char* e = getenv("DIP_CSIZE")) want = atoi(e);
+  if (tiles < 2 * 148) return 1;
+  while (want > 1 && (n_rows % (8 * want) != 0)) want >>= 1;
+  return want < 1 ? 1 : want;
+}
 
 // ------------------------------------------------------------------------------------------------ kernel timing
 // Optional CUDA-event brackets around every tensor-core launch (bench.py roofline: algorithmic FLOPs / device time).
@@ -190,8 +199,17 @@ struct ConvOp {
     int bw, bh;
     pick_tile(out_w, out_h, &bw, &bh);
     fp = TcConvParams{};
-    DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
-    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N));
+    const bool patch_ok = getenv("DIP_NO_PATCH") == nullptr;
+    if (k == 3 && stride == 1 && patch_ok) {
+      // patch mode: tile 8 wide x 16 tall, one 10 x 18 input patch per 32-channel block feeds all nine taps
+      bw = 8; bh = 16;
+      fp.patch = 1; fp.pw = bw + 2; fp.ph = bh + 2;
+      DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, 1, fp.pw, fp.ph));
+    } else {
+      DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
+    }
+    fp.csize = pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
     fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
@@ -206,8 +224,15 @@ struct ConvOp {
     if (has_dgrad) {
       pick_tile(dg_out_w, dg_out_h, &bw, &bh);
       dg = TcConvParams{};
-      DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows));
+      if (k == 3 && patch_ok) {
+        bw = 8; bh = 16;
+        dg.patch = 1; dg.pw = bw + 2; dg.ph = bh + 2;
+        DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, dg.pw, dg.ph));
+      } else {
+        DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+      }
+      dg.csize = pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, C, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;

@@ -173,16 +173,37 @@ void launch_input_pad(const float* z, const float* noise, float sigma, float* ds
   k_input_pad<<<grid, block, 0, s>>>(z, noise, sigma, dst, C, H, W);
 }
 
+// ------------------------------------------------------------------------------------------------ item loop
+// Grid-stride loop with U independent items in flight per thread: all loads of the U items are issued before any of
+// them is consumed (memory-level parallelism is what these latency-bound streaming kernels lack otherwise).
+template <int U, class Load, class Use>
+__device__ __forceinline__ void item_loop(int first, int stride, int n, Load load, Use use) {
+  for (int p0 = first; p0 < n; p0 += U * stride) {
+    decltype(load(0)) d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * stride;
+      if (p < n) d[u] = load(p);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * stride;
+      if (p < n) use(p, d[u]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ channel_stats
-__global__ void k_channel_stats(const float* __restrict__ x, int ld, int VL, int PPB, int npix,
-                                double* __restrict__ fwd, int C) {
+__global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__ x, int ld, int VL, int PPB, int npix,
+                                                       double* __restrict__ fwd, int C) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   float4 acc[2] = {f4zero(), f4zero()};
-  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-    const float4 t = ld4(x + static_cast<size_t>(p) * ld + 4 * v);
-    acc[0] = f4add(acc[0], t);
-    acc[1] = f4mla(t, t, acc[1]);
-  }
+  item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, npix,
+               [&](int p) { return ld4(x + static_cast<size_t>(p) * ld + 4 * v); },
+               [&](int, float4 t) {
+                 acc[0] = f4add(acc[0], t);
+                 acc[1] = f4mla(t, t, acc[1]);
+               });
   double* const dst[2] = {fwd, fwd + C};
   block_reduce_atomic<2>(acc, VL, PPB, dst);
 }
@@ -192,20 +213,24 @@ void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, 
 }
 
 // ------------------------------------------------------------------------------------------------ bn_act_write
-__global__ void k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
-                               float* __restrict__ dst, int ld_out, int pad, int act, int VL, int PPB) {
+__global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
+                                                      float* __restrict__ dst, int ld_out, int pad, int act, int VL,
+                                                      int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
-  const int nout = Ho * Wo;
-  for (int p = blockIdx.x * PPB + slot; p < nout; p += gridDim.x * PPB) {
-    const int yo = p / Wo, xo = p - yo * Wo;
-    const int yi = pad ? reflect_idx(yo - 1, H) : yo;
-    const int xi = pad ? reflect_idx(xo - 1, W) : xo;
-    float4 y = bn_apply(cf, ld4(raw + (static_cast<size_t>(yi) * W + xi) * ld_in + 4 * v));
-    if (act) y = lrelu4(y);
-    st4(dst + static_cast<size_t>(p) * ld_out + 4 * v, y);
-  }
+  item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, Ho * Wo,
+               [&](int p) {
+                 const int yo = p / Wo, xo = p - yo * Wo;
+                 const int yi = pad ? reflect_idx(yo - 1, H) : yo;
+                 const int xi = pad ? reflect_idx(xo - 1, W) : xo;
+                 return ld4(raw + (static_cast<size_t>(yi) * W + xi) * ld_in + 4 * v);
+               },
+               [&](int p, float4 x) {
+                 float4 y = bn_apply(cf, x);
+                 if (act) y = lrelu4(y);
+                 st4(dst + static_cast<size_t>(p) * ld_out + 4 * v, y);
+               });
 }
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
                          int act, cudaStream_t s) {
@@ -220,21 +245,24 @@ __global__ void __launch_bounds__(256) k_bn_act_head(const float* __restrict__ r
   float4 w[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = k < head.K ? ld4(head.w + k * 128 + 4 * lane) : f4zero();
-  for (int p = blockIdx.x * 8 + wslot; p < npix; p += gridDim.x * 8) {
-    const float4 y = lrelu4(bn_apply(cf, ld4(raw + static_cast<size_t>(p) * 128 + 4 * lane)));
-    float d[4];
+  const float hb = lane < head.K ? head.b[lane] : 0.f;
+  item_loop<4>(blockIdx.x * 8 + wslot, gridDim.x * 8, npix,
+               [&](int p) { return ld4(raw + static_cast<size_t>(p) * 128 + 4 * lane); },
+               [&](int p, float4 x) {
+                 const float4 y = lrelu4(bn_apply(cf, x));
+                 float d[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) d[k] = f4dot(y, w[k]);
+                 for (int k = 0; k < 4; ++k) d[k] = f4dot(y, w[k]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+                 for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
-    }
-    if (lane < head.K) {
-      const float t = (lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]) + head.b[lane];
-      head.out[static_cast<size_t>(lane) * npix + p] = 1.f / (1.f + expf(-t));
-    }
-  }
+                   for (int k = 0; k < 4; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
+                 }
+                 if (lane < head.K) {
+                   const float t = (lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]) + hb;
+                   head.out[static_cast<size_t>(lane) * npix + p] = 1.f / (1.f + expf(-t));
+                 }
+               });
 }
 void launch_bn_act_head(const float* raw, BnRef bn, int H, int W, HeadRef head, cudaStream_t s) {
   const int npix = H * W;
@@ -453,70 +481,51 @@ __device__ __forceinline__ float4 lrelu_bwd4(float4 y, float4 g) {
 }
 
 // ------------------------------------------------------------------------------------------------ BN(+LReLU) backward
+struct BwdItem {
+  float4 x, g;
+  float dl[4];
+};
 template <int KIND>
-__global__ void k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
-                                double* __restrict__ bwd, int VL, int PPB) {
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+                                                       int H, int W, double* __restrict__ bwd, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
-  const int npix = H * W;
-  constexpr int K = KIND == 3 ? 7 : 2;
-  float4 acc[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = f4zero();
-  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-    const int i = p / W, j = p - i * W;
-    const float4 x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-    float dl[4];
-    float4 dz = grad_read<KIND>(src, sr, H, W, p, i, j, v, dl);
-    const float4 y = bn_apply(cf, x);
-    if constexpr (KIND == 3) {
-      // the head's own gradients: dW[k][c] += dl[k] * act(y)[c], db[k] += dl[k]
-      const float4 u = act ? lrelu4(y) : y;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[2 + k] = f4fma(dl[k], u, acc[2 + k]);
-      if (v == 0) acc[6] = f4add(acc[6], make_float4(dl[0], dl[1], dl[2], dl[3]));
-    }
-    if (act) dz = lrelu_bwd4(y, dz);
-    acc[0] = f4add(acc[0], dz);
-    acc[1] = f4mla(dz, bn_xhat(cf, x), acc[1]);
-  }
-  if constexpr (KIND == 3) {
-    // dwh rows are [K][C]: rows k >= nh are not stored
-    double* const dst[K] = {bwd, bwd + bn.C, src.dwh, src.nh > 1 ? src.dwh + bn.C : nullptr,
-                            src.nh > 2 ? src.dwh + 2 * bn.C : nullptr, src.nh > 3 ? src.dwh + 3 * bn.C : nullptr, nullptr};
-    // db: only lane v == 0 carries data -> handled separately below (dst[6] == nullptr skips the generic path)
-    block_reduce_atomic<K>(acc, VL, PPB, dst);
-    // acc[6] of lanes v == 0 was staged in red_smem by block_reduce_atomic: slot layout (k * nparts + part) * VL + v
-    if (threadIdx.x == 0) {
-      extern __shared__ float4 red_smem[];
-      const int nparts = (VL < 32 && (VL & (VL - 1)) == 0) ? (blockDim.x >> 5) : PPB;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      for (int pp = 0; pp < nparts; ++pp) {
-        const float4 t = red_smem[(6 * nparts + pp) * VL];
-        s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
-      }
-      const double sv[4] = {s0, s1, s2, s3};
-      for (int k = 0; k < src.nh; ++k) atomicAdd(src.dbh + k, sv[k]);
-    }
-  } else {
-    double* const dst[2] = {bwd, bwd + bn.C};
-    block_reduce_atomic<K>(acc, VL, PPB, dst);
-  }
+  float4 acc[2] = {f4zero(), f4zero()};
+  item_loop<(KIND == 0 || KIND == 3) ? 4 : 2>(
+      blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+      [&](int p) {
+        BwdItem it;
+        const int i = p / W, j = p - i * W;
+        it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v, it.dl);
+        return it;
+      },
+      [&](int, const BwdItem& it) {
+        float4 dz = it.g;
+        if (act) dz = lrelu_bwd4(bn_apply(cf, it.x), dz);
+        acc[0] = f4add(acc[0], dz);
+        acc[1] = f4mla(dz, bn_xhat(cf, it.x), acc[1]);
+      });
+  double* const dst[2] = {bwd, bwd + bn.C};
+  block_reduce_atomic<2>(acc, VL, PPB, dst);
 }
 void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
                           cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
-  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, red_bytes(g, 2), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, red_bytes(g, 2), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, red_bytes(g, 2), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else k_bn_bwd_reduce<3><<<g.blocks, g.threads, red_bytes(g, 7), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  const size_t sm = red_bytes(g, 2);
+  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else k_bn_bwd_reduce<3><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
 }
 
+// apply pass; for the head source (KIND 3) it also accumulates the head's own gradients:
+//   dW_head[k][c] += dl[k] * act(bn(raw))[c],  db_head[k] += dl[k]
 template <int KIND>
-__global__ void k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
-                               const double* __restrict__ bwd, float* __restrict__ draw, float* __restrict__ zs,
-                               double* __restrict__ dbias, int VL, int PPB) {
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+                                                      int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
+                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
@@ -526,35 +535,69 @@ __global__ void k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef 
   m1.z = static_cast<float>(bwd[4 * v + 2] * bn.inv_n); m1.w = static_cast<float>(bwd[4 * v + 3] * bn.inv_n);
   m2.x = static_cast<float>(bwd[C + 4 * v + 0] * bn.inv_n); m2.y = static_cast<float>(bwd[C + 4 * v + 1] * bn.inv_n);
   m2.z = static_cast<float>(bwd[C + 4 * v + 2] * bn.inv_n); m2.w = static_cast<float>(bwd[C + 4 * v + 3] * bn.inv_n);
-  const int npix = H * W;
-  float4 acc[1] = {f4zero()};
-  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-    const int i = p / W, j = p - i * W;
-    const float4 x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-    float dl[4];
-    float4 dz = grad_read<KIND>(src, sr, H, W, p, i, j, v, dl);
-    if (act) dz = lrelu_bwd4(bn_apply(cf, x), dz);
-    const float4 xh = bn_xhat(cf, x);
-    float4 dx;
-    dx.x = cf.scale.x * (dz.x - m1.x - xh.x * m2.x);
-    dx.y = cf.scale.y * (dz.y - m1.y - xh.y * m2.y);
-    dx.z = cf.scale.z * (dz.z - m1.z - xh.z * m2.z);
-    dx.w = cf.scale.w * (dz.w - m1.w - xh.w * m2.w);
-    st4(draw + static_cast<size_t>(p) * C + 4 * v, dx);
-    if (zs != nullptr) st4(zs + (static_cast<size_t>(2 * i) * (2 * W) + 2 * j) * C + 4 * v, dx);
-    acc[0] = f4add(acc[0], dx);
+  constexpr int K = KIND == 3 ? 6 : 1;
+  float4 acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = f4zero();
+  item_loop<KIND == 0 ? 4 : 2>(
+      blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+      [&](int p) {
+        BwdItem it;
+        const int i = p / W, j = p - i * W;
+        it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v, it.dl);
+        return it;
+      },
+      [&](int p, const BwdItem& it) {
+        float4 dz = it.g;
+        const float4 y = bn_apply(cf, it.x);
+        if constexpr (KIND == 3) {
+          const float4 u = act ? lrelu4(y) : y;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[1 + k] = f4fma(it.dl[k], u, acc[1 + k]);
+          if (v == 0) acc[5] = f4add(acc[5], make_float4(it.dl[0], it.dl[1], it.dl[2], it.dl[3]));
+        }
+        if (act) dz = lrelu_bwd4(y, dz);
+        const float4 xh = bn_xhat(cf, it.x);
+        float4 dx;
+        dx.x = cf.scale.x * (dz.x - m1.x - xh.x * m2.x);
+        dx.y = cf.scale.y * (dz.y - m1.y - xh.y * m2.y);
+        dx.z = cf.scale.z * (dz.z - m1.z - xh.z * m2.z);
+        dx.w = cf.scale.w * (dz.w - m1.w - xh.w * m2.w);
+        st4(draw + static_cast<size_t>(p) * C + 4 * v, dx);
+        if (zs != nullptr) {
+          const int i = p / W, j = p - i * W;
+          st4(zs + (static_cast<size_t>(2 * i) * (2 * W) + 2 * j) * C + 4 * v, dx);
+        }
+        acc[0] = f4add(acc[0], dx);
+      });
+  if constexpr (KIND == 3) {
+    double* const dst[K] = {dbias, src.dwh, src.nh > 1 ? src.dwh + C : nullptr, src.nh > 2 ? src.dwh + 2 * C : nullptr,
+                            src.nh > 3 ? src.dwh + 3 * C : nullptr, nullptr};
+    block_reduce_atomic<K>(acc, VL, PPB, dst);
+    // acc[5] (db_head, lanes v == 0 only) was staged in red_smem: slot layout (k * nparts + part) * VL + v
+    if (threadIdx.x == 0) {
+      extern __shared__ float4 red_smem[];
+      const int nparts = (VL < 32 && (VL & (VL - 1)) == 0) ? (blockDim.x >> 5) : PPB;
+      double sv[4] = {0, 0, 0, 0};
+      for (int pp = 0; pp < nparts; ++pp) {
+        const float4 t = red_smem[(5 * nparts + pp) * VL];
+        sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
+      }
+      for (int k = 0; k < src.nh; ++k) atomicAdd(src.dbh + k, sv[k]);
+    }
+  } else {
+    double* const dst[1] = {dbias};
+    block_reduce_atomic<K>(acc, VL, PPB, dst);
   }
-  double* const dst[1] = {dbias};
-  block_reduce_atomic<1>(acc, VL, PPB, dst);
 }
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
                          const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
-  const size_t sm = red_bytes(g, 1);
-  if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else k_bn_bwd_apply<3><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else k_bn_bwd_apply<3><<<g.blocks, g.threads, red_bytes(g, 6), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
@@ -703,31 +746,42 @@ __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, con
   float4 wv[4];
   for (int n = 0; n < 4; ++n) wv[n] = n < N ? ld4(w + n * C + 4 * v) : f4zero();
   float4 acc[5] = {f4zero(), f4zero(), f4zero(), f4zero(), f4zero()};  // dw rows 0..3, db (lane v == 0 only)
-  for (int p = blockIdx.x * PPB + slot; p < npix; p += gridDim.x * PPB) {
-    const int i = p / W, j = p - i * W;
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (mode == 0 && N == 4) {
-      const float4 d = ld4(dy + static_cast<size_t>(p) * 4);
-      g[0] = d.x; g[1] = d.y; g[2] = d.z; g[3] = d.w;
-    } else {
-      for (int n = 0; n < N; ++n) {
-        if (mode == 0) g[n] = dy[static_cast<size_t>(p) * N + n];
-        else {
-          const float d = dy[static_cast<size_t>(n) * npix + p];
-          if (mode == 1) { const float o = out_nchw[static_cast<size_t>(n) * npix + p]; g[n] = d * o * (1.f - o); } else g[n] = d;
-        }
-      }
-    }
-    const float4 xv = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
-    float4 d = f4zero();
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      acc[n] = f4fma(g[n], xv, acc[n]);
-      d = f4fma(g[n], wv[n], d);
-    }
-    if (v == 0) acc[4] = f4add(acc[4], make_float4(g[0], g[1], g[2], g[3]));
-    if (dx != nullptr) st4(dx + static_cast<size_t>(p) * C + 4 * v, d);
-  }
+  struct Item { float4 g, x; };
+  item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, npix,
+               [&](int p) {
+                 Item it;
+                 const int i = p / W, j = p - i * W;
+                 float g[4] = {0.f, 0.f, 0.f, 0.f};
+                 if (mode == 0 && N == 4) {
+                   it.g = ld4(dy + static_cast<size_t>(p) * 4);
+                 } else {
+                   for (int n = 0; n < N; ++n) {
+                     if (mode == 0) g[n] = dy[static_cast<size_t>(p) * N + n];
+                     else {
+                       const float d = dy[static_cast<size_t>(n) * npix + p];
+                       if (mode == 1) { const float o = out_nchw[static_cast<size_t>(n) * npix + p]; g[n] = d * o * (1.f - o); } else g[n] = d;
+                     }
+                   }
+                   it.g = make_float4(g[0], g[1], g[2], g[3]);
+                 }
+                 it.x = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
+                 return it;
+               },
+               [&](int p, const Item& it) {
+                 acc[0] = f4fma(it.g.x, it.x, acc[0]);
+                 acc[1] = f4fma(it.g.y, it.x, acc[1]);
+                 acc[2] = f4fma(it.g.z, it.x, acc[2]);
+                 acc[3] = f4fma(it.g.w, it.x, acc[3]);
+                 if (v == 0) acc[4] = f4add(acc[4], it.g);
+                 if (dx != nullptr) {
+                   float4 d = f4zero();
+                   d = f4fma(it.g.x, wv[0], d);
+                   d = f4fma(it.g.y, wv[1], d);
+                   d = f4fma(it.g.z, wv[2], d);
+                   d = f4fma(it.g.w, wv[3], d);
+                   st4(dx + static_cast<size_t>(p) * C + 4 * v, d);
+                 }
+               });
   double* const dst[5] = {dw, N > 1 ? dw + C : nullptr, N > 2 ? dw + 2 * C : nullptr, N > 3 ? dw + 3 * C : nullptr, nullptr};
   block_reduce_atomic<5>(acc, VL, PPB, dst);
   if (threadIdx.x == 0 && db != nullptr) {

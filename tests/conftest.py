@@ -11,6 +11,12 @@ for p in (ROOT, PKG):
 
 
 def pytest_configure(config):
+    try:
+        import torch
+        # the GPU box exposes 100+ logical cores; torch-CPU (the oracle) is fastest with a handful of threads
+        torch.set_num_threads(min(8, os.cpu_count() or 1))
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
 
 
