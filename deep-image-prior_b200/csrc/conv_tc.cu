@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   // per-tap mode: stage = [A tile 16 KB][B tile]; patch mode: two input patches up front, stages hold B tiles only
   const int patch_bytes = p.patch ? p.pw * p.ph * 128 : 0;
   const int patch_alloc = (patch_bytes + 1023) & ~1023;
-  const int stage_bytes = (p.patch ? 0 : kABytes) + ((b_bytes + 1023) & ~1023);
+  const int tps = p.patch ? p.tps : 1;  // filter taps per B stage (patch mode)
+  const int stage_bytes = (p.patch ? 0 : kABytes) + ((tps * b_bytes + 1023) & ~1023);
   uint8_t* patch_base = smem;
   uint8_t* stage_base = smem + 2 * patch_alloc;
   uint8_t* staging = stage_base + p.stages * stage_bytes;
@@ -101,7 +102,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and addresses stay in uniform registers); one elected
+    // lane issues the TMA instructions.
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int b_rows = p.n_mma / csize;
@@ -117,16 +120,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           const int taps = p.kh * p.kw;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&ctl->a_empty[ab], aphase ^ 1);
-            mbar_expect_tx(&ctl->a_full[ab], patch_bytes);
-            tma_load_5d(patch_base + ab * patch_alloc, &p.tmA, &ctl->a_full[ab], kb * 32, 0, x0 + p.offx, 0, y0 + p.offy);
+            if (elect_one()) {
+              if (p.dbg_flags & 1) mbar_arrive(&ctl->a_full[ab]);
+              else {
+                mbar_expect_tx(&ctl->a_full[ab], patch_bytes);
+                tma_load_5d(patch_base + ab * patch_alloc, &p.tmA, &ctl->a_full[ab], kb * 32, 0, x0 + p.offx, 0, y0 + p.offy);
+              }
+            }
+            __syncwarp();
             if (++ab == 2) { ab = 0; aphase ^= 1; }
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap = 0; tap < taps; tap += tps) {
+              if (p.dbg_flags & (64 | 128)) { if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
               mbar_wait(&ctl->empty[stage], phase ^ 1);
               uint8_t* sb = stage_base + stage * stage_bytes;
-              mbar_expect_tx(&ctl->full[stage], b_bytes);
-              if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
-              else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
-                                  tap * p.n_mma + crank * b_rows, cmask);
+              if (elect_one()) {
+                if (p.dbg_flags & 2) mbar_arrive(&ctl->full[stage]);
+                else {
+                  // the box always spans tps taps; rows past the last tap are out of range -> zero-filled, never read
+                  mbar_expect_tx(&ctl->full[stage], tps * b_bytes);
+                  if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+                  else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                                      tap * p.n_mma + crank * b_rows, cmask);
+                }
+              }
+              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -147,11 +164,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
               mbar_wait(&ctl->empty[stage], phase ^ 1);
               uint8_t* sa = stage_base + stage * stage_bytes;
               uint8_t* sb = sa + kABytes;
-              mbar_expect_tx(&ctl->full[stage], kABytes + b_bytes);
-              tma_load_5d(sa, &p.tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
-              if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
-              else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
-                                  tap * p.n_mma + crank * b_rows, cmask);
+              if (elect_one()) {
+                const bool ldA = !(p.dbg_flags & 1), ldB = !(p.dbg_flags & 2);
+                if (ldA || ldB) mbar_expect_tx(&ctl->full[stage], (ldA ? kABytes : 0) + (ldB ? b_bytes : 0));
+                else mbar_arrive(&ctl->full[stage]);
+                if (ldA) tma_load_5d(sa, &p.tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
+                if (ldB) {
+                  if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+                  else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                                      tap * p.n_mma + crank * b_rows, cmask);
+                }
+              }
+              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -160,8 +184,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // One thread; its instruction stream is the critical path (a lone warp issues a dependent instruction only every
+    // few cycles), so the loop is kept minimal: descriptors are (lo, hi) 32-bit pairs, K advances by adding 2 to lo.
+    // All 32 lanes run the (warp-uniform) loop; one elected lane issues the MMAs and the commits.
+    {
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_mma, 0, 0);
+      const uint32_t bhi = desc_hi(1024, 2);
+      const uint32_t stage_lo0 = desc_lo(smem_u32(stage_base) + (p.patch ? 0 : kABytes), 16);
+      const uint32_t stage_lo_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      const bool skip_mma = (p.dbg_flags & 8) != 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -172,55 +203,99 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
+        uint32_t accf = 0;  // 0 for the first MMA of the tile (overwrite), 1 afterwards
         if (p.patch) {
-          const int taps = p.kh * p.kw;
+          // tile row ty = 8 consecutive patch pixels starting at ((ty + r) * pw + sx): 8-row groups pw*128 B apart.  The
+          // group starts are not 1024 B aligned: UMMA and TMA both swizzle on absolute smem address bits (verified
+          // by scripts/exp_desc_shift.py), so a tap is just an address offset into the patch.
+          const uint32_t ahi = desc_hi(p.pw * 128, 2);
+          const uint32_t row_step = static_cast<uint32_t>(p.pw) * 8;  // one patch row, in 16-byte units
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&ctl->a_full[ab], aphase);
             tc_fence_after();
-            const uint32_t pa = smem_u32(patch_base + ab * patch_alloc);
-            const int nmma = (kb == p.kblocks - 1) ? p.tail_mmas : 4;
-            for (int tap = 0; tap < taps; ++tap) {
-              mbar_wait(&ctl->full[stage], phase);
-              tc_fence_after();
-              const uint32_t sb = smem_u32(stage_base + stage * stage_bytes);
-              const int r = tap / p.kw, sx = tap - r * p.kw;
-              // tile row ty = 8 consecutive patch pixels starting at ((ty + r) * pw + sx): 8-row groups pw*128 B apart.
-              // The group starts are not 1024 B aligned; UMMA and TMA both swizzle on absolute smem address bits.
-              const uint32_t a0 = pa + (r * p.pw + sx) * 128;
-              for (int k = 0; k < nmma; ++k) {
-                const uint64_t adesc = make_smem_desc_sw128(a0 + k * 32, 16, p.pw * 128);
-                const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            uint32_t row_lo = desc_lo(smem_u32(patch_base + ab * patch_alloc), 16);
+            const int nmma = p.dbg_nmma ? p.dbg_nmma : ((kb == p.kblocks - 1) ? p.tail_mmas : 4);
+            const int taps = p.kh * p.kw;
+            const uint32_t tap_lo_step = static_cast<uint32_t>(b_bytes) >> 4;  // next tap inside a B stage
+            int sx = 0;
+            for (int tap = 0; tap < taps; tap += tps) {
+              if (!(p.dbg_flags & 128)) mbar_wait(&ctl->full[stage], phase);
+              if (!(p.dbg_flags & 32)) tc_fence_after();
+              const uint32_t b_lo = stage_lo0 + stage * stage_lo_step;
+              // A operand of tap (r, sx): the patch shifted by r rows and sx pixels
+              const uint32_t a_lo0 = row_lo + sx * 8;
+              if (++sx == p.kw) { sx = 0; row_lo += row_step; }
+              const uint32_t a_lo1 = row_lo + sx * 8;
+              const bool two = tps == 2 && tap + 1 < taps;
+              if (two) { if (++sx == p.kw) { sx = 0; row_lo += row_step; } }
+              if (elect_one()) {
+                if (!skip_mma || accf == 0) {
+                  if (nmma == 4) {
+                    mma_tf32_lohi(tmem_d, a_lo0, ahi, b_lo, bhi, idesc, accf);
+                    mma_tf32_lohi(tmem_d, a_lo0 + 2, ahi, b_lo + 2, bhi, idesc, 1u);
+                    mma_tf32_lohi(tmem_d, a_lo0 + 4, ahi, b_lo + 4, bhi, idesc, 1u);
+                    mma_tf32_lohi(tmem_d, a_lo0 + 6, ahi, b_lo + 6, bhi, idesc, 1u);
+                    if (two) {
+                      const uint32_t b1 = b_lo + tap_lo_step;
+                      mma_tf32_lohi(tmem_d, a_lo1, ahi, b1, bhi, idesc, 1u);
+                      mma_tf32_lohi(tmem_d, a_lo1 + 2, ahi, b1 + 2, bhi, idesc, 1u);
+                      mma_tf32_lohi(tmem_d, a_lo1 + 4, ahi, b1 + 4, bhi, idesc, 1u);
+                      mma_tf32_lohi(tmem_d, a_lo1 + 6, ahi, b1 + 6, bhi, idesc, 1u);
+                    }
+                  } else {
+                    for (int k = 0; k < nmma; ++k)
+                      mma_tf32_lohi(tmem_d, a_lo0 + 2 * (k & 3), ahi, b_lo + 2 * (k & 3), bhi, idesc, k > 0 ? 1u : accf);
+                    if (two)
+                      for (int k = 0; k < nmma; ++k)
+                        mma_tf32_lohi(tmem_d, a_lo1 + 2 * (k & 3), ahi, b_lo + tap_lo_step + 2 * (k & 3), bhi, idesc, 1u);
+                  }
+                }
+                if (!(p.dbg_flags & 64)) {
+                  if (csize == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], cmask);
+                }
               }
-              if (csize == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], cmask);
+              __syncwarp();
+              accf = 1u;
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            tc_commit(&ctl->a_empty[ab]);
+            if (elect_one()) tc_commit(&ctl->a_empty[ab]);
+            __syncwarp();
             if (++ab == 2) { ab = 0; aphase ^= 1; }
           }
-          tc_commit(&ctl->tmem_full[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
-        for (int kbt = 0; kbt < kb_per_tile; ++kbt) {
-          mbar_wait(&ctl->full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const bool last_kb = ((kbt % p.kblocks) == p.kblocks - 1);
-          const int nmma = last_kb ? p.tail_mmas : 4;
-          for (int k = 0; k < nmma; ++k) {
-            // K-major SW128: 8-row groups are 1024 B apart; advancing K by 8 fp32 = +32 B inside the swizzle atom
-            uint64_t adesc = make_smem_desc_sw128(sa + p.dbg_shift * 128 + k * 32, 16, 1024);
-            if (p.dbg_bo) adesc |= static_cast<uint64_t>(((sa + p.dbg_shift * 128) >> 7) & 7) << 49;
-            const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (kbt > 0 || k > 0) ? 1u : 0u);
+        } else {
+          const uint32_t ahi = desc_hi(1024, 2);
+          const uint32_t a_off = stage_lo0 - (kABytes >> 4) + ((static_cast<uint32_t>(p.dbg_shift) * 128) >> 4);
+          int kb = 0;
+          for (int kbt = 0; kbt < kb_per_tile; ++kbt) {
+            mbar_wait(&ctl->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_lo = a_off + stage * stage_lo_step;
+            const uint32_t b_lo = stage_lo0 + stage * stage_lo_step;
+            const int nmma = (kb == p.kblocks - 1) ? p.tail_mmas : 4;
+            if (++kb == p.kblocks) kb = 0;
+            if (elect_one()) {
+              if (!skip_mma || accf == 0) {
+                if (nmma == 4) {
+                  // K-major SW128: 8-row groups are 1024 B apart; advancing K by 8 fp32 = +32 B inside the swizzle atom
+                  mma_tf32_lohi(tmem_d, a_lo, ahi, b_lo, bhi, idesc, accf);
+                  mma_tf32_lohi(tmem_d, a_lo + 2, ahi, b_lo + 2, bhi, idesc, 1u);
+                  mma_tf32_lohi(tmem_d, a_lo + 4, ahi, b_lo + 4, bhi, idesc, 1u);
+                  mma_tf32_lohi(tmem_d, a_lo + 6, ahi, b_lo + 6, bhi, idesc, 1u);
+                } else {
+                  for (int k = 0; k < nmma; ++k)
+                    mma_tf32_lohi(tmem_d, a_lo + 2 * k, ahi, b_lo + 2 * k, bhi, idesc, k > 0 ? 1u : accf);
+                }
+              }
+              // frees this smem stage (in every CTA that multicasts into it) once the MMAs above have read it
+              if (csize == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], cmask);
+            }
+            __syncwarp();
+            accf = 1u;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          // frees this smem stage (in every CTA that multicasts into it) once the MMAs above have read it
-          if (csize == 1) tc_commit(&ctl->empty[stage]); else tc_commit_mc(&ctl->empty[stage], cmask);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&ctl->tmem_full[acc]);
+        if (elect_one()) tc_commit(&ctl->tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -231,6 +306,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     const int row = ew * 32 + lane;      // tile row (pixel) owned by this thread
     int acc = 0;
     uint32_t acc_phase = 0;
+    double stat_s1 = 0.0, stat_s2 = 0.0;
+    const int bw_shift = 31 - __clz(p.bw);  // tile widths are powers of two
     for (int it = 0; it < n_iters; ++it) {
       const int tile = tile0 + it * gridDim.x;
       const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -241,6 +318,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       if (et == 0) tma_store_wait_read0();
       named_bar_sync(1, 128);
       const uint32_t taddr = tmem_base + acc * acc_cols + (static_cast<uint32_t>(ew * 32) << 16);
+      if (p.dbg_flags & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int j = 0; j < p.n_chunks; ++j) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + j * 32, v);
@@ -266,27 +350,38 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
         for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, j * 32, x0, y0);
         tma_store_commit();
       }
-      if (p.stats != nullptr) {
-        // per-channel sum / sum-of-squares over the valid rows of this tile (feeds the following BatchNorm)
-        for (int c = et; c < p.n_chunks * 32; c += 128) {
-          const int j = c >> 5, q = (c & 31) >> 2, e = c & 3;
-          const uint8_t* cb = staging + j * kChunkBytes + e * 4;
-          float s1 = 0.f, s2 = 0.f;
+      if (p.stats != nullptr && et < p.n_mma) {
+        // per-channel sum / sum-of-squares of this tile (feeds the following BatchNorm): thread = channel et, running
+        // totals stay in registers across all tiles of this persistent CTA (one fp64 atomic pair per thread at the end)
+        const int c = et;
+        const int j = c >> 5, q = (c & 31) >> 2, e = c & 3;
+        const uint8_t* cb = staging + j * kChunkBytes + e * 4;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        if (x0 + p.bw <= p.out_w && y0 + p.bh <= p.out_h) {
+#pragma unroll 8
+          for (int m = 0; m < kTileM; m += 2) {
+            const float x = *reinterpret_cast<const float*>(cb + m * 128 + ((q ^ (m & 7)) << 4));
+            const float y = *reinterpret_cast<const float*>(cb + (m + 1) * 128 + ((q ^ ((m + 1) & 7)) << 4));
+            a0 += x; b0 = fmaf(x, x, b0);
+            a1 += y; b1 = fmaf(y, y, b1);
+          }
+        } else {
           for (int m = 0; m < kTileM; ++m) {
-            const int px = m % p.bw, py = m / p.bw;
+            const int py = m >> bw_shift, px = m & (p.bw - 1);
             if (x0 + px < p.out_w && y0 + py < p.out_h) {
               const float x = *reinterpret_cast<const float*>(cb + m * 128 + ((q ^ (m & 7)) << 4));
-              s1 += x;
-              s2 = fmaf(x, x, s2);
+              a0 += x; b0 = fmaf(x, x, b0);
             }
           }
-          if (c < p.stats_ld) {
-            atomicAdd(&p.stats[c], static_cast<double>(s1));
-            atomicAdd(&p.stats[p.stats_ld + c], static_cast<double>(s2));
-          }
         }
+        stat_s1 += static_cast<double>(a0 + a1);
+        stat_s2 += static_cast<double>(b0 + b1);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.stats != nullptr && et < p.n_mma && et < p.stats_ld) {
+      atomicAdd(&p.stats[et], stat_s1);
+      atomicAdd(&p.stats[p.stats_ld + et], stat_s2);
     }
     if (et == 0) tma_store_wait_all0();
   }
@@ -348,7 +443,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
@@ -356,6 +451,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         const int x0 = (blk % p.px_blocks_x) * p.kp;
         mbar_wait(&ctl->empty[stage], phase ^ 1);
         uint8_t* sy = smem + stage * stage_bytes;
+        if (elect_one()) {
         mbar_expect_tx(&ctl->full[stage], stage_bytes);
         for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * chunk_bytes, &p.tmY, &ctl->full[stage], j * 32, x0, y);
         for (int s = 0; s < p.kw; ++s) {
@@ -370,33 +466,46 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
           for (int j = 0; j < p.c_chunks; ++j)
             tma_load_5d(sx + j * chunk_bytes, &p.tmX, &ctl->full[stage], j * 32, cpx, cx, cpy, cy);
         }
+        }
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // A = dY (M = 128 output channels), B = X (N = c_pad input channels); both MN-major, K = pixels.
       const uint32_t idesc = make_idesc_tf32(128, c_pad, 1, 1);
+      // MN-major tf32 must use the 32-byte-atom 128B swizzle: 32-channel chunks are LBO = chunk_bytes apart,
+      // 4-pixel K atoms are SBO = 512 B apart; one K=8 MMA consumes 8 pixel rows = 1024 B (lo += 64).
+      const uint32_t hi = desc_hi(512, 1);
+      const uint32_t y_lo0 = desc_lo(smem_u32(smem), chunk_bytes);
+      const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
+      const uint32_t x_off = static_cast<uint32_t>(y_bytes) >> 4, x_step = static_cast<uint32_t>(x_bytes) >> 4;
+      const int nk = p.kp / 8;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t accf = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
         mbar_wait(&ctl->full[stage], phase);
         tc_fence_after();
-        const uint32_t sy = smem_u32(smem + stage * stage_bytes);
-        for (int s = 0; s < p.kw; ++s) {
-          const uint32_t sx = sy + y_bytes + s * x_bytes;
-          for (int k = 0; k < p.kp / 8; ++k) {
-            // MN-major tf32 must use the 32-byte-atom 128B swizzle: 32-channel chunks are LBO = chunk_bytes apart,
-            // 4-pixel K atoms are SBO = 512 B apart; one K=8 MMA consumes 8 pixel rows = 1024 B.
-            const uint64_t adesc = make_smem_desc(sy + k * 1024, chunk_bytes, 512, 1);
-            const uint64_t bdesc = make_smem_desc(sx + k * 1024, chunk_bytes, 512, 1);
-            mma_tf32_ss(tmem_base + s * c_pad, adesc, bdesc, idesc, (blk > blk0 || k > 0) ? 1u : 0u);
+        const uint32_t y_lo = y_lo0 + stage * stage_step;
+        if (elect_one()) {
+          uint32_t x_lo = y_lo + x_off;
+          uint32_t td = tmem_base;
+          for (int s = 0; s < p.kw; ++s) {
+            mma_tf32_lohi(td, y_lo, hi, x_lo, hi, idesc, accf);
+            for (int k = 1; k < nk; ++k) mma_tf32_lohi(td, y_lo + 64 * k, hi, x_lo + 64 * k, hi, idesc, 1u);
+            x_lo += x_step;
+            td += c_pad;
           }
+          tc_commit(&ctl->empty[stage]);
         }
-        tc_commit(&ctl->empty[stage]);
+        __syncwarp();
+        accf = 1u;
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&ctl->tmem_full);
+      if (elect_one()) tc_commit(&ctl->tmem_full);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
@@ -440,7 +549,8 @@ static constexpr size_t kMaxSmem = 232448;  // 227 KB
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
   const size_t b_bytes = (static_cast<size_t>(p.n_mma) * 128 + 1023) & ~size_t(1023);
   const size_t patch = p.patch ? ((static_cast<size_t>(p.pw) * p.ph * 128 + 1023) & ~size_t(1023)) : 0;
-  return 1024 + 2 * patch + p.stages * ((p.patch ? 0 : kABytes) + b_bytes) + static_cast<size_t>(p.n_chunks) * kChunkBytes +
+  const size_t tps = p.patch ? (p.tps < 1 ? 1 : p.tps) : 1;
+  return 1024 + 2 * patch + p.stages * ((p.patch ? 0 : kABytes) + tps * b_bytes) + static_cast<size_t>(p.n_chunks) * kChunkBytes +
          sizeof(SmemCtl);
 }
 size_t tc_wgrad_smem_bytes(const TcWgradParams& p) {

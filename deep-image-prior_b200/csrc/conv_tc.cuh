@@ -28,11 +28,14 @@ struct TcConvParams {
   int stages;              // smem pipeline depth
   int patch;               // 1: 3x3 stride-1 patch mode (tile 8 x 16; one (bw+2) x (bh+2) input patch serves all taps)
   int pw, ph;              // patch extent in pixels
+  int tps;                 // patch mode: filter taps per weight stage (1 or 2)
   int csize;               // thread-block cluster size (1, 2, 4): the weight tile is multicast across the cluster
   const float* bias;       // [n_mma] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
   int stats_ld;
   int dbg_shift;           // experiment: start the A descriptor `dbg_shift` 128-byte rows into the stage
+  int dbg_flags;           // experiments: 1 skip A loads, 2 skip B loads, 4 skip epilogue, 8 skip MMAs
+  int dbg_nmma;            // experiment: MMAs issued per k-block (patch mode)
   int dbg_bo;              // experiment: set the descriptor's base_offset field to ((addr >> 7) & 7)
 };
 

@@ -209,7 +209,8 @@ struct ConvOp {
       DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
     }
     fp.csize = pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
-    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize));
+    fp.tps = (fp.patch && fp.csize == 1 && N == 128 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, fp.tps * N / fp.csize));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
     fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
@@ -232,7 +233,8 @@ struct ConvOp {
         DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
       }
       dg.csize = pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize));
+      dg.tps = (dg.patch && dg.csize == 1 && crows == 128 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, dg.tps * crows / dg.csize));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, C, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
@@ -266,6 +268,9 @@ struct ConvOp {
       p.bias = bias;
       if (const char* e = getenv("DIP_DBG_SHIFT")) p.dbg_shift = atoi(e);
       if (const char* e = getenv("DIP_DBG_BO")) p.dbg_bo = atoi(e);
+      if (const char* e = getenv("DIP_DBG_FLAGS")) p.dbg_flags = atoi(e);
+      if (const char* e = getenv("DIP_DBG_NMMA")) p.dbg_nmma = atoi(e);
+      if (const char* e = getenv("DIP_DBG_STAGES")) { const int st = atoi(e); if (st >= 1 && st < p.stages) p.stages = st; }
       TimeScope ts(timer, 0, alg_flops(), s);
       DIP_CUDA(tc_conv_launch(p, g_num_sms, s));
     } else {
@@ -427,7 +432,7 @@ struct dip_plan {
   double* acc_bwd = nullptr; size_t acc_bwd_n = 0;
   float* partial = nullptr;
   // runner scratch
-  float* zbuf = nullptr; float* dout = nullptr;
+  float* zbuf = nullptr; float* dout = nullptr; float* dl4 = nullptr;
   static constexpr int kLossRing = 65536;
   double* loss_ring = nullptr;   // [kLossRing] loss slots of the runner when the caller passes no history buffer
   int* it_dev = nullptr;         // [2] device counters: {global Adam step, iteration index of this call}
@@ -601,6 +606,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->out_saved = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->zbuf = A.get<float>((size_t)P->H * P->W * d.in_channels);
   P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
+  P->dl4 = A.get<float>((size_t)P->H * P->W * 4);
   P->loss_ring = A.get<double>(dip_plan::kLossRing);
   P->it_dev = A.get<int>(4);
   // ---- conv ops
@@ -851,7 +857,8 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
   GradSrc sh{};
-  sh.kind = 3; sh.dout = dout; sh.outv = P->out_saved; sh.wh = P->params[P->p_head_w]; sh.nh = P->desc.out_channels;
+  launch_head_dlogit(dout, P->out_saved, P->desc.out_channels, P->H * P->W, P->dl4, s);
+  sh.kind = 3; sh.dl4 = P->dl4; sh.wh = P->params[P->p_head_w]; sh.nh = P->desc.out_channels;
   sh.dwh = P->dw_head; sh.dbh = P->db_head;
   nl += 1;
   DIP_CHECK(bwd_level(P, 0, sh, s, nl));

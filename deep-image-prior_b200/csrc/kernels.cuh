@@ -66,13 +66,15 @@ struct GradSrc {
   int n2;
   int bilinear;        // kind 2
   // kind 3: g[p][c] = sum_k dout[k][p] * o[k][p] * (1 - o[k][p]) * wh[k][c]; also accumulates the head's own gradients
-  const float* dout;   // NCHW [K][npix]
-  const float* outv;   // NCHW [K][npix] (sigmoid output)
+  const float* dl4;    // [npix][4] logit gradients dout * o * (1 - o) (launch_head_dlogit)
   const float* wh;     // [K][C]
   int nh;
   double* dwh;         // [K][C] fp64 accumulators (reduce pass)
   double* dbh;         // [K]
 };
+
+// dl4[p][k] = dout[k][p] * o[k][p] * (1 - o[k][p]) (k < K, else 0); dout / outv are NCHW [K][npix]
+void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s);
 
 // BN(+LeakyReLU) backward. reduce: bwd[0..C) += sum dz, bwd[C..2C) += sum dz*xhat.
 // apply: dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)); writes draw plain [H][W][C];

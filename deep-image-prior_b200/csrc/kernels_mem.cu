@@ -14,6 +14,9 @@
 
 #include <math.h>
 
+#include <map>
+#include <utility>
+
 namespace dip {
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -136,6 +139,23 @@ __device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, in
   }
 }
 static size_t red_bytes(const VecGeom& g, int K) { return static_cast<size_t>(K) * g.threads * sizeof(float4); }
+// Grid-stride kernels get exactly one resident wave (no tail wave): blocks = min(needed, SMs * occupancy).
+template <class Kern>
+static void fit_grid(VecGeom& g, Kern kernel, size_t smem) {
+  static std::map<std::pair<const void*, int>, int> cache;
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), g.threads);
+  auto it = cache.find(key);
+  int per_sm;
+  if (it == cache.end()) {
+    per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, g.threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cache[key] = per_sm;
+  } else {
+    per_sm = it->second;
+  }
+  const int cap = 148 * per_sm;
+  if (g.blocks > cap) g.blocks = cap;
+}
 
 // ------------------------------------------------------------------------------------------------ input_pad
 __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict__ noise, float sigma,
@@ -209,6 +229,7 @@ __global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__
 }
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s) {
   VecGeom g = vec_geom(C, npix);
+  fit_grid(g, k_channel_stats, red_bytes(g, 2));
   k_channel_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(x, ld, g.VL, g.PPB, npix, fwd, C);
 }
 
@@ -235,6 +256,7 @@ __global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ 
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
                          int act, cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H + 2 * pad) * (W + 2 * pad));
+  fit_grid(g, k_bn_act_write, 0);
   k_bn_act_write<<<g.blocks, g.threads, 0, s>>>(raw, ld_in, bn, H, W, dst, ld_out, pad, act, g.VL, g.PPB);
 }
 
@@ -341,6 +363,7 @@ __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB
 }
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+  fit_grid(g, k_cat_stats, red_bytes(g, 2));
   k_cat_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, fwd_cat, g.VL, g.PPB);
 }
 
@@ -376,6 +399,7 @@ __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, in
 }
 void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+  fit_grid(g, k_cat_write, 0);
   k_cat_write<<<g.blocks, g.threads, 0, s>>>(a, bn_cat, dst, g.VL, g.PPB);
 }
 
@@ -461,18 +485,14 @@ __device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr,
     return r;
   }
   if (KIND == 2) return upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
-  // KIND == 3
-  const int npix = H * W;
+  // KIND == 3: logit gradients precomputed per pixel (k_head_dlogit)
+  const float4 d = ld4(s.dl4 + static_cast<size_t>(p) * 4);
+  dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
   float4 r = f4zero();
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    dl[k] = 0.f;
-    if (k < s.nh) {
-      const float o = s.outv[static_cast<size_t>(k) * npix + p];
-      dl[k] = s.dout[static_cast<size_t>(k) * npix + p] * o * (1.f - o);
-      r = f4fma(dl[k], sr.w[k], r);
-    }
-  }
+  r = f4fma(d.x, sr.w[0], r);
+  r = f4fma(d.y, sr.w[1], r);
+  r = f4fma(d.z, sr.w[2], r);
+  r = f4fma(d.w, sr.w[3], r);
   return r;
 }
 __device__ __forceinline__ float4 lrelu_bwd4(float4 y, float4 g) {
@@ -485,6 +505,26 @@ struct BwdItem {
   float4 x, g;
   float dl[4];
 };
+struct RedItem {
+  float4 x, g;
+};
+// dl4[p] = dout[k][p] * o[k][p] * (1 - o[k][p]) for k < K (else 0): sigmoid' folded into the logit gradient once per pixel
+__global__ void k_head_dlogit(const float* __restrict__ dout, const float* __restrict__ outv, int K, int npix,
+                              float* __restrict__ dl4) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) {
+      const float o = outv[static_cast<size_t>(k) * npix + p];
+      d[k] = dout[static_cast<size_t>(k) * npix + p] * o * (1.f - o);
+    }
+    st4(dl4 + static_cast<size_t>(p) * 4, make_float4(d[0], d[1], d[2], d[3]));
+  }
+}
+void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s) {
+  int blocks = (npix + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_head_dlogit<<<blocks, 256, 0, s>>>(dout, outv, K, npix, dl4);
+}
 template <int KIND>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                        int H, int W, double* __restrict__ bwd, int VL, int PPB) {
@@ -495,13 +535,14 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
   item_loop<(KIND == 0 || KIND == 3) ? 4 : 2>(
       blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
       [&](int p) {
-        BwdItem it;
+        RedItem it;
         const int i = p / W, j = p - i * W;
+        float dl[4];
         it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v, it.dl);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v, dl);
         return it;
       },
-      [&](int, const BwdItem& it) {
+      [&](int, const RedItem& it) {
         float4 dz = it.g;
         if (act) dz = lrelu_bwd4(bn_apply(cf, it.x), dz);
         acc[0] = f4add(acc[0], dz);
@@ -514,6 +555,10 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
                           cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
   const size_t sm = red_bytes(g, 2);
+  if (src.kind == 0) fit_grid(g, k_bn_bwd_reduce<0>, sm);
+  else if (src.kind == 1) fit_grid(g, k_bn_bwd_reduce<1>, sm);
+  else if (src.kind == 2) fit_grid(g, k_bn_bwd_reduce<2>, sm);
+  else fit_grid(g, k_bn_bwd_reduce<3>, sm);
   if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
   else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
   else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
@@ -594,6 +639,10 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
                          const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
+  if (src.kind == 0) fit_grid(g, k_bn_bwd_apply<0>, red_bytes(g, 1));
+  else if (src.kind == 1) fit_grid(g, k_bn_bwd_apply<1>, red_bytes(g, 1));
+  else if (src.kind == 2) fit_grid(g, k_bn_bwd_apply<2>, red_bytes(g, 1));
+  else fit_grid(g, k_bn_bwd_apply<3>, red_bytes(g, 6));
   if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
   else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
   else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
@@ -624,6 +673,7 @@ __global__ void k_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* __restric
 }
 void launch_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, double* bwd, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+  fit_grid(g, k_cat_bwd_reduce, red_bytes(g, 2));
   k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, bn_cat, gp, ld_gp, bwd, g.VL, g.PPB);
 }
 __global__ void k_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* __restrict__ gp, int ld_gp,
@@ -660,6 +710,7 @@ __global__ void k_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* __restrict
 void launch_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, const double* bwd, float* dcat,
                           cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+  fit_grid(g, k_cat_bwd_apply, 0);
   k_cat_bwd_apply<<<g.blocks, g.threads, 0, s>>>(a, bn_cat, gp, ld_gp, bwd, dcat, g.VL, g.PPB);
 }
 
@@ -799,6 +850,7 @@ void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
                        cudaStream_t s) {
   VecGeom g = vec_geom(C, static_cast<long long>(H) * W);
+  fit_grid(g, k_skinny_bwd, red_bytes(g, 5));
   k_skinny_bwd<<<g.blocks, g.threads, red_bytes(g, 5), s>>>(x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
                                                              g.VL, g.PPB);
 }
