@@ -136,11 +136,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
               if (elect_one()) {
                 if (p.dbg_flags & 2) mbar_arrive(&ctl->full[stage]);
                 else {
-                  // the box always spans tps taps; rows past the last tap are out of range -> zero-filled, never read
+                  // one box per tap; a box past the last tap is out of range -> zero-filled, never read
                   mbar_expect_tx(&ctl->full[stage], tps * b_bytes);
-                  if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
-                  else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
-                                      tap * p.n_mma + crank * b_rows, cmask);
+                  if (csize == 1) {
+                    tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+                    if (tps == 2) tma_load_2d(sb + b_bytes, &p.tmB, &ctl->full[stage], kb * 32, (tap + 1) * p.n_mma);
+                  } else {
+                    tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                                   tap * p.n_mma + crank * b_rows, cmask);
+                  }
                 }
               }
               __syncwarp();
@@ -408,8 +412,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int chunk_bytes = p.kp * 128;                          // kp pixel rows x 32 channels
   const int y_bytes = 4 * chunk_bytes;                         // dY: 128 channels
-  const int x_bytes = p.c_chunks * chunk_bytes;                // X : c_pad channels, per tap column
-  const int stage_bytes = y_bytes + p.kw * x_bytes;            // multiple of 2048
+  // X operand: per tap column its own kp-pixel tile, or (xshare: stride 1) ONE (kp + kw - 1)-pixel tile that all tap
+  // columns read through row-shifted descriptors (swizzling is a function of the absolute smem address)
+  const int xrows = p.xshare ? p.kp + p.kw - 1 : p.kp;
+  const int xchunk = p.xshare ? ((xrows * 128 + 1023) & ~1023) : chunk_bytes;
+  const int x_bytes = p.c_chunks * xchunk;                     // X : c_pad channels
+  const int stage_bytes = y_bytes + (p.xshare ? 1 : p.kw) * x_bytes;
+  const int stage_tx = y_bytes + (p.xshare ? p.c_chunks * xrows * 128 : p.kw * x_bytes);
   SmemCtlW* ctl = reinterpret_cast<SmemCtlW*>(smem + p.stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
@@ -452,8 +461,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         mbar_wait(&ctl->empty[stage], phase ^ 1);
         uint8_t* sy = smem + stage * stage_bytes;
         if (elect_one()) {
-        mbar_expect_tx(&ctl->full[stage], stage_bytes);
+        mbar_expect_tx(&ctl->full[stage], stage_tx);
         for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * chunk_bytes, &p.tmY, &ctl->full[stage], j * 32, x0, y);
+        if (p.xshare) {
+          uint8_t* sx = sy + y_bytes;
+          for (int j = 0; j < p.c_chunks; ++j)
+            tma_load_5d(sx + j * xchunk, &p.tmX, &ctl->full[stage], j * 32, 0, x0 + p.offx, 0, y + p.offy + r);
+        } else
         for (int s = 0; s < p.kw; ++s) {
           const int ix = p.offx + s, iy = p.offy + r;
           int cpx, cx, cpy, cy;
@@ -480,7 +494,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
       const uint32_t hi = desc_hi(512, 1);
       const uint32_t y_lo0 = desc_lo(smem_u32(smem), chunk_bytes);
       const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
-      const uint32_t x_off = static_cast<uint32_t>(y_bytes) >> 4, x_step = static_cast<uint32_t>(x_bytes) >> 4;
+      // X descriptor: LBO = its own chunk stride; per tap column either the next tile or +1 pixel row (128 B)
+      const uint32_t x_off = ((static_cast<uint32_t>(y_bytes) >> 4) + ((static_cast<uint32_t>(xchunk) >> 4) << 16)) -
+                             ((static_cast<uint32_t>(chunk_bytes) >> 4) << 16);
+      const uint32_t x_step = p.xshare ? 8u : (static_cast<uint32_t>(x_bytes) >> 4);
       const int nk = p.kp / 8;
       int stage = 0;
       uint32_t phase = 0;
@@ -555,7 +572,8 @@ size_t tc_conv_smem_bytes(const TcConvParams& p) {
 }
 size_t tc_wgrad_smem_bytes(const TcWgradParams& p) {
   const size_t chunk = static_cast<size_t>(p.kp) * 128;
-  return 1024 + p.stages * (4 * chunk + static_cast<size_t>(p.kw) * p.c_chunks * chunk) + sizeof(SmemCtlW);
+  const size_t xchunk = p.xshare ? ((static_cast<size_t>(p.kp + p.kw - 1) * 128 + 1023) & ~size_t(1023)) : chunk;
+  return 1024 + p.stages * (4 * chunk + static_cast<size_t>(p.xshare ? 1 : p.kw) * p.c_chunks * xchunk) + sizeof(SmemCtlW);
 }
 
 cudaError_t tc_kernels_init() {

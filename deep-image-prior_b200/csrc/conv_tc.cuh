@@ -52,6 +52,7 @@ struct TcWgradParams {
   int px_blocks;           // total pixel blocks = H * px_blocks_x
   int kp;                  // pixels per K block (box width): 16 or 32
   int c_chunks;            // 32-channel chunks of X (c_pad = 32*c_chunks)
+  int xshare;              // 1: stride-1 taps of a filter row share one (kp + kw - 1)-pixel X tile
   int ksplits;             // CTAs per tap row
   int stages;
 };

@@ -209,8 +209,8 @@ struct ConvOp {
       DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
     }
     fp.csize = pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
-    fp.tps = (fp.patch && fp.csize == 1 && N == 128 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
-    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, fp.tps * N / fp.csize));
+    fp.tps = (fp.patch && fp.csize == 1 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
     fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
@@ -233,8 +233,8 @@ struct ConvOp {
         DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
       }
       dg.csize = pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
-      dg.tps = (dg.patch && dg.csize == 1 && crows == 128 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, dg.tps * crows / dg.csize));
+      dg.tps = (dg.patch && dg.csize == 1 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, C, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
@@ -249,7 +249,8 @@ struct ConvOp {
     wg = TcWgradParams{};
     wg.kp = (wg_w % 32 == 0) ? 32 : 16;
     DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1, true));
-    DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.kp, 1, true));
+    wg.xshare = (stride == 1 && k == 3 && getenv("DIP_NO_XSHARE") == nullptr) ? 1 : 0;
+    DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.xshare ? wg.kp + k - 1 : wg.kp, 1, true));
     wg.partial = partial;
     wg.kh = wg.kw = k; wg.stride = stride; wg.offx = offx; wg.offy = offy;
     wg.px_blocks_x = (wg_w + wg.kp - 1) / wg.kp;
@@ -441,6 +442,11 @@ struct dip_plan {
   cudaGraphExec_t gexec = nullptr;
   cudaStream_t gstream = nullptr;
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
+  // weight-gradient chain runs on a private side stream, forked/joined with events (also inside graph capture)
+  cudaStream_t wstream = nullptr;
+  std::vector<cudaEvent_t> wev;
+  size_t wev_used = 0;
+  bool side_on = false;
   // tables
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
   int n_pack = 0, n_cvt = 0, n_run = 0;
@@ -797,6 +803,31 @@ static GradSrc src_fold(const float* gp, int ld, const float* ds, const float* w
 }
 static GradSrc src_upadj(const float* d, int ld, int bilinear) { GradSrc s{}; s.kind = 2; s.g = d; s.ld = ld; s.coff = 0; s.bilinear = bilinear; return s; }
 
+// Stream on which the weight-gradient work that depends on everything recorded so far on `s` may run concurrently.
+static cudaStream_t fork_side(dip_plan* P, cudaStream_t s) {
+  if (!P->side_on) return s;
+  if (P->wev_used == P->wev.size()) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    P->wev.push_back(e);
+  }
+  cudaEvent_t e = P->wev[P->wev_used++];
+  cudaEventRecord(e, s);
+  cudaStreamWaitEvent(P->wstream, e, 0);
+  return P->wstream;
+}
+static void join_side(dip_plan* P, cudaStream_t s) {
+  if (!P->side_on) return;
+  if (P->wev_used == P->wev.size()) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    P->wev.push_back(e);
+  }
+  cudaEvent_t e = P->wev[P->wev_used++];
+  cudaEventRecord(e, P->wstream);
+  cudaStreamWaitEvent(s, e, 0);
+}
+
 static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl) {
   Level& v = P->lv[l];
   const int prec = P->desc.precision;
@@ -806,12 +837,12 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   const int wl = prec == DIP_PRECISION_TF32 ? 2 : 2;
   // 1x1 conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl));
-  DIP_CHECK(v.c11.run_wgrad(prec, P->partial, P->grads[v.c11.p_w], s));
+  DIP_CHECK(v.c11.run_wgrad(prec, P->partial, P->grads[v.c11.p_w], fork_side(P, s)));
   DIP_CHECK(v.c11.run_dgrad(prec, s));
   nl += wl + 1;
   // up conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl));
-  DIP_CHECK(v.up.run_wgrad(prec, P->partial, P->grads[v.up.p_w], s));
+  DIP_CHECK(v.up.run_wgrad(prec, P->partial, P->grads[v.up.p_w], fork_side(P, s)));
   DIP_CHECK(v.up.run_dgrad(prec, s));
   nl += wl + 1;
   // concat BN
@@ -826,7 +857,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
     // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
     launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
-                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, s);
+                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, fork_side(P, s));
     nl += 1;
   }
   // deeper branch
@@ -839,11 +870,11 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
     src_d2 = src_upadj(v.dCat, CC, P->desc.upsample_bilinear);
   }
   DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl));
-  DIP_CHECK(v.d2.run_wgrad(prec, P->partial, P->grads[v.d2.p_w], s));
+  DIP_CHECK(v.d2.run_wgrad(prec, P->partial, P->grads[v.d2.p_w], fork_side(P, s)));
   DIP_CHECK(v.d2.run_dgrad(prec, s));
   nl += wl + 1;
   DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, l > 0 ? v.ZS : nullptr, s, nl));
-  DIP_CHECK(v.d1.run_wgrad(prec, P->partial, P->grads[v.d1.p_w], s));
+  DIP_CHECK(v.d1.run_wgrad(prec, P->partial, P->grads[v.d1.p_w], fork_side(P, s)));
   nl += wl;
   if (l > 0) { DIP_CHECK(v.d1.run_dgrad(prec, s)); nl += 1; }
   DIP_CUDA(cudaGetLastError());
@@ -854,6 +885,9 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   if (!P->bound) return fail("dip_backward: parameters not bound");
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
+  P->side_on = getenv("DIP_NO_SIDE") == nullptr;
+  if (P->side_on && P->wstream == nullptr) DIP_CUDA(cudaStreamCreateWithFlags(&P->wstream, cudaStreamNonBlocking));
+  P->wev_used = 0;
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
   GradSrc sh{};
@@ -862,6 +896,7 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   sh.dwh = P->dw_head; sh.dbh = P->db_head;
   nl += 1;
   DIP_CHECK(bwd_level(P, 0, sh, s, nl));
+  join_side(P, s);
   k_cvt_table<<<P->n_cvt, 128, 0, s>>>(P->d_cvt);
   nl += 1;
   DIP_CUDA(cudaGetLastError());
@@ -914,6 +949,8 @@ void dip_plan_destroy(dip_plan* plan) {
   if (plan->gev_in) cudaEventDestroy(plan->gev_in);
   if (plan->gev_out) cudaEventDestroy(plan->gev_out);
   for (cudaEvent_t e : plan->timer.pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : plan->wev) cudaEventDestroy(e);
+  if (plan->wstream) cudaStreamDestroy(plan->wstream);
   delete plan;
 }
 int dip_plan_num_params(const dip_plan* plan) { return (int)plan->numel.size(); }
