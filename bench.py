@@ -32,6 +32,9 @@ SIGMA_REG = 1.0 / 30.0
 LR = 0.01
 ITERS_PER_IMAGE = 2000           # BASELINE.json config[0]/[1]
 ALG_GFLOP_PER_ITER = 460.07      # SURVEY.md section 6 (2*M*N*K over the 26 convs, fwd+dgrad+wgrad)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the committed `ncu --set full` capture
+# (profiles/r01_ncu_conv_l0up.txt); None until captured for the current kernel version
+ROOFLINE_TRAFFIC_BYTES = None
 METRIC = "optimisation iterations/sec (512x512 skip-net denoising, sum over independent images)"
 
 
@@ -255,7 +258,7 @@ def run_ours(args):
     plan.set_timing(True)
     device_steps(roof_steps)
     torch.cuda.synchronize()
-    timing = plan.get_timing()
+    records = plan.get_timing_records()
     plan.set_timing(False)
     os.environ.pop("DIP_NO_SIDE", None)
     fwd_l, bwd_l = plan.num_launches()
@@ -315,13 +318,18 @@ def run_ours(args):
                              device=dev)
 
     if rank == 0:
-        conv_ms = timing["fprop"][0] + timing["dgrad"][0]
-        conv_fl = timing["fprop"][1] + timing["dgrad"][1]
-        conv_n = timing["fprop"][2] + timing["dgrad"][2]
-        wg_ms, wg_fl, wg_n = timing["wgrad"]
+        def agg(pred):
+            sel = [r for r in records if pred(r)]
+            ms_ = sum(r[2] for r in sel)
+            fl_ = sum(r[1] for r in sel)
+            return ms_, fl_, len(sel), (fl_ / (ms_ / 1000.0) / 1e12 if ms_ > 0 else 0.0)
+        conv_ms, conv_fl, conv_n, conv_all = agg(lambda r: r[0] in (0, 1))
+        wg_ms, wg_fl, wg_n, wg_ach = agg(lambda r: r[0] == 2)
+        # dominant launch = the largest single tensor-core launch of the step (level-0 3x3 conv 132->128 at 512x512,
+        # 79.7 algorithmic GFLOP): its fprop instances
+        big = max(r[1] for r in records)
+        dom_ms, dom_fl, dom_n, achieved = agg(lambda r: r[0] == 0 and r[1] == big)
         tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
-        achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-        wg_ach = wg_fl / (wg_ms / 1000.0) / 1e12 if wg_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -339,16 +347,24 @@ def run_ours(args):
                     "api": "models.get_net(...).type(cuda) + closure-style zero_grad/forward/MSELoss/backward/FusedAdam.step"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"kernel": "tc_conv_kernel (tcgen05 tf32 implicit-GEMM fprop+dgrad)", "bound": "tensor",
-                         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None,
+            "roofline": {"kernel": "tc_conv_kernel, dominant launch: level-0 3x3 conv 132->128 @512x512 fprop "
+                                   "(tcgen05 tf32 implicit GEMM, smem input patch shared by the 9 taps)",
+                         "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf32_peak if tf32_peak else None, "traffic": ROOFLINE_TRAFFIC_BYTES,
+                         "algorithmic_flops_per_launch": dom_fl / max(dom_n, 1), "launches": dom_n,
+                         "us_per_launch": 1000.0 * dom_ms / max(dom_n, 1),
                          "peak_note": "tf32 dense = 1/2 of the measured sustained bf16 cuBLAS rate (" + peak_src + ")",
-                         "launches": conv_n, "ms_per_step": conv_ms / roof_steps,
-                         "share_of_step": (conv_ms / roof_steps) / (ms / args.steps) if ms > 0 else None, "timed": "CUDA events around every launch in a %d-step eager pass right after the graph-replayed timed region" % roof_steps},
-            "roofline_wgrad": {"kernel": "tc_wgrad_kernel (tcgen05 tf32, MN-major operands, split-K)", "bound": "tensor",
-                               "achieved": wg_ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "timed": "CUDA events around every launch in a %d-step eager pass right after the "
+                                  "graph-replayed timed region (side stream off so that kernels run alone)" % roof_steps},
+            "roofline_all_conv": {"kernel": "tc_conv_kernel, all %d fprop+dgrad launches of a step" % (conv_n // max(roof_steps, 1)),
+                                  "achieved": conv_all, "peak": tf32_peak, "unit": "TFLOP/s", "frac": conv_all / tf32_peak,
+                                  "ms_per_step": conv_ms / roof_steps,
+                                  "share_of_step": (conv_ms / roof_steps) / (ms / args.steps) if ms > 0 else None},
+            "roofline_wgrad": {"kernel": "tc_wgrad_kernel (tcgen05 tf32, MN-major operands, split-K), all launches",
+                               "bound": "tensor", "achieved": wg_ach, "peak": tf32_peak, "unit": "TFLOP/s",
                                "frac": wg_ach / tf32_peak if tf32_peak else None, "launches": wg_n,
-                               "ms_per_step": wg_ms / roof_steps, "share_of_step": (wg_ms / roof_steps) / (ms / args.steps) if ms > 0 else None},
+                               "ms_per_step": wg_ms / roof_steps,
+                               "share_of_step": (wg_ms / roof_steps) / (ms / args.steps) if ms > 0 else None},
             "step_tflops": ALG_GFLOP_PER_ITER / 1000.0 / (ms_max / args.steps / 1000.0),
             "per_rank": [{"psnr_gt": r[0], "final_loss": r[1], "it_per_s": r[2]} for r in recs],
         }

@@ -400,6 +400,7 @@ struct BnLayer {
 struct Level {
   int H, W, h, w, Cin;
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
+  float *dUp;  // [h][w][128] adjoint of the upsampling applied to dCat
   float *dRaw_v, *dA_u, *dRaw_u, *dP_cat, *dCat, *dRaw_s, *dRaw_d2, *dP_d1, *dRaw_d1, *ZS, *dPin;
   BnLayer bn_s, bn_d1, bn_d2, bn_cat, bn_u, bn_v;
   int p_skip_w, p_skip_b;
@@ -579,6 +580,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.dP_cat = A.get<float>(HWp * (128 + CS));
     v.dCat = A.get<float>(HW * (128 + CS));
     v.dRaw_s = A.get<float>(HW * CS);
+    v.dUp = A.get<float>(hw * 128);
     v.dRaw_d2 = A.get<float>(hw * 128);
     v.dP_d1 = A.get<float>(hwp * 128);
     v.dRaw_d1 = A.get<float>(hw * 128);
@@ -846,11 +848,12 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(v.up.run_dgrad(prec, s));
   nl += wl + 1;
   // concat BN
-  CatArgs ca = cat_args(P, v, level_usrc(P, l));
   BnRef rc = bn_ref(P, v.bn_cat);
-  launch_cat_bwd_reduce(ca, rc, v.dP_cat, CC, v.bn_cat.bwd, s);
-  launch_cat_bwd_apply(ca, rc, v.dP_cat, CC, v.bn_cat.bwd, v.dCat, s);
-  nl += 2;
+  launch_cat_bwd_reduce(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, s);
+  launch_cat_bwd_apply(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, v.dCat, s);
+  // gradient w.r.t. the low-resolution tensor that was upsampled into this concat (adjoint of x2 upsampling), once
+  launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, P->desc.upsample_bilinear, v.dUp, s);
+  nl += 3;
   // skip branch
   DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, s, nl));
   {
@@ -863,11 +866,11 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   // deeper branch
   GradSrc src_d2;
   if (!last) {
-    DIP_CHECK(bwd_level(P, l + 1, src_upadj(v.dCat, CC, P->desc.upsample_bilinear), s, nl));
+    DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), s, nl));
     Level& n = P->lv[l + 1];
     src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
   } else {
-    src_d2 = src_upadj(v.dCat, CC, P->desc.upsample_bilinear);
+    src_d2 = src_plain(v.dUp, 128, 0);
   }
   DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl));
   DIP_CHECK(v.d2.run_wgrad(prec, P->partial, P->grads[v.d2.p_w], fork_side(P, s)));
@@ -1140,6 +1143,19 @@ int dip_plan_get_timing(dip_plan* plan, double* ms3, double* flops3, int* launch
   }
   plan->timer.reset();
   return 0;
+}
+int dip_plan_get_timing_records(dip_plan* plan, int max_records, int* cls, double* flops, double* ms) {
+  int n = 0;
+  for (const Timer::Rec& r : plan->timer.recs) {
+    if (n >= max_records) break;
+    DIP_CUDA(cudaEventSynchronize(plan->timer.pool[r.e1]));
+    float t = 0.f;
+    DIP_CUDA(cudaEventElapsedTime(&t, plan->timer.pool[r.e0], plan->timer.pool[r.e1]));
+    cls[n] = r.cls; flops[n] = r.flops; ms[n] = t;
+    ++n;
+  }
+  plan->timer.reset();
+  return n;
 }
 int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {
   *fwd = plan->launches_fwd; *bwd = plan->launches_bwd;

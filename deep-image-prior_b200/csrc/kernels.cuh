@@ -84,10 +84,14 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
                          const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s);
 
-// Concat-BN backward (no activation). Gradient = fold of the padded dgrad output gp [(H+2)][(W+2)][ld_gp].
-void launch_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, double* bwd, cudaStream_t s);
-void launch_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, const double* bwd, float* dcat,
-                          cudaStream_t s);
+// Concat-BN backward (no activation). pcat = the stored BN output (padded [(H+2)][(W+2)][ld], ld = bn_cat.C), from which
+// xhat is recovered; gradient = fold of the padded dgrad output gp [(H+2)][(W+2)][ld]; dcat plain [H][W][C].
+void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, double* bwd,
+                           cudaStream_t s);
+void launch_cat_bwd_apply(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, const double* bwd,
+                          float* dcat, cudaStream_t s);
+// adjoint of the x2 upsampling, once per level: dst[h][w][C] <- D[2h][2w][ld] channels [coff, coff+C)
+void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bilinear, float* dst, cudaStream_t s);
 
 // Skinny 1x1 convs (N <= 4 outputs): y[p][n] = b[n] + sum_c x[p][c] w[n][c]
 //   x: pixel (i,j) at x + (i*x_rs + j)*ldx floats (works for padded interiors)

@@ -650,68 +650,115 @@ void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSr
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
-__global__ void k_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* __restrict__ gp, int ld_gp,
-                                 double* __restrict__ bwd, int VL, int PPB) {
-  const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
-  const CatLane l = cat_lane(a, v);
-  const Bn4 cf = bn_coef(bn_cat, v);
-  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
-  float4 acc[2] = {f4zero(), f4zero()};
-  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
-    const int si = p / w, sj = p - si * w;
-    float4 q[4];
-    cat_quad(a, l, si, sj, v, q);
+// The concat BN has no activation behind it, and its output y = gamma * xhat + beta is still in HBM (the padded conv
+// input P_cat), so xhat = (y - beta) / gamma is recovered from the stored tensor instead of re-running the upsampling.
+// (gamma == 0 exactly: xhat is taken as 0; dx is 0 in that case anyway.)
+struct CatBwdCoef {
+  float4 beta, inv_gamma, scale;
+};
+__device__ __forceinline__ CatBwdCoef cat_bwd_coef(const BnRef& bn, int v) {
+  float b[4], ig[4], sc[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float4 dz = fold_read(gp, ld_gp, 0, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v);
-      acc[0] = f4add(acc[0], dz);
-      acc[1] = f4mla(dz, bn_xhat(cf, q[e]), acc[1]);
-    }
+  for (int e = 0; e < 4; ++e) {
+    const int c = 4 * v + e;
+    const int ct = (c + bn.rot) % bn.C;
+    const double m = bn.fwd[c] * static_cast<double>(bn.inv_n);
+    double var = bn.fwd[bn.C + c] * static_cast<double>(bn.inv_n) - m * m;
+    if (var < 0.0) var = 0.0;
+    const float g = bn.gamma[ct];
+    b[e] = bn.beta[ct];
+    ig[e] = g != 0.f ? 1.f / g : 0.f;
+    sc[e] = g * static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
   }
+  CatBwdCoef r;
+  r.beta = make_float4(b[0], b[1], b[2], b[3]);
+  r.inv_gamma = make_float4(ig[0], ig[1], ig[2], ig[3]);
+  r.scale = make_float4(sc[0], sc[1], sc[2], sc[3]);
+  return r;
+}
+__device__ __forceinline__ float4 cat_xhat(const CatBwdCoef& c, float4 y) {
+  return make_float4((y.x - c.beta.x) * c.inv_gamma.x, (y.y - c.beta.y) * c.inv_gamma.y, (y.z - c.beta.z) * c.inv_gamma.z,
+                     (y.w - c.beta.w) * c.inv_gamma.w);
+}
+__global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
+                                                        int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+  const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
+  const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
+  const int Wp = W + 2;
+  float4 acc[2] = {f4zero(), f4zero()};
+  item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+               [&](int p) {
+                 RedItem it;
+                 const int i = p / W, j = p - i * W;
+                 it.x = ld4(pcat + (static_cast<size_t>(i + 1) * Wp + (j + 1)) * ld + 4 * v);
+                 it.g = fold_read(gp, ld, 0, H, W, i, j, v);
+                 return it;
+               },
+               [&](int, const RedItem& it) {
+                 acc[0] = f4add(acc[0], it.g);
+                 acc[1] = f4mla(it.g, cat_xhat(cf, it.x), acc[1]);
+               });
   double* const dst[2] = {bwd, bwd + bn_cat.C};
   block_reduce_atomic<2>(acc, VL, PPB, dst);
 }
-void launch_cat_bwd_reduce(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, double* bwd, cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, double* bwd,
+                           cudaStream_t s) {
+  VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_reduce, red_bytes(g, 2));
-  k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, bn_cat, gp, ld_gp, bwd, g.VL, g.PPB);
+  k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB);
 }
-__global__ void k_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* __restrict__ gp, int ld_gp,
-                                const double* __restrict__ bwd, float* __restrict__ dcat, int VL, int PPB) {
+__global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
+                                                       int ld, int H, int W, const double* __restrict__ bwd,
+                                                       float* __restrict__ dcat, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
-  const CatLane l = cat_lane(a, v);
-  const Bn4 cf = bn_coef(bn_cat, v);
+  const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int C = bn_cat.C;
-  float m1[4], m2[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    m1[e] = static_cast<float>(bwd[4 * v + e] * bn_cat.inv_n);
-    m2[e] = static_cast<float>(bwd[C + 4 * v + e] * bn_cat.inv_n);
-  }
-  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
-  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
-    const int si = p / w, sj = p - si * w;
-    float4 q[4];
-    cat_quad(a, l, si, sj, v, q);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int i = 2 * si + (e >> 1), j = 2 * sj + (e & 1);
-      const float4 xh = bn_xhat(cf, q[e]);
-      const float4 dz = fold_read(gp, ld_gp, 0, a.H, a.W, i, j, v);
-      float4 dx;
-      dx.x = cf.scale.x * (dz.x - m1[0] - xh.x * m2[0]);
-      dx.y = cf.scale.y * (dz.y - m1[1] - xh.y * m2[1]);
-      dx.z = cf.scale.z * (dz.z - m1[2] - xh.z * m2[2]);
-      dx.w = cf.scale.w * (dz.w - m1[3] - xh.w * m2[3]);
-      st4(dcat + (static_cast<size_t>(i) * a.W + j) * C + 4 * v, dx);
-    }
-  }
+  const int Wp = W + 2;
+  float4 m1, m2;
+  m1.x = static_cast<float>(bwd[4 * v + 0] * bn_cat.inv_n); m1.y = static_cast<float>(bwd[4 * v + 1] * bn_cat.inv_n);
+  m1.z = static_cast<float>(bwd[4 * v + 2] * bn_cat.inv_n); m1.w = static_cast<float>(bwd[4 * v + 3] * bn_cat.inv_n);
+  m2.x = static_cast<float>(bwd[C + 4 * v + 0] * bn_cat.inv_n); m2.y = static_cast<float>(bwd[C + 4 * v + 1] * bn_cat.inv_n);
+  m2.z = static_cast<float>(bwd[C + 4 * v + 2] * bn_cat.inv_n); m2.w = static_cast<float>(bwd[C + 4 * v + 3] * bn_cat.inv_n);
+  item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+               [&](int p) {
+                 RedItem it;
+                 const int i = p / W, j = p - i * W;
+                 it.x = ld4(pcat + (static_cast<size_t>(i + 1) * Wp + (j + 1)) * ld + 4 * v);
+                 it.g = fold_read(gp, ld, 0, H, W, i, j, v);
+                 return it;
+               },
+               [&](int p, const RedItem& it) {
+                 const float4 xh = cat_xhat(cf, it.x);
+                 float4 dx;
+                 dx.x = cf.scale.x * (it.g.x - m1.x - xh.x * m2.x);
+                 dx.y = cf.scale.y * (it.g.y - m1.y - xh.y * m2.y);
+                 dx.z = cf.scale.z * (it.g.z - m1.z - xh.z * m2.z);
+                 dx.w = cf.scale.w * (it.g.w - m1.w - xh.w * m2.w);
+                 st4(dcat + static_cast<size_t>(p) * C + 4 * v, dx);
+               });
 }
-void launch_cat_bwd_apply(CatArgs a, BnRef bn_cat, const float* gp, int ld_gp, const double* bwd, float* dcat,
-                          cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
+void launch_cat_bwd_apply(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, const double* bwd,
+                          float* dcat, cudaStream_t s) {
+  VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_apply, 0);
-  k_cat_bwd_apply<<<g.blocks, g.threads, 0, s>>>(a, bn_cat, gp, ld_gp, bwd, dcat, g.VL, g.PPB);
+  k_cat_bwd_apply<<<g.blocks, g.threads, 0, s>>>(pcat, bn_cat, gp, ld, H, W, bwd, dcat, g.VL, g.PPB);
+}
+
+// Adjoint of the x2 upsampling, materialised once: dst[h][w][C] <- D[2h][2w][ld] (channels coff..coff+C)
+__global__ void __launch_bounds__(256) k_upadj(const float* __restrict__ D, int ld, int coff, int h, int w, int C, int bilinear,
+                                               float* __restrict__ dst, int VL, int PPB) {
+  const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
+  item_loop<1>(blockIdx.x * PPB + slot, gridDim.x * PPB, h * w,
+               [&](int p) {
+                 const int i = p / w, j = p - i * w;
+                 return upadj_read(D, ld, coff, h, w, i, j, v, bilinear);
+               },
+               [&](int p, float4 g) { st4(dst + static_cast<size_t>(p) * C + 4 * v, g); });
+}
+void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bilinear, float* dst, cudaStream_t s) {
+  VecGeom g = vec_geom(C, static_cast<long long>(h) * w);
+  fit_grid(g, k_upadj, 0);
+  k_upadj<<<g.blocks, g.threads, 0, s>>>(D, ld, coff, h, w, C, bilinear, dst, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ skinny 1x1 convs

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "dip_last_error", "dip_version", "dip_plan_workspace_bytes", "dip_plan_create", "dip_plan_destroy",
     "dip_plan_num_params", "dip_plan_num_bn", "dip_plan_param_numel", "dip_plan_bind", "dip_forward", "dip_backward",
     "dip_loss_mse", "dip_noise_perturb", "dip_adam_create", "dip_adam_destroy", "dip_adam_bind", "dip_adam_step",
-    "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_plan_set_timing", "dip_plan_get_timing", "dip_op_scratch_bytes", "dip_op_conv_fprop",
+    "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_plan_set_timing", "dip_plan_get_timing", "dip_plan_get_timing_records", "dip_op_scratch_bytes", "dip_op_conv_fprop",
     "dip_op_conv_dgrad", "dip_op_conv_wgrad",
 ]
 
@@ -92,6 +92,7 @@ def lib():
     L.dip_plan_num_launches.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.dip_plan_set_timing.argtypes = [vp, i32]
     L.dip_plan_get_timing.argtypes = [vp, ctypes.POINTER(f64), ctypes.POINTER(f64), ctypes.POINTER(i32)]
+    L.dip_plan_get_timing_records.argtypes = [vp, i32, ctypes.POINTER(i32), ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.dip_op_scratch_bytes.restype = sz
     L.dip_op_conv_fprop.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32,
                                     vp, vp]
@@ -206,6 +207,14 @@ class Plan:
         ms, fl, n = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_int * 3)()
         check(lib().dip_plan_get_timing(self.h, ms, fl, n))
         return {k: (ms[i], fl[i], n[i]) for i, k in enumerate(("fprop", "dgrad", "wgrad"))}
+
+    def get_timing_records(self, max_records=65536):
+        """[(class 0 fprop | 1 dgrad | 2 wgrad, algorithmic flops, ms)] per tensor-core launch since the last call."""
+        cls, fl, ms = (ctypes.c_int * max_records)(), (ctypes.c_double * max_records)(), (ctypes.c_double * max_records)()
+        n = lib().dip_plan_get_timing_records(self.h, max_records, cls, fl, ms)
+        if n < 0:
+            check(n)
+        return [(cls[i], fl[i], ms[i]) for i in range(n)]
 
     def num_launches(self):
         a, b = ctypes.c_int(), ctypes.c_int()

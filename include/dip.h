@@ -93,6 +93,8 @@ int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd);
  * index 0 = fprop, 1 = dgrad (both tc_conv_kernel), 2 = wgrad (tc_wgrad_kernel); flops are algorithmic (2*M*N*K). */
 int dip_plan_set_timing(dip_plan* plan, int enable);
 int dip_plan_get_timing(dip_plan* plan, double* ms3, double* flops3, int* launches3);
+/* same records one by one (class, algorithmic flops, device ms); returns the number written (<= max_records) */
+int dip_plan_get_timing_records(dip_plan* plan, int max_records, int* cls, double* flops, double* ms);
 
 /* ---- single-op entry points (same kernels as the plan; used by the per-kernel parity tests).
  * Convolution of an NHWC fp32 tensor a[a_h][a_w][a_c] with torch OIHW weights w[N][C][k][k]:
