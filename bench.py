@@ -34,7 +34,7 @@ ITERS_PER_IMAGE = 2000           # BASELINE.json config[0]/[1]
 ALG_GFLOP_PER_ITER = 460.07      # SURVEY.md section 6 (2*M*N*K over the 26 convs, fwd+dgrad+wgrad)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the committed `ncu --set full` capture
 # (profiles/r01_ncu_conv_l0up.txt); None until captured for the current kernel version
-ROOFLINE_TRAFFIC_BYTES = None
+ROOFLINE_TRAFFIC_BYTES = 232614656  # 140.30 MB read + 92.31 MB written (algorithmic: 143.2 MB in + 0.8 MB weights + 134.2 MB out)
 METRIC = "optimisation iterations/sec (512x512 skip-net denoising, sum over independent images)"
 
 
@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
