@@ -19,6 +19,7 @@ static constexpr int kTileM = 128;            // output pixels per tile (UMMA M)
 static constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 32 fp32
 static constexpr int kChunkBytes = kTileM * 128;
 static constexpr int kNumThreads = 256;
+static constexpr int kAccStride = 16;  // fp64 accumulators: one per 128-byte line (kAccS in kernels.cuh)
 
 struct SmemCtl {
   uint64_t full[8];
@@ -384,8 +385,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.stats != nullptr && et < p.n_mma && et < p.stats_ld) {
-      atomicAdd(&p.stats[et], stat_s1);
-      atomicAdd(&p.stats[p.stats_ld + et], stat_s2);
+      atomicAdd(&p.stats[et * kAccStride], stat_s1);
+      atomicAdd(&p.stats[(p.stats_ld + et) * kAccStride], stat_s2);
     }
     if (et == 0) tma_store_wait_all0();
   }

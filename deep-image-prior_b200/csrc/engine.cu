@@ -354,7 +354,7 @@ struct CvtEntry {
 };
 __global__ void k_cvt_table(const CvtEntry* __restrict__ tab) {
   const CvtEntry e = tab[blockIdx.x];
-  for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)e.src[i];
+  for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)e.src[(size_t)i * kAccS];
 }
 struct RunEntry {
   const double* fwd; float* rm; float* rv; void* nb; int C, rot; float n; int nb_is_float;
@@ -364,8 +364,8 @@ __global__ void k_running_table(const RunEntry* __restrict__ tab) {
   if (e.rm == nullptr) return;
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
     const int ct = (c + e.rot) % e.C;
-    const double m = e.fwd[c] / e.n;
-    double var = e.fwd[e.C + c] / e.n - m * m;
+    const double m = e.fwd[c * kAccS] / e.n;
+    double var = e.fwd[(e.C + c) * kAccS] / e.n - m * m;
     if (var < 0) var = 0;
     const double unb = e.n > 1.f ? var * e.n / (e.n - 1.0) : var;
     e.rm[ct] = 0.9f * e.rm[ct] + 0.1f * (float)m;
@@ -448,6 +448,7 @@ struct dip_plan {
   std::vector<cudaEvent_t> wev;
   size_t wev_used = 0;
   bool side_on = false;
+  RedScratch scr_main{nullptr, nullptr}, scr_side{nullptr, nullptr};
   // tables
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
   int n_pack = 0, n_cvt = 0, n_run = 0;
@@ -540,20 +541,20 @@ static int build_plan(dip_plan* P, Arena& A) {
   size_t skinny_acc = 0;
   for (int l = 0; l < L; ++l) skinny_acc += (size_t)CS * P->lv[l].Cin;
   skinny_acc += (size_t)d.out_channels * 128 + 8;
-  P->acc_fwd_n = acc_f;
-  P->acc_bwd_n = acc_b + skinny_acc;
+  P->acc_fwd_n = acc_f * kAccS;
+  P->acc_bwd_n = (acc_b + skinny_acc) * kAccS;
   P->acc_fwd = A.get<double>(P->acc_fwd_n);
   P->acc_bwd = A.get<double>(P->acc_bwd_n);
   {
     double* f = P->acc_fwd; double* b = P->acc_bwd;
     for (BnLayer* bn : P->bns) {
-      bn->fwd = f; f = f ? f + 2 * bn->C : nullptr;
-      bn->bwd = b; bn->dbias = b ? b + 2 * bn->C : nullptr; b = b ? b + 3 * bn->C : nullptr;
+      bn->fwd = f; f = f ? f + 2 * bn->C * kAccS : nullptr;
+      bn->bwd = b; bn->dbias = b ? b + 2 * bn->C * kAccS : nullptr; b = b ? b + 3 * bn->C * kAccS : nullptr;
     }
-    for (int l = 0; l < L; ++l) { P->lv[l].dw_s = b; b = b ? b + (size_t)CS * P->lv[l].Cin : nullptr; }
-    P->dw_head = b; b = b ? b + (size_t)d.out_channels * 128 : nullptr;
+    for (int l = 0; l < L; ++l) { P->lv[l].dw_s = b; b = b ? b + (size_t)CS * P->lv[l].Cin * kAccS : nullptr; }
+    P->dw_head = b; b = b ? b + (size_t)d.out_channels * 128 * kAccS : nullptr;
     P->db_head = b;
-    P->db_scratch = b ? b + 4 : nullptr;
+    P->db_scratch = b ? b + 4 * kAccS : nullptr;
   }
   // ---- activations
   auto reg = [&](const std::string& name, void* p, int rows, int cols, int ld, int c) { P->bufs[name] = BufInfo{p, rows, cols, ld, c}; };
@@ -616,6 +617,10 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->dl4 = A.get<float>((size_t)P->H * P->W * 4);
   P->loss_ring = A.get<double>(dip_plan::kLossRing);
+  P->scr_main.part = A.get<double>(kernels_scratch_doubles());
+  P->scr_side.part = A.get<double>(kernels_scratch_doubles());
+  P->scr_main.counter = A.get<unsigned int>(4);
+  P->scr_side.counter = A.get<unsigned int>(4);
   P->it_dev = A.get<int>(4);
   // ---- conv ops
   size_t partial_max = 0;
@@ -672,6 +677,9 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->d_run = A.get<RunEntry>(P->n_run);
   if (P->dry) return 0;
   // ---- device-side setup
+  DIP_CUDA(cudaMemset(P->scr_main.counter, 0, 16));
+  DIP_CUDA(cudaMemset(P->scr_side.counter, 0, 16));
+  DIP_CUDA(cudaStreamCreateWithFlags(&P->wstream, cudaStreamNonBlocking));
   // The zero-stuffed buffers are written at even positions only: clear them once.
   for (int l = 1; l < L; ++l) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
   if (prec == DIP_PRECISION_TF32)
@@ -695,7 +703,7 @@ static int upload_tables(dip_plan* P) {
   DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
   std::vector<CvtEntry> cv;
   for (BnLayer* b : P->bns) {
-    cv.push_back(CvtEntry{b->bwd + b->C, P->grads[b->p_gamma], b->C, b->rot});  // dgamma = sum dz*xhat
+    cv.push_back(CvtEntry{b->bwd + b->C * kAccS, P->grads[b->p_gamma], b->C, b->rot});  // dgamma = sum dz*xhat
     cv.push_back(CvtEntry{b->bwd, P->grads[b->p_beta], b->C, b->rot});          // dbeta  = sum dz
     if (b->p_bias >= 0) cv.push_back(CvtEntry{b->dbias, P->grads[b->p_bias], b->C, 0});
     else cv.push_back(CvtEntry{b->dbias, nullptr, 0, 0});
@@ -770,6 +778,9 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
 
 static int plan_forward(dip_plan* P, const float* z, const float* noise, float sigma, float* out, cudaStream_t s) {
   if (!P->bound) return fail("dip_forward: parameters not bound (call dip_plan_bind)");
+  // grid-wide reductions: fp64 atomics onto line-strided accumulators (default) or the deterministic last-block sum
+  if (getenv("DIP_LASTBLOCK") != nullptr) kernels_set_scratch(P->scr_main, P->scr_side, P->wstream);
+  else kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_fwd, 0, P->acc_fwd_n * sizeof(double), s));
   {
@@ -886,10 +897,11 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
 
 static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   if (!P->bound) return fail("dip_backward: parameters not bound");
+  if (getenv("DIP_LASTBLOCK") != nullptr) kernels_set_scratch(P->scr_main, P->scr_side, P->wstream);
+  else kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
   P->side_on = getenv("DIP_NO_SIDE") == nullptr;
-  if (P->side_on && P->wstream == nullptr) DIP_CUDA(cudaStreamCreateWithFlags(&P->wstream, cudaStreamNonBlocking));
   P->wev_used = 0;
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
@@ -947,6 +959,7 @@ int dip_plan_create(const dip_net_desc* desc, int H, int W, void* workspace, siz
 }
 void dip_plan_destroy(dip_plan* plan) {
   if (plan == nullptr) return;
+  kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);  // never leave dangling scratch
   if (plan->gexec) cudaGraphExecDestroy(plan->gexec);
   if (plan->gstream) cudaStreamDestroy(plan->gstream);
   if (plan->gev_in) cudaEventDestroy(plan->gev_in);
@@ -1166,6 +1179,7 @@ int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {
 size_t dip_op_scratch_bytes(void) { return (size_t)96 << 20; }
 
 static int op_common(ConvOp& op, int N, int C, int k, int stride, int rot, float* scratch, const float* w, cudaStream_t s) {
+  kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);  // single ops: atomics path
   if (N != 128) return fail("dip_op_conv_*: N must be 128");
   if (C % 4 != 0 || C > 160) return fail("dip_op_conv_*: C must be a multiple of 4 and <= 160");
   op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;

@@ -8,6 +8,9 @@ namespace dip {
 
 static constexpr float kBnEps = 1e-5f;
 static constexpr float kLreluSlope = 0.2f;
+// fp64 accumulators are spread one per 128-byte line (stride in doubles): hundreds of blocks add to them at the end of
+// every reduction kernel, and neighbouring channels must not share an L2 atomic unit
+static constexpr int kAccS = 16;
 
 // Statistics of one BatchNorm layer: fp64 accumulators, zeroed once per iteration.
 //   fwd[0..C)   sum x          fwd[C..2C)   sum x^2
@@ -29,6 +32,15 @@ struct HeadRef {
   int K;               // <= 4
   float* out;          // NCHW [K][H*W]
 };
+
+// Scratch of the grid-wide reductions: per-block partial sums + a ticket counter (zeroed once; self-resetting).
+// Two sets because the weight-gradient chain runs concurrently on a side stream.
+struct RedScratch {
+  double* part;            // [kernels_scratch_doubles()]
+  unsigned int* counter;
+};
+size_t kernels_scratch_doubles();
+void kernels_set_scratch(RedScratch main_scr, RedScratch side_scr, cudaStream_t side_stream);
 
 // z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
@@ -114,7 +126,7 @@ void launch_mse(const float* out, const float* target, const float* mask, int C,
 // stream = offset + *it_dev)
 void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, size_t n,
                   cudaStream_t s);
-// *it_dev += 1 (iteration counter of the graph-captured runner)
+// it_dev[0] += 1, it_dev[1] += 1 (step / iteration counters of the graph-captured runner)
 void launch_advance(int* it_dev, cudaStream_t s);
 
 // weight repacking ---------------------------------------------------------------------------------

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <utility>
@@ -54,8 +55,8 @@ __device__ __forceinline__ Bn4 bn_coef(const BnRef& bn, int v) {
   for (int e = 0; e < 4; ++e) {
     const int c = 4 * v + e;
     const int ct = (c + bn.rot) % bn.C;
-    const double m = bn.fwd[c] * static_cast<double>(bn.inv_n);
-    double var = bn.fwd[bn.C + c] * static_cast<double>(bn.inv_n) - m * m;
+    const double m = bn.fwd[c * kAccS] * static_cast<double>(bn.inv_n);
+    double var = bn.fwd[(bn.C + c) * kAccS] * static_cast<double>(bn.inv_n) - m * m;
     if (var < 0.0) var = 0.0;
     mean[e] = static_cast<float>(m);
     rstd[e] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
@@ -96,12 +97,18 @@ static VecGeom vec_geom(int C, long long nitems) {
   return g;
 }
 
-// Block reduction of K float4 accumulators over the item slots of the block, then fp64 atomics: dst[k][4v+e].
+// Block reduction of K float4 accumulators over the item slots of the block, then a grid-wide sum into dst[k][c].
 // Threads are laid out tid = slot * VL + v.  For VL in {1,2,4,8,16} the lanes that share v are first folded with
 // warp shuffles (blockDim is then a multiple of 32).
+// Grid-wide step: fp64 atomics from every block cost ~0.5 ms per iteration (hundreds of blocks hammering the same 256
+// addresses at the end of a single-wave kernel), so each block stores its partial sums and the LAST block to finish
+// (ticket counter) adds them up in block order -- deterministic, no contention.  wid[k] = valid channels of dst[k].
+__constant__ int g_dbg_noatom = 0;  // experiment: skip the final accumulation (results wrong) to measure its cost
 template <int K>
-__device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, int PPB, double* const* dst) {
+__device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, int PPB, double* const* dst, const int* wid,
+                                                    RedScratch scr) {
   extern __shared__ float4 red_smem[];
+  __shared__ unsigned int s_ticket;
   const int tid = threadIdx.x;
   int nparts, part;
   if (VL < 32 && (VL & (VL - 1)) == 0) {
@@ -122,26 +129,68 @@ __device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, in
     for (int k = 0; k < K; ++k) red_smem[(k * nparts + part) * VL + (tid % VL)] = acc[k];
   }
   __syncthreads();
+  const int C4 = 4 * VL;
   if (tid < VL) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (dst[k] == nullptr) continue;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      double sv[4] = {0, 0, 0, 0};
       for (int pp = 0; pp < nparts; ++pp) {
         const float4 t = red_smem[(k * nparts + pp) * VL + tid];
-        s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
+        sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
       }
-      atomicAdd(dst[k] + 4 * tid + 0, s0);
-      atomicAdd(dst[k] + 4 * tid + 1, s1);
-      atomicAdd(dst[k] + 4 * tid + 2, s2);
-      atomicAdd(dst[k] + 4 * tid + 3, s3);
+      if (g_dbg_noatom) continue;
+      if (scr.part != nullptr) {
+        double* pp = scr.part + (static_cast<size_t>(blockIdx.x) * K + k) * C4 + 4 * tid;
+        pp[0] = sv[0]; pp[1] = sv[1]; pp[2] = sv[2]; pp[3] = sv[3];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * tid + e < wid[k]) atomicAdd(dst[k] + (4 * tid + e) * kAccS, sv[e]);
+      }
     }
   }
+  if (scr.part == nullptr || g_dbg_noatom) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(scr.counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  for (int idx = tid; idx < K * C4; idx += blockDim.x) {
+    const int k = idx / C4, c = idx - k * C4;
+    if (dst[k] == nullptr || c >= wid[k]) continue;
+    const double* src = scr.part + static_cast<size_t>(k) * C4 + c;
+    const size_t bstride = static_cast<size_t>(K) * C4;
+    double sum = 0.0;
+    for (unsigned int bb = 0; bb < gridDim.x; ++bb) sum += src[bb * bstride];
+    dst[k][c * kAccS] += sum;
+  }
+  if (tid == 0) *scr.counter = 0u;
 }
+static RedScratch g_scr_main = {nullptr, nullptr}, g_scr_side = {nullptr, nullptr};
+static cudaStream_t g_side_stream = nullptr;
+void kernels_set_scratch(RedScratch main_scr, RedScratch side_scr, cudaStream_t side_stream) {
+  g_scr_main = main_scr; g_scr_side = side_scr; g_side_stream = side_stream;
+}
+static RedScratch pick_scratch(cudaStream_t s) {
+  return (g_side_stream != nullptr && s == g_side_stream) ? g_scr_side : g_scr_main;
+}
+size_t kernels_scratch_doubles() { return static_cast<size_t>(148 * 8) * 6 * 136; }
 static size_t red_bytes(const VecGeom& g, int K) { return static_cast<size_t>(K) * g.threads * sizeof(float4); }
+static void dbg_init_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (getenv("DIP_DBG_NOATOM") != nullptr) {
+    const int one = 1;
+    cudaMemcpyToSymbol(g_dbg_noatom, &one, sizeof(int));
+  }
+}
 // Grid-stride kernels get exactly one resident wave (no tail wave): blocks = min(needed, SMs * occupancy).
 template <class Kern>
 static void fit_grid(VecGeom& g, Kern kernel, size_t smem) {
+  dbg_init_once();
   static std::map<std::pair<const void*, int>, int> cache;
   const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), g.threads);
   auto it = cache.find(key);
@@ -215,7 +264,7 @@ __device__ __forceinline__ void item_loop(int first, int stride, int n, Load loa
 
 // ------------------------------------------------------------------------------------------------ channel_stats
 __global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__ x, int ld, int VL, int PPB, int npix,
-                                                       double* __restrict__ fwd, int C) {
+                                                       double* __restrict__ fwd, int C, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   float4 acc[2] = {f4zero(), f4zero()};
   item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, npix,
@@ -224,13 +273,14 @@ __global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__
                  acc[0] = f4add(acc[0], t);
                  acc[1] = f4mla(t, t, acc[1]);
                });
-  double* const dst[2] = {fwd, fwd + C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst);
+  double* const dst[2] = {fwd, fwd + C * kAccS};
+  const int wid[2] = {C, C};
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
 }
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s) {
   VecGeom g = vec_geom(C, npix);
   fit_grid(g, k_channel_stats, red_bytes(g, 2));
-  k_channel_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(x, ld, g.VL, g.PPB, npix, fwd, C);
+  k_channel_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(x, ld, g.VL, g.PPB, npix, fwd, C, pick_scratch(s));
 }
 
 // ------------------------------------------------------------------------------------------------ bn_act_write
@@ -343,7 +393,7 @@ __device__ __forceinline__ void cat_quad(const CatArgs& a, const CatLane& l, int
   }
 }
 
-__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
+__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
@@ -358,13 +408,14 @@ __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB
       acc[1] = f4mla(q[e], q[e], acc[1]);
     }
   }
-  double* const dst[2] = {fwd, fwd + (a.Cu + a.Cs)};
-  block_reduce_atomic<2>(acc, VL, PPB, dst);
+  double* const dst[2] = {fwd, fwd + (a.Cu + a.Cs) * kAccS};
+  const int wid[2] = {a.Cu + a.Cs, a.Cu + a.Cs};
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
 }
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_stats, red_bytes(g, 2));
-  k_cat_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, fwd_cat, g.VL, g.PPB);
+  k_cat_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, fwd_cat, g.VL, g.PPB, pick_scratch(s));
 }
 
 // store the value of interior pixel (i, j) at its padded position and at every halo position that mirrors it
@@ -527,7 +578,7 @@ void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, f
 }
 template <int KIND>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
-                                                       int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+                                                       int H, int W, double* __restrict__ bwd, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
@@ -548,8 +599,9 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
         acc[0] = f4add(acc[0], dz);
         acc[1] = f4mla(dz, bn_xhat(cf, it.x), acc[1]);
       });
-  double* const dst[2] = {bwd, bwd + bn.C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst);
+  double* const dst[2] = {bwd, bwd + bn.C * kAccS};
+  const int wid[2] = {bn.C, bn.C};
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
 }
 void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
                           cudaStream_t s) {
@@ -559,10 +611,10 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_reduce<1>, sm);
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_reduce<2>, sm);
   else fit_grid(g, k_bn_bwd_reduce<3>, sm);
-  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
-  else k_bn_bwd_reduce<3><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  else k_bn_bwd_reduce<3><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
 }
 
 // apply pass; for the head source (KIND 3) it also accumulates the head's own gradients:
@@ -570,16 +622,16 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
 template <int KIND>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                       int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
-                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
+                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
   const int C = bn.C;
   float4 m1, m2;
-  m1.x = static_cast<float>(bwd[4 * v + 0] * bn.inv_n); m1.y = static_cast<float>(bwd[4 * v + 1] * bn.inv_n);
-  m1.z = static_cast<float>(bwd[4 * v + 2] * bn.inv_n); m1.w = static_cast<float>(bwd[4 * v + 3] * bn.inv_n);
-  m2.x = static_cast<float>(bwd[C + 4 * v + 0] * bn.inv_n); m2.y = static_cast<float>(bwd[C + 4 * v + 1] * bn.inv_n);
-  m2.z = static_cast<float>(bwd[C + 4 * v + 2] * bn.inv_n); m2.w = static_cast<float>(bwd[C + 4 * v + 3] * bn.inv_n);
+  m1.x = static_cast<float>(bwd[(4 * v + 0) * kAccS] * bn.inv_n); m1.y = static_cast<float>(bwd[(4 * v + 1) * kAccS] * bn.inv_n);
+  m1.z = static_cast<float>(bwd[(4 * v + 2) * kAccS] * bn.inv_n); m1.w = static_cast<float>(bwd[(4 * v + 3) * kAccS] * bn.inv_n);
+  m2.x = static_cast<float>(bwd[(C + 4 * v + 0) * kAccS] * bn.inv_n); m2.y = static_cast<float>(bwd[(C + 4 * v + 1) * kAccS] * bn.inv_n);
+  m2.z = static_cast<float>(bwd[(C + 4 * v + 2) * kAccS] * bn.inv_n); m2.w = static_cast<float>(bwd[(C + 4 * v + 3) * kAccS] * bn.inv_n);
   constexpr int K = KIND == 3 ? 6 : 1;
   float4 acc[K];
 #pragma unroll
@@ -617,23 +669,15 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
         acc[0] = f4add(acc[0], dx);
       });
   if constexpr (KIND == 3) {
-    double* const dst[K] = {dbias, src.dwh, src.nh > 1 ? src.dwh + C : nullptr, src.nh > 2 ? src.dwh + 2 * C : nullptr,
-                            src.nh > 3 ? src.dwh + 3 * C : nullptr, nullptr};
-    block_reduce_atomic<K>(acc, VL, PPB, dst);
-    // acc[5] (db_head, lanes v == 0 only) was staged in red_smem: slot layout (k * nparts + part) * VL + v
-    if (threadIdx.x == 0) {
-      extern __shared__ float4 red_smem[];
-      const int nparts = (VL < 32 && (VL & (VL - 1)) == 0) ? (blockDim.x >> 5) : PPB;
-      double sv[4] = {0, 0, 0, 0};
-      for (int pp = 0; pp < nparts; ++pp) {
-        const float4 t = red_smem[(5 * nparts + pp) * VL];
-        sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
-      }
-      for (int k = 0; k < src.nh; ++k) atomicAdd(src.dbh + k, sv[k]);
-    }
+    double* const dst[K] = {dbias, src.dwh, src.nh > 1 ? src.dwh + C * kAccS : nullptr,
+                            src.nh > 2 ? src.dwh + 2 * C * kAccS : nullptr, src.nh > 3 ? src.dwh + 3 * C * kAccS : nullptr, src.dbh};
+    // acc[5] (db_head) is non-zero on lanes v == 0 only: its 4 leading "channels" are the per-output bias gradients
+    const int wid[K] = {C, C, C, C, C, src.nh};
+    block_reduce_atomic<K>(acc, VL, PPB, dst, wid, scr);
   } else {
     double* const dst[1] = {dbias};
-    block_reduce_atomic<K>(acc, VL, PPB, dst);
+    const int wid[1] = {C};
+    block_reduce_atomic<K>(acc, VL, PPB, dst, wid, scr);
   }
 }
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
@@ -643,10 +687,10 @@ void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSr
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_apply<1>, red_bytes(g, 1));
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_apply<2>, red_bytes(g, 1));
   else fit_grid(g, k_bn_bwd_apply<3>, red_bytes(g, 6));
-  if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else k_bn_bwd_apply<3><<<g.blocks, g.threads, red_bytes(g, 6), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  else k_bn_bwd_apply<3><<<g.blocks, g.threads, red_bytes(g, 6), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
@@ -662,8 +706,8 @@ __device__ __forceinline__ CatBwdCoef cat_bwd_coef(const BnRef& bn, int v) {
   for (int e = 0; e < 4; ++e) {
     const int c = 4 * v + e;
     const int ct = (c + bn.rot) % bn.C;
-    const double m = bn.fwd[c] * static_cast<double>(bn.inv_n);
-    double var = bn.fwd[bn.C + c] * static_cast<double>(bn.inv_n) - m * m;
+    const double m = bn.fwd[c * kAccS] * static_cast<double>(bn.inv_n);
+    double var = bn.fwd[(bn.C + c) * kAccS] * static_cast<double>(bn.inv_n) - m * m;
     if (var < 0.0) var = 0.0;
     const float g = bn.gamma[ct];
     b[e] = bn.beta[ct];
@@ -681,7 +725,7 @@ __device__ __forceinline__ float4 cat_xhat(const CatBwdCoef& c, float4 y) {
                      (y.w - c.beta.w) * c.inv_gamma.w);
 }
 __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
-                                                        int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+                                                        int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int Wp = W + 2;
@@ -698,14 +742,15 @@ __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict_
                  acc[0] = f4add(acc[0], it.g);
                  acc[1] = f4mla(it.g, cat_xhat(cf, it.x), acc[1]);
                });
-  double* const dst[2] = {bwd, bwd + bn_cat.C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst);
+  double* const dst[2] = {bwd, bwd + bn_cat.C * kAccS};
+  const int wid[2] = {bn_cat.C, bn_cat.C};
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
 }
 void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, double* bwd,
                            cudaStream_t s) {
   VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_reduce, red_bytes(g, 2));
-  k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB);
+  k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
 }
 __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
                                                        int ld, int H, int W, const double* __restrict__ bwd,
@@ -715,10 +760,10 @@ __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__
   const int C = bn_cat.C;
   const int Wp = W + 2;
   float4 m1, m2;
-  m1.x = static_cast<float>(bwd[4 * v + 0] * bn_cat.inv_n); m1.y = static_cast<float>(bwd[4 * v + 1] * bn_cat.inv_n);
-  m1.z = static_cast<float>(bwd[4 * v + 2] * bn_cat.inv_n); m1.w = static_cast<float>(bwd[4 * v + 3] * bn_cat.inv_n);
-  m2.x = static_cast<float>(bwd[C + 4 * v + 0] * bn_cat.inv_n); m2.y = static_cast<float>(bwd[C + 4 * v + 1] * bn_cat.inv_n);
-  m2.z = static_cast<float>(bwd[C + 4 * v + 2] * bn_cat.inv_n); m2.w = static_cast<float>(bwd[C + 4 * v + 3] * bn_cat.inv_n);
+  m1.x = static_cast<float>(bwd[(4 * v + 0) * kAccS] * bn_cat.inv_n); m1.y = static_cast<float>(bwd[(4 * v + 1) * kAccS] * bn_cat.inv_n);
+  m1.z = static_cast<float>(bwd[(4 * v + 2) * kAccS] * bn_cat.inv_n); m1.w = static_cast<float>(bwd[(4 * v + 3) * kAccS] * bn_cat.inv_n);
+  m2.x = static_cast<float>(bwd[(C + 4 * v + 0) * kAccS] * bn_cat.inv_n); m2.y = static_cast<float>(bwd[(C + 4 * v + 1) * kAccS] * bn_cat.inv_n);
+  m2.z = static_cast<float>(bwd[(C + 4 * v + 2) * kAccS] * bn_cat.inv_n); m2.w = static_cast<float>(bwd[(C + 4 * v + 3) * kAccS] * bn_cat.inv_n);
   item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
                [&](int p) {
                  RedItem it;
@@ -765,7 +810,7 @@ void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bil
 // VL = C/4 lanes per pixel (power of two <= 32); warp-shuffle reduction over the pixel's lanes.
 __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
                                                     const float* __restrict__ b, int C, int N, int H, int W,
-                                                    float* __restrict__ y, int mode, double* __restrict__ stats) {
+                                                    float* __restrict__ y, int mode, double* __restrict__ stats, RedScratch scr) {
   const int VL = C / 4;
   const int PPB = 256 / VL;
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
@@ -809,23 +854,11 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
     }
   }
   if (stats != nullptr) {
-    // only lanes v == 0 hold data; fold across the block
-    __shared__ float4 sm1[8], sm2[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 = f4add(s1, shfl_xor4(s1, o));
-      s2 = f4add(s2, shfl_xor4(s2, o));
-    }
-    if ((threadIdx.x & 31) == 0) { sm1[threadIdx.x >> 5] = s1; sm2[threadIdx.x >> 5] = s2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-      for (int k = 0; k < 8; ++k) {
-        a[0] += sm1[k].x; a[1] += sm1[k].y; a[2] += sm1[k].z; a[3] += sm1[k].w;
-        q[0] += sm2[k].x; q[1] += sm2[k].y; q[2] += sm2[k].z; q[3] += sm2[k].w;
-      }
-      for (int n = 0; n < N; ++n) { atomicAdd(stats + n, a[n]); atomicAdd(stats + N + n, q[n]); }
-    }
+    // only lanes v == 0 hold data; treat every thread as a slot of one 4-channel group (VL = 1)
+    float4 acc2[2] = {s1, s2};
+    double* const dst[2] = {stats, stats + N * kAccS};
+    const int wid[2] = {N, N};
+    block_reduce_atomic<2>(acc2, 1, 256, dst, wid, scr);
   }
 }
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
@@ -833,12 +866,12 @@ void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const 
   const int PPB = 256 / (C / 4);
   long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
   if (nb > 148 * 8) nb = 148 * 8;
-  k_skinny_fwd<<<static_cast<int>(nb), 256, 0, s>>>(x, ldx, x_rs, w, b, C, N, H, W, y, mode, stats);
+  k_skinny_fwd<<<static_cast<int>(nb), 256, 2 * 8 * sizeof(float4), s>>>(x, ldx, x_rs, w, b, C, N, H, W, y, mode, stats, pick_scratch(s));
 }
 
 __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
                              int H, int W, const float* __restrict__ dy, const float* __restrict__ out_nchw, int mode,
-                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB) {
+                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const int npix = H * W;
   float4 wv[4];
@@ -880,18 +913,10 @@ __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, con
                    st4(dx + static_cast<size_t>(p) * C + 4 * v, d);
                  }
                });
-  double* const dst[5] = {dw, N > 1 ? dw + C : nullptr, N > 2 ? dw + 2 * C : nullptr, N > 3 ? dw + 3 * C : nullptr, nullptr};
-  block_reduce_atomic<5>(acc, VL, PPB, dst);
-  if (threadIdx.x == 0 && db != nullptr) {
-    extern __shared__ float4 red_smem[];
-    const int nparts = (VL < 32 && (VL & (VL - 1)) == 0) ? (blockDim.x >> 5) : PPB;
-    double sv[4] = {0, 0, 0, 0};
-    for (int pp = 0; pp < nparts; ++pp) {
-      const float4 t = red_smem[(4 * nparts + pp) * VL];
-      sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
-    }
-    for (int n = 0; n < N; ++n) atomicAdd(db + n, sv[n]);
-  }
+  double* const dst[5] = {dw, N > 1 ? dw + C * kAccS : nullptr, N > 2 ? dw + 2 * C * kAccS : nullptr,
+                          N > 3 ? dw + 3 * C * kAccS : nullptr, db};
+  const int wid[5] = {C, C, C, C, N};  // acc[4] (bias gradient) lives on lanes v == 0 only
+  block_reduce_atomic<5>(acc, VL, PPB, dst, wid, scr);
 }
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
@@ -899,7 +924,7 @@ void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C,
   VecGeom g = vec_geom(C, static_cast<long long>(H) * W);
   fit_grid(g, k_skinny_bwd, red_bytes(g, 5));
   k_skinny_bwd<<<g.blocks, g.threads, red_bytes(g, 5), s>>>(x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
-                                                             g.VL, g.PPB);
+                                                             g.VL, g.PPB, pick_scratch(s));
 }
 
 // ------------------------------------------------------------------------------------------------ MSE loss
@@ -977,7 +1002,7 @@ void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_noise<<<blocks, 256, 0, s>>>(z0, z, sigma, seed, offset, it_dev, n4);
 }
-__global__ void k_advance(int* it) { *it += 1; }
+__global__ void k_advance(int* it) { it[0] += 1; it[1] += 1; }  // {global Adam step, iteration index of this call}
 void launch_advance(int* it_dev, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(it_dev); }
 
 // ------------------------------------------------------------------------------------------------ weight packing

@@ -21,7 +21,7 @@ for patch in ("1", "0"):
     else: os.environ.pop("DIP_NO_PATCH", None)
     for flags, name in ((0, "baseline"), (4, "no epilogue"), (1, "no A loads"), (2, "no B loads"), (3, "no loads"), (8, "no MMAs"), (12, "no MMA, no epilogue"), (7, "only MMAs")):
         os.environ["DIP_DBG_FLAGS"] = str(flags)
-        stats = torch.zeros(256, dtype=torch.float64, device="cuda")
+        stats = torch.zeros(256 * 16, dtype=torch.float64, device="cuda")
         t3 = timeit(lambda: de.op_conv_fprop(a, w, b, 3, 1, 0, 0, H, W, rot=4, stats=stats))
         t3n = timeit(lambda: de.op_conv_fprop(a, w, b, 3, 1, 0, 0, H, W, rot=4, stats=None))
         t1 = timeit(lambda: de.op_conv_fprop(a1, w1, b, 1, 1, 0, 0, H, W, stats=stats))

@@ -252,4 +252,5 @@ def test_run_iterations_decreases_loss():
     de.run_iterations(plan, adam, z0.cuda(), target.cuda(), None, 1. / 30, 7, 40, 0.01, out=out, loss_hist=hist)
     torch.cuda.synchronize()
     h = hist.cpu().numpy()
-    assert np.all(np.isfinite(h)) and h[-5:].mean() < h[:5].mean()
+    assert np.all(np.isfinite(h)) and np.all(h > 0) and h[-5:].mean() < h[:5].mean()
+    assert h.max() < 1.0   # one loss per slot (not an accumulated sum)
