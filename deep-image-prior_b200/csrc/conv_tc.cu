@@ -12,6 +12,7 @@
 //   tc_wgrad_kernel : weight gradient, both operands MN-major straight from NHWC activations, split-K over CTAs.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include "kernels.cuh"
 
 namespace dip {
 
@@ -19,7 +20,7 @@ static constexpr int kTileM = 128;            // output pixels per tile (UMMA M)
 static constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 32 fp32
 static constexpr int kChunkBytes = kTileM * 128;
 static constexpr int kNumThreads = 256;
-static constexpr int kAccStride = 16;  // fp64 accumulators: one per 128-byte line (kAccS in kernels.cuh)
+static constexpr int kAccStride = kAccS;  // fp64 accumulators: kAccR replicas x one 128-byte line each (kernels.cuh)
 
 struct SmemCtl {
   uint64_t full[8];
@@ -385,8 +386,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.stats != nullptr && et < p.n_mma && et < p.stats_ld) {
-      atomicAdd(&p.stats[et * kAccStride], stat_s1);
-      atomicAdd(&p.stats[(p.stats_ld + et) * kAccStride], stat_s2);
+      const int rep = (blockIdx.x % kAccR) * kAccLine;
+      atomicAdd(&p.stats[et * kAccStride + rep], stat_s1);
+      atomicAdd(&p.stats[(p.stats_ld + et) * kAccStride + rep], stat_s2);
     }
     if (et == 0) tma_store_wait_all0();
   }

@@ -354,7 +354,7 @@ struct CvtEntry {
 };
 __global__ void k_cvt_table(const CvtEntry* __restrict__ tab) {
   const CvtEntry e = tab[blockIdx.x];
-  for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)e.src[(size_t)i * kAccS];
+  for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)acc_get(e.src + (size_t)i * kAccS);
 }
 struct RunEntry {
   const double* fwd; float* rm; float* rv; void* nb; int C, rot; float n; int nb_is_float;
@@ -364,8 +364,8 @@ __global__ void k_running_table(const RunEntry* __restrict__ tab) {
   if (e.rm == nullptr) return;
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
     const int ct = (c + e.rot) % e.C;
-    const double m = e.fwd[c * kAccS] / e.n;
-    double var = e.fwd[(e.C + c) * kAccS] / e.n - m * m;
+    const double m = acc_get(e.fwd + c * kAccS) / e.n;
+    double var = acc_get(e.fwd + (e.C + c) * kAccS) / e.n - m * m;
     if (var < 0) var = 0;
     const double unb = e.n > 1.f ? var * e.n / (e.n - 1.0) : var;
     e.rm[ct] = 0.9f * e.rm[ct] + 0.1f * (float)m;

@@ -9,8 +9,21 @@ namespace dip {
 static constexpr float kBnEps = 1e-5f;
 static constexpr float kLreluSlope = 0.2f;
 // fp64 accumulators are spread one per 128-byte line (stride in doubles): hundreds of blocks add to them at the end of
-// every reduction kernel, and neighbouring channels must not share an L2 atomic unit
-static constexpr int kAccS = 16;
+// every reduction kernel: neighbouring channels must not share an L2 atomic unit, and each accumulator is split into
+// kAccR replicas (same-address atomics serialise) that readers add up
+static constexpr int kAccLine = 16;            // one 128-byte line
+#ifndef DIP_ACC_R
+#define DIP_ACC_R 1
+#endif
+static constexpr int kAccR = DIP_ACC_R;        // replicas per accumulator (block b adds to replica b % kAccR)
+static constexpr int kAccS = kAccLine * kAccR; // stride between consecutive accumulators, in doubles
+// value of the accumulator whose replica 0 is *p
+__host__ __device__ inline double acc_get(const double* p) {
+  double s = p[0];
+#pragma unroll
+  for (int r = 1; r < kAccR; ++r) s += p[r * kAccLine];
+  return s;
+}
 
 // Statistics of one BatchNorm layer: fp64 accumulators, zeroed once per iteration.
 //   fwd[0..C)   sum x          fwd[C..2C)   sum x^2

@@ -12,11 +12,14 @@
 //   mse / adam / noise: torch.nn.MSELoss, torch.optim.Adam.step, noise.normal_()  (common_utils.py:225-230)
 #include "kernels.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
 #include <map>
 #include <utility>
+
+namespace cg = cooperative_groups;
 
 namespace dip {
 
@@ -49,27 +52,48 @@ __device__ __forceinline__ float4 shfl_xor4(float4 a, int o) {
 struct Bn4 {
   float4 mean, rstd, scale, shift;
 };
+// Block-cooperative: thread c (< C) evaluates channel c once in fp64 (sum of the accumulator replicas -> mean, rstd),
+// the coefficients are broadcast through shared memory as float4s.  Every thread of the block must call it (barrier);
+// TAG distinguishes the static buffers when a kernel needs two BatchNorms.  v < 0: this thread needs no coefficients.
+template <int TAG>
 __device__ __forceinline__ Bn4 bn_coef(const BnRef& bn, int v) {
-  float mean[4], rstd[4], g[4], b[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int c = 4 * v + e;
+  __shared__ __align__(16) float s_mean[136], s_rstd[136], s_scale[136], s_shift[136];
+  for (int c = threadIdx.x; c < bn.C; c += blockDim.x) {
     const int ct = (c + bn.rot) % bn.C;
-    const double m = bn.fwd[c * kAccS] * static_cast<double>(bn.inv_n);
-    double var = bn.fwd[(bn.C + c) * kAccS] * static_cast<double>(bn.inv_n) - m * m;
+    const double m = acc_get(bn.fwd + c * kAccS) * static_cast<double>(bn.inv_n);
+    double var = acc_get(bn.fwd + (bn.C + c) * kAccS) * static_cast<double>(bn.inv_n) - m * m;
     if (var < 0.0) var = 0.0;
-    mean[e] = static_cast<float>(m);
-    rstd[e] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
-    g[e] = bn.gamma[ct];
-    b[e] = bn.beta[ct];
+    const float mean = static_cast<float>(m);
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+    const float sc = bn.gamma[ct] * rstd;
+    s_mean[c] = mean;
+    s_rstd[c] = rstd;
+    s_scale[c] = sc;
+    s_shift[c] = bn.beta[ct] - mean * sc;
   }
+  __syncthreads();
   Bn4 r;
-  r.mean = make_float4(mean[0], mean[1], mean[2], mean[3]);
-  r.rstd = make_float4(rstd[0], rstd[1], rstd[2], rstd[3]);
-  r.scale = make_float4(g[0] * rstd[0], g[1] * rstd[1], g[2] * rstd[2], g[3] * rstd[3]);
-  r.shift = make_float4(b[0] - mean[0] * r.scale.x, b[1] - mean[1] * r.scale.y, b[2] - mean[2] * r.scale.z,
-                        b[3] - mean[3] * r.scale.w);
+  if (v >= 0 && 4 * v + 3 < bn.C) {
+    r.mean = *reinterpret_cast<const float4*>(&s_mean[4 * v]);
+    r.rstd = *reinterpret_cast<const float4*>(&s_rstd[4 * v]);
+    r.scale = *reinterpret_cast<const float4*>(&s_scale[4 * v]);
+    r.shift = *reinterpret_cast<const float4*>(&s_shift[4 * v]);
+  } else {
+    r.mean = r.rstd = r.scale = r.shift = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   return r;
+}
+// means of the backward sums (sum dz / n, sum dz*xhat / n), block-cooperative like bn_coef
+template <int TAG>
+__device__ __forceinline__ void bwd_means(const double* __restrict__ bwd, int C, float inv_n, int v, float4& m1, float4& m2) {
+  __shared__ __align__(16) float s_m1[136], s_m2[136];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_m1[c] = static_cast<float>(acc_get(bwd + c * kAccS) * inv_n);
+    s_m2[c] = static_cast<float>(acc_get(bwd + (C + c) * kAccS) * inv_n);
+  }
+  __syncthreads();
+  m1 = *reinterpret_cast<const float4*>(&s_m1[4 * v]);
+  m2 = *reinterpret_cast<const float4*>(&s_m2[4 * v]);
 }
 __device__ __forceinline__ float4 bn_apply(const Bn4& c, float4 x) {
   return make_float4(fmaf(x.x, c.scale.x, c.shift.x), fmaf(x.y, c.scale.y, c.shift.y), fmaf(x.z, c.scale.z, c.shift.z),
@@ -130,26 +154,54 @@ __device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, in
   }
   __syncthreads();
   const int C4 = 4 * VL;
+  // Reduction kernels are launched as clusters of 8 blocks: the 8 per-block sums are combined through distributed
+  // shared memory and only block 0 of each cluster touches the global accumulators (8x fewer contended atomics).
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int cn = cluster.num_blocks();
+  double* dsum = reinterpret_cast<double*>(red_smem + static_cast<size_t>(K) * blockDim.x);  // [K][C4]
+  double sv[K][4];
   if (tid < VL) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      if (dst[k] == nullptr) continue;
-      double sv[4] = {0, 0, 0, 0};
+      sv[k][0] = sv[k][1] = sv[k][2] = sv[k][3] = 0.0;
       for (int pp = 0; pp < nparts; ++pp) {
         const float4 t = red_smem[(k * nparts + pp) * VL + tid];
-        sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
+        sv[k][0] += t.x; sv[k][1] += t.y; sv[k][2] += t.z; sv[k][3] += t.w;
       }
-      if (g_dbg_noatom) continue;
-      if (scr.part != nullptr) {
-        double* pp = scr.part + (static_cast<size_t>(blockIdx.x) * K + k) * C4 + 4 * tid;
-        pp[0] = sv[0]; pp[1] = sv[1]; pp[2] = sv[2]; pp[3] = sv[3];
-      } else {
+      if (cn > 1) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (4 * tid + e < wid[k]) atomicAdd(dst[k] + (4 * tid + e) * kAccS, sv[e]);
+        for (int e = 0; e < 4; ++e) dsum[k * C4 + 4 * tid + e] = sv[k][e];
       }
     }
   }
+  if (cn > 1) {
+    cluster.sync();
+    if (cluster.block_rank() == 0 && tid < VL) {
+      for (unsigned int r = 1; r < cn; ++r) {
+        const double* remote = cluster.map_shared_rank(dsum, r);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sv[k][e] += remote[k * C4 + 4 * tid + e];
+      }
+    }
+  }
+  if (tid < VL && (cn == 1 || cluster.block_rank() == 0)) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (dst[k] == nullptr) continue;
+      if (g_dbg_noatom) continue;
+      if (scr.part != nullptr) {
+        double* pp = scr.part + (static_cast<size_t>(blockIdx.x) * K + k) * C4 + 4 * tid;
+        pp[0] = sv[k][0]; pp[1] = sv[k][1]; pp[2] = sv[k][2]; pp[3] = sv[k][3];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * tid + e < wid[k]) atomicAdd(dst[k] + (4 * tid + e) * kAccS + (blockIdx.x % kAccR) * kAccLine, sv[k][e]);
+      }
+    }
+  }
+  if (cn > 1) cluster.sync();  // remote shared memory must stay alive until block 0 has read it
   if (scr.part == nullptr || g_dbg_noatom) return;
   __threadfence();
   __syncthreads();
@@ -177,7 +229,30 @@ static RedScratch pick_scratch(cudaStream_t s) {
   return (g_side_stream != nullptr && s == g_side_stream) ? g_scr_side : g_scr_main;
 }
 size_t kernels_scratch_doubles() { return static_cast<size_t>(148 * 8) * 6 * 136; }
-static size_t red_bytes(const VecGeom& g, int K) { return static_cast<size_t>(K) * g.threads * sizeof(float4); }
+static size_t red_bytes(const VecGeom& g, int K) {
+  return static_cast<size_t>(K) * g.threads * sizeof(float4) + static_cast<size_t>(K) * 4 * g.VL * sizeof(double);
+}
+// launch with thread-block clusters of 8 (grid rounded up; surplus blocks find no work)
+template <class... KArgs, class... Args>
+static void launch_cluster8(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t s, Args... args) {
+  if (blocks < 8 || getenv("DIP_CLUSTER_REDUCE") == nullptr) {  // measured slower than plain launches: off by default
+    kernel<<<blocks, threads, smem, s>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((blocks + 7) / 8 * 8);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 8;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 static void dbg_init_once() {
   static bool done = false;
   if (done) return;
@@ -280,7 +355,7 @@ __global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s) {
   VecGeom g = vec_geom(C, npix);
   fit_grid(g, k_channel_stats, red_bytes(g, 2));
-  k_channel_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(x, ld, g.VL, g.PPB, npix, fwd, C, pick_scratch(s));
+  launch_cluster8(k_channel_stats, g.blocks, g.threads, red_bytes(g, 2), s, x, ld, g.VL, g.PPB, npix, fwd, C, pick_scratch(s));
 }
 
 // ------------------------------------------------------------------------------------------------ bn_act_write
@@ -288,7 +363,7 @@ __global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ 
                                                       float* __restrict__ dst, int ld_out, int pad, int act, int VL,
                                                       int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
-  const Bn4 cf = bn_coef(bn, v);
+  const Bn4 cf = bn_coef<0>(bn, v);
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
   item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, Ho * Wo,
                [&](int p) {
@@ -313,7 +388,7 @@ void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, fl
 // BN + LeakyReLU + RGB head + sigmoid: one warp per pixel (C = 128 -> 32 lanes x float4), nothing but out is written.
 __global__ void __launch_bounds__(256) k_bn_act_head(const float* __restrict__ raw, BnRef bn, int npix, HeadRef head) {
   const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
-  const Bn4 cf = bn_coef(bn, lane);
+  const Bn4 cf = bn_coef<0>(bn, lane);
   float4 w[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = k < head.K ? ld4(head.w + k * 128 + 4 * lane) : f4zero();
@@ -353,7 +428,7 @@ struct CatLane {
 __device__ __forceinline__ CatLane cat_lane(const CatArgs& a, int v) {
   CatLane l;
   l.is_up = v < a.Cu / 4;
-  if (!l.is_up) l.bs = bn_coef(a.bn_s, v - a.Cu / 4);
+  l.bs = bn_coef<1>(a.bn_s, l.is_up ? -1 : v - a.Cu / 4);
   return l;
 }
 // out[0..3] = pre-BN concat values at (2si,2sj), (2si,2sj+1), (2si+1,2sj), (2si+1,2sj+1)
@@ -415,7 +490,7 @@ __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_stats, red_bytes(g, 2));
-  k_cat_stats<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(a, fwd_cat, g.VL, g.PPB, pick_scratch(s));
+  launch_cluster8(k_cat_stats, g.blocks, g.threads, red_bytes(g, 2), s, a, fwd_cat, g.VL, g.PPB, pick_scratch(s));
 }
 
 // store the value of interior pixel (i, j) at its padded position and at every halo position that mirrors it
@@ -436,7 +511,7 @@ __device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld,
 __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
-  const Bn4 cf = bn_coef(bn_cat, v);
+  const Bn4 cf = bn_coef<0>(bn_cat, v);
   const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   const int ld = a.Cu + a.Cs;
   for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
@@ -580,7 +655,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                        int H, int W, double* __restrict__ bwd, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
-  const Bn4 cf = bn_coef(bn, v);
+  const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
   float4 acc[2] = {f4zero(), f4zero()};
   item_loop<(KIND == 0 || KIND == 3) ? 4 : 2>(
@@ -611,10 +686,10 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_reduce<1>, sm);
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_reduce<2>, sm);
   else fit_grid(g, k_bn_bwd_reduce<3>, sm);
-  if (src.kind == 0) k_bn_bwd_reduce<0><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 1) k_bn_bwd_reduce<1><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 2) k_bn_bwd_reduce<2><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
-  else k_bn_bwd_reduce<3><<<g.blocks, g.threads, sm, s>>>(raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  if (src.kind == 0) launch_cluster8(k_bn_bwd_reduce<0>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 1) launch_cluster8(k_bn_bwd_reduce<1>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 2) launch_cluster8(k_bn_bwd_reduce<2>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  else launch_cluster8(k_bn_bwd_reduce<3>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
 }
 
 // apply pass; for the head source (KIND 3) it also accumulates the head's own gradients:
@@ -624,14 +699,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
                                                       float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB, RedScratch scr) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
-  const Bn4 cf = bn_coef(bn, v);
+  const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
   const int C = bn.C;
   float4 m1, m2;
-  m1.x = static_cast<float>(bwd[(4 * v + 0) * kAccS] * bn.inv_n); m1.y = static_cast<float>(bwd[(4 * v + 1) * kAccS] * bn.inv_n);
-  m1.z = static_cast<float>(bwd[(4 * v + 2) * kAccS] * bn.inv_n); m1.w = static_cast<float>(bwd[(4 * v + 3) * kAccS] * bn.inv_n);
-  m2.x = static_cast<float>(bwd[(C + 4 * v + 0) * kAccS] * bn.inv_n); m2.y = static_cast<float>(bwd[(C + 4 * v + 1) * kAccS] * bn.inv_n);
-  m2.z = static_cast<float>(bwd[(C + 4 * v + 2) * kAccS] * bn.inv_n); m2.w = static_cast<float>(bwd[(C + 4 * v + 3) * kAccS] * bn.inv_n);
+  bwd_means<0>(bwd, C, bn.inv_n, v, m1, m2);
   constexpr int K = KIND == 3 ? 6 : 1;
   float4 acc[K];
 #pragma unroll
@@ -687,10 +759,10 @@ void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSr
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_apply<1>, red_bytes(g, 1));
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_apply<2>, red_bytes(g, 1));
   else fit_grid(g, k_bn_bwd_apply<3>, red_bytes(g, 6));
-  if (src.kind == 0) k_bn_bwd_apply<0><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 1) k_bn_bwd_apply<1><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 2) k_bn_bwd_apply<2><<<g.blocks, g.threads, red_bytes(g, 1), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
-  else k_bn_bwd_apply<3><<<g.blocks, g.threads, red_bytes(g, 6), s>>>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  if (src.kind == 0) launch_cluster8(k_bn_bwd_apply<0>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 1) launch_cluster8(k_bn_bwd_apply<1>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  else if (src.kind == 2) launch_cluster8(k_bn_bwd_apply<2>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  else launch_cluster8(k_bn_bwd_apply<3>, g.blocks, g.threads, red_bytes(g, 6), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
@@ -701,23 +773,22 @@ struct CatBwdCoef {
   float4 beta, inv_gamma, scale;
 };
 __device__ __forceinline__ CatBwdCoef cat_bwd_coef(const BnRef& bn, int v) {
-  float b[4], ig[4], sc[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int c = 4 * v + e;
+  __shared__ __align__(16) float s_beta[136], s_ig[136], s_sc[136];
+  for (int c = threadIdx.x; c < bn.C; c += blockDim.x) {
     const int ct = (c + bn.rot) % bn.C;
-    const double m = bn.fwd[c * kAccS] * static_cast<double>(bn.inv_n);
-    double var = bn.fwd[(bn.C + c) * kAccS] * static_cast<double>(bn.inv_n) - m * m;
+    const double m = acc_get(bn.fwd + c * kAccS) * static_cast<double>(bn.inv_n);
+    double var = acc_get(bn.fwd + (bn.C + c) * kAccS) * static_cast<double>(bn.inv_n) - m * m;
     if (var < 0.0) var = 0.0;
     const float g = bn.gamma[ct];
-    b[e] = bn.beta[ct];
-    ig[e] = g != 0.f ? 1.f / g : 0.f;
-    sc[e] = g * static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+    s_beta[c] = bn.beta[ct];
+    s_ig[c] = g != 0.f ? 1.f / g : 0.f;
+    s_sc[c] = g * static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
   }
+  __syncthreads();
   CatBwdCoef r;
-  r.beta = make_float4(b[0], b[1], b[2], b[3]);
-  r.inv_gamma = make_float4(ig[0], ig[1], ig[2], ig[3]);
-  r.scale = make_float4(sc[0], sc[1], sc[2], sc[3]);
+  r.beta = *reinterpret_cast<const float4*>(&s_beta[4 * v]);
+  r.inv_gamma = *reinterpret_cast<const float4*>(&s_ig[4 * v]);
+  r.scale = *reinterpret_cast<const float4*>(&s_sc[4 * v]);
   return r;
 }
 __device__ __forceinline__ float4 cat_xhat(const CatBwdCoef& c, float4 y) {
@@ -750,7 +821,7 @@ void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int
                            cudaStream_t s) {
   VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_reduce, red_bytes(g, 2));
-  k_cat_bwd_reduce<<<g.blocks, g.threads, red_bytes(g, 2), s>>>(pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  launch_cluster8(k_cat_bwd_reduce, g.blocks, g.threads, red_bytes(g, 2), s, pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
 }
 __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
                                                        int ld, int H, int W, const double* __restrict__ bwd,
@@ -760,10 +831,7 @@ __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__
   const int C = bn_cat.C;
   const int Wp = W + 2;
   float4 m1, m2;
-  m1.x = static_cast<float>(bwd[(4 * v + 0) * kAccS] * bn_cat.inv_n); m1.y = static_cast<float>(bwd[(4 * v + 1) * kAccS] * bn_cat.inv_n);
-  m1.z = static_cast<float>(bwd[(4 * v + 2) * kAccS] * bn_cat.inv_n); m1.w = static_cast<float>(bwd[(4 * v + 3) * kAccS] * bn_cat.inv_n);
-  m2.x = static_cast<float>(bwd[(C + 4 * v + 0) * kAccS] * bn_cat.inv_n); m2.y = static_cast<float>(bwd[(C + 4 * v + 1) * kAccS] * bn_cat.inv_n);
-  m2.z = static_cast<float>(bwd[(C + 4 * v + 2) * kAccS] * bn_cat.inv_n); m2.w = static_cast<float>(bwd[(C + 4 * v + 3) * kAccS] * bn_cat.inv_n);
+  bwd_means<0>(bwd, C, bn_cat.inv_n, v, m1, m2);
   item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
                [&](int p) {
                  RedItem it;
@@ -866,7 +934,8 @@ void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const 
   const int PPB = 256 / (C / 4);
   long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
   if (nb > 148 * 8) nb = 148 * 8;
-  k_skinny_fwd<<<static_cast<int>(nb), 256, 2 * 8 * sizeof(float4), s>>>(x, ldx, x_rs, w, b, C, N, H, W, y, mode, stats, pick_scratch(s));
+  launch_cluster8(k_skinny_fwd, static_cast<int>(nb), 256, 2 * 256 * sizeof(float4) + 2 * 4 * sizeof(double), s, x, ldx, x_rs, w, b, C, N, H, W,
+                  y, mode, stats, pick_scratch(s));
 }
 
 __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
@@ -923,7 +992,7 @@ void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C,
                        cudaStream_t s) {
   VecGeom g = vec_geom(C, static_cast<long long>(H) * W);
   fit_grid(g, k_skinny_bwd, red_bytes(g, 5));
-  k_skinny_bwd<<<g.blocks, g.threads, red_bytes(g, 5), s>>>(x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
+  launch_cluster8(k_skinny_bwd, g.blocks, g.threads, red_bytes(g, 5), s, x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
                                                              g.VL, g.PPB, pick_scratch(s));
 }
 

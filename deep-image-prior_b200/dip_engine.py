@@ -11,7 +11,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdip.so")
+LIB_PATH = os.environ.get("DIP_LIB") or os.path.join(_HERE, "libdip.so")  # DIP_LIB: experiment builds
 
 PRECISION_TF32 = 0
 PRECISION_FP32 = 1

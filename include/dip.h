@@ -100,7 +100,8 @@ int dip_plan_get_timing_records(dip_plan* plan, int max_records, int* cls, doubl
  * Convolution of an NHWC fp32 tensor a[a_h][a_w][a_c] with torch OIHW weights w[N][C][k][k]:
  *   d[y][x][n] = bias[n] + sum a[y*stride+offy+r][x*stride+offx+s][c] * w[n][(c+rot)%C][r][s], out-of-range reads = 0.
  * scratch: device buffer of at least dip_op_scratch_bytes(). stats (nullable): 2*N fp64
- * accumulators (sum, sum^2), one per 128-byte line (element i at stats[16*i]), accumulated. */
+ * accumulators (sum, sum^2), accumulated: element i lives at stats[16*i] (one accumulator per 128-byte line, so the
+ * fp64 atomics of neighbouring channels never share an L2 line); the buffer holds 2*N*16 doubles. */
 size_t dip_op_scratch_bytes(void);
 int dip_op_conv_fprop(const void* a, int a_h, int a_w, int a_c, const void* w, const void* bias, int N, int C, int k,
                       int stride, int offx, int offy, int rot, void* d, int d_h, int d_w, double* stats,

@@ -59,7 +59,7 @@ def test_fprop(case, prec):
     assert err < TOL[prec]
     s1 = ref.sum((1, 2))
     s2 = (ref * ref).sum((1, 2))
-    st = stats[::16]
+    st = stats.view(256, 16)[:, 0]
     assert rel_err(st[:128], s1) < 10 * TOL[prec] + 1e-6 or (st[:128].cpu() - s1).abs().max() < 1e-2
     assert rel_err(st[128:], s2) < 10 * TOL[prec]
 
