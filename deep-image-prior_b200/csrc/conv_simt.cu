@@ -10,6 +10,7 @@ namespace dip {
 // Block: 16 consecutive output pixels of one row x all n_rows outputs (thread = output channel).
 static constexpr int kSimtPx = 16;
 __global__ void __launch_bounds__(160) k_simt_conv(SimtConvArgs a) {
+  pdl_enter();
   __shared__ __align__(16) float As[32][kSimtPx];  // [c][px]
   __shared__ float Ws[160][33];                    // [n][c] (+1 pad)
   const int n = threadIdx.x;
@@ -63,12 +64,13 @@ __global__ void __launch_bounds__(160) k_simt_conv(SimtConvArgs a) {
 }
 void launch_simt_conv(SimtConvArgs a, cudaStream_t s) {
   dim3 grid((a.d_w + kSimtPx - 1) / kSimtPx, a.d_h);
-  k_simt_conv<<<grid, 160, 0, s>>>(a);
+  launch_k(k_simt_conv, dim3(grid), dim3(160), 0, s, 1, a);
 }
 
 // partial[ks][tap][n][c] = sum over the rows of split ks of dY[y][x][n] * X[y*stride+offy+r][x*stride+offx+s][c]
 // Block: (tap, group of 8 output channels, split); thread = input channel c.
 __global__ void __launch_bounds__(160) k_simt_wgrad(SimtWgradArgs a) {
+  pdl_enter();
   const int tap = blockIdx.x, ng = blockIdx.y, ks = blockIdx.z;
   const int r = tap / a.kw, s = tap % a.kw;
   const int c = threadIdx.x;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(160) k_simt_wgrad(SimtWgradArgs a) {
 }
 void launch_simt_wgrad(SimtWgradArgs a, cudaStream_t s) {
   dim3 grid(a.kh * a.kw, 16, a.ksplits);
-  k_simt_wgrad<<<grid, 160, 0, s>>>(a);
+  launch_k(k_simt_wgrad, dim3(grid), dim3(160), 0, s, 1, a);
 }
 
 }  // namespace dip

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   const int tile0 = (blockIdx.x / csize) * csize + crank;  // first tile of this CTA; stride gridDim.x
   const uint32_t acc_cols = (p.n_mma + 31) & ~31;  // column stride between the two accumulators
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     tmem_alloc(&ctl->tmem_base, tmem_cols_pow2(2 * acc_cols));
     tmem_relinquish();
   }
+  pdl_wait();  // everything above is independent of the previous kernel's results
   if (warp == 3) {
     for (int i = lane; i < 160; i += 32) ctl->bias[i] = (p.bias != nullptr && i < p.n_mma) ? p.bias[i] : 0.f;
   }
@@ -141,8 +143,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                   // one box per tap; a box past the last tap is out of range -> zero-filled, never read
                   mbar_expect_tx(&ctl->full[stage], tps * b_bytes);
                   if (csize == 1) {
-                    tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
-                    if (tps == 2) tma_load_2d(sb + b_bytes, &p.tmB, &ctl->full[stage], kb * 32, (tap + 1) * p.n_mma);
+                    for (int t = 0; t < tps; ++t)
+                      tma_load_2d(sb + t * b_bytes, &p.tmB, &ctl->full[stage], kb * 32, (tap + t) * p.n_mma);
                   } else {
                     tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
                                    tap * p.n_mma + crank * b_rows, cmask);
@@ -228,32 +230,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
               if (!(p.dbg_flags & 128)) mbar_wait(&ctl->full[stage], phase);
               if (!(p.dbg_flags & 32)) tc_fence_after();
               const uint32_t b_lo = stage_lo0 + stage * stage_lo_step;
-              // A operand of tap (r, sx): the patch shifted by r rows and sx pixels
-              const uint32_t a_lo0 = row_lo + sx * 8;
-              if (++sx == p.kw) { sx = 0; row_lo += row_step; }
-              const uint32_t a_lo1 = row_lo + sx * 8;
-              const bool two = tps == 2 && tap + 1 < taps;
-              if (two) { if (++sx == p.kw) { sx = 0; row_lo += row_step; } }
+              // A operand of tap (r, sx): the patch shifted by r rows and sx pixels; up to 3 taps share this round
+              const int nt = min(tps, taps - tap);
+              uint32_t a_lo[3];
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+                a_lo[t] = row_lo + sx * 8;
+                if (t < nt && ++sx == p.kw) { sx = 0; row_lo += row_step; }
+              }
               if (elect_one()) {
                 if (!skip_mma || accf == 0) {
                   if (nmma == 4) {
-                    mma_tf32_lohi(tmem_d, a_lo0, ahi, b_lo, bhi, idesc, accf);
-                    mma_tf32_lohi(tmem_d, a_lo0 + 2, ahi, b_lo + 2, bhi, idesc, 1u);
-                    mma_tf32_lohi(tmem_d, a_lo0 + 4, ahi, b_lo + 4, bhi, idesc, 1u);
-                    mma_tf32_lohi(tmem_d, a_lo0 + 6, ahi, b_lo + 6, bhi, idesc, 1u);
-                    if (two) {
-                      const uint32_t b1 = b_lo + tap_lo_step;
-                      mma_tf32_lohi(tmem_d, a_lo1, ahi, b1, bhi, idesc, 1u);
-                      mma_tf32_lohi(tmem_d, a_lo1 + 2, ahi, b1 + 2, bhi, idesc, 1u);
-                      mma_tf32_lohi(tmem_d, a_lo1 + 4, ahi, b1 + 4, bhi, idesc, 1u);
-                      mma_tf32_lohi(tmem_d, a_lo1 + 6, ahi, b1 + 6, bhi, idesc, 1u);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                      if (t < nt) {
+                        const uint32_t bt = b_lo + t * tap_lo_step;
+                        mma_tf32_lohi(tmem_d, a_lo[t], ahi, bt, bhi, idesc, t == 0 ? accf : 1u);
+                        mma_tf32_lohi(tmem_d, a_lo[t] + 2, ahi, bt + 2, bhi, idesc, 1u);
+                        mma_tf32_lohi(tmem_d, a_lo[t] + 4, ahi, bt + 4, bhi, idesc, 1u);
+                        mma_tf32_lohi(tmem_d, a_lo[t] + 6, ahi, bt + 6, bhi, idesc, 1u);
+                      }
                     }
                   } else {
-                    for (int k = 0; k < nmma; ++k)
-                      mma_tf32_lohi(tmem_d, a_lo0 + 2 * (k & 3), ahi, b_lo + 2 * (k & 3), bhi, idesc, k > 0 ? 1u : accf);
-                    if (two)
+                    for (int t = 0; t < nt; ++t)
                       for (int k = 0; k < nmma; ++k)
-                        mma_tf32_lohi(tmem_d, a_lo1 + 2 * (k & 3), ahi, b_lo + tap_lo_step + 2 * (k & 3), bhi, idesc, 1u);
+                        mma_tf32_lohi(tmem_d, a_lo[t] + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi, idesc,
+                                      (t | k) > 0 ? 1u : accf);
                   }
                 }
                 if (!(p.dbg_flags & 64)) {
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   const int blk0 = static_cast<int>((static_cast<long long>(p.px_blocks) * ks) / p.ksplits);
   const int blk1 = static_cast<int>((static_cast<long long>(p.px_blocks) * (ks + 1)) / p.ksplits);
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmY);
     tma_prefetch_desc(&p.tmX);
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
     tmem_alloc(&ctl->tmem_base, ncols);
     tmem_relinquish();
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -593,30 +597,13 @@ cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
   if (grid > cap) grid = cap;
   const size_t smem = tc_conv_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
-  if (cs == 1) {
-    tc_conv_kernel<<<grid, kNumThreads, smem, s>>>(p);
-    return cudaGetLastError();
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tc_conv_kernel, p);
+  return launch_k(tc_conv_kernel, dim3(grid), dim3(kNumThreads), smem, s, cs, p);
 }
 
 cudaError_t tc_wgrad_launch(const TcWgradParams& p, cudaStream_t s) {
   const size_t smem = tc_wgrad_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
-  tc_wgrad_kernel<<<p.kh * p.ksplits, kNumThreads, smem, s>>>(p);
-  return cudaGetLastError();
+  return launch_k(tc_wgrad_kernel, dim3(p.kh * p.ksplits), dim3(kNumThreads), smem, s, 1, p);
 }
 
 }  // namespace dip

@@ -153,6 +153,20 @@ struct TimeScope {
 };
 
 // ------------------------------------------------------------------------------------------------ conv op
+// Filter taps per weight stage of the patch-mode convs: a barrier round costs the MMA-issuing thread a fixed ~0.2 us, so a
+// whole filter row (3 taps = 12 MMAs) per round when the stages fit, else 2 (env DIP_TPS overrides).
+static int pick_tps() {
+  if (const char* e = getenv("DIP_TPS")) { const int t = atoi(e); if (t >= 1 && t <= 3) return t; }
+  return 3;
+}
+static void fit_stages(TcConvParams& p) {
+  for (;;) {
+    p.stages = 6;
+    while (tc_conv_smem_bytes(p) > 232448 && p.stages > 2) p.stages--;
+    if (tc_conv_smem_bytes(p) <= 232448 || p.tps <= 1) return;
+    p.tps--;  // two stages of 3 taps do not fit (wide dgrad tiles): fall back to 2 taps per stage
+  }
+}
 struct ConvOp {
   Timer* timer = nullptr;
   double alg_flops() const { return 2.0 * out_h * out_w * 128.0 * C * k * k; }
@@ -209,7 +223,7 @@ struct ConvOp {
       DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
     }
     fp.csize = pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
-    fp.tps = (fp.patch && fp.csize == 1 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
+    fp.tps = (fp.patch && fp.csize == 1) ? pick_tps() : 1;
     DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
@@ -219,8 +233,7 @@ struct ConvOp {
     fp.tail_mmas = (C % 32 == 0) ? 4 : (C % 32 + 7) / 8;
     fp.n_mma = N; fp.n_chunks = N / 32;
     fp.bias = nullptr; fp.stats = stats; fp.stats_ld = N;
-    fp.stages = 6;
-    while (tc_conv_smem_bytes(fp) > 232448 && fp.stages > 2) fp.stages--;
+    fit_stages(fp);
     // ---- dgrad
     if (has_dgrad) {
       pick_tile(dg_out_w, dg_out_h, &bw, &bh);
@@ -233,7 +246,7 @@ struct ConvOp {
         DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
       }
       dg.csize = pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
-      dg.tps = (dg.patch && dg.csize == 1 && getenv("DIP_TPS1") == nullptr) ? 2 : 1;
+      dg.tps = (dg.patch && dg.csize == 1) ? pick_tps() : 1;
       DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, C, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
@@ -242,8 +255,7 @@ struct ConvOp {
       dg.kblocks = 4; dg.tail_mmas = 4;
       dg.n_mma = crows; dg.n_chunks = (crows + 31) / 32;
       dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
-      dg.stages = 6;
-      while (tc_conv_smem_bytes(dg) > 232448 && dg.stages > 2) dg.stages--;
+      fit_stages(dg);
     }
     // ---- wgrad
     wg = TcWgradParams{};
@@ -329,6 +341,7 @@ struct PackEntry {
   int N, C, k, rot, n_rows, c_pad, c_rows;
 };
 __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
+  pdl_enter();
   const PackEntry e = tab[blockIdx.y];
   const int taps = e.k * e.k;
   const long long nf = (long long)taps * e.n_rows * e.c_pad;
@@ -353,6 +366,7 @@ struct CvtEntry {
   const double* src; float* dst; int n, rot;
 };
 __global__ void k_cvt_table(const CvtEntry* __restrict__ tab) {
+  pdl_enter();
   const CvtEntry e = tab[blockIdx.x];
   for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)acc_get(e.src + (size_t)i * kAccS);
 }
@@ -360,6 +374,7 @@ struct RunEntry {
   const double* fwd; float* rm; float* rv; void* nb; int C, rot; float n; int nb_is_float;
 };
 __global__ void k_running_table(const RunEntry* __restrict__ tab) {
+  pdl_enter();
   const RunEntry e = tab[blockIdx.x];
   if (e.rm == nullptr) return;
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
@@ -448,7 +463,6 @@ struct dip_plan {
   std::vector<cudaEvent_t> wev;
   size_t wev_used = 0;
   bool side_on = false;
-  RedScratch scr_main{nullptr, nullptr}, scr_side{nullptr, nullptr};
   // tables
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
   int n_pack = 0, n_cvt = 0, n_run = 0;
@@ -617,10 +631,6 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->dl4 = A.get<float>((size_t)P->H * P->W * 4);
   P->loss_ring = A.get<double>(dip_plan::kLossRing);
-  P->scr_main.part = A.get<double>(kernels_scratch_doubles());
-  P->scr_side.part = A.get<double>(kernels_scratch_doubles());
-  P->scr_main.counter = A.get<unsigned int>(4);
-  P->scr_side.counter = A.get<unsigned int>(4);
   P->it_dev = A.get<int>(4);
   // ---- conv ops
   size_t partial_max = 0;
@@ -677,8 +687,6 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->d_run = A.get<RunEntry>(P->n_run);
   if (P->dry) return 0;
   // ---- device-side setup
-  DIP_CUDA(cudaMemset(P->scr_main.counter, 0, 16));
-  DIP_CUDA(cudaMemset(P->scr_side.counter, 0, 16));
   DIP_CUDA(cudaStreamCreateWithFlags(&P->wstream, cudaStreamNonBlocking));
   // The zero-stuffed buffers are written at even positions only: clear them once.
   for (int l = 1; l < L; ++l) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
@@ -779,13 +787,11 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
 static int plan_forward(dip_plan* P, const float* z, const float* noise, float sigma, float* out, cudaStream_t s) {
   if (!P->bound) return fail("dip_forward: parameters not bound (call dip_plan_bind)");
   // grid-wide reductions: fp64 atomics onto line-strided accumulators (default) or the deterministic last-block sum
-  if (getenv("DIP_LASTBLOCK") != nullptr) kernels_set_scratch(P->scr_main, P->scr_side, P->wstream);
-  else kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_fwd, 0, P->acc_fwd_n * sizeof(double), s));
   {
     dim3 grid((unsigned)((P->pack_max + 255) / 256 < 64 ? (P->pack_max + 255) / 256 : 64), P->n_pack);
-    k_pack_table<<<grid, 256, 0, s>>>(P->d_pack);
+    launch_k(k_pack_table, dim3(grid), dim3(256), 0, s, 1, P->d_pack);
   }
   Level& v0 = P->lv[0];
   launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s);
@@ -793,7 +799,7 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
   DIP_CHECK(fwd_level(P, 0, s, nl));
   if (out != nullptr && out != P->out_saved)
     DIP_CUDA(cudaMemcpyAsync(out, P->out_saved, (size_t)v0.H * v0.W * P->desc.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  k_running_table<<<P->n_run, 160, 0, s>>>(P->d_run);
+  launch_k(k_running_table, dim3(P->n_run), dim3(160), 0, s, 1, P->d_run);
   nl += 3;
   DIP_CUDA(cudaGetLastError());
   P->launches_fwd = nl;
@@ -897,8 +903,6 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
 
 static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   if (!P->bound) return fail("dip_backward: parameters not bound");
-  if (getenv("DIP_LASTBLOCK") != nullptr) kernels_set_scratch(P->scr_main, P->scr_side, P->wstream);
-  else kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
   P->side_on = getenv("DIP_NO_SIDE") == nullptr;
@@ -912,7 +916,7 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   nl += 1;
   DIP_CHECK(bwd_level(P, 0, sh, s, nl));
   join_side(P, s);
-  k_cvt_table<<<P->n_cvt, 128, 0, s>>>(P->d_cvt);
+  launch_k(k_cvt_table, dim3(P->n_cvt), dim3(128), 0, s, 1, P->d_cvt);
   nl += 1;
   DIP_CUDA(cudaGetLastError());
   P->launches_bwd = nl;
@@ -959,7 +963,6 @@ int dip_plan_create(const dip_net_desc* desc, int H, int W, void* workspace, siz
 }
 void dip_plan_destroy(dip_plan* plan) {
   if (plan == nullptr) return;
-  kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);  // never leave dangling scratch
   if (plan->gexec) cudaGraphExecDestroy(plan->gexec);
   if (plan->gstream) cudaStreamDestroy(plan->gstream);
   if (plan->gev_in) cudaEventDestroy(plan->gev_in);
@@ -1179,7 +1182,6 @@ int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {
 size_t dip_op_scratch_bytes(void) { return (size_t)96 << 20; }
 
 static int op_common(ConvOp& op, int N, int C, int k, int stride, int rot, float* scratch, const float* w, cudaStream_t s) {
-  kernels_set_scratch(RedScratch{nullptr, nullptr}, RedScratch{nullptr, nullptr}, nullptr);  // single ops: atomics path
   if (N != 128) return fail("dip_op_conv_*: N must be 128");
   if (C % 4 != 0 || C > 160) return fail("dip_op_conv_*: C must be a multiple of 4 and <= 160");
   op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;

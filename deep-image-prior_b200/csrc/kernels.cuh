@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace dip {
 
@@ -25,6 +26,46 @@ __host__ __device__ inline double acc_get(const double* p) {
   return s;
 }
 
+// Programmatic dependent launch: every kernel of the step calls pdl_trigger() first (the next kernel of the stream may
+// be scheduled as SMs drain) and pdl_wait() before it touches global memory (returns once the previous kernel has
+// completed and its writes are visible), so the launch latency and the prologue of kernel k+1 overlap the tail of k.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+#endif
+inline bool pdl_enabled() {
+  static const bool on = getenv("DIP_PDL") != nullptr;  // measured: no gain inside the CUDA graph (296 vs 299 it/s) -> opt-in
+  return on;
+}
+// kernel<<<grid, block, smem, s>>>(args...) with the programmatic-serialization attribute (and an optional cluster)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster,
+                            Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Statistics of one BatchNorm layer: fp64 accumulators, zeroed once per iteration.
 //   fwd[0..C)   sum x          fwd[C..2C)   sum x^2
 //   bwd[0..C)   sum dz         bwd[C..2C)   sum dz * xhat          (dz = grad wrt BN output)
@@ -45,15 +86,6 @@ struct HeadRef {
   int K;               // <= 4
   float* out;          // NCHW [K][H*W]
 };
-
-// Scratch of the grid-wide reductions: per-block partial sums + a ticket counter (zeroed once; self-resetting).
-// Two sets because the weight-gradient chain runs concurrently on a side stream.
-struct RedScratch {
-  double* part;            // [kernels_scratch_doubles()]
-  unsigned int* counter;
-};
-size_t kernels_scratch_doubles();
-void kernels_set_scratch(RedScratch main_scr, RedScratch side_scr, cudaStream_t side_stream);
 
 // z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,

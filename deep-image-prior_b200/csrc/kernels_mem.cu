@@ -12,14 +12,12 @@
 //   mse / adam / noise: torch.nn.MSELoss, torch.optim.Adam.step, noise.normal_()  (common_utils.py:225-230)
 #include "kernels.cuh"
 
-#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
 #include <map>
 #include <utility>
 
-namespace cg = cooperative_groups;
 
 namespace dip {
 
@@ -121,18 +119,16 @@ static VecGeom vec_geom(int C, long long nitems) {
   return g;
 }
 
-// Block reduction of K float4 accumulators over the item slots of the block, then a grid-wide sum into dst[k][c].
+// Block reduction of K float4 accumulators over the item slots of the block, then fp64 atomics into dst[k][c].
 // Threads are laid out tid = slot * VL + v.  For VL in {1,2,4,8,16} the lanes that share v are first folded with
-// warp shuffles (blockDim is then a multiple of 32).
-// Grid-wide step: fp64 atomics from every block cost ~0.5 ms per iteration (hundreds of blocks hammering the same 256
-// addresses at the end of a single-wave kernel), so each block stores its partial sums and the LAST block to finish
-// (ticket counter) adds them up in block order -- deterministic, no contention.  wid[k] = valid channels of dst[k].
-__constant__ int g_dbg_noatom = 0;  // experiment: skip the final accumulation (results wrong) to measure its cost
+// warp shuffles (blockDim is then a multiple of 32).  wid[k] = valid channels of dst[k].
+// The accumulators live one per 128-byte line (kAccS): hundreds of blocks add to the same 2*C addresses at the end of a
+// single-wave kernel, and neighbouring channels sharing an L2 atomic unit cost ~0.3 ms per iteration.  (Per-block
+// partials + last-block sum, cluster/DSMEM pre-reduction and replicated accumulators were all measured slower:
+// profiles/r01_experiments.md.)
 template <int K>
-__device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, int PPB, double* const* dst, const int* wid,
-                                                    RedScratch scr) {
+__device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, int PPB, double* const* dst, const int* wid) {
   extern __shared__ float4 red_smem[];
-  __shared__ unsigned int s_ticket;
   const int tid = threadIdx.x;
   int nparts, part;
   if (VL < 32 && (VL & (VL - 1)) == 0) {
@@ -153,119 +149,31 @@ __device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, in
     for (int k = 0; k < K; ++k) red_smem[(k * nparts + part) * VL + (tid % VL)] = acc[k];
   }
   __syncthreads();
-  const int C4 = 4 * VL;
-  // Reduction kernels are launched as clusters of 8 blocks: the 8 per-block sums are combined through distributed
-  // shared memory and only block 0 of each cluster touches the global accumulators (8x fewer contended atomics).
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned int cn = cluster.num_blocks();
-  double* dsum = reinterpret_cast<double*>(red_smem + static_cast<size_t>(K) * blockDim.x);  // [K][C4]
-  double sv[K][4];
-  if (tid < VL) {
+  // one (k, v) pair per thread (K <= PPB always): the column is summed in fp64 and added to the global accumulators
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      sv[k][0] = sv[k][1] = sv[k][2] = sv[k][3] = 0.0;
-      for (int pp = 0; pp < nparts; ++pp) {
-        const float4 t = red_smem[(k * nparts + pp) * VL + tid];
-        sv[k][0] += t.x; sv[k][1] += t.y; sv[k][2] += t.z; sv[k][3] += t.w;
-      }
-      if (cn > 1) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dsum[k * C4 + 4 * tid + e] = sv[k][e];
-      }
+  for (int k = 0; k < K; ++k) {
+    const int v = tid - k * VL;
+    if (v < 0 || v >= VL || dst[k] == nullptr) continue;
+    double sv[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int pp = 0; pp < nparts; ++pp) {
+      const float4 t = red_smem[(k * nparts + pp) * VL + v];
+      sv[0] += t.x; sv[1] += t.y; sv[2] += t.z; sv[3] += t.w;
     }
-  }
-  if (cn > 1) {
-    cluster.sync();
-    if (cluster.block_rank() == 0 && tid < VL) {
-      for (unsigned int r = 1; r < cn; ++r) {
-        const double* remote = cluster.map_shared_rank(dsum, r);
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sv[k][e] += remote[k * C4 + 4 * tid + e];
-      }
-    }
+    for (int e = 0; e < 4; ++e)
+      if (4 * v + e < wid[k]) atomicAdd(dst[k] + (4 * v + e) * kAccS + (blockIdx.x % kAccR) * kAccLine, sv[e]);
   }
-  if (tid < VL && (cn == 1 || cluster.block_rank() == 0)) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (dst[k] == nullptr) continue;
-      if (g_dbg_noatom) continue;
-      if (scr.part != nullptr) {
-        double* pp = scr.part + (static_cast<size_t>(blockIdx.x) * K + k) * C4 + 4 * tid;
-        pp[0] = sv[k][0]; pp[1] = sv[k][1]; pp[2] = sv[k][2]; pp[3] = sv[k][3];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (4 * tid + e < wid[k]) atomicAdd(dst[k] + (4 * tid + e) * kAccS + (blockIdx.x % kAccR) * kAccLine, sv[k][e]);
-      }
-    }
-  }
-  if (cn > 1) cluster.sync();  // remote shared memory must stay alive until block 0 has read it
-  if (scr.part == nullptr || g_dbg_noatom) return;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_ticket = atomicAdd(scr.counter, 1u);
-  __syncthreads();
-  if (s_ticket != gridDim.x - 1) return;
-  __threadfence();
-  for (int idx = tid; idx < K * C4; idx += blockDim.x) {
-    const int k = idx / C4, c = idx - k * C4;
-    if (dst[k] == nullptr || c >= wid[k]) continue;
-    const double* src = scr.part + static_cast<size_t>(k) * C4 + c;
-    const size_t bstride = static_cast<size_t>(K) * C4;
-    double sum = 0.0;
-    for (unsigned int bb = 0; bb < gridDim.x; ++bb) sum += src[bb * bstride];
-    dst[k][c * kAccS] += sum;
-  }
-  if (tid == 0) *scr.counter = 0u;
 }
-static RedScratch g_scr_main = {nullptr, nullptr}, g_scr_side = {nullptr, nullptr};
-static cudaStream_t g_side_stream = nullptr;
-void kernels_set_scratch(RedScratch main_scr, RedScratch side_scr, cudaStream_t side_stream) {
-  g_scr_main = main_scr; g_scr_side = side_scr; g_side_stream = side_stream;
-}
-static RedScratch pick_scratch(cudaStream_t s) {
-  return (g_side_stream != nullptr && s == g_side_stream) ? g_scr_side : g_scr_main;
-}
-size_t kernels_scratch_doubles() { return static_cast<size_t>(148 * 8) * 6 * 136; }
 static size_t red_bytes(const VecGeom& g, int K) {
-  return static_cast<size_t>(K) * g.threads * sizeof(float4) + static_cast<size_t>(K) * 4 * g.VL * sizeof(double);
+  return static_cast<size_t>(K) * g.threads * sizeof(float4);
 }
-// launch with thread-block clusters of 8 (grid rounded up; surplus blocks find no work)
 template <class... KArgs, class... Args>
-static void launch_cluster8(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t s, Args... args) {
-  if (blocks < 8 || getenv("DIP_CLUSTER_REDUCE") == nullptr) {  // measured slower than plain launches: off by default
-    kernel<<<blocks, threads, smem, s>>>(args...);
-    return;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((blocks + 7) / 8 * 8);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 8;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-static void dbg_init_once() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  if (getenv("DIP_DBG_NOATOM") != nullptr) {
-    const int one = 1;
-    cudaMemcpyToSymbol(g_dbg_noatom, &one, sizeof(int));
-  }
+static void launch_red(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t s, Args... args) {
+  launch_k(kernel, dim3(blocks), dim3(threads), smem, s, 1, args...);
 }
 // Grid-stride kernels get exactly one resident wave (no tail wave): blocks = min(needed, SMs * occupancy).
 template <class Kern>
 static void fit_grid(VecGeom& g, Kern kernel, size_t smem) {
-  dbg_init_once();
   static std::map<std::pair<const void*, int>, int> cache;
   const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), g.threads);
   auto it = cache.find(key);
@@ -284,6 +192,7 @@ static void fit_grid(VecGeom& g, Kern kernel, size_t smem) {
 // ------------------------------------------------------------------------------------------------ input_pad
 __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict__ noise, float sigma,
                             float* __restrict__ dst, int C, int H, int W) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int Wp = W + 2;
   const int yy = blockIdx.y;
@@ -314,7 +223,7 @@ __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
                       cudaStream_t s) {
   dim3 grid((W + 2 + 31) / 32, H + 2), block(32, 8);
-  k_input_pad<<<grid, block, 0, s>>>(z, noise, sigma, dst, C, H, W);
+  launch_k(k_input_pad, dim3(grid), dim3(block), 0, s, 1, z, noise, sigma, dst, C, H, W);
 }
 
 // ------------------------------------------------------------------------------------------------ item loop
@@ -339,7 +248,8 @@ __device__ __forceinline__ void item_loop(int first, int stride, int n, Load loa
 
 // ------------------------------------------------------------------------------------------------ channel_stats
 __global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__ x, int ld, int VL, int PPB, int npix,
-                                                       double* __restrict__ fwd, int C, RedScratch scr) {
+                                                       double* __restrict__ fwd, int C) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   float4 acc[2] = {f4zero(), f4zero()};
   item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, npix,
@@ -350,18 +260,19 @@ __global__ void __launch_bounds__(256) k_channel_stats(const float* __restrict__
                });
   double* const dst[2] = {fwd, fwd + C * kAccS};
   const int wid[2] = {C, C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s) {
   VecGeom g = vec_geom(C, npix);
   fit_grid(g, k_channel_stats, red_bytes(g, 2));
-  launch_cluster8(k_channel_stats, g.blocks, g.threads, red_bytes(g, 2), s, x, ld, g.VL, g.PPB, npix, fwd, C, pick_scratch(s));
+  launch_red(k_channel_stats, g.blocks, g.threads, red_bytes(g, 2), s, x, ld, g.VL, g.PPB, npix, fwd, C);
 }
 
 // ------------------------------------------------------------------------------------------------ bn_act_write
 __global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
                                                       float* __restrict__ dst, int ld_out, int pad, int act, int VL,
                                                       int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
@@ -382,11 +293,12 @@ void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, fl
                          int act, cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H + 2 * pad) * (W + 2 * pad));
   fit_grid(g, k_bn_act_write, 0);
-  k_bn_act_write<<<g.blocks, g.threads, 0, s>>>(raw, ld_in, bn, H, W, dst, ld_out, pad, act, g.VL, g.PPB);
+  launch_k(k_bn_act_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, raw, ld_in, bn, H, W, dst, ld_out, pad, act, g.VL, g.PPB);
 }
 
 // BN + LeakyReLU + RGB head + sigmoid: one warp per pixel (C = 128 -> 32 lanes x float4), nothing but out is written.
 __global__ void __launch_bounds__(256) k_bn_act_head(const float* __restrict__ raw, BnRef bn, int npix, HeadRef head) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
   const Bn4 cf = bn_coef<0>(bn, lane);
   float4 w[4];
@@ -415,7 +327,7 @@ void launch_bn_act_head(const float* raw, BnRef bn, int H, int W, HeadRef head, 
   const int npix = H * W;
   int blocks = (npix + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_bn_act_head<<<blocks, 256, 0, s>>>(raw, bn, npix, head);
+  launch_k(k_bn_act_head, dim3(blocks), dim3(256), 0, s, 1, raw, bn, npix, head);
 }
 
 // ------------------------------------------------------------------------------------------------ concat stage
@@ -468,7 +380,8 @@ __device__ __forceinline__ void cat_quad(const CatArgs& a, const CatLane& l, int
   }
 }
 
-__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB, RedScratch scr) {
+__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
@@ -485,12 +398,12 @@ __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB
   }
   double* const dst[2] = {fwd, fwd + (a.Cu + a.Cs) * kAccS};
   const int wid[2] = {a.Cu + a.Cs, a.Cu + a.Cs};
-  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_stats, red_bytes(g, 2));
-  launch_cluster8(k_cat_stats, g.blocks, g.threads, red_bytes(g, 2), s, a, fwd_cat, g.VL, g.PPB, pick_scratch(s));
+  launch_red(k_cat_stats, g.blocks, g.threads, red_bytes(g, 2), s, a, fwd_cat, g.VL, g.PPB);
 }
 
 // store the value of interior pixel (i, j) at its padded position and at every halo position that mirrors it
@@ -509,6 +422,7 @@ __device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld,
 }
 
 __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const Bn4 cf = bn_coef<0>(bn_cat, v);
@@ -526,7 +440,7 @@ __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, in
 void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_write, 0);
-  k_cat_write<<<g.blocks, g.threads, 0, s>>>(a, bn_cat, dst, g.VL, g.PPB);
+  launch_k(k_cat_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, a, bn_cat, dst, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ gradient sources
@@ -596,8 +510,7 @@ __device__ __forceinline__ SrcRegs src_regs(const GradSrc& s, int C, int v) {
 }
 // gradient w.r.t. the BN(+act) output at pixel p = (i, j); dl (kind 3) returns the head's logit gradients
 template <int KIND>
-__device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr, int H, int W, int p, int i, int j, int v,
-                                            float (&dl)[4]) {
+__device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr, int H, int W, int p, int i, int j, int v) {
   if (KIND == 0) return ld4(s.g + static_cast<size_t>(p) * s.ld + s.coff + 4 * v);
   if (KIND == 1) {
     float4 r = fold_read(s.g, s.ld, s.coff, H, W, i, j, v);
@@ -611,9 +524,11 @@ __device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr,
     return r;
   }
   if (KIND == 2) return upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
-  // KIND == 3: logit gradients precomputed per pixel (k_head_dlogit)
-  const float4 d = ld4(s.dl4 + static_cast<size_t>(p) * 4);
-  dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
+  // KIND == 3: the item carries the 4 logit gradients of the pixel (k_head_dlogit); head_grad() expands them when consumed
+  return ld4(s.dl4 + static_cast<size_t>(p) * 4);
+}
+// head source: gradient w.r.t. the last activation = sum_k dl[k] * w_head[k][c]
+__device__ __forceinline__ float4 head_grad(const SrcRegs& sr, float4 d) {
   float4 r = f4zero();
   r = f4fma(d.x, sr.w[0], r);
   r = f4fma(d.y, sr.w[1], r);
@@ -627,16 +542,14 @@ __device__ __forceinline__ float4 lrelu_bwd4(float4 y, float4 g) {
 }
 
 // ------------------------------------------------------------------------------------------------ BN(+LReLU) backward
-struct BwdItem {
-  float4 x, g;
-  float dl[4];
-};
 struct RedItem {
-  float4 x, g;
+  float4 x, g;  // raw conv output, gradient w.r.t. the BN(+act) output (head source: the pixel's logit gradients)
 };
+typedef RedItem BwdItem;
 // dl4[p] = dout[k][p] * o[k][p] * (1 - o[k][p]) for k < K (else 0): sigmoid' folded into the logit gradient once per pixel
 __global__ void k_head_dlogit(const float* __restrict__ dout, const float* __restrict__ outv, int K, int npix,
                               float* __restrict__ dl4) {
+  pdl_enter();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
     float d[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k = 0; k < K; ++k) {
@@ -649,34 +562,34 @@ __global__ void k_head_dlogit(const float* __restrict__ dout, const float* __res
 void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s) {
   int blocks = (npix + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_head_dlogit<<<blocks, 256, 0, s>>>(dout, outv, K, npix, dl4);
+  launch_k(k_head_dlogit, dim3(blocks), dim3(256), 0, s, 1, dout, outv, K, npix, dl4);
 }
 template <int KIND>
-__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
-                                                       int H, int W, double* __restrict__ bwd, int VL, int PPB, RedScratch scr) {
+__global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+                                                       int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
   float4 acc[2] = {f4zero(), f4zero()};
-  item_loop<(KIND == 0 || KIND == 3) ? 4 : 2>(
+  item_loop<KIND == 3 ? 8 : (KIND == 0 ? 4 : 2)>(
       blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
       [&](int p) {
         RedItem it;
         const int i = p / W, j = p - i * W;
-        float dl[4];
         it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v, dl);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v);
         return it;
       },
       [&](int, const RedItem& it) {
-        float4 dz = it.g;
+        float4 dz = KIND == 3 ? head_grad(sr, it.g) : it.g;
         if (act) dz = lrelu_bwd4(bn_apply(cf, it.x), dz);
         acc[0] = f4add(acc[0], dz);
         acc[1] = f4mla(dz, bn_xhat(cf, it.x), acc[1]);
       });
   double* const dst[2] = {bwd, bwd + bn.C * kAccS};
   const int wid[2] = {bn.C, bn.C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
 void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
                           cudaStream_t s) {
@@ -686,18 +599,19 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_reduce<1>, sm);
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_reduce<2>, sm);
   else fit_grid(g, k_bn_bwd_reduce<3>, sm);
-  if (src.kind == 0) launch_cluster8(k_bn_bwd_reduce<0>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 1) launch_cluster8(k_bn_bwd_reduce<1>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 2) launch_cluster8(k_bn_bwd_reduce<2>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
-  else launch_cluster8(k_bn_bwd_reduce<3>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  if (src.kind == 0) launch_red(k_bn_bwd_reduce<0>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else if (src.kind == 1) launch_red(k_bn_bwd_reduce<1>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else if (src.kind == 2) launch_red(k_bn_bwd_reduce<2>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
+  else launch_red(k_bn_bwd_reduce<3>, g.blocks, g.threads, sm, s, raw, ld_raw, bn, act, src, H, W, bwd, g.VL, g.PPB);
 }
 
 // apply pass; for the head source (KIND 3) it also accumulates the head's own gradients:
 //   dW_head[k][c] += dl[k] * act(bn(raw))[c],  db_head[k] += dl[k]
 template <int KIND>
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+__global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                       int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
-                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB, RedScratch scr) {
+                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
@@ -708,23 +622,26 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
   float4 acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = f4zero();
-  item_loop<KIND == 0 ? 4 : 2>(
+  item_loop<(KIND == 0 || KIND == 3) ? 4 : 2>(
       blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
       [&](int p) {
         BwdItem it;
         const int i = p / W, j = p - i * W;
         it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v, it.dl);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v);
         return it;
       },
       [&](int p, const BwdItem& it) {
-        float4 dz = it.g;
+        float4 dz = KIND == 3 ? head_grad(sr, it.g) : it.g;
         const float4 y = bn_apply(cf, it.x);
         if constexpr (KIND == 3) {
           const float4 u = act ? lrelu4(y) : y;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[1 + k] = f4fma(it.dl[k], u, acc[1 + k]);
-          if (v == 0) acc[5] = f4add(acc[5], make_float4(it.dl[0], it.dl[1], it.dl[2], it.dl[3]));
+          acc[1] = f4fma(it.g.x, u, acc[1]);
+          acc[2] = f4fma(it.g.y, u, acc[2]);
+          acc[3] = f4fma(it.g.z, u, acc[3]);
+          acc[4] = f4fma(it.g.w, u, acc[4]);
+          if (v == 0) acc[5] = f4add(acc[5], it.g);
         }
         if (act) dz = lrelu_bwd4(y, dz);
         const float4 xh = bn_xhat(cf, it.x);
@@ -745,11 +662,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                             src.nh > 2 ? src.dwh + 2 * C * kAccS : nullptr, src.nh > 3 ? src.dwh + 3 * C * kAccS : nullptr, src.dbh};
     // acc[5] (db_head) is non-zero on lanes v == 0 only: its 4 leading "channels" are the per-output bias gradients
     const int wid[K] = {C, C, C, C, C, src.nh};
-    block_reduce_atomic<K>(acc, VL, PPB, dst, wid, scr);
+    block_reduce_atomic<K>(acc, VL, PPB, dst, wid);
   } else {
     double* const dst[1] = {dbias};
     const int wid[1] = {C};
-    block_reduce_atomic<K>(acc, VL, PPB, dst, wid, scr);
+    block_reduce_atomic<K>(acc, VL, PPB, dst, wid);
   }
 }
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
@@ -759,10 +676,10 @@ void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSr
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_apply<1>, red_bytes(g, 1));
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_apply<2>, red_bytes(g, 1));
   else fit_grid(g, k_bn_bwd_apply<3>, red_bytes(g, 6));
-  if (src.kind == 0) launch_cluster8(k_bn_bwd_apply<0>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 1) launch_cluster8(k_bn_bwd_apply<1>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
-  else if (src.kind == 2) launch_cluster8(k_bn_bwd_apply<2>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
-  else launch_cluster8(k_bn_bwd_apply<3>, g.blocks, g.threads, red_bytes(g, 6), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, pick_scratch(s));
+  if (src.kind == 0) launch_red(k_bn_bwd_apply<0>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else if (src.kind == 1) launch_red(k_bn_bwd_apply<1>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else if (src.kind == 2) launch_red(k_bn_bwd_apply<2>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  else launch_red(k_bn_bwd_apply<3>, g.blocks, g.threads, red_bytes(g, 6), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
@@ -796,7 +713,8 @@ __device__ __forceinline__ float4 cat_xhat(const CatBwdCoef& c, float4 y) {
                      (y.w - c.beta.w) * c.inv_gamma.w);
 }
 __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
-                                                        int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB, RedScratch scr) {
+                                                        int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int Wp = W + 2;
@@ -815,17 +733,18 @@ __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict_
                });
   double* const dst[2] = {bwd, bwd + bn_cat.C * kAccS};
   const int wid[2] = {bn_cat.C, bn_cat.C};
-  block_reduce_atomic<2>(acc, VL, PPB, dst, wid, scr);
+  block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
 void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, double* bwd,
                            cudaStream_t s) {
   VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_reduce, red_bytes(g, 2));
-  launch_cluster8(k_cat_bwd_reduce, g.blocks, g.threads, red_bytes(g, 2), s, pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB, pick_scratch(s));
+  launch_red(k_cat_bwd_reduce, g.blocks, g.threads, red_bytes(g, 2), s, pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB);
 }
 __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
                                                        int ld, int H, int W, const double* __restrict__ bwd,
                                                        float* __restrict__ dcat, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int C = bn_cat.C;
@@ -854,12 +773,13 @@ void launch_cat_bwd_apply(const float* pcat, BnRef bn_cat, const float* gp, int 
                           float* dcat, cudaStream_t s) {
   VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_apply, 0);
-  k_cat_bwd_apply<<<g.blocks, g.threads, 0, s>>>(pcat, bn_cat, gp, ld, H, W, bwd, dcat, g.VL, g.PPB);
+  launch_k(k_cat_bwd_apply, dim3(g.blocks), dim3(g.threads), 0, s, 1, pcat, bn_cat, gp, ld, H, W, bwd, dcat, g.VL, g.PPB);
 }
 
 // Adjoint of the x2 upsampling, materialised once: dst[h][w][C] <- D[2h][2w][ld] (channels coff..coff+C)
 __global__ void __launch_bounds__(256) k_upadj(const float* __restrict__ D, int ld, int coff, int h, int w, int C, int bilinear,
                                                float* __restrict__ dst, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   item_loop<1>(blockIdx.x * PPB + slot, gridDim.x * PPB, h * w,
                [&](int p) {
@@ -871,14 +791,15 @@ __global__ void __launch_bounds__(256) k_upadj(const float* __restrict__ D, int 
 void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bilinear, float* dst, cudaStream_t s) {
   VecGeom g = vec_geom(C, static_cast<long long>(h) * w);
   fit_grid(g, k_upadj, 0);
-  k_upadj<<<g.blocks, g.threads, 0, s>>>(D, ld, coff, h, w, C, bilinear, dst, g.VL, g.PPB);
+  launch_k(k_upadj, dim3(g.blocks), dim3(g.threads), 0, s, 1, D, ld, coff, h, w, C, bilinear, dst, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ skinny 1x1 convs
 // VL = C/4 lanes per pixel (power of two <= 32); warp-shuffle reduction over the pixel's lanes.
 __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
                                                     const float* __restrict__ b, int C, int N, int H, int W,
-                                                    float* __restrict__ y, int mode, double* __restrict__ stats, RedScratch scr) {
+                                                    float* __restrict__ y, int mode, double* __restrict__ stats) {
+  pdl_enter();
   const int VL = C / 4;
   const int PPB = 256 / VL;
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
@@ -926,7 +847,7 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
     float4 acc2[2] = {s1, s2};
     double* const dst[2] = {stats, stats + N * kAccS};
     const int wid[2] = {N, N};
-    block_reduce_atomic<2>(acc2, 1, 256, dst, wid, scr);
+    block_reduce_atomic<2>(acc2, 1, 256, dst, wid);
   }
 }
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
@@ -934,13 +855,14 @@ void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const 
   const int PPB = 256 / (C / 4);
   long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
   if (nb > 148 * 8) nb = 148 * 8;
-  launch_cluster8(k_skinny_fwd, static_cast<int>(nb), 256, 2 * 256 * sizeof(float4) + 2 * 4 * sizeof(double), s, x, ldx, x_rs, w, b, C, N, H, W,
-                  y, mode, stats, pick_scratch(s));
+  launch_red(k_skinny_fwd, static_cast<int>(nb), 256, 2 * 256 * sizeof(float4) + 2 * 4 * sizeof(double), s, x, ldx, x_rs, w, b, C, N, H, W,
+                  y, mode, stats);
 }
 
 __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
                              int H, int W, const float* __restrict__ dy, const float* __restrict__ out_nchw, int mode,
-                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB, RedScratch scr) {
+                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB) {
+  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const int npix = H * W;
   float4 wv[4];
@@ -985,20 +907,21 @@ __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, con
   double* const dst[5] = {dw, N > 1 ? dw + C * kAccS : nullptr, N > 2 ? dw + 2 * C * kAccS : nullptr,
                           N > 3 ? dw + 3 * C * kAccS : nullptr, db};
   const int wid[5] = {C, C, C, C, N};  // acc[4] (bias gradient) lives on lanes v == 0 only
-  block_reduce_atomic<5>(acc, VL, PPB, dst, wid, scr);
+  block_reduce_atomic<5>(acc, VL, PPB, dst, wid);
 }
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
                        cudaStream_t s) {
   VecGeom g = vec_geom(C, static_cast<long long>(H) * W);
   fit_grid(g, k_skinny_bwd, red_bytes(g, 5));
-  launch_cluster8(k_skinny_bwd, g.blocks, g.threads, red_bytes(g, 5), s, x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
-                                                             g.VL, g.PPB, pick_scratch(s));
+  launch_red(k_skinny_bwd, g.blocks, g.threads, red_bytes(g, 5), s, x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
+                                                             g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ MSE loss
 __global__ void k_mse(const float* __restrict__ out, const float* __restrict__ target, const float* __restrict__ mask,
                       int C, int HW, double* __restrict__ loss, float* __restrict__ dout, const int* __restrict__ it_dev) {
+  pdl_enter();
   const int n = C * HW;
   const float inv_n = 1.f / static_cast<float>(n);
   float acc = 0.f;
@@ -1023,7 +946,7 @@ void launch_mse(const float* out, const float* target, const float* mask, int C,
   const long long n = static_cast<long long>(C) * HW;
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  k_mse<<<blocks, 256, 0, s>>>(out, target, mask, C, HW, loss, dout, it_dev);
+  launch_k(k_mse, dim3(blocks), dim3(256), 0, s, 1, out, target, mask, C, HW, loss, dout, it_dev);
 }
 
 // ------------------------------------------------------------------------------------------------ Philox noise
@@ -1035,6 +958,7 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 }
 __global__ void k_noise(const float* __restrict__ z0, float* __restrict__ z, float sigma, uint64_t seed,
                         uint64_t offset, const int* __restrict__ it_dev, size_t n4) {
+  pdl_enter();
   if (it_dev != nullptr) offset += static_cast<uint64_t>(*it_dev);
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1069,14 +993,16 @@ void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_
   const size_t n4 = n / 4;
   int blocks = static_cast<int>((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_noise<<<blocks, 256, 0, s>>>(z0, z, sigma, seed, offset, it_dev, n4);
+  launch_k(k_noise, dim3(blocks), dim3(256), 0, s, 1, z0, z, sigma, seed, offset, it_dev, n4);
 }
-__global__ void k_advance(int* it) { it[0] += 1; it[1] += 1; }  // {global Adam step, iteration index of this call}
-void launch_advance(int* it_dev, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(it_dev); }
+__global__ void k_advance(int* it) {
+  pdl_enter(); it[0] += 1; it[1] += 1; }  // {global Adam step, iteration index of this call}
+void launch_advance(int* it_dev, cudaStream_t s) { launch_k(k_advance, dim3(1), dim3(1), 0, s, 1, it_dev); }
 
 // ------------------------------------------------------------------------------------------------ weight packing
 __global__ void k_pack_fprop(const float* __restrict__ w, int N, int C, int kh, int kw, int rot, float* __restrict__ dst,
                              int n_rows, int c_pad) {
+  pdl_enter();
   const long long total = static_cast<long long>(kh) * kw * n_rows * c_pad;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1091,10 +1017,11 @@ __global__ void k_pack_fprop(const float* __restrict__ w, int N, int C, int kh, 
 void launch_pack_fprop(const float* w, int N, int C, int kh, int kw, int rot, float* dst, int n_rows, int c_pad,
                        cudaStream_t s) {
   const long long total = static_cast<long long>(kh) * kw * n_rows * c_pad;
-  k_pack_fprop<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(w, N, C, kh, kw, rot, dst, n_rows, c_pad);
+  launch_k(k_pack_fprop, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, 1, w, N, C, kh, kw, rot, dst, n_rows, c_pad);
 }
 __global__ void k_pack_dgrad(const float* __restrict__ w, int N, int C, int kh, int kw, int rot, float* __restrict__ dst,
                              int c_rows, int n_pad) {
+  pdl_enter();
   const long long total = static_cast<long long>(kh) * kw * c_rows * n_pad;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1110,13 +1037,14 @@ __global__ void k_pack_dgrad(const float* __restrict__ w, int N, int C, int kh, 
 void launch_pack_dgrad(const float* w, int N, int C, int kh, int kw, int rot, float* dst, int c_rows, int n_pad,
                        cudaStream_t s) {
   const long long total = static_cast<long long>(kh) * kw * c_rows * n_pad;
-  k_pack_dgrad<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(w, N, C, kh, kw, rot, dst, c_rows, n_pad);
+  launch_k(k_pack_dgrad, dim3(static_cast<int>((total + 255) / 256)), dim3(256), 0, s, 1, w, N, C, kh, kw, rot, dst, c_rows, n_pad);
 }
 
 // Split-K reduction.  Block = 32 float4 columns x 8 split-parts: a warp reads 512 contiguous bytes of one split;
 // the 8 parts are folded through shared memory (deterministic order), then scattered to the OIHW gradient.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int ksplits, int N, int C, int taps,
                                                       int rot, int c_pad, float* __restrict__ dw) {
+  pdl_enter();
   __shared__ float4 sm[8][32];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int c4n = c_pad / 4;
@@ -1152,7 +1080,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
 void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh, int kw, int rot, int c_pad,
                          float* dw, cudaStream_t s) {
   const int total4 = kh * kw * 128 * (c_pad / 4);
-  k_wgrad_reduce<<<(total4 + 31) / 32, 256, 0, s>>>(partial, ksplits, N, C, kh * kw, rot, c_pad, dw);
+  launch_k(k_wgrad_reduce, dim3((total4 + 31) / 32), dim3(256), 0, s, 1, partial, ksplits, N, C, kh * kw, rot, c_pad, dw);
 }
 
 // ------------------------------------------------------------------------------------------------ Adam
@@ -1161,6 +1089,7 @@ void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh
 // step number can come from a device counter (CUDA-graph replay).
 static constexpr int kAdamChunk = 2048;
 __global__ void k_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, const int* __restrict__ it_dev) {
+  pdl_enter();
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const int st = step + (it_dev != nullptr ? *it_dev : 0);
@@ -1193,7 +1122,7 @@ __global__ void k_adam(AdamTable t, double lr, double b1, double b2, double eps,
   }
 }
 void launch_adam(AdamTable t, double lr, double b1, double b2, double eps, int step, const int* it_dev, cudaStream_t s) {
-  k_adam<<<t.nblocks, 256, 0, s>>>(t, lr, b1, b2, eps, step, it_dev);
+  launch_k(k_adam, dim3(t.nblocks), dim3(256), 0, s, 1, t, lr, b1, b2, eps, step, it_dev);
 }
 int adam_chunk() { return kAdamChunk; }
 
