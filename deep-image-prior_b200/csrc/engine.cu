@@ -450,6 +450,12 @@ struct dip_plan {
   float* partial = nullptr;
   // runner scratch
   float* zbuf = nullptr; float* dout = nullptr; float* dl4 = nullptr;
+  // super-resolution operator applied between the network output and the loss (dip_plan_set_downsampler)
+  static constexpr int kDownMaxK = 64;
+  float* ds_kern = nullptr;      // [K][K] taps
+  float* ds_y = nullptr;         // [C_out][Ho][Wo] downsampled output
+  float* ds_dy = nullptr;        // [C_out][Ho][Wo] dL/d(ds_y)
+  int ds_K = 0, ds_f = 1, ds_pad = 0, ds_Ho = 0, ds_Wo = 0;
   static constexpr int kLossRing = 65536;
   double* loss_ring = nullptr;   // [kLossRing] loss slots of the runner when the caller passes no history buffer
   int* it_dev = nullptr;         // [2] device counters: {global Adam step, iteration index of this call}
@@ -630,6 +636,9 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->zbuf = A.get<float>((size_t)P->H * P->W * d.in_channels);
   P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->dl4 = A.get<float>((size_t)P->H * P->W * 4);
+  P->ds_kern = A.get<float>(dip_plan::kDownMaxK * dip_plan::kDownMaxK);
+  P->ds_y = A.get<float>((size_t)P->H * P->W * d.out_channels);
+  P->ds_dy = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->loss_ring = A.get<double>(dip_plan::kLossRing);
   P->it_dev = A.get<int>(4);
   // ---- conv ops
@@ -1011,6 +1020,35 @@ int dip_noise_perturb(const void* z0, void* z, float sigma, uint64_t seed, uint6
   return 0;
 }
 
+int dip_lanczos_down_fwd(const void* x, int C, int H, int W, const void* kern, int K, int factor, int pad, void* y,
+                         dip_stream_t stream) {
+  if (K < 1 || factor < 1 || pad < 0) return fail("dip_lanczos_down_fwd: bad K / factor / pad");
+  if (down_out_size(H, K, factor, pad) < 1 || down_out_size(W, K, factor, pad) < 1)
+    return fail("dip_lanczos_down_fwd: image smaller than the filter");
+  DIP_CUDA(launch_down_fwd((const float*)x, C, H, W, (const float*)kern, K, factor, pad, (float*)y, (cudaStream_t)stream));
+  return 0;
+}
+int dip_lanczos_down_bwd(const void* dy, int C, int H, int W, const void* kern, int K, int factor, int pad, void* dx,
+                         dip_stream_t stream) {
+  if (K < 1 || factor < 1 || pad < 0) return fail("dip_lanczos_down_bwd: bad K / factor / pad");
+  if (down_out_size(H, K, factor, pad) < 1 || down_out_size(W, K, factor, pad) < 1)
+    return fail("dip_lanczos_down_bwd: image smaller than the filter");
+  DIP_CUDA(launch_down_bwd((const float*)dy, C, H, W, (const float*)kern, K, factor, pad, (float*)dx, (cudaStream_t)stream));
+  return 0;
+}
+int dip_lanczos_down_out_size(int n, int K, int factor, int pad) { return down_out_size(n, K, factor, pad); }
+
+int dip_plan_set_downsampler(dip_plan* P, const float* kern_host, int K, int factor, int pad) {
+  if (P->gexec != nullptr) { cudaGraphExecDestroy(P->gexec); P->gexec = nullptr; }   // the captured step changes
+  if (kern_host == nullptr || K == 0) { P->ds_K = 0; return 0; }
+  if (K < 1 || K > dip_plan::kDownMaxK || factor < 1 || pad < 0) return fail("dip_plan_set_downsampler: bad K / factor / pad");
+  const int Ho = down_out_size(P->H, K, factor, pad), Wo = down_out_size(P->W, K, factor, pad);
+  if (Ho < 1 || Wo < 1 || Ho > P->H || Wo > P->W) return fail("dip_plan_set_downsampler: unsupported output size");
+  DIP_CUDA(cudaMemcpy(P->ds_kern, kern_host, (size_t)K * K * sizeof(float), cudaMemcpyHostToDevice));
+  P->ds_K = K; P->ds_f = factor; P->ds_pad = pad; P->ds_Ho = Ho; P->ds_Wo = Wo;
+  return 0;
+}
+
 int dip_adam_create(int ntensors, const long long* numel, dip_adam** out) {
   dip_adam* a = new dip_adam();
   a->n = ntensors;
@@ -1071,7 +1109,17 @@ static int run_body(dip_plan* P, dip_adam* adam, const float* z0, const float* t
     zin = P->zbuf;
   }
   DIP_CHECK(plan_forward(P, zin, nullptr, 0.f, out, s));
-  launch_mse(P->out_saved, target, mask, P->desc.out_channels, hw, loss_slot, P->dout, it_dev != nullptr ? it_dev + 1 : nullptr, s);
+  const int* slot_idx = it_dev != nullptr ? it_dev + 1 : nullptr;
+  if (P->ds_K > 0) {
+    // super-resolution: loss on the downsampled output (super-resolution.ipynb c10:8-11); the operator's adjoint
+    // turns the low-resolution loss gradient into dL/d(out)
+    const int co = P->desc.out_channels;
+    DIP_CUDA(launch_down_fwd(P->out_saved, co, P->H, P->W, P->ds_kern, P->ds_K, P->ds_f, P->ds_pad, P->ds_y, s));
+    launch_mse(P->ds_y, target, mask, co, P->ds_Ho * P->ds_Wo, loss_slot, P->ds_dy, slot_idx, s);
+    DIP_CUDA(launch_down_bwd(P->ds_dy, co, P->H, P->W, P->ds_kern, P->ds_K, P->ds_f, P->ds_pad, P->dout, s));
+  } else {
+    launch_mse(P->out_saved, target, mask, P->desc.out_channels, hw, loss_slot, P->dout, slot_idx, s);
+  }
   DIP_CHECK(plan_backward(P, P->dout, s));
   if (!adam->bound) return fail("dip_run_iterations: adam not bound");
   AdamTable t{adam->d_p, adam->d_g, adam->d_m, adam->d_v, adam->d_blk_tensor, adam->d_blk_start, adam->d_numel, adam->nblocks};

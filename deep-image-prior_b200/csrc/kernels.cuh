@@ -174,6 +174,15 @@ void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_
 // it_dev[0] += 1, it_dev[1] += 1 (step / iteration counters of the graph-captured runner)
 void launch_advance(int* it_dev, cudaStream_t s);
 
+// Downsampler (super-resolution operator, models/downsampler.py:58-71): planes [C][H][W], taps kern[K][K] (device),
+// replication pad `pad`, stride f; output planes [C][Ho][Wo] with Ho = down_out_size(H, K, f, pad).   (downsample.cu)
+int down_out_size(int n, int K, int f, int pad);
+cudaError_t launch_down_fwd(const float* x, int C, int H, int W, const float* kern, int K, int f, int pad, float* y,
+                            cudaStream_t s);
+// adjoint: dy [C][Ho][Wo] -> dx [C][H][W] (every element written)
+cudaError_t launch_down_bwd(const float* dy, int C, int H, int W, const float* kern, int K, int f, int pad, float* dx,
+                            cudaStream_t s);
+
 // weight repacking ---------------------------------------------------------------------------------
 // torch OIHW [N][C][kh][kw]  ->  fprop pack [tap][n_rows][c_pad] (K-major), channel rotation c_t = (c + rot) % C
 void launch_pack_fprop(const float* w, int N, int C, int kh, int kw, int rot, float* dst, int n_rows, int c_pad,

@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "dip_loss_mse", "dip_noise_perturb", "dip_adam_create", "dip_adam_destroy", "dip_adam_bind", "dip_adam_step",
     "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_plan_set_timing", "dip_plan_get_timing", "dip_plan_get_timing_records", "dip_op_scratch_bytes", "dip_op_conv_fprop",
     "dip_op_conv_dgrad", "dip_op_conv_wgrad",
+    "dip_lanczos_down_out_size", "dip_lanczos_down_fwd", "dip_lanczos_down_bwd", "dip_plan_set_downsampler",
 ]
 
 
@@ -98,6 +99,10 @@ def lib():
                                     vp, vp]
     L.dip_op_conv_dgrad.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     L.dip_op_conv_wgrad.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp]
+    L.dip_lanczos_down_out_size.argtypes = [i32, i32, i32, i32]
+    L.dip_lanczos_down_fwd.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    L.dip_lanczos_down_bwd.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    L.dip_plan_set_downsampler.argtypes = [vp, ctypes.POINTER(f32), i32, i32, i32]
     _lib = L
     return L
 
@@ -188,6 +193,17 @@ class Plan:
     def backward(self, dout):
         with torch.cuda.device(self.device):
             check(lib().dip_backward(self.h, _ptr(dout), _stream()))
+
+    def set_downsampler(self, kernel, factor, pad):
+        """Loss of the runner is taken on downsampler(out) (dip_plan_set_downsampler); kernel: K x K taps or None."""
+        if kernel is None:
+            check(lib().dip_plan_set_downsampler(self.h, None, 0, 1, 0))
+            return
+        k = torch.as_tensor(kernel, dtype=torch.float32).contiguous().cpu()
+        assert k.dim() == 2 and k.shape[0] == k.shape[1]
+        arr = (ctypes.c_float * k.numel())(*k.flatten().tolist())
+        with torch.cuda.device(self.device):
+            check(lib().dip_plan_set_downsampler(self.h, arr, int(k.shape[0]), int(factor), int(pad)))
 
     def buffer(self, name):
         """Copy of an internal NHWC buffer as a (rows, cols, channels) tensor (tests / debugging)."""
@@ -283,6 +299,37 @@ def run_iterations(plan, adam, z0, target, mask, sigma, seed, iters, lr, out=Non
         check(lib().dip_run_iterations(plan.h, adam.h, _ptr(z0), _ptr(target), _ptr(mask), float(sigma), int(seed),
                                        adam.step_count, int(iters), float(lr), _ptr(out), _ptr(loss_hist), _stream()))
     adam.step_count += iters
+
+
+# ------------------------------------------------------------------------------------------------ downsampler
+def down_out_size(n, K, factor, pad):
+    return (n + 2 * pad - K) // factor + 1 if n + 2 * pad >= K else 0
+
+
+def lanczos_down_fwd(x, kern, factor, pad):
+    """x: (1|N) x C x H x W CUDA fp32 planes, kern: K x K CUDA fp32 taps -> planes downsampled by `factor`."""
+    assert x.is_cuda and x.dtype == torch.float32 and kern.is_cuda and kern.dtype == torch.float32
+    x = x.contiguous()
+    kern = kern.contiguous()
+    n, c, H, W = x.shape
+    K = int(kern.shape[-1])
+    y = torch.empty((n, c, down_out_size(H, K, factor, pad), down_out_size(W, K, factor, pad)), dtype=torch.float32,
+                    device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().dip_lanczos_down_fwd(_ptr(x), n * c, H, W, _ptr(kern), K, int(factor), int(pad), _ptr(y), _stream()))
+    return y
+
+
+def lanczos_down_bwd(dy, kern, factor, pad, H, W):
+    assert dy.is_cuda and dy.dtype == torch.float32
+    dy = dy.contiguous()
+    kern = kern.contiguous()
+    n, c = dy.shape[0], dy.shape[1]
+    K = int(kern.shape[-1])
+    dx = torch.empty((n, c, H, W), dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        check(lib().dip_lanczos_down_bwd(_ptr(dy), n * c, H, W, _ptr(kern), K, int(factor), int(pad), _ptr(dx), _stream()))
+    return dx
 
 
 # ------------------------------------------------------------------------------------------------ single ops (tests)

@@ -2,7 +2,8 @@
 
 Same constructor and numerics as the reference: a fixed K x K Lanczos / Gauss / box filter applied per channel with
 stride `factor`, optional replication padding.  The filter is separable (outer product of 1-D taps), which is how it
-is built here.  Round 1: executed with stock torch conv (super-resolution is a "next" row of SURVEY.md section 8f).
+is built here.  CUDA tensors run on the engine's stencil kernels (dip_lanczos_down_fwd / _bwd in include/dip.h, one
+autograd node); there is no CPU path unless models.allow_torch_execution(True) opts in to the stock torch modules.
 """
 import numpy as np
 import torch
@@ -50,6 +51,21 @@ def get_kernel(factor, kernel_type, phase, kernel_width, support=None, sigma=Non
     return kernel
 
 
+class _DownFn(torch.autograd.Function):
+    """out_LR = downsampler(out_HR) on the engine (reference: models/downsampler.py:58-71)."""
+
+    @staticmethod
+    def forward(ctx, x, kern, factor, pad):
+        import dip_engine as de
+        ctx.kern, ctx.factor, ctx.pad, ctx.hw = kern, factor, pad, (int(x.shape[2]), int(x.shape[3]))
+        return de.lanczos_down_fwd(x, kern, factor, pad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        import dip_engine as de
+        return de.lanczos_down_bwd(dy, ctx.kern, ctx.factor, ctx.pad, *ctx.hw), None, None, None
+
+
 class Downsampler(nn.Module):
     def __init__(self, n_planes, factor, kernel_type, phase=0, kernel_width=None, support=None, sigma=None,
                  preserve_size=False):
@@ -73,13 +89,28 @@ class Downsampler(nn.Module):
             for c in range(n_planes):
                 op.weight[c, c] = k
         self.downsampler_ = op
+        self.factor = factor
+        self.pad = 0
         if preserve_size:
             ks = self.kernel.shape[0]
             pad = int((ks - 1) / 2.) if ks % 2 == 1 else int((ks - factor) / 2.)
             self.padding = nn.ReplicationPad2d(pad)
+            self.pad = pad
         self.preserve_size = preserve_size
 
     def forward(self, input):
+        if input.is_cuda:
+            # engine path: the K x K taps of plane 0 (the weight is plane-diagonal by construction; the conv bias is
+            # zero by construction and not applied -- optimising the operator itself, OPT_OVER='down', is out of scope)
+            if input.dtype != torch.float32 or self.downsampler_.weight.device != input.device:
+                raise RuntimeError("dip-b200: Downsampler needs float32 CUDA tensors on the module's device "
+                                   "(downsampler.type(torch.cuda.FloatTensor))")
+            kern = self.downsampler_.weight.detach()[0, 0]
+            return _DownFn.apply(input, kern, self.factor, self.pad)
+        from .skip import _ALLOW_TORCH
+        if not _ALLOW_TORCH:
+            raise RuntimeError("dip-b200: Downsampler runs on CUDA tensors; there is no CPU fallback "
+                               "(models.allow_torch_execution(True) opts in to stock torch)")
         x = self.padding(input) if self.preserve_size else input
         self.x = x
         return self.downsampler_(x)

@@ -72,6 +72,21 @@ int dip_loss_mse(const void* out, const void* target, const void* mask, int chan
 int dip_noise_perturb(const void* z0, void* z, float sigma, uint64_t seed, uint64_t offset, size_t n,
                       dip_stream_t stream);
 
+/* ---- Downsampler.forward and its adjoint (reference: models/downsampler.py:58-71 = nn.ReplicationPad2d(pad) +
+ *      nn.Conv2d(C, C, KxK, stride=factor) with the plane-diagonal weight built at models/downsampler.py:44-56;
+ *      used as `out_LR = downsampler(out_HR)` in super-resolution.ipynb c10:8).  x: planes [C][H][W]; kern: DEVICE
+ *      [K][K] fp32 taps (any of the reference's kernel types; Lanczos-2, K = 16 for factor 4); y: [C][Ho][Wo] with
+ *      Ho = dip_lanczos_down_out_size(H, K, factor, pad) = (H + 2 pad - K) / factor + 1.  bwd: dy -> dx (overwrites). */
+int dip_lanczos_down_out_size(int n, int K, int factor, int pad);
+int dip_lanczos_down_fwd(const void* x, int C, int H, int W, const void* kern, int K, int factor, int pad, void* y,
+                         dip_stream_t stream);
+int dip_lanczos_down_bwd(const void* dy, int C, int H, int W, const void* kern, int K, int factor, int pad, void* dx,
+                         dip_stream_t stream);
+/* Runner option for the super-resolution closure (super-resolution.ipynb c10:8-11: total_loss = mse(downsampler(out),
+ * img_LR)): dip_run_iterations then computes the loss on the downsampled output; `target` (and `mask`) are
+ * [C_out][Ho][Wo].  kern_host: HOST [K][K] fp32 taps, copied; K = 0 / NULL switches the option off. Synchronous setup call. */
+int dip_plan_set_downsampler(dip_plan* plan, const float* kern_host, int K, int factor, int pad);
+
 /* ---- torch.optim.Adam(parameters, lr).step() as one multi-tensor launch (utils/common_utils.py:225-230). */
 int dip_adam_create(int ntensors, const long long* numel, dip_adam** out);
 void dip_adam_destroy(dip_adam* a);

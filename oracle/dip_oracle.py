@@ -13,6 +13,7 @@ installed here: torch 2.11 -- so the oracle restates the reference's *graph* on 
   * optimiser                       torch.optim.Adam defaults, utils/common_utils.py:225-230
   * input perturbation              denoising.ipynb c10:12-13
   * get_noise                       utils/common_utils.py:127-153
+  * Downsampler / get_kernel        models/downsampler.py:5-135 (super-resolution operator, super-resolution.ipynb c10:8)
 
 Pinning: the reference has NO golden vectors / tests.  The oracle is pinned instead against
 outputs of the reference itself, generated in the build container by tests/golden/make_golden.py (which imports
@@ -198,15 +199,63 @@ class Adam:
                 p.addcdiv_(m, denom, value=-self.lr / bc1)
 
 
-def run(cfg, params, z0, target, noises, sigma, lr, mask=None, record=None):
+def down_kernel(factor, kernel_type, phase=0.5, kernel_width=None, support=None, sigma=None):
+    """K x K float64 filter of the Downsampler, normalised to sum 1 (models/downsampler.py:73-135, element by element;
+    presets lanczos2 / lanczos3 / gauss12 / gauss1sq2 as at models/downsampler.py:14-33)."""
+    presets = {"lanczos2": ("lanczos", 2, 4 * factor + 1, None), "lanczos3": ("lanczos", 3, 6 * factor + 1, None),
+               "gauss12": ("gauss", None, 7, 0.5), "gauss1sq2": ("gauss", None, 9, 1.0 / math.sqrt(2.0))}
+    if kernel_type in presets:
+        kernel_type, sup, kernel_width, sig = presets[kernel_type]
+        support = sup if sup is not None else support
+        sigma = sig if sig is not None else sigma
+    n = kernel_width - 1 if (phase == 0.5 and kernel_type != "box") else kernel_width
+    k = np.zeros((n, n), dtype=np.float64)
+    centre = (kernel_width + 1) / 2.0
+    for i in range(1, n + 1):
+        for j in range(1, n + 1):
+            if kernel_type == "box":
+                k[i - 1, j - 1] = 1.0 / (kernel_width * kernel_width)
+            elif kernel_type == "gauss":
+                di, dj = (i - centre) / 2.0, (j - centre) / 2.0
+                k[i - 1, j - 1] = math.exp(-(di * di + dj * dj) / (2 * sigma * sigma)) / (2.0 * math.pi * sigma * sigma)
+            else:
+                shift = 0.5 if phase == 0.5 else 0.0
+                val = 1.0
+                for d in (abs(i + shift - centre) / factor, abs(j + shift - centre) / factor):
+                    if d != 0:
+                        val *= support * math.sin(math.pi * d) * math.sin(math.pi * d / support) / (math.pi * math.pi * d * d)
+                k[i - 1, j - 1] = val
+    return k / k.sum()
+
+
+def down_pad(K, factor):
+    """Replication pad of preserve_size=True (models/downsampler.py:54-59)."""
+    return int((K - 1) / 2.0) if K % 2 == 1 else int((K - factor) / 2.0)
+
+
+def downsample(x, kernel, factor, pad):
+    """Downsampler.forward (models/downsampler.py:64-71): ReplicationPad2d(pad) + a dense Conv2d(C, C, K, stride=factor)
+    whose weight carries `kernel` on the plane diagonal and zeros elsewhere, zero bias."""
+    C = x.shape[1]
+    k = torch.as_tensor(kernel).to(x.dtype)
+    w = torch.zeros(C, C, k.shape[0], k.shape[1], dtype=x.dtype)
+    for c in range(C):
+        w[c, c] = k
+    if pad > 0:
+        x = F.pad(x, (pad,) * 4, mode="replicate")
+    return F.conv2d(x, w, torch.zeros(C, dtype=x.dtype), stride=factor)
+
+
+def run(cfg, params, z0, target, noises, sigma, lr, mask=None, record=None, down=None):
     """`len(noises)` iterations of the lean closure: z = z0 + noise*sigma; out = net(z); loss; backward; Adam.
-    Returns (losses, last_out).  record(i, out, loss, grads) is called before the Adam step."""
+    Returns (losses, last_out).  record(i, out, loss, grads) is called before the Adam step.
+    down = (kernel, factor, pad): super-resolution closure, loss = mse(downsample(out), target) (super-resolution.ipynb c10)."""
     opt = Adam(params, lr)
     losses, out = [], None
     for i, nz in enumerate(noises):
         z = z0 + nz * sigma if nz is not None else z0
         out = skip_forward(params, z, cfg)
-        loss = mse_loss(out, target, mask)
+        loss = mse_loss(out if down is None else downsample(out, *down), target, mask)
         grads = torch.autograd.grad(loss, params)
         if record is not None:
             record(i, out.detach(), loss.item(), grads)

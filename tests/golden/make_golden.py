@@ -61,7 +61,83 @@ def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtyp
     print(name, 'losses', losses)
 
 
+DOWN_CASES = [  # (tag, ctor kwargs, H, W)
+    ('lanczos2_f4', dict(factor=4, kernel_type='lanczos2', phase=0.5, preserve_size=True), 64, 96),
+    ('lanczos2_f2', dict(factor=2, kernel_type='lanczos2', phase=0.5, preserve_size=True), 38, 50),
+    ('lanczos3_f4', dict(factor=4, kernel_type='lanczos3', phase=0.5, preserve_size=True), 64, 64),
+    ('lanczos2_f8', dict(factor=8, kernel_type='lanczos2', phase=0.5, preserve_size=True), 64, 128),
+    ('gauss12_f2', dict(factor=2, kernel_type='gauss12', phase=0, preserve_size=True), 33, 47),
+    ('box_f4', dict(factor=4, kernel_type='box', phase=0.5, kernel_width=4, preserve_size=True), 32, 40),
+    ('lanczos2_f4_nopad', dict(factor=4, kernel_type='lanczos2', phase=0.5, preserve_size=False), 45, 70),
+]
+
+
+def run_downsampler_cases():
+    """Forward + input gradient of the reference's Downsampler on seeded inputs (fp32, as the notebooks run it)."""
+    out = {}
+    with ref_harness.reference_modules() as ref:
+        for tag, kw, H, W in DOWN_CASES:
+            ds = ref.models.downsampler.Downsampler(n_planes=3, **kw).type(torch.FloatTensor)
+            g = torch.Generator().manual_seed(11)
+            x = torch.rand(1, 3, H, W, generator=g).requires_grad_(True)
+            y = ds(x)
+            dy = torch.randn(y.shape, generator=g)
+            y.backward(dy)
+            out[tag + '.kernel'] = ds.kernel
+            out[tag + '.x'] = x.detach().numpy()
+            out[tag + '.y'] = y.detach().numpy()
+            out[tag + '.dy'] = dy.numpy()
+            out[tag + '.dx'] = x.grad.numpy()
+            print(tag, 'kernel', ds.kernel.shape, 'y', tuple(y.shape))
+    np.savez_compressed(os.path.join(HERE, 'downsampler_cases.npz'), **out)
+
+
+def run_sr_case(name, H, W, iters, dtype, factor=4, sigma=0.03, lr=0.01, threads=8):
+    """super-resolution.ipynb c8-c10 on a small synthetic pair: loss = mse(downsampler(net(z)), img_LR)."""
+    torch.set_num_threads(threads)
+    with ref_harness.reference_modules() as ref:
+        torch.manual_seed(0)
+        net = ref.models.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                                 upsample_mode='bilinear').type(dtype)
+        torch.manual_seed(1)
+        z0 = ref.common_utils.get_noise(32, 'noise', (H, W)).type(dtype).detach()
+        g = torch.Generator().manual_seed(2)
+        target = torch.rand(1, 3, H // factor, W // factor, generator=g).type(dtype)
+        ds = ref.models.downsampler.Downsampler(n_planes=3, factor=factor, kernel_type='lanczos2', phase=0.5,
+                                    preserve_size=True).type(dtype)
+        gn = torch.Generator().manual_seed(123)
+        mse = torch.nn.MSELoss()
+        params = ref.common_utils.get_params('net', net, z0)
+        opt = torch.optim.Adam(params, lr=lr)
+        losses = []
+        for i in range(iters):
+            noise = torch.randn(z0.shape, generator=gn).type(dtype)
+            opt.zero_grad()
+            out = net(z0 + noise * sigma)
+            loss = mse(ds(out), target)
+            loss.backward()
+            if i == 0:
+                out0 = out.detach().clone()
+                gnorm0 = np.array([p.grad.double().norm().item() for p in params])
+                gsum0 = np.array([p.grad.double().sum().item() for p in params])
+            losses.append(loss.item())
+            opt.step()
+        pnorm = np.array([p.detach().double().norm().item() for p in params])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), H=H, W=W, factor=factor, iters=iters, sigma=sigma, lr=lr,
+                        losses=np.array(losses), out0=out0.numpy(), gnorm0=gnorm0, gsum0=gsum0, pnorm=pnorm,
+                        dtype=str(dtype))
+    print(name, 'losses', losses)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'sr':   # only the super-resolution fixtures
+        run_downsampler_cases()
+        run_sr_case('sr64x96_fp64', 64, 96, 3, torch.float64)
+        run_sr_case('sr64x96_fp32', 64, 96, 3, torch.float32)
+        sys.exit(0)
     run_case('denoise64_bilinear_fp32', 64, 64, 'bilinear', 4)
     run_case('denoise64_bilinear_fp64', 64, 64, 'bilinear', 4, dtype=torch.float64)
     run_case('denoise96x64_nearest_masked_fp64', 96, 64, 'nearest', 3, sigma=0.03, masked=True, dtype=torch.float64)
+    run_downsampler_cases()
+    run_sr_case('sr64x96_fp64', 64, 96, 3, torch.float64)
+    run_sr_case('sr64x96_fp32', 64, 96, 3, torch.float32)
