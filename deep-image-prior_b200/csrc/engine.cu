@@ -171,6 +171,12 @@ struct ConvOp {
   Timer* timer = nullptr;
   double alg_flops() const { return 2.0 * out_h * out_w * 128.0 * C * k * k; }
   int N = 128, C = 0, k = 1, stride = 1, rot = 0;
+  // An op may cover a SLICE [coff, coff + C) of the (engine-order) input channels of a wider convolution whose weight has
+  // Ctot input channels (the 256-channel up conv of the skip=128 configuration: fprop runs as one op with 8 K blocks,
+  // dgrad / wgrad as two 128-channel halves -- TMEM holds 512 accumulator columns).  Ctot == 0: the op is the whole conv.
+  int Ctot = 0, coff = 0;
+  bool do_fprop = true, do_wgrad = true;
+  int dg_ld = 0;   // channel stride of dg_out (0: C)
   int c_pad = 0;   // fprop K extent per tap (multiple of 32)
   int crows = 0;   // dgrad UMMA N (input channels rounded to 16)
   // forward
@@ -193,6 +199,8 @@ struct ConvOp {
   void set_shapes() {
     c_pad = round_up(C, 32);
     crows = round_up(C, 16);
+    if (Ctot == 0) Ctot = C;
+    if (dg_ld == 0) dg_ld = C;
   }
   size_t wp_f_elems() const { return (size_t)k * k * N * c_pad; }
   size_t wp_d_elems() const { return (size_t)k * k * crows * 128; }
@@ -214,7 +222,8 @@ struct ConvOp {
     pick_tile(out_w, out_h, &bw, &bh);
     fp = TcConvParams{};
     const bool patch_ok = getenv("DIP_NO_PATCH") == nullptr;
-    if (k == 3 && stride == 1 && patch_ok) {
+    if (!do_fprop) {
+    } else if (k == 3 && stride == 1 && patch_ok) {
       // patch mode: tile 8 wide x 16 tall, one 10 x 18 input patch per 32-channel block feeds all nine taps
       bw = 8; bh = 16;
       fp.patch = 1; fp.pw = bw + 2; fp.ph = bh + 2;
@@ -222,6 +231,7 @@ struct ConvOp {
     } else {
       DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
     }
+    if (do_fprop) {
     fp.csize = pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
     fp.tps = (fp.patch && fp.csize == 1) ? pick_tps() : 1;
     DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize));
@@ -234,6 +244,7 @@ struct ConvOp {
     fp.n_mma = N; fp.n_chunks = N / 32;
     fp.bias = nullptr; fp.stats = stats; fp.stats_ld = N;
     fit_stages(fp);
+    }
     // ---- dgrad
     if (has_dgrad) {
       pick_tile(dg_out_w, dg_out_h, &bw, &bh);
@@ -248,7 +259,7 @@ struct ConvOp {
       dg.csize = pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
       dg.tps = (dg.patch && dg.csize == 1) ? pick_tps() : 1;
       DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize));
-      DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, C, C, bw, bh));
+      DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
       dg.kh = dg.kw = k; dg.stride = 1; dg.offx = dg.offy = dg_off;
@@ -259,6 +270,7 @@ struct ConvOp {
     }
     // ---- wgrad
     wg = TcWgradParams{};
+    if (!do_wgrad) return 0;
     wg.kp = (wg_w % 32 == 0) ? 32 : 16;
     DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1, true));
     wg.xshare = (stride == 1 && k == 3 && getenv("DIP_NO_XSHARE") == nullptr) ? 1 : 0;
@@ -306,7 +318,7 @@ struct ConvOp {
       SimtConvArgs a{};
       a.A = dg_in; a.a_h = dg_in_h; a.a_w = dg_in_w; a.a_ld = 128; a.a_c = 128;
       a.Wp = wp_d; a.n_rows = crows; a.c_pad = 128;
-      a.D = dg_out; a.d_h = dg_out_h; a.d_w = dg_out_w; a.d_ld = C; a.d_c = C;
+      a.D = dg_out; a.d_h = dg_out_h; a.d_w = dg_out_w; a.d_ld = dg_ld; a.d_c = C;
       a.kh = a.kw = k; a.stride = 1; a.offx = a.offy = dg_off; a.bias = nullptr;
       launch_simt_conv(a, s);
       DIP_CUDA(cudaGetLastError());
@@ -329,7 +341,7 @@ struct ConvOp {
       a.partial = partial; a.c_pad = c_pad; a.ksplits = ks = simt_ksplits;
       launch_simt_wgrad(a, s);
     }
-    launch_wgrad_reduce(partial, ks, N, C, k, k, rot, c_pad, dw, s);
+    launch_wgrad_reduce(partial, ks, N, C, k, k, rot, c_pad, dw, s, Ctot, coff);
     DIP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -339,25 +351,26 @@ struct ConvOp {
 struct PackEntry {
   const float* w; float* dst_f; float* dst_d;
   int N, C, k, rot, n_rows, c_pad, c_rows;
+  int Ctot, coff;   // weight has Ctot input channels; this entry packs engine channels [coff, coff + C)
 };
 __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
   pdl_enter();
   const PackEntry e = tab[blockIdx.y];
   const int taps = e.k * e.k;
-  const long long nf = (long long)taps * e.n_rows * e.c_pad;
+  const long long nf = e.dst_f != nullptr ? (long long)taps * e.n_rows * e.c_pad : 0;
   const long long nd = e.dst_d != nullptr ? (long long)taps * e.c_rows * 128 : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (long long)gridDim.x * blockDim.x) {
     if (i < nf) {
       const int c = (int)(i % e.c_pad), n = (int)((i / e.c_pad) % e.n_rows), tap = (int)(i / ((long long)e.c_pad * e.n_rows));
       float v = 0.f;
-      if (n < e.N && c < e.C) v = e.w[((long long)n * e.C + (c + e.rot) % e.C) * taps + tap];
+      if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
       e.dst_f[i] = v;
     } else {
       const long long j = i - nf;
       const int n = (int)(j % 128), c = (int)((j / 128) % e.c_rows), tapf = (int)(j / (128LL * e.c_rows));
       const int tap = taps - 1 - tapf;
       float v = 0.f;
-      if (n < e.N && c < e.C) v = e.w[((long long)n * e.C + (c + e.rot) % e.C) * taps + tap];
+      if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
       e.dst_d[j] = v;
     }
   }
@@ -416,11 +429,13 @@ struct Level {
   int H, W, h, w, Cin;
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
   float *dUp;  // [h][w][128] adjoint of the upsampling applied to dCat
+  float *dS;   // skip=128: [H][W][Cin] input gradient of the (tensor-core) skip conv, levels > 0
   float *dRaw_v, *dA_u, *dRaw_u, *dP_cat, *dCat, *dRaw_s, *dRaw_d2, *dP_d1, *dRaw_d1, *ZS, *dPin;
   BnLayer bn_s, bn_d1, bn_d2, bn_cat, bn_u, bn_v;
   int p_skip_w, p_skip_b;
   double* dw_s;
   ConvOp d1, d2, up, c11;
+  ConvOp sk, up_a, up_b;   // skip=128 only: 1x1 skip conv Cin -> 128; channel halves of the 256 -> 128 up conv (dgrad / wgrad)
 };
 
 }  // namespace dip
@@ -492,7 +507,8 @@ static int build_plan(dip_plan* P, Arena& A) {
   const dip_net_desc& d = P->desc;
   const int L = d.num_scales, CH = d.channels, CS = d.skip_channels;
   if (CH != 128) return fail("dip-b200: only num_channels_down == num_channels_up == 128 is supported by the engine");
-  if (CS != 4) return fail("dip-b200: only num_channels_skip == 4 is supported by the engine (round 1)");
+  if (CS != 4 && CS != 128) return fail("dip-b200: num_channels_skip must be 4 or 128");
+  const bool wide = CS == 128;   // skip branch on the tensor cores, 256-channel concat
   if (d.in_channels % 4 != 0 || d.in_channels < 4 || d.in_channels > 128 || (d.in_channels & (d.in_channels - 1)))
     return fail("dip-b200: input depth must be a power of two in [4,128]");
   if (d.out_channels < 1 || d.out_channels > 4) return fail("dip-b200: num_output_channels must be <= 4");
@@ -540,6 +556,15 @@ static int build_plan(dip_plan* P, Arena& A) {
     bn_init(v.bn_cat, 128 + CS, CS, v.H * v.W, b1 + 0, -1);
     // up 3x3 (128+CS) -> 128
     v.up.C = 128 + CS; v.up.k = 3; v.up.stride = 1; v.up.rot = CS; v.up.p_w = b1 + 2; v.up.p_b = b1 + 3;
+    if (wide) {
+      v.up.do_wgrad = false;
+      v.sk.C = v.Cin; v.sk.k = 1; v.sk.stride = 1; v.sk.p_w = b0; v.sk.p_b = b0 + 1;
+      for (ConvOp* h : {&v.up_a, &v.up_b}) {
+        h->C = 128; h->Ctot = 128 + CS; h->k = 3; h->stride = 1; h->rot = CS; h->p_w = b1 + 2; h->p_b = b1 + 3;
+        h->do_fprop = false; h->dg_ld = 128 + CS;
+      }
+      v.up_b.coff = 128;
+    }
     P->numel[b1 + 2] = 128LL * (128 + CS) * 9; P->numel[b1 + 3] = 128;
     bn_init(v.bn_u, 128, 0, v.H * v.W, b1 + 4, b1 + 3);
     // 1x1 128 -> 128
@@ -606,6 +631,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.dP_d1 = A.get<float>(hwp * 128);
     v.dRaw_d1 = A.get<float>(hw * 128);
     v.ZS = l > 0 ? A.get<float>(HW * 128) : nullptr;
+    v.dS = (wide && l > 0) ? A.get<float>(HW * 128) : nullptr;
     v.dPin = l > 0 ? A.get<float>(HWp * 128) : nullptr;
     reg(pf + "Pin", v.Pin, v.H + 2, v.W + 2, v.Cin, v.Cin);
     reg(pf + "raw_s", v.raw_s, v.H, v.W, CS, CS);
@@ -666,7 +692,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     c.set_shapes();
     c.in = v.P_cat; c.in_rows = v.H + 2; c.in_cols = v.W + 2; c.in_ld = 128 + CS; c.offx = c.offy = 0;
     c.out = v.raw_u; c.out_h = v.H; c.out_w = v.W; c.stats = v.bn_u.fwd;
-    c.has_dgrad = true;
+    c.has_dgrad = !wide;
     c.dg_in = v.dRaw_u; c.dg_in_h = v.H; c.dg_in_w = v.W; c.dg_out = v.dP_cat; c.dg_out_h = v.H + 2; c.dg_out_w = v.W + 2; c.dg_off = -2;
     c.wg_dy = v.dRaw_u; c.wg_h = v.H; c.wg_w = v.W;
     // 1x1: A_u -> raw_v
@@ -677,12 +703,34 @@ static int build_plan(dip_plan* P, Arena& A) {
     e.has_dgrad = true;
     e.dg_in = v.dRaw_v; e.dg_in_h = v.H; e.dg_in_w = v.W; e.dg_out = v.dA_u; e.dg_out_h = v.H; e.dg_out_w = v.W; e.dg_off = 0;
     e.wg_dy = v.dRaw_v; e.wg_h = v.H; e.wg_w = v.W;
-    for (ConvOp* op : {&a, &b, &c, &e}) {
-      op->wp_f = A.get<float>(op->wp_f_elems());
+    std::vector<ConvOp*> ops = {&a, &b, &c, &e};
+    if (wide) {
+      // skip conv 1x1 on the interior of the padded level input
+      ConvOp& k1 = v.sk;
+      k1.set_shapes();
+      k1.in = v.Pin; k1.in_rows = v.H + 2; k1.in_cols = v.W + 2; k1.in_ld = v.Cin; k1.offx = k1.offy = 1;
+      k1.out = v.raw_s; k1.out_h = v.H; k1.out_w = v.W; k1.stats = v.bn_s.fwd;
+      k1.has_dgrad = l > 0;
+      k1.dg_in = v.dRaw_s; k1.dg_in_h = v.H; k1.dg_in_w = v.W; k1.dg_out = v.dS; k1.dg_out_h = v.H; k1.dg_out_w = v.W; k1.dg_off = 0;
+      k1.wg_dy = v.dRaw_s; k1.wg_h = v.H; k1.wg_w = v.W;
+      ops.push_back(&k1);
+      for (ConvOp* h : {&v.up_a, &v.up_b}) {
+        h->set_shapes();
+        h->in = v.P_cat + h->coff; h->in_rows = v.H + 2; h->in_cols = v.W + 2; h->in_ld = 128 + CS; h->offx = h->offy = 0;
+        h->out = v.raw_u; h->out_h = v.H; h->out_w = v.W; h->stats = nullptr;
+        h->has_dgrad = true;
+        h->dg_in = v.dRaw_u; h->dg_in_h = v.H; h->dg_in_w = v.W;
+        h->dg_out = v.dP_cat + h->coff; h->dg_out_h = v.H + 2; h->dg_out_w = v.W + 2; h->dg_off = -2;
+        h->wg_dy = v.dRaw_u; h->wg_h = v.H; h->wg_w = v.W;
+        ops.push_back(h);
+      }
+    }
+    for (ConvOp* op : ops) {
+      op->wp_f = op->do_fprop ? A.get<float>(op->wp_f_elems()) : nullptr;
       op->wp_d = op->has_dgrad ? A.get<float>(op->wp_d_elems()) : nullptr;
       op->simt_ksplits = op->wg_h < 64 ? op->wg_h : 64;
       op->timer = &P->timer;
-      const size_t pe = op->partial_elems(prec);
+      const size_t pe = op->do_wgrad ? op->partial_elems(prec) : 0;
       if (pe > partial_max) partial_max = pe;
       P->convs.push_back(op);
     }
@@ -703,7 +751,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     for (ConvOp* op : P->convs) DIP_CHECK(op->build_tc(P->partial));
   P->pack_max = 0;
   for (ConvOp* op : P->convs) {
-    const long long n = (long long)op->wp_f_elems() + (op->has_dgrad ? (long long)op->wp_d_elems() : 0);
+    const long long n = (op->do_fprop ? (long long)op->wp_f_elems() : 0) + (op->has_dgrad ? (long long)op->wp_d_elems() : 0);
     if (n > P->pack_max) P->pack_max = n;
   }
   return 0;
@@ -713,8 +761,9 @@ static int upload_tables(dip_plan* P) {
   std::vector<PackEntry> pk;
   for (ConvOp* op : P->convs) {
     PackEntry e{};
-    e.w = P->params[op->p_w]; e.dst_f = op->wp_f; e.dst_d = op->has_dgrad ? op->wp_d : nullptr;
+    e.w = P->params[op->p_w]; e.dst_f = op->do_fprop ? op->wp_f : nullptr; e.dst_d = op->has_dgrad ? op->wp_d : nullptr;
     e.N = op->N; e.C = op->C; e.k = op->k; e.rot = op->rot; e.n_rows = op->N; e.c_pad = op->c_pad; e.c_rows = op->crows;
+    e.Ctot = op->Ctot; e.coff = op->coff;
     pk.push_back(e);
   }
   DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
@@ -725,8 +774,11 @@ static int upload_tables(dip_plan* P) {
     if (b->p_bias >= 0) cv.push_back(CvtEntry{b->dbias, P->grads[b->p_bias], b->C, 0});
     else cv.push_back(CvtEntry{b->dbias, nullptr, 0, 0});
   }
-  for (size_t l = 0; l < P->lv.size(); ++l)
-    cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0});
+  for (size_t l = 0; l < P->lv.size(); ++l) {
+    // skip=128: the skip conv's weight gradient comes from the tensor-core wgrad, not from fp64 accumulators
+    if (P->desc.skip_channels == 128) cv.push_back(CvtEntry{P->lv[l].dw_s, nullptr, 0, 0});
+    else cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0});
+  }
   cv.push_back(CvtEntry{P->dw_head, P->grads[P->p_head_w], (int)P->numel[P->p_head_w], 0});
   cv.push_back(CvtEntry{P->db_head, P->grads[P->p_head_b], (int)P->numel[P->p_head_b], 0});
   if ((int)cv.size() != P->n_cvt) return fail("internal: cvt table size mismatch");
@@ -764,9 +816,14 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   const bool last = l == (int)P->lv.size() - 1;
   const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
   // skip branch: 1x1 conv Cin -> CS (+ statistics)
-  launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
-                    v.bn_s.fwd, s);
-  nl += 1;
+  if (CS == 128) {
+    DIP_CHECK(v.sk.run_fprop(prec, P->params[v.p_skip_b], s));
+    nl += prec == DIP_PRECISION_FP32 ? 2 : 1;
+  } else {
+    launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
+                      v.bn_s.fwd, s);
+    nl += 1;
+  }
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
   launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, v.P_d1, 128, 1, 1, s);
@@ -870,9 +927,18 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   nl += wl + 1;
   // up conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl));
-  DIP_CHECK(v.up.run_wgrad(prec, P->partial, P->grads[v.up.p_w], fork_side(P, s)));
-  DIP_CHECK(v.up.run_dgrad(prec, s));
-  nl += wl + 1;
+  if (CS == 128) {
+    cudaStream_t ws = fork_side(P, s);
+    DIP_CHECK(v.up_a.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
+    DIP_CHECK(v.up_b.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
+    DIP_CHECK(v.up_a.run_dgrad(prec, s));
+    DIP_CHECK(v.up_b.run_dgrad(prec, s));
+    nl += 2 * (wl + 1);
+  } else {
+    DIP_CHECK(v.up.run_wgrad(prec, P->partial, P->grads[v.up.p_w], fork_side(P, s)));
+    DIP_CHECK(v.up.run_dgrad(prec, s));
+    nl += wl + 1;
+  }
   // concat BN
   BnRef rc = bn_ref(P, v.bn_cat);
   launch_cat_bwd_reduce(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, s);
@@ -882,7 +948,11 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   nl += 3;
   // skip branch
   DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, s, nl));
-  {
+  if (CS == 128) {
+    DIP_CHECK(v.sk.run_wgrad(prec, P->partial, P->grads[v.p_skip_w], fork_side(P, s)));
+    nl += wl;
+    if (l > 0) { DIP_CHECK(v.sk.run_dgrad(prec, s)); nl += 1; }   // dS, added to the fold of dPin by the level above
+  } else {
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
     // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
     launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
@@ -894,7 +964,8 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   if (!last) {
     DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), s, nl));
     Level& n = P->lv[l + 1];
-    src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
+    if (CS == 128) { src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = 128; }
+    else src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
   } else {
     src_d2 = src_plain(v.dUp, 128, 0);
   }
@@ -1229,9 +1300,10 @@ int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {
 // ---------------------------------------------------------------------------------------------- single-op entry points
 size_t dip_op_scratch_bytes(void) { return (size_t)96 << 20; }
 
-static int op_common(ConvOp& op, int N, int C, int k, int stride, int rot, float* scratch, const float* w, cudaStream_t s) {
+static int op_common(ConvOp& op, int N, int C, int k, int stride, int rot, float* scratch, const float* w, cudaStream_t s,
+                     int max_c = 160) {
   if (N != 128) return fail("dip_op_conv_*: N must be 128");
-  if (C % 4 != 0 || C > 160) return fail("dip_op_conv_*: C must be a multiple of 4 and <= 160");
+  if (C % 4 != 0 || C > max_c) return fail("dip_op_conv_*: C must be a multiple of 4 and <= " + std::to_string(max_c));
   op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;
   op.set_shapes();
   op.wp_f = scratch;
@@ -1251,7 +1323,7 @@ int dip_op_conv_fprop(const void* a, int a_h, int a_w, int a_c, const void* w, c
   DIP_CHECK(engine_init());
   cudaStream_t s = (cudaStream_t)stream;
   ConvOp op;
-  DIP_CHECK(op_common(op, N, C, k, stride, rot, (float*)scratch, (const float*)w, s));
+  DIP_CHECK(op_common(op, N, C, k, stride, rot, (float*)scratch, (const float*)w, s, 256));
   op.in = (const float*)a; op.in_rows = a_h; op.in_cols = a_w; op.in_ld = a_c; op.offx = offx; op.offy = offy;
   op.out = (float*)d; op.out_h = d_h; op.out_w = d_w; op.stats = stats;
   op.has_dgrad = false;

@@ -121,6 +121,9 @@ struct GradSrc {
   const float* ds;     // [H][W][n2] or null
   const float* w2;     // [n2][C]
   int n2;
+  // kind 1: optional plain addend (skip=128: the tensor-core dgrad of the next level's skip conv): g += add[p][c]
+  const float* add;    // [H][W][ld_add] or null
+  int ld_add;
   int bilinear;        // kind 2
   // kind 3: g[p][c] = sum_k dout[k][p] * o[k][p] * (1 - o[k][p]) * wh[k][c]; also accumulates the head's own gradients
   const float* dl4;    // [npix][4] logit gradients dout * o * (1 - o) (launch_head_dlogit)
@@ -191,8 +194,10 @@ void launch_pack_fprop(const float* w, int N, int C, int kh, int kw, int rot, fl
 void launch_pack_dgrad(const float* w, int N, int C, int kh, int kw, int rot, float* dst, int c_rows, int n_pad,
                        cudaStream_t s);
 // split-K partials [ksplits][tap][128][c_pad] -> OIHW gradient [N][C][kh][kw]
+//   dw has Ctot input channels; the partials cover engine channels [coff, coff + C): torch channel (c + coff + rot) % Ctot
+//   (Ctot = 0: Ctot = C)
 void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh, int kw, int rot, int c_pad,
-                         float* dw, cudaStream_t s);
+                         float* dw, cudaStream_t s, int Ctot = 0, int coff = 0);
 
 // Adam ---------------------------------------------------------------------------------------------
 struct AdamTable {

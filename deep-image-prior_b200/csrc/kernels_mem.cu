@@ -46,6 +46,7 @@ __device__ __forceinline__ float4 shfl_xor4(float4 a, int o) {
                      __shfl_xor_sync(0xffffffffu, a.z, o), __shfl_xor_sync(0xffffffffu, a.w, o));
 }
 
+static constexpr int kMaxBnC = 264;   // widest BatchNorm: the 256-channel concat of the skip=128 configuration
 // per-thread BN coefficients for channels 4v..4v+3
 struct Bn4 {
   float4 mean, rstd, scale, shift;
@@ -55,7 +56,7 @@ struct Bn4 {
 // TAG distinguishes the static buffers when a kernel needs two BatchNorms.  v < 0: this thread needs no coefficients.
 template <int TAG>
 __device__ __forceinline__ Bn4 bn_coef(const BnRef& bn, int v) {
-  __shared__ __align__(16) float s_mean[136], s_rstd[136], s_scale[136], s_shift[136];
+  __shared__ __align__(16) float s_mean[kMaxBnC], s_rstd[kMaxBnC], s_scale[kMaxBnC], s_shift[kMaxBnC];
   for (int c = threadIdx.x; c < bn.C; c += blockDim.x) {
     const int ct = (c + bn.rot) % bn.C;
     const double m = acc_get(bn.fwd + c * kAccS) * static_cast<double>(bn.inv_n);
@@ -84,7 +85,7 @@ __device__ __forceinline__ Bn4 bn_coef(const BnRef& bn, int v) {
 // means of the backward sums (sum dz / n, sum dz*xhat / n), block-cooperative like bn_coef
 template <int TAG>
 __device__ __forceinline__ void bwd_means(const double* __restrict__ bwd, int C, float inv_n, int v, float4& m1, float4& m2) {
-  __shared__ __align__(16) float s_m1[136], s_m2[136];
+  __shared__ __align__(16) float s_m1[kMaxBnC], s_m2[kMaxBnC];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_m1[c] = static_cast<float>(acc_get(bwd + c * kAccS) * inv_n);
     s_m2[c] = static_cast<float>(acc_get(bwd + (C + c) * kAccS) * inv_n);
@@ -521,6 +522,7 @@ __device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr,
       r = f4fma(d.z, sr.w[2], r);
       r = f4fma(d.w, sr.w[3], r);
     }
+    if (s.add != nullptr) r = f4add(r, ld4(s.add + static_cast<size_t>(p) * s.ld_add + 4 * v));
     return r;
   }
   if (KIND == 2) return upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
@@ -690,7 +692,7 @@ struct CatBwdCoef {
   float4 beta, inv_gamma, scale;
 };
 __device__ __forceinline__ CatBwdCoef cat_bwd_coef(const BnRef& bn, int v) {
-  __shared__ __align__(16) float s_beta[136], s_ig[136], s_sc[136];
+  __shared__ __align__(16) float s_beta[kMaxBnC], s_ig[kMaxBnC], s_sc[kMaxBnC];
   for (int c = threadIdx.x; c < bn.C; c += blockDim.x) {
     const int ct = (c + bn.rot) % bn.C;
     const double m = acc_get(bn.fwd + c * kAccS) * static_cast<double>(bn.inv_n);
@@ -1043,7 +1045,7 @@ void launch_pack_dgrad(const float* w, int N, int C, int kh, int kw, int rot, fl
 // Split-K reduction.  Block = 32 float4 columns x 8 split-parts: a warp reads 512 contiguous bytes of one split;
 // the 8 parts are folded through shared memory (deterministic order), then scattered to the OIHW gradient.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int ksplits, int N, int C, int taps,
-                                                      int rot, int c_pad, float* __restrict__ dw) {
+                                                      int rot, int c_pad, float* __restrict__ dw, int Ctot, int coff) {
   pdl_enter();
   __shared__ float4 sm[8][32];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
@@ -1072,15 +1074,16 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
     if (n < N) {
       for (int q = 0; q < 4; ++q) {
         const int c = 4 * c4 + q;
-        if (c < C) dw[(static_cast<size_t>(n) * C + (c + rot) % C) * taps + tap] = sv[q];
+        if (c < C) dw[(static_cast<size_t>(n) * Ctot + (c + coff + rot) % Ctot) * taps + tap] = sv[q];
       }
     }
   }
 }
 void launch_wgrad_reduce(const float* partial, int ksplits, int N, int C, int kh, int kw, int rot, int c_pad,
-                         float* dw, cudaStream_t s) {
+                         float* dw, cudaStream_t s, int Ctot, int coff) {
   const int total4 = kh * kw * 128 * (c_pad / 4);
-  launch_k(k_wgrad_reduce, dim3((total4 + 31) / 32), dim3(256), 0, s, 1, partial, ksplits, N, C, kh * kw, rot, c_pad, dw);
+  launch_k(k_wgrad_reduce, dim3((total4 + 31) / 32), dim3(256), 0, s, 1, partial, ksplits, N, C, kh * kw, rot, c_pad, dw,
+           Ctot > 0 ? Ctot : C, coff);
 }
 
 // ------------------------------------------------------------------------------------------------ Adam

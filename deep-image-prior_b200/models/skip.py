@@ -205,8 +205,8 @@ def skip(num_input_channels=2, num_output_channels=3,
     chans = set(num_channels_down) | set(num_channels_up)
     if chans != {128}:
         why = 'num_channels_down/up must all be 128'
-    elif set(num_channels_skip) != {4}:
-        why = 'num_channels_skip must all be 4'
+    elif set(num_channels_skip) not in ({4}, {128}):
+        why = 'num_channels_skip must all be 4 or all be 128'
     elif set(filter_size_down) != {3} or set(filter_size_up) != {3} or filter_skip_size != 1:
         why = 'filter sizes must be 3/3/1'
     elif pad != 'reflection':
@@ -223,7 +223,7 @@ def skip(num_input_channels=2, num_output_channels=3,
         why = 'num_output_channels <= 4 and num_input_channels in {4,...,128} (power of two)'
     if why is None:
         net._dip_spec = dict(in_channels=num_input_channels, out_channels=num_output_channels, num_scales=n,
-                             channels=128, skip_channels=4, bilinear=upsample_mode[0] == 'bilinear')
+                             channels=128, skip_channels=num_channels_skip[0], bilinear=upsample_mode[0] == 'bilinear')
     else:
         net._dip_why = why
     return net

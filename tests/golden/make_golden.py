@@ -17,11 +17,11 @@ from oracle import ref_harness  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtype=torch.float32, threads=8):
+def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtype=torch.float32, threads=8, skip_n11=4):
     torch.set_num_threads(threads)
     with ref_harness.reference_modules() as ref:
         torch.manual_seed(0)
-        net = ref.models.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+        net = ref.models.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=skip_n11, num_scales=5,
                                  upsample_mode=mode).type(dtype)
         torch.manual_seed(1)
         z0 = ref.common_utils.get_noise(32, 'noise', (H, W)).type(dtype).detach()
@@ -57,7 +57,7 @@ def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtyp
     np.savez_compressed(os.path.join(HERE, name + '.npz'), H=H, W=W, mode=mode, iters=iters, sigma=sigma, lr=lr,
                         masked=masked, losses=np.array(losses), out0=out0.numpy(), gnorm0=gnorm0, gsum0=gsum0,
                         g_head_w=g_head_w, g_up0_w_slice=g_up0_w_slice, pnorm=pnorm, rm=rm, rv=rv, nbt=nbt,
-                        dtype=str(dtype), state_keys=np.array(keys))
+                        dtype=str(dtype), state_keys=np.array(keys), skip_n11=skip_n11)
     print(name, 'losses', losses)
 
 
@@ -130,6 +130,12 @@ def run_sr_case(name, H, W, iters, dtype, factor=4, sigma=0.03, lr=0.01, threads
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'inpaint':   # only the inpainting (skip=128) fixtures
+        run_case('inpaint64x96_nearest_masked_skip128_fp64', 64, 96, 'nearest', 3, sigma=0.03, masked=True,
+                 dtype=torch.float64, skip_n11=128)
+        run_case('inpaint64x96_nearest_masked_skip128_fp32', 64, 96, 'nearest', 3, sigma=0.03, masked=True,
+                 dtype=torch.float32, skip_n11=128)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sr':   # only the super-resolution fixtures
         run_downsampler_cases()
         run_sr_case('sr64x96_fp64', 64, 96, 3, torch.float64)
@@ -138,6 +144,10 @@ if __name__ == '__main__':
     run_case('denoise64_bilinear_fp32', 64, 64, 'bilinear', 4)
     run_case('denoise64_bilinear_fp64', 64, 64, 'bilinear', 4, dtype=torch.float64)
     run_case('denoise96x64_nearest_masked_fp64', 96, 64, 'nearest', 3, sigma=0.03, masked=True, dtype=torch.float64)
+    run_case('inpaint64x96_nearest_masked_skip128_fp64', 64, 96, 'nearest', 3, sigma=0.03, masked=True,
+             dtype=torch.float64, skip_n11=128)
+    run_case('inpaint64x96_nearest_masked_skip128_fp32', 64, 96, 'nearest', 3, sigma=0.03, masked=True,
+             dtype=torch.float32, skip_n11=128)
     run_downsampler_cases()
     run_sr_case('sr64x96_fp64', 64, 96, 3, torch.float64)
     run_sr_case('sr64x96_fp32', 64, 96, 3, torch.float32)

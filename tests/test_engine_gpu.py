@@ -28,8 +28,8 @@ def rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
-def make_problem(H, W, mode, seed=0, masked=False):
-    cfg = O.SkipConfig(upsample_mode=mode)
+def make_problem(H, W, mode, seed=0, masked=False, skip_channels=4):
+    cfg = O.SkipConfig(upsample_mode=mode, skip_channels=skip_channels)
     params = O.init_params(cfg, seed=seed)
     z0 = O.get_noise(32, (H, W), seed=1)
     g = torch.Generator().manual_seed(2)
@@ -40,7 +40,7 @@ def make_problem(H, W, mode, seed=0, masked=False):
 
 def make_engine(cfg, params, H, W, prec):
     import dip_engine as de
-    plan = de.Plan(32, 3, cfg.num_scales, 128, 4, cfg.upsample_mode == "bilinear", H, W,
+    plan = de.Plan(32, 3, cfg.num_scales, 128, cfg.skip_channels, cfg.upsample_mode == "bilinear", H, W,
                    precision=de.PRECISION_TF32 if prec == "tf32" else de.PRECISION_FP32)
     dparams = [p.detach().cuda().contiguous() for p in params]
     dgrads = [torch.zeros_like(p) for p in dparams]
@@ -80,10 +80,11 @@ def check_tf32_gradients_like_cudnn(cfg, params, z0, target, dgrads, names):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
-@pytest.mark.parametrize("shape_mode", [(64, 64, "bilinear"), (96, 64, "nearest"), (64, 128, "bilinear")])
+@pytest.mark.parametrize("shape_mode", [(64, 64, "bilinear", 4), (96, 64, "nearest", 4), (64, 128, "bilinear", 4),
+                                        (64, 96, "nearest", 128), (128, 64, "bilinear", 128)])
 def test_forward_backward_vs_oracle(shape_mode, prec):
-    H, W, mode = shape_mode
-    cfg, params, z0, target, _ = make_problem(H, W, mode)
+    H, W, mode, cs = shape_mode   # cs = 128: the inpainting configuration (BASELINE config 4: skip=128, 256-channel concat)
+    cfg, params, z0, target, _ = make_problem(H, W, mode, skip_channels=cs)
     tape = {}
     out_ref = O.skip_forward(params, z0, cfg, tape=tape)
     loss = O.mse_loss(out_ref, target)
@@ -123,19 +124,23 @@ def test_forward_backward_vs_oracle(shape_mode, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
-def test_against_reference_golden(prec):
-    g = np.load(os.path.join(GOLD, "denoise64_bilinear_fp32.npz"))
+@pytest.mark.parametrize("name", ["denoise64_bilinear_fp32", "inpaint64x96_nearest_masked_skip128_fp32"])
+def test_against_reference_golden(name, prec):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
     H, W = int(g["H"]), int(g["W"])
-    cfg, params, z0, target, _ = make_problem(H, W, "bilinear")
+    masked = bool(g["masked"])
+    cfg, params, z0, target, mask = make_problem(H, W, str(g["mode"]), masked=masked,
+                                                 skip_channels=int(g["skip_n11"]) if "skip_n11" in g else 4)
     gn = torch.Generator().manual_seed(123)
     noise = torch.randn(z0.shape, generator=gn)
     plan, dparams, dgrads = make_engine(cfg, params, H, W, prec)
     out = plan.forward(z0.cuda(), noise=noise.cuda(), sigma=float(g["sigma"]))
     torch.cuda.synchronize()
     assert np.abs(out.cpu().numpy() - g["out0"]).max() < FWD_TOL[prec]
-    loss = ((out.cpu() - target) ** 2).mean().item()
+    m = mask if masked else torch.ones(1, 1, H, W)
+    loss = ((m * (out.cpu() - target)) ** 2).mean().item()
     assert abs(loss - float(g["losses"][0])) < (1e-5 if prec == "fp32" else 1e-3)
-    dout = (2.0 * (out - target.cuda()) / out.numel()).contiguous()
+    dout = (2.0 * (m * m).cuda() * (out - target.cuda()) / out.numel()).contiguous()
     plan.backward(dout)
     torch.cuda.synchronize()
     if prec == "tf32":

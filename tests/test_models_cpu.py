@@ -26,6 +26,20 @@ def test_state_dict_keys_match_reference():
     assert len(list(net.parameters())) == 112
 
 
+def test_inpainting_config_is_accelerated_and_matches_reference_layout():
+    """BASELINE config 4 (inpainting.ipynb kate: skip(32, 3, [128]*5, [128]*5, [128]*5, nearest, reflection))."""
+    g = np.load(os.path.join(GOLD, "inpaint64x96_nearest_masked_skip128_fp32.npz"))
+    torch.manual_seed(0)
+    net = models.skip(32, 3, num_channels_down=[128] * 5, num_channels_up=[128] * 5, num_channels_skip=[128] * 5,
+                      upsample_mode="nearest", need_sigmoid=True, need_bias=True, pad="reflection", act_fun="LeakyReLU")
+    assert net._dip_spec is not None and net._dip_spec["skip_channels"] == 128 and not net._dip_spec["bilinear"]
+    assert list(net.state_dict().keys()) == [str(k) for k in g["state_keys"]]
+    assert sum(p.numel() for p in net.parameters()) == 3002627
+    params = O.init_params(O.SkipConfig(skip_channels=128, upsample_mode="nearest"), seed=0)
+    for a, b in zip(net.parameters(), params):
+        assert a.shape == b.shape and torch.equal(a.detach(), b.detach())
+
+
 def test_init_matches_oracle_order():
     net = build(seed=5)
     params = O.init_params(O.SkipConfig(), seed=5)

@@ -18,7 +18,7 @@ def load(name):
 
 def run_oracle(g, dtype, iters=None):
     H, W = int(g["H"]), int(g["W"])
-    cfg = O.SkipConfig(upsample_mode=str(g["mode"]))
+    cfg = O.SkipConfig(upsample_mode=str(g["mode"]), skip_channels=int(g["skip_n11"]) if "skip_n11" in g else 4)
     params = O.init_params(cfg, seed=0, dtype=dtype)
     z0 = O.get_noise(32, (H, W), seed=1).to(dtype)
     gen = torch.Generator().manual_seed(2)
@@ -38,7 +38,8 @@ def run_oracle(g, dtype, iters=None):
     return cfg, params, losses, rec
 
 
-@pytest.mark.parametrize("name", ["denoise64_bilinear_fp64", "denoise96x64_nearest_masked_fp64"])
+@pytest.mark.parametrize("name", ["denoise64_bilinear_fp64", "denoise96x64_nearest_masked_fp64",
+                                  "inpaint64x96_nearest_masked_skip128_fp64"])
 def test_oracle_matches_golden_fp64(name):
     torch.set_num_threads(8)
     g = load(name)
@@ -62,6 +63,14 @@ def test_oracle_matches_golden_fp32():
     assert np.allclose(rec["out0"].numpy(), g["out0"], atol=2e-6)
     assert abs(losses[0] - g["losses"][0]) < 1e-6
     assert abs(losses[1] - g["losses"][1]) < 2e-3
+
+
+def test_inpaint_param_layout_matches_reference():
+    g = load("inpaint64x96_nearest_masked_skip128_fp64")
+    keys = [k for k in g["state_keys"] if not ("running" in k or "num_batches" in k)]
+    lay = O.param_layout(O.SkipConfig(skip_channels=128, upsample_mode="nearest"))
+    assert len(lay) == len(keys) == 112
+    assert sum(int(np.prod(s)) for _, s in lay) == 3002627
 
 
 def test_param_layout_matches_reference_state_dict():
