@@ -67,8 +67,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   const int csize = p.csize;
   const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
-  const int n_iters = (num_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile0 = (blockIdx.x / csize) * csize + crank;  // first tile of this CTA; stride gridDim.x
+  // N split (small levels, fewer tiles than SMs): n_split CTAs share a pixel tile, each computes n_mma = N / n_split
+  // output channels -> each CTA ingests 1/n_split of the weights (per-SM ingest is what bounds a lone tile) and the
+  // tile's work spreads over more SMs.  CTA = (tile slot, n_part); n_split == 1: slots == gridDim.x.
+  const int n_split = p.n_split < 1 ? 1 : p.n_split;
+  const int n_part = blockIdx.x % n_split;
+  const int n_off = n_part * p.n_mma;             // first output channel of this CTA
+  const int n_total = p.n_mma * n_split;          // rows per tap of the packed weights
+  const int tile_stride = gridDim.x / n_split;
+  const int n_iters = (num_tiles + tile_stride - 1) / tile_stride;
+  const int tile0 = n_split > 1 ? blockIdx.x / n_split : (blockIdx.x / csize) * csize + crank;  // first tile; stride tile_stride
   const uint32_t acc_cols = (p.n_mma + 31) & ~31;  // column stride between the two accumulators
 
   pdl_trigger();
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   }
   pdl_wait();  // everything above is independent of the previous kernel's results
   if (warp == 3) {
-    for (int i = lane; i < 160; i += 32) ctl->bias[i] = (p.bias != nullptr && i < p.n_mma) ? p.bias[i] : 0.f;
+    for (int i = lane; i < 160; i += 32) ctl->bias[i] = (p.bias != nullptr && i < p.n_mma) ? p.bias[n_off + i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       int ab = 0;
       uint32_t aphase = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int tile = tile0 + it * gridDim.x;
+        const int tile = tile0 + it * tile_stride;
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
         const int x0 = tx * p.bw, y0 = ty * p.bh;
         if (p.patch) {
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                   mbar_expect_tx(&ctl->full[stage], tps * b_bytes);
                   if (csize == 1) {
                     for (int t = 0; t < tps; ++t)
-                      tma_load_2d(sb + t * b_bytes, &p.tmB, &ctl->full[stage], kb * 32, (tap + t) * p.n_mma);
+                      tma_load_2d(sb + t * b_bytes, &p.tmB, &ctl->full[stage], kb * 32, (tap + t) * n_total + n_off);
                   } else {
                     tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
                                    tap * p.n_mma + crank * b_rows, cmask);
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                 else mbar_arrive(&ctl->full[stage]);
                 if (ldA) tma_load_5d(sa, &p.tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
                 if (ldB) {
-                  if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * p.n_mma);
+                  if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * n_total + n_off);
                   else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
                                       tap * p.n_mma + crank * b_rows, cmask);
                 }
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     double stat_s1 = 0.0, stat_s2 = 0.0;
     const int bw_shift = 31 - __clz(p.bw);  // tile widths are powers of two
     for (int it = 0; it < n_iters; ++it) {
-      const int tile = tile0 + it * gridDim.x;
+      const int tile = tile0 + it * tile_stride;
       const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
       const int x0 = tx * p.bw, y0 = ty * p.bh;
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (et == 0) {
-        for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, j * 32, x0, y0);
+        for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, n_off + j * 32, x0, y0);
         tma_store_commit();
       }
       if (p.stats != nullptr && et < p.n_mma) {
@@ -387,10 +395,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.stats != nullptr && et < p.n_mma && et < p.stats_ld) {
+    if (p.stats != nullptr && et < p.n_mma && n_off + et < p.stats_ld) {
       const int rep = (blockIdx.x % kAccR) * kAccLine;
-      atomicAdd(&p.stats[et * kAccStride + rep], stat_s1);
-      atomicAdd(&p.stats[(p.stats_ld + et) * kAccStride + rep], stat_s2);
+      atomicAdd(&p.stats[(n_off + et) * kAccStride + rep], stat_s1);
+      atomicAdd(&p.stats[(p.stats_ld + n_off + et) * kAccStride + rep], stat_s2);
     }
     if (et == 0) tma_store_wait_all0();
   }
@@ -595,6 +603,10 @@ cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
   int grid = (tiles + cs - 1) / cs * cs;
   const int cap = num_sms / cs * cs;
   if (grid > cap) grid = cap;
+  if (p.n_split > 1) {
+    if (cs != 1 || tiles * p.n_split > num_sms) return cudaErrorInvalidValue;
+    grid = tiles * p.n_split;   // one CTA per (tile, channel part)
+  }
   const size_t smem = tc_conv_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
   return launch_k(tc_conv_kernel, dim3(grid), dim3(kNumThreads), smem, s, cs, p);

@@ -30,6 +30,7 @@ struct TcConvParams {
   int pw, ph;              // patch extent in pixels
   int tps;                 // patch mode: filter taps per weight stage (1 or 2)
   int csize;               // thread-block cluster size (1, 2, 4): the weight tile is multicast across the cluster
+  int n_split;             // 1, 2 or 4 CTAs per pixel tile, each computing n_mma = N / n_split output channels (small levels)
   const float* bias;       // [n_mma] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
   int stats_ld;

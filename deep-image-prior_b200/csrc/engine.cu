@@ -159,6 +159,14 @@ static int pick_tps() {
   if (const char* e = getenv("DIP_TPS")) { const int t = atoi(e); if (t >= 1 && t <= 3) return t; }
   return 3;
 }
+// CTAs per pixel tile (output channels split across them) for launches with fewer tiles than SMs: n_rows % (32 * split) == 0
+static int pick_nsplit(int tiles, int n_rows) {
+  int mx = 4;
+  if (const char* e = getenv("DIP_NSPLIT_MAX")) mx = atoi(e);
+  int sp = 1;
+  while (sp * 2 <= mx && tiles * sp * 2 <= 148 && n_rows % (32 * sp * 2) == 0) sp *= 2;
+  return sp;
+}
 static void fit_stages(TcConvParams& p) {
   for (;;) {
     p.stages = 6;
@@ -234,14 +242,15 @@ struct ConvOp {
     if (do_fprop) {
     fp.csize = pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
     fp.tps = (fp.patch && fp.csize == 1) ? pick_tps() : 1;
-    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize));
+    fp.n_split = fp.csize == 1 ? pick_nsplit(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N) : 1;
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize / fp.n_split));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
     fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
     fp.kh = fp.kw = k; fp.stride = stride; fp.offx = offx; fp.offy = offy;
     fp.kblocks = c_pad / 32;
     fp.tail_mmas = (C % 32 == 0) ? 4 : (C % 32 + 7) / 8;
-    fp.n_mma = N; fp.n_chunks = N / 32;
+    fp.n_mma = N / fp.n_split; fp.n_chunks = fp.n_mma / 32;
     fp.bias = nullptr; fp.stats = stats; fp.stats_ld = N;
     fit_stages(fp);
     }
@@ -258,13 +267,14 @@ struct ConvOp {
       }
       dg.csize = pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
       dg.tps = (dg.patch && dg.csize == 1) ? pick_tps() : 1;
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize));
+      dg.n_split = dg.csize == 1 ? pick_nsplit(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows) : 1;
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize / dg.n_split));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
       dg.kh = dg.kw = k; dg.stride = 1; dg.offx = dg.offy = dg_off;
       dg.kblocks = 4; dg.tail_mmas = 4;
-      dg.n_mma = crows; dg.n_chunks = (crows + 31) / 32;
+      dg.n_mma = crows / dg.n_split; dg.n_chunks = (dg.n_mma + 31) / 32;
       dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
       fit_stages(dg);
     }
@@ -477,13 +487,20 @@ struct dip_plan {
   struct GraphKey { const void *z0, *target, *mask, *out, *slots, *adam; float sigma; uint64_t seed; double lr; };
   GraphKey gkey{};
   cudaGraphExec_t gexec = nullptr;
+  // notebook path (dip_forward / dip_backward called once per closure): each is replayed as its own CUDA graph over the
+  // plan's fixed staging buffers (zbuf / out_saved / dout); rebuilt when the bound pointers change
+  cudaGraphExec_t gfwd = nullptr, gbwd = nullptr;
   cudaStream_t gstream = nullptr;
   cudaEvent_t gev_in = nullptr, gev_out = nullptr;
   // weight-gradient chain runs on a private side stream, forked/joined with events (also inside graph capture)
   cudaStream_t wstream = nullptr;
+  // the skip branches (1x1 conv + BN of every level, forward and backward) are independent of the deeper-level chain:
+  // they run on a second side stream
+  cudaStream_t sstream = nullptr;
   std::vector<cudaEvent_t> wev;
   size_t wev_used = 0;
   bool side_on = false;
+  bool prepacked = false;   // the runner already issued the weight repack of this forward (beside the noise kernel)
   // tables
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
   int n_pack = 0, n_cvt = 0, n_run = 0;
@@ -745,6 +762,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   if (P->dry) return 0;
   // ---- device-side setup
   DIP_CUDA(cudaStreamCreateWithFlags(&P->wstream, cudaStreamNonBlocking));
+  DIP_CUDA(cudaStreamCreateWithFlags(&P->sstream, cudaStreamNonBlocking));
   // The zero-stuffed buffers are written at even positions only: clear them once.
   for (int l = 1; l < L; ++l) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
   if (prec == DIP_PRECISION_TF32)
@@ -797,6 +815,41 @@ static int upload_tables(dip_plan* P) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ side streams
+// Dependency edge between two streams (event record + wait; inside graph capture this becomes a graph edge).
+static void stream_edge(dip_plan* P, cudaStream_t from, cudaStream_t to) {
+  if (P->wev_used == P->wev.size()) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    P->wev.push_back(e);
+  }
+  cudaEvent_t e = P->wev[P->wev_used++];
+  cudaEventRecord(e, from);
+  cudaStreamWaitEvent(to, e, 0);
+}
+// Stream on which the weight-gradient work that depends on everything recorded so far on `s` may run concurrently.
+static cudaStream_t fork_side(dip_plan* P, cudaStream_t s) {
+  if (!P->side_on) return s;
+  stream_edge(P, s, P->wstream);
+  return P->wstream;
+}
+static void join_side(dip_plan* P, cudaStream_t s) {
+  if (P->side_on) stream_edge(P, P->wstream, s);
+}
+// Same for the skip-branch stream.
+static bool skip_stream_on(const dip_plan* P) {
+  static const bool off = getenv("DIP_NO_SKIPSTREAM") != nullptr;   // experiment switch
+  return P->side_on && !off;
+}
+static cudaStream_t fork_skip(dip_plan* P, cudaStream_t s) {
+  if (!skip_stream_on(P)) return s;
+  stream_edge(P, s, P->sstream);
+  return P->sstream;
+}
+static void join_skip(dip_plan* P, cudaStream_t s) {
+  if (skip_stream_on(P)) stream_edge(P, P->sstream, s);
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 static CatArgs cat_args(const dip_plan* P, const Level& v, const float* Usrc) {
   CatArgs a;
@@ -815,14 +868,17 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   const int CS = P->desc.skip_channels;
   const bool last = l == (int)P->lv.size() - 1;
   const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
-  // skip branch: 1x1 conv Cin -> CS (+ statistics)
-  if (CS == 128) {
-    DIP_CHECK(v.sk.run_fprop(prec, P->params[v.p_skip_b], s));
-    nl += prec == DIP_PRECISION_FP32 ? 2 : 1;
-  } else {
-    launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
-                      v.bn_s.fwd, s);
-    nl += 1;
+  // skip branch: 1x1 conv Cin -> CS (+ statistics); independent of the deeper branch until the concat -> skip stream
+  {
+    cudaStream_t ks = fork_skip(P, s);
+    if (CS == 128) {
+      DIP_CHECK(v.sk.run_fprop(prec, P->params[v.p_skip_b], ks));
+      nl += prec == DIP_PRECISION_FP32 ? 2 : 1;
+    } else {
+      launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
+                        v.bn_s.fwd, ks);
+      nl += 1;
+    }
   }
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
@@ -832,6 +888,7 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   nl += 4 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
   if (!last) DIP_CHECK(fwd_level(P, l + 1, s, nl));
   // upsample + concat + BN + pad
+  join_skip(P, s);
   CatArgs ca = cat_args(P, v, level_usrc(P, l));
   launch_cat_stats(ca, v.bn_cat.fwd, s);
   launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s);
@@ -850,17 +907,24 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   return 0;
 }
 
+// one table-driven launch repacks the weights of all wide convs (OIHW -> per-tap K-major fprop / dgrad operands)
+static void plan_pack(dip_plan* P, cudaStream_t s) {
+  dim3 grid((unsigned)((P->pack_max + 255) / 256 < 64 ? (P->pack_max + 255) / 256 : 64), P->n_pack);
+  launch_k(k_pack_table, dim3(grid), dim3(256), 0, s, 1, P->d_pack);
+}
+
 static int plan_forward(dip_plan* P, const float* z, const float* noise, float sigma, float* out, cudaStream_t s) {
   if (!P->bound) return fail("dip_forward: parameters not bound (call dip_plan_bind)");
   // grid-wide reductions: fp64 atomics onto line-strided accumulators (default) or the deterministic last-block sum
   int nl = 0;
+  P->side_on = getenv("DIP_NO_SIDE") == nullptr;
+  if (!P->prepacked) P->wev_used = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_fwd, 0, P->acc_fwd_n * sizeof(double), s));
-  {
-    dim3 grid((unsigned)((P->pack_max + 255) / 256 < 64 ? (P->pack_max + 255) / 256 : 64), P->n_pack);
-    launch_k(k_pack_table, dim3(grid), dim3(256), 0, s, 1, P->d_pack);
-  }
+  if (!P->prepacked) plan_pack(P, fork_side(P, s));   // weight repack runs beside the input transform
+  P->prepacked = false;
   Level& v0 = P->lv[0];
   launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s);
+  join_side(P, s);
   nl += 3;
   DIP_CHECK(fwd_level(P, 0, s, nl));
   if (out != nullptr && out != P->out_saved)
@@ -887,31 +951,6 @@ static GradSrc src_fold(const float* gp, int ld, const float* ds, const float* w
   GradSrc s{}; s.kind = 1; s.g = gp; s.ld = ld; s.coff = 0; s.ds = ds; s.w2 = w2; s.n2 = n2; return s;
 }
 static GradSrc src_upadj(const float* d, int ld, int bilinear) { GradSrc s{}; s.kind = 2; s.g = d; s.ld = ld; s.coff = 0; s.bilinear = bilinear; return s; }
-
-// Stream on which the weight-gradient work that depends on everything recorded so far on `s` may run concurrently.
-static cudaStream_t fork_side(dip_plan* P, cudaStream_t s) {
-  if (!P->side_on) return s;
-  if (P->wev_used == P->wev.size()) {
-    cudaEvent_t e;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    P->wev.push_back(e);
-  }
-  cudaEvent_t e = P->wev[P->wev_used++];
-  cudaEventRecord(e, s);
-  cudaStreamWaitEvent(P->wstream, e, 0);
-  return P->wstream;
-}
-static void join_side(dip_plan* P, cudaStream_t s) {
-  if (!P->side_on) return;
-  if (P->wev_used == P->wev.size()) {
-    cudaEvent_t e;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    P->wev.push_back(e);
-  }
-  cudaEvent_t e = P->wev[P->wev_used++];
-  cudaEventRecord(e, P->wstream);
-  cudaStreamWaitEvent(s, e, 0);
-}
 
 static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl) {
   Level& v = P->lv[l];
@@ -943,26 +982,28 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   BnRef rc = bn_ref(P, v.bn_cat);
   launch_cat_bwd_reduce(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, s);
   launch_cat_bwd_apply(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, v.dCat, s);
+  // skip branch (on the skip stream: independent of the deeper levels; the level above joins before it reads dRaw_s / dS)
+  cudaStream_t ks = fork_skip(P, s);
   // gradient w.r.t. the low-resolution tensor that was upsampled into this concat (adjoint of x2 upsampling), once
   launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, P->desc.upsample_bilinear, v.dUp, s);
   nl += 3;
-  // skip branch
-  DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, s, nl));
+  DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl));
   if (CS == 128) {
-    DIP_CHECK(v.sk.run_wgrad(prec, P->partial, P->grads[v.p_skip_w], fork_side(P, s)));
+    DIP_CHECK(v.sk.run_wgrad(prec, P->partial, P->grads[v.p_skip_w], fork_side(P, ks)));
     nl += wl;
-    if (l > 0) { DIP_CHECK(v.sk.run_dgrad(prec, s)); nl += 1; }   // dS, added to the fold of dPin by the level above
+    if (l > 0) { DIP_CHECK(v.sk.run_dgrad(prec, ks)); nl += 1; }   // dS, added to the fold of dPin by the level above
   } else {
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
     // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
     launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
-                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, fork_side(P, s));
+                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks);
     nl += 1;
   }
   // deeper branch
   GradSrc src_d2;
   if (!last) {
     DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), s, nl));
+    join_skip(P, s);   // the next level's skip-branch gradients (dRaw_s / dS) feed the BN backward below
     Level& n = P->lv[l + 1];
     if (CS == 128) { src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = 128; }
     else src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
@@ -986,7 +1027,6 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   int nl = 0;
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
   P->side_on = getenv("DIP_NO_SIDE") == nullptr;
-  P->wev_used = 0;
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
   GradSrc sh{};
@@ -996,6 +1036,7 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   nl += 1;
   DIP_CHECK(bwd_level(P, 0, sh, s, nl));
   join_side(P, s);
+  join_skip(P, s);
   launch_k(k_cvt_table, dim3(P->n_cvt), dim3(128), 0, s, 1, P->d_cvt);
   nl += 1;
   DIP_CUDA(cudaGetLastError());
@@ -1014,6 +1055,44 @@ struct dip_adam {
   int* d_blk_tensor = nullptr; int* d_blk_start = nullptr; int* d_numel = nullptr;
   bool bound = false;
 };
+
+static void drop_graphs(dip_plan* P) {
+  for (cudaGraphExec_t* g : {&P->gexec, &P->gfwd, &P->gbwd})
+    if (*g != nullptr) { cudaGraphExecDestroy(*g); *g = nullptr; }
+}
+static bool graphs_enabled(const dip_plan* P) { return !P->timer.on && getenv("DIP_NO_GRAPH") == nullptr; }
+static int ensure_gstream(dip_plan* P) {
+  // the legacy default stream cannot be captured: graphs replay on a private stream, ordered against the caller's stream
+  if (P->gstream == nullptr) {
+    DIP_CUDA(cudaStreamCreateWithFlags(&P->gstream, cudaStreamNonBlocking));
+    DIP_CUDA(cudaEventCreateWithFlags(&P->gev_in, cudaEventDisableTiming));
+    DIP_CUDA(cudaEventCreateWithFlags(&P->gev_out, cudaEventDisableTiming));
+  }
+  return 0;
+}
+// Captures body(gstream) once into *exec, then replays it between two event edges to / from the caller's stream `s`.
+template <class Body>
+static int replay_graph(dip_plan* P, cudaGraphExec_t* exec, cudaStream_t s, Body body) {
+  DIP_CHECK(ensure_gstream(P));
+  cudaStream_t gs = P->gstream;
+  DIP_CUDA(cudaEventRecord(P->gev_in, s));
+  DIP_CUDA(cudaStreamWaitEvent(gs, P->gev_in, 0));
+  if (*exec == nullptr) {
+    cudaGraph_t graph = nullptr;
+    DIP_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(gs);
+    cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { *exec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+  }
+  DIP_CUDA(cudaGraphLaunch(*exec, gs));
+  DIP_CUDA(cudaEventRecord(P->gev_out, gs));
+  DIP_CUDA(cudaStreamWaitEvent(s, P->gev_out, 0));
+  return 0;
+}
 
 extern "C" {
 
@@ -1044,12 +1123,15 @@ int dip_plan_create(const dip_net_desc* desc, int H, int W, void* workspace, siz
 void dip_plan_destroy(dip_plan* plan) {
   if (plan == nullptr) return;
   if (plan->gexec) cudaGraphExecDestroy(plan->gexec);
+  if (plan->gfwd) cudaGraphExecDestroy(plan->gfwd);
+  if (plan->gbwd) cudaGraphExecDestroy(plan->gbwd);
   if (plan->gstream) cudaStreamDestroy(plan->gstream);
   if (plan->gev_in) cudaEventDestroy(plan->gev_in);
   if (plan->gev_out) cudaEventDestroy(plan->gev_out);
   for (cudaEvent_t e : plan->timer.pool) cudaEventDestroy(e);
   for (cudaEvent_t e : plan->wev) cudaEventDestroy(e);
   if (plan->wstream) cudaStreamDestroy(plan->wstream);
+  if (plan->sstream) cudaStreamDestroy(plan->sstream);
   delete plan;
 }
 int dip_plan_num_params(const dip_plan* plan) { return (int)plan->numel.size(); }
@@ -1059,6 +1141,7 @@ long long dip_plan_param_numel(const dip_plan* plan, int index) {
   return plan->numel[index];
 }
 int dip_plan_bind(dip_plan* P, void* const* params, void* const* grads, void* const* bn_running, int nbt_is_float) {
+  drop_graphs(P);   // captured launches hold the old pointers
   P->nbt_is_float = nbt_is_float;
   const int n = (int)P->numel.size();
   P->params.resize(n); P->grads.resize(n);
@@ -1073,10 +1156,25 @@ int dip_plan_bind(dip_plan* P, void* const* params, void* const* grads, void* co
   return 0;
 }
 int dip_forward(dip_plan* P, const void* z, const void* noise, float sigma, void* out, dip_stream_t stream) {
-  return plan_forward(P, (const float*)z, (const float*)noise, sigma, (float*)out, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!P->bound) return fail("dip_forward: parameters not bound (call dip_plan_bind)");
+  if (noise != nullptr || !graphs_enabled(P))
+    return plan_forward(P, (const float*)z, (const float*)noise, sigma, (float*)out, s);
+  // stage the input in the plan's fixed buffer, replay the captured forward, hand the result out
+  const size_t nz = (size_t)P->H * P->W * P->desc.in_channels * sizeof(float);
+  DIP_CUDA(cudaMemcpyAsync(P->zbuf, z, nz, cudaMemcpyDeviceToDevice, s));
+  DIP_CHECK(replay_graph(P, &P->gfwd, s, [&](cudaStream_t gs) { return plan_forward(P, P->zbuf, nullptr, 0.f, nullptr, gs); }));
+  if (out != nullptr && out != P->out_saved)
+    DIP_CUDA(cudaMemcpyAsync(out, P->out_saved, (size_t)P->H * P->W * P->desc.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
 }
 int dip_backward(dip_plan* P, const void* dout, dip_stream_t stream) {
-  return plan_backward(P, (const float*)dout, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!P->bound) return fail("dip_backward: parameters not bound");
+  if (!graphs_enabled(P)) return plan_backward(P, (const float*)dout, s);
+  if (dout != P->dout)
+    DIP_CUDA(cudaMemcpyAsync(P->dout, dout, (size_t)P->H * P->W * P->desc.out_channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return replay_graph(P, &P->gbwd, s, [&](cudaStream_t gs) { return plan_backward(P, P->dout, gs); });
 }
 int dip_loss_mse(const void* out, const void* target, const void* mask, int channels, int hw, double* loss, void* dout,
                  dip_stream_t stream) {
@@ -1175,6 +1273,13 @@ static int run_body(dip_plan* P, dip_adam* adam, const float* z0, const float* t
   const size_t nz = (size_t)P->H * P->W * P->desc.in_channels;
   const int hw = P->H * P->W;
   const float* zin = z0;
+  P->side_on = getenv("DIP_NO_SIDE") == nullptr;
+  P->wev_used = 0;
+  if (P->side_on && P->bound) {
+    // weight repack on the side stream from the very start of the iteration (beside the noise kernel); plan_forward joins it
+    plan_pack(P, fork_side(P, s));
+    P->prepacked = true;
+  }
   if (sigma > 0.f) {
     launch_noise(z0, P->zbuf, sigma, seed, (uint64_t)step_base, it_dev, nz, s);
     zin = P->zbuf;
@@ -1223,11 +1328,7 @@ int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* 
     return 0;
   }
   // the legacy default stream cannot be captured: replay on a private stream, ordered against the caller's stream
-  if (P->gstream == nullptr) {
-    DIP_CUDA(cudaStreamCreateWithFlags(&P->gstream, cudaStreamNonBlocking));
-    DIP_CUDA(cudaEventCreateWithFlags(&P->gev_in, cudaEventDisableTiming));
-    DIP_CUDA(cudaEventCreateWithFlags(&P->gev_out, cudaEventDisableTiming));
-  }
+  DIP_CHECK(ensure_gstream(P));
   cudaStream_t gs = P->gstream;
   DIP_CUDA(cudaEventRecord(P->gev_in, s));
   DIP_CUDA(cudaStreamWaitEvent(gs, P->gev_in, 0));

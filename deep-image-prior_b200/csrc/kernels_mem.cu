@@ -21,6 +21,14 @@
 
 namespace dip {
 
+// items in flight per thread (item_loop) of the kernels whose gradient source is a reflection-pad fold: tuning knobs
+#ifndef DIP_U_BWD1
+#define DIP_U_BWD1 4
+#endif
+#ifndef DIP_U_CATBWD
+#define DIP_U_CATBWD 2
+#endif
+
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
@@ -448,18 +456,24 @@ void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
 // fold: adjoint of ReflectionPad2d(1). Interior (i,j) <- padded (i+1,j+1) plus mirrored halo rows/cols.
 __device__ __forceinline__ float4 fold_read(const float* __restrict__ gp, int ld, int coff, int H, int W, int i, int j,
                                             int v) {
-  int rows[3], cols[3];
-  int nr = 0, nc = 0;
-  rows[nr++] = i + 1;
-  if (i == 1) rows[nr++] = 0;
-  if (i == H - 2) rows[nr++] = H + 1;
-  cols[nc++] = j + 1;
-  if (j == 1) cols[nc++] = 0;
-  if (j == W - 2) cols[nc++] = W + 1;
   const int Wp = W + 2;
-  float4 r = f4zero();
-  for (int a = 0; a < nr; ++a)
-    for (int b = 0; b < nc; ++b) r = f4add(r, ld4(gp + (static_cast<size_t>(rows[a]) * Wp + cols[b]) * ld + coff + 4 * v));
+  const float* base = gp + coff + 4 * v;
+  // the interior load is unconditional (issued at once, so several items' loads are in flight together); only the
+  // one-pixel ring next to the border has mirrored halo positions to add
+  float4 r = ld4(base + (static_cast<size_t>(i + 1) * Wp + (j + 1)) * ld);
+  if (i == 1 || i == H - 2 || j == 1 || j == W - 2) {
+    int rows[3], cols[3];
+    int nr = 0, nc = 0;
+    rows[nr++] = i + 1;
+    if (i == 1) rows[nr++] = 0;
+    if (i == H - 2) rows[nr++] = H + 1;
+    cols[nc++] = j + 1;
+    if (j == 1) cols[nc++] = 0;
+    if (j == W - 2) cols[nc++] = W + 1;
+    for (int a = 0; a < nr; ++a)
+      for (int b = 0; b < nc; ++b)
+        if (a + b > 0) r = f4add(r, ld4(base + (static_cast<size_t>(rows[a]) * Wp + cols[b]) * ld));
+  }
   return r;
 }
 // adjoint of x2 upsampling: D is [2H][2W][ld]
@@ -574,7 +588,7 @@ __global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bw
   const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
   float4 acc[2] = {f4zero(), f4zero()};
-  item_loop<KIND == 3 ? 8 : (KIND == 0 ? 4 : 2)>(
+  item_loop<KIND == 3 ? 8 : (KIND == 0 ? 4 : (KIND == 1 ? DIP_U_BWD1 : 2))>(
       blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
       [&](int p) {
         RedItem it;
@@ -624,7 +638,7 @@ __global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const f
   float4 acc[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) acc[k] = f4zero();
-  item_loop<(KIND == 0 || KIND == 3) ? 4 : 2>(
+  item_loop<(KIND == 0 || KIND == 3) ? 4 : (KIND == 1 ? DIP_U_BWD1 : 2)>(
       blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
       [&](int p) {
         BwdItem it;
@@ -721,7 +735,7 @@ __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict_
   const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int Wp = W + 2;
   float4 acc[2] = {f4zero(), f4zero()};
-  item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+  item_loop<DIP_U_CATBWD>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
                [&](int p) {
                  RedItem it;
                  const int i = p / W, j = p - i * W;
@@ -753,7 +767,7 @@ __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__
   const int Wp = W + 2;
   float4 m1, m2;
   bwd_means<0>(bwd, C, bn_cat.inv_n, v, m1, m2);
-  item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+  item_loop<DIP_U_CATBWD>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
                [&](int p) {
                  RedItem it;
                  const int i = p / W, j = p - i * W;
