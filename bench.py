@@ -33,8 +33,9 @@ LR = 0.01
 ITERS_PER_IMAGE = 2000           # BASELINE.json config[0]/[1]
 ALG_GFLOP_PER_ITER = 460.07      # SURVEY.md section 6 (2*M*N*K over the 26 convs, fwd+dgrad+wgrad)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the committed `ncu --set full` capture
-# (profiles/r01_ncu_conv_l0up.txt); None until captured for the current kernel version
-ROOFLINE_TRAFFIC_BYTES = 232614656  # 140.30 MB read + 92.31 MB written (algorithmic: 143.2 MB in + 0.8 MB weights + 134.2 MB out)
+# (profiles/r01_ncu_conv_l0up_v6.txt); None until captured for the current kernel version
+ROOFLINE_TRAFFIC_BYTES = 232083456  # 140.32 MB read + 91.76 MB written (profiles/r01_ncu_conv_l0up_v6.txt; algorithmic: 143.2 MB in + 0.8 MB weights + 134.2 MB out)
+ROOFLINE_HBM_TRAFFIC_BYTES = 370134272  # 268.58 MB read + 101.55 MB written (profiles/r01_ncu_bn_bwd_apply_l0.txt)
 METRIC = "optimisation iterations/sec (512x512 skip-net denoising, sum over independent images)"
 
 
@@ -328,9 +329,15 @@ def run_ours(args):
         wg_ms, wg_fl, wg_n, wg_ach = agg(lambda r: r[0] == 2)
         # dominant launch = the largest single tensor-core launch of the step (level-0 3x3 conv 132->128 at 512x512,
         # 79.7 algorithmic GFLOP): its fprop instances
-        big = max(r[1] for r in records)
+        big = max(r[1] for r in records if r[0] == 0)
         dom_ms, dom_fl, dom_n, achieved = agg(lambda r: r[0] == 0 and r[1] == big)
         tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
+        # dominant HBM-bound launch: BatchNorm+LeakyReLU backward (apply pass) of the level-0 3x3 up conv, 128 ch @512x512
+        hbm = [r for r in records if r[0] == 3]
+        hbm_big = max((r[1] for r in hbm), default=0.0)
+        hbm_sel = [r for r in hbm if r[1] == hbm_big]
+        hbm_ms = sum(r[2] for r in hbm_sel)
+        hbm_gbs = (hbm_big * len(hbm_sel) / (hbm_ms / 1000.0) / 1e9) if hbm_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -366,6 +373,16 @@ def run_ours(args):
                                "frac": wg_ach / tf32_peak if tf32_peak else None, "launches": wg_n,
                                "ms_per_step": wg_ms / roof_steps,
                                "share_of_step": (wg_ms / roof_steps) / (ms / args.steps) if ms > 0 else None},
+            "roofline_hbm": {"kernel": "k_bn_bwd_apply<plain>: BatchNorm+LeakyReLU backward (apply pass) behind the level-0 up conv, "
+                                       "128 ch @512x512 (largest HBM-bound launch of the step)",
+                             "bound": "hbm", "achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": hbm_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                             "algorithmic_bytes_per_launch": hbm_big, "launches": len(hbm_sel),
+                             "us_per_launch": 1000.0 * hbm_ms / max(len(hbm_sel), 1),
+                             "traffic": ROOFLINE_HBM_TRAFFIC_BYTES,
+                             "note": "algorithmic bytes = read raw + read gradient + write input gradient (3 x 134.2 MB); "
+                                     "traffic = dram read+write of one launch from profiles/r01_ncu_bn_bwd_apply_l0.txt "
+                                     "(part of the gradient is still in L2 from the producing conv)"},
             "step_tflops": ALG_GFLOP_PER_ITER / 1000.0 / (ms_max / args.steps / 1000.0),
             "per_rank": [{"psnr_gt": r[0], "final_loss": r[1], "it_per_s": r[2]} for r in recs],
         }

@@ -59,17 +59,36 @@ class SkipNet(nn.Sequential):
         self.precision = 'tf32'      # 'tf32' (tcgen05 tensor cores, default) | 'fp32' (exact CUDA-core parity mode)
 
     # ---- engine plumbing -------------------------------------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        # .type() / .cuda() / .to() / .float() replace parameter and buffer storage: rebuild the engine binding
+        self._dip_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _engine_state(self, z):
+        """(plan, parameters) for input z; everything derived from the module tree is cached between calls and
+        re-validated cheaply (storage of the first / last parameter and of one BatchNorm buffer): after the per-step
+        loss read-back of a notebook closure the GPU idles until this returns, so it must cost microseconds."""
+        import dip_engine as de
+        prec = de.PRECISION_TF32 if self.precision == 'tf32' else de.PRECISION_FP32
+        key = (int(z.shape[2]), int(z.shape[3]), z.device, prec)
+        c = getattr(self, '_dip_cache', None)
+        if c is not None and c['key'] == key:
+            ps = c['params']
+            if (ps[0].data_ptr() == c['p0'] and ps[-1].data_ptr() == c['p1'] and c['bn0'].data_ptr() == c['b0']
+                    and ps[0].dtype == torch.float32):
+                return c['plan'], ps
+        return self._engine_state_slow(z, key, prec)
+
+    def _engine_state_slow(self, z, key, prec):
         import dip_engine as de
         spec = self._dip_spec
-        H, W = int(z.shape[2]), int(z.shape[3])
-        prec = de.PRECISION_TF32 if self.precision == 'tf32' else de.PRECISION_FP32
-        key = (H, W, str(z.device), prec)
-        plan = self._dip_plans.get(key)
+        H, W = key[0], key[1]
+        pkey = (H, W, str(z.device), prec)
+        plan = self._dip_plans.get(pkey)
         if plan is None:
             plan = de.Plan(spec['in_channels'], spec['out_channels'], spec['num_scales'], spec['channels'],
                            spec['skip_channels'], spec['bilinear'], H, W, precision=prec, device=z.device)
-            self._dip_plans[key] = plan
+            self._dip_plans[pkey] = plan
         params = list(self.parameters())
         for p in params:
             if p.device != z.device or p.dtype != torch.float32:
@@ -90,6 +109,8 @@ class SkipNet(nn.Sequential):
             if isinstance(m, nn.BatchNorm2d):
                 running += [m.running_mean, m.running_var, m.num_batches_tracked]
         plan.bind([p.data for p in params], self._dip_grad_views, running)
+        self._dip_cache = dict(key=key, plan=plan, params=params, p0=params[0].data_ptr(), p1=params[-1].data_ptr(),
+                               bn0=running[0], b0=running[0].data_ptr())
         return plan, params
 
     def _engine_forward(self, z):
@@ -100,7 +121,8 @@ class SkipNet(nn.Sequential):
 
     def _engine_backward(self, dout):
         plan = self._dip_active_plan
-        params = list(self.parameters())
+        c = getattr(self, '_dip_cache', None)
+        params = c['params'] if c is not None else list(self.parameters())
         views = self._dip_grad_views
         # gradients already attached to the arena (no zero_grad() since the last backward) must be accumulated
         stale = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views)]

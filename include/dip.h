@@ -108,7 +108,9 @@ int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd);
  * index 0 = fprop, 1 = dgrad (both tc_conv_kernel), 2 = wgrad (tc_wgrad_kernel); flops are algorithmic (2*M*N*K). */
 int dip_plan_set_timing(dip_plan* plan, int enable);
 int dip_plan_get_timing(dip_plan* plan, double* ms3, double* flops3, int* launches3);
-/* same records one by one (class, algorithmic flops, device ms); returns the number written (<= max_records) */
+/* same records one by one (class, algorithmic flops, device ms); returns the number written (<= max_records).
+ * Class 3 = k_bn_bwd_apply with a plain gradient source (HBM-bound; `flops` then holds the algorithmic BYTES:
+ * read raw + read gradient + write input gradient), class 4 = the other BN-backward apply launches (bytes likewise). */
 int dip_plan_get_timing_records(dip_plan* plan, int max_records, int* cls, double* flops, double* ms);
 
 /* ---- single-op entry points (same kernels as the plan; used by the per-kernel parity tests).
