@@ -761,8 +761,14 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->d_run = A.get<RunEntry>(P->n_run);
   if (P->dry) return 0;
   // ---- device-side setup
-  DIP_CUDA(cudaStreamCreateWithFlags(&P->wstream, cudaStreamNonBlocking));
-  DIP_CUDA(cudaStreamCreateWithFlags(&P->sstream, cudaStreamNonBlocking));
+  {
+    // side streams at the lowest priority, the graph stream (= main chain of the captured step) at the highest
+    int lo = 0, hi = 0;
+    DIP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (getenv("DIP_NO_PRIO") != nullptr) lo = hi = 0;
+    DIP_CUDA(cudaStreamCreateWithPriority(&P->wstream, cudaStreamNonBlocking, lo));
+    DIP_CUDA(cudaStreamCreateWithPriority(&P->sstream, cudaStreamNonBlocking, lo));
+  }
   // The zero-stuffed buffers are written at even positions only: clear them once.
   for (int l = 1; l < L; ++l) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
   if (prec == DIP_PRECISION_TF32)
@@ -957,6 +963,19 @@ static GradSrc src_fold(const float* gp, int ld, const float* ds, const float* w
 }
 static GradSrc src_upadj(const float* d, int ld, int bilinear) { GradSrc s{}; s.kind = 2; s.g = d; s.ld = ld; s.coff = 0; s.bilinear = bilinear; return s; }
 
+// Weight gradient (side stream) and input gradient (main stream, on the critical path) of one conv.  Both are persistent
+// kernels that fill every SM, so they run one after the other whichever way: the dgrad is enqueued first and the main
+// stream has the higher priority, so that the wgrad overlaps the HBM-bound kernels that follow the dgrad instead of
+// delaying it.  (DIP_WGRAD_FIRST=1: the old order, for A/B runs.)
+static int conv_backward(dip_plan* P, ConvOp& op, bool dgrad, int prec, cudaStream_t s) {
+  static const bool wgrad_first = getenv("DIP_WGRAD_FIRST") != nullptr;
+  cudaStream_t ws = fork_side(P, s);
+  if (wgrad_first) DIP_CHECK(op.run_wgrad(prec, P->partial, P->grads[op.p_w], ws));
+  if (dgrad) DIP_CHECK(op.run_dgrad(prec, s));
+  if (!wgrad_first) DIP_CHECK(op.run_wgrad(prec, P->partial, P->grads[op.p_w], ws));
+  return 0;
+}
+
 static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl) {
   Level& v = P->lv[l];
   const int prec = P->desc.precision;
@@ -966,21 +985,19 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   const int wl = prec == DIP_PRECISION_TF32 ? 2 : 2;
   // 1x1 conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl));
-  DIP_CHECK(v.c11.run_wgrad(prec, P->partial, P->grads[v.c11.p_w], fork_side(P, s)));
-  DIP_CHECK(v.c11.run_dgrad(prec, s));
+  DIP_CHECK(conv_backward(P, v.c11, true, prec, s));
   nl += wl + 1;
   // up conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl));
   if (CS == 128) {
     cudaStream_t ws = fork_side(P, s);
-    DIP_CHECK(v.up_a.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
-    DIP_CHECK(v.up_b.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
     DIP_CHECK(v.up_a.run_dgrad(prec, s));
     DIP_CHECK(v.up_b.run_dgrad(prec, s));
+    DIP_CHECK(v.up_a.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
+    DIP_CHECK(v.up_b.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
     nl += 2 * (wl + 1);
   } else {
-    DIP_CHECK(v.up.run_wgrad(prec, P->partial, P->grads[v.up.p_w], fork_side(P, s)));
-    DIP_CHECK(v.up.run_dgrad(prec, s));
+    DIP_CHECK(conv_backward(P, v.up, true, prec, s));
     nl += wl + 1;
   }
   // concat BN
@@ -1016,13 +1033,11 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
     src_d2 = src_plain(v.dUp, 128, 0);
   }
   DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl));
-  DIP_CHECK(v.d2.run_wgrad(prec, P->partial, P->grads[v.d2.p_w], fork_side(P, s)));
-  DIP_CHECK(v.d2.run_dgrad(prec, s));
+  DIP_CHECK(conv_backward(P, v.d2, true, prec, s));
   nl += wl + 1;
   DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, l > 0 ? v.ZS : nullptr, s, nl));
-  DIP_CHECK(v.d1.run_wgrad(prec, P->partial, P->grads[v.d1.p_w], fork_side(P, s)));
-  nl += wl;
-  if (l > 0) { DIP_CHECK(v.d1.run_dgrad(prec, s)); nl += 1; }
+  DIP_CHECK(conv_backward(P, v.d1, l > 0, prec, s));
+  nl += wl + (l > 0 ? 1 : 0);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1069,7 +1084,10 @@ static bool graphs_enabled(const dip_plan* P) { return !P->timer.on && getenv("D
 static int ensure_gstream(dip_plan* P) {
   // the legacy default stream cannot be captured: graphs replay on a private stream, ordered against the caller's stream
   if (P->gstream == nullptr) {
-    DIP_CUDA(cudaStreamCreateWithFlags(&P->gstream, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;
+    DIP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (getenv("DIP_NO_PRIO") != nullptr) hi = 0;
+    DIP_CUDA(cudaStreamCreateWithPriority(&P->gstream, cudaStreamNonBlocking, hi));
     DIP_CUDA(cudaEventCreateWithFlags(&P->gev_in, cudaEventDisableTiming));
     DIP_CUDA(cudaEventCreateWithFlags(&P->gev_out, cudaEventDisableTiming));
   }
