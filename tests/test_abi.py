@@ -28,3 +28,42 @@ def test_workspace_query_needs_no_gpu():
     bad = de.NetDesc(32, 3, 5, 64, 4, 1, 1, 0)
     assert de.lib().dip_plan_workspace_bytes(ctypes.byref(bad), 512, 512) == 0
     assert b"128" in de.lib().dip_last_error()
+
+
+def test_workspace_query_rejects_unsupported_configurations_with_a_reason():
+    """Host logic of the plan builder (no GPU): every rejected configuration returns 0 and sets dip_last_error()."""
+    import dip_engine as de
+    L = de.lib()
+
+    def q(desc, H=512, W=512):
+        return L.dip_plan_workspace_bytes(ctypes.byref(desc), H, W), L.dip_last_error().decode()
+
+    ok = de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0)
+    base, _ = q(ok)
+    assert base > 0
+    for desc, H, W, word in [
+        (de.NetDesc(32, 3, 5, 128, 8, 1, 1, 0), 512, 512, "num_channels_skip"),      # skip width other than 4 / 128
+        (de.NetDesc(24, 3, 5, 128, 4, 1, 1, 0), 512, 512, "input depth"),            # not a power of two
+        (de.NetDesc(32, 5, 5, 128, 4, 1, 1, 0), 512, 512, "num_output_channels"),
+        (de.NetDesc(32, 3, 9, 128, 4, 1, 1, 0), 512, 512, "scales"),
+        (de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0), 500, 512, "divisible"),              # 500 % 32 != 0
+        (de.NetDesc(32, 3, 5, 128, 4, 1, 0, 0), 512, 512, "need_sigmoid"),
+    ]:
+        n, err = q(desc, H, W)
+        assert n == 0 and word in err, (n, err)
+    # supported variants: inpainting (skip=128, nearest), other depths / sizes; bigger configurations need more memory
+    wide, _ = q(de.NetDesc(32, 3, 5, 128, 128, 0, 1, 0))
+    assert wide > base
+    big, _ = q(ok, 1024, 1024)
+    assert 3.5 * base < big < 4.5 * base
+    small, _ = q(de.NetDesc(8, 1, 3, 128, 4, 0, 1, 1), 64, 96)
+    assert 0 < small < base
+
+
+def test_downsampler_output_size_matches_torch_conv_arithmetic():
+    import dip_engine as de
+    L = de.lib()
+    for n, K, f, pad in [(384, 16, 4, 6), (576, 16, 4, 6), (1024, 16, 4, 6), (33, 7, 2, 3), (45, 16, 4, 0), (64, 32, 8, 12),
+                         (15, 16, 4, 0)]:
+        want = (n + 2 * pad - K) // f + 1 if n + 2 * pad >= K else 0
+        assert L.dip_lanczos_down_out_size(n, K, f, pad) == want == de.down_out_size(n, K, f, pad)
