@@ -287,3 +287,47 @@ def test_graph_replayed_forward_backward_equals_eager():
             assert torch.allclose(res[("graph", i)][0], res[(mode, i)][0], rtol=0, atol=1e-6)
             for a, b in zip(res[("graph", i)][1], res[(mode, i)][1]):
                 assert rel(a, b) < 1e-4 or b.norm().item() < 1e-6
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_inpainting_closure_through_modules_vs_golden(prec):
+    """inpainting.ipynb c14-c17 (kate configuration) through the notebook-facing API: skip(32, 3, [128]*5, [128]*5,
+    [128]*5, nearest, reflection), total_loss = mse(out * mask, img * mask), optimize('adam', ...)."""
+    import models
+    from utils.common_utils import get_noise, get_params, optimize
+    g = np.load(os.path.join(GOLD, "inpaint64x96_nearest_masked_skip128_fp32.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    dtype = torch.cuda.FloatTensor
+    torch.manual_seed(0)
+    net = models.skip(32, 3, num_channels_down=[128] * 5, num_channels_up=[128] * 5, num_channels_skip=[128] * 5,
+                      upsample_mode="nearest", need_sigmoid=True, need_bias=True, pad="reflection",
+                      act_fun="LeakyReLU").type(dtype)
+    net.precision = prec
+    torch.manual_seed(1)
+    z0 = get_noise(32, "noise", (H, W)).type(dtype).detach()
+    gen = torch.Generator().manual_seed(2)
+    img_var = torch.rand(1, 3, H, W, generator=gen).type(dtype)
+    mask_var = (torch.rand(1, 1, H, W, generator=gen) > 0.3).type(dtype)
+    gn = torch.Generator().manual_seed(123)
+    mse = torch.nn.MSELoss().type(dtype)
+    losses, outs = [], []
+
+    def closure():
+        net_input = z0 + torch.randn(z0.shape, generator=gn).type(dtype) * float(g["sigma"])
+        out = net(net_input)
+        total_loss = mse(out * mask_var, img_var * mask_var)
+        total_loss.backward()
+        losses.append(total_loss.item())
+        outs.append(out.detach())
+        return total_loss
+
+    params = get_params("net", net, z0)
+    optimize("adam", params, closure, float(g["lr"]), 1)
+    gnorm = np.array([p.grad.double().norm().item() for p in params])
+    assert np.abs(outs[0].cpu().numpy() - g["out0"]).max() < FWD_TOL[prec]
+    assert abs(losses[0] - float(g["losses"][0])) < (1e-5 if prec == "fp32" else 1e-3)
+    big = g["gnorm0"] > 1e-4 * g["gnorm0"].max()
+    dev = np.abs(gnorm[big] / g["gnorm0"][big] - 1)
+    assert (np.median(dev) if prec == "tf32" else dev.max()) < (0.1 if prec == "tf32" else GRAD_TOL[prec]), dev.max()
+    optimize("adam", params, closure, float(g["lr"]), 2)           # keeps running (3 iterations like the fixture)
+    assert np.isfinite(losses).all() and abs(losses[1] - float(g["losses"][1])) < 2e-2
