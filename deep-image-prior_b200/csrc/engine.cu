@@ -387,11 +387,15 @@ __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
 }
 struct CvtEntry {
   const double* src; float* dst; int n, rot;
+  int row, row_ld;   // dst rows of `row` elements come from accumulator rows of `row_ld` (0: contiguous)
 };
 __global__ void k_cvt_table(const CvtEntry* __restrict__ tab) {
   pdl_enter();
   const CvtEntry e = tab[blockIdx.x];
-  for (int i = threadIdx.x; i < e.n; i += blockDim.x) e.dst[(i + e.rot) % e.n] = (float)acc_get(e.src + (size_t)i * kAccS);
+  for (int i = threadIdx.x; i < e.n; i += blockDim.x) {
+    const int si = e.row > 0 ? (i / e.row) * e.row_ld + i % e.row : i;
+    e.dst[(i + e.rot) % e.n] = (float)acc_get(e.src + (size_t)si * kAccS);
+  }
 }
 struct RunEntry {
   const double* fwd; float* rm; float* rv; void* nb; int C, rot; float n; int nb_is_float;
@@ -436,7 +440,9 @@ struct BnLayer {
   int p_gamma = -1, p_beta = -1, p_bias = -1, idx = -1;
 };
 struct Level {
-  int H, W, h, w, Cin;
+  int H, W, h, w, Cin;   // Cin: stored depth of the level input (power of two >= 4)
+  int Cin_act;           // depth of the conv weights that read it (differs at level 0 for input depths like 3)
+  int bilinear;          // x2 upsampling into this level: 1 bilinear, 0 nearest (skip.py:81, upsample_mode[i])
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
   float *dUp;  // [h][w][128] adjoint of the upsampling applied to dCat
   float *dS;   // skip=128: [H][W][Cin] input gradient of the (tensor-core) skip conv, levels > 0
@@ -526,8 +532,11 @@ static int build_plan(dip_plan* P, Arena& A) {
   if (CH != 128) return fail("dip-b200: only num_channels_down == num_channels_up == 128 is supported by the engine");
   if (CS != 4 && CS != 128) return fail("dip-b200: num_channels_skip must be 4 or 128");
   const bool wide = CS == 128;   // skip branch on the tensor cores, 256-channel concat
-  if (d.in_channels % 4 != 0 || d.in_channels < 4 || d.in_channels > 128 || (d.in_channels & (d.in_channels - 1)))
-    return fail("dip-b200: input depth must be a power of two in [4,128]");
+  if (d.in_channels < 1 || d.in_channels > 128) return fail("dip-b200: input depth must be in [1,128]");
+  // level-0 activations are stored with the input depth rounded up to a power of two >= 4 (zero channels); the conv
+  // weights keep their real depth (TMA zero-fills the missing channels, the 1x1 skip conv reads its rows by element)
+  int cin_eng = 4;
+  while (cin_eng < d.in_channels) cin_eng *= 2;
   if (d.out_channels < 1 || d.out_channels > 4) return fail("dip-b200: num_output_channels must be <= 4");
   if (L < 1 || L > 8) return fail("dip-b200: 1..8 scales supported");
   if (P->H % (1 << L) || P->W % (1 << L)) return fail("dip-b200: H and W must be divisible by 2^num_scales");
@@ -555,15 +564,17 @@ static int build_plan(dip_plan* P, Arena& A) {
   for (int l = 0; l < L; ++l) {
     Level& v = P->lv[l];
     v.H = P->H >> l; v.W = P->W >> l; v.h = v.H / 2; v.w = v.W / 2;
-    v.Cin = l == 0 ? d.in_channels : CH;
+    v.Cin = l == 0 ? cin_eng : CH;
+    v.Cin_act = l == 0 ? d.in_channels : CH;
+    v.bilinear = d.upsample_bilinear < 0 ? (d.upsample_mask >> l) & 1 : (d.upsample_bilinear != 0);
     const int b0 = pre[l], b1 = post[l];
     // skip conv 1x1 Cin -> CS
     v.p_skip_w = b0; v.p_skip_b = b0 + 1;
-    P->numel[b0] = (long long)CS * v.Cin; P->numel[b0 + 1] = CS;
+    P->numel[b0] = (long long)CS * v.Cin_act; P->numel[b0 + 1] = CS;
     bn_init(v.bn_s, CS, 0, v.H * v.W, b0 + 2, b0 + 1);
     // down1 3x3 s2
-    v.d1.C = v.Cin; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + 4; v.d1.p_b = b0 + 5;
-    P->numel[b0 + 4] = 128LL * v.Cin * 9; P->numel[b0 + 5] = 128;
+    v.d1.C = v.Cin_act; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + 4; v.d1.p_b = b0 + 5;
+    P->numel[b0 + 4] = 128LL * v.Cin_act * 9; P->numel[b0 + 5] = 128;
     bn_init(v.bn_d1, 128, 0, v.h * v.w, b0 + 6, b0 + 5);
     // down2 3x3
     v.d2.C = 128; v.d2.k = 3; v.d2.stride = 1; v.d2.p_w = b0 + 8; v.d2.p_b = b0 + 9;
@@ -575,7 +586,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.up.C = 128 + CS; v.up.k = 3; v.up.stride = 1; v.up.rot = CS; v.up.p_w = b1 + 2; v.up.p_b = b1 + 3;
     if (wide) {
       v.up.do_wgrad = false;
-      v.sk.C = v.Cin; v.sk.k = 1; v.sk.stride = 1; v.sk.p_w = b0; v.sk.p_b = b0 + 1;
+      v.sk.C = v.Cin_act; v.sk.k = 1; v.sk.stride = 1; v.sk.p_w = b0; v.sk.p_b = b0 + 1;
       for (ConvOp* h : {&v.up_a, &v.up_b}) {
         h->C = 128; h->Ctot = 128 + CS; h->k = 3; h->stride = 1; h->rot = CS; h->p_w = b1 + 2; h->p_b = b1 + 3;
         h->do_fprop = false; h->dg_ld = 128 + CS;
@@ -801,7 +812,8 @@ static int upload_tables(dip_plan* P) {
   for (size_t l = 0; l < P->lv.size(); ++l) {
     // skip=128: the skip conv's weight gradient comes from the tensor-core wgrad, not from fp64 accumulators
     if (P->desc.skip_channels == 128) cv.push_back(CvtEntry{P->lv[l].dw_s, nullptr, 0, 0});
-    else cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0});
+    else cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0,
+                               P->lv[l].Cin_act, P->lv[l].Cin});   // accumulator rows hold the stored depth
   }
   cv.push_back(CvtEntry{P->dw_head, P->grads[P->p_head_w], (int)P->numel[P->p_head_w], 0});
   cv.push_back(CvtEntry{P->db_head, P->grads[P->p_head_b], (int)P->numel[P->p_head_b], 0});
@@ -860,7 +872,7 @@ static void join_skip(dip_plan* P, cudaStream_t s) {
 static CatArgs cat_args(const dip_plan* P, const Level& v, const float* Usrc) {
   CatArgs a;
   a.U = Usrc; a.raw_s = v.raw_s; a.bn_s = bn_ref(P, v.bn_s);
-  a.Cu = 128; a.Cs = P->desc.skip_channels; a.H = v.H; a.W = v.W; a.bilinear = P->desc.upsample_bilinear;
+  a.Cu = 128; a.Cs = P->desc.skip_channels; a.H = v.H; a.W = v.W; a.bilinear = v.bilinear;
   return a;
 }
 static const float* level_usrc(const dip_plan* P, int l) {
@@ -882,7 +894,7 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
       nl += prec == DIP_PRECISION_FP32 ? 2 : 1;
     } else {
       launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
-                        v.bn_s.fwd, ks);
+                        v.bn_s.fwd, ks, v.Cin_act);
       nl += 1;
     }
   }
@@ -929,7 +941,7 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
   if (!P->prepacked) plan_pack(P, fork_side(P, s));   // weight repack runs beside the input transform
   P->prepacked = false;
   Level& v0 = P->lv[0];
-  launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s);
+  launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act);
   join_side(P, s);
   nl += 3;
   DIP_CHECK(fwd_level(P, 0, s, nl));
@@ -1007,7 +1019,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   // skip branch (on the skip stream: independent of the deeper levels; the level above joins before it reads dRaw_s / dS)
   cudaStream_t ks = fork_skip(P, s);
   // gradient w.r.t. the low-resolution tensor that was upsampled into this concat (adjoint of x2 upsampling), once
-  launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, P->desc.upsample_bilinear, v.dUp, s);
+  launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp, s);
   nl += 3;
   DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl));
   if (CS == 128) {
@@ -1018,7 +1030,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
     // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
     launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
-                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks);
+                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks, v.Cin_act);
     nl += 1;
   }
   // deeper branch

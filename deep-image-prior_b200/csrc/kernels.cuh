@@ -88,8 +88,9 @@ struct HeadRef {
 };
 
 // z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
+// C = stored depth of dst; c_src (0: C) = depth of z / noise, the remaining channels are written as zeros
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
-                      cudaStream_t s);
+                      cudaStream_t s, int c_src = 0);
 
 // generic per-channel sum / sum^2 of a plain NHWC tensor (SIMT-conv path and skinny convs)
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s);
@@ -157,13 +158,14 @@ void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bil
 //   x: pixel (i,j) at x + (i*x_rs + j)*ldx floats (works for padded interiors)
 //   mode 0: y NHWC [H][W][N]; mode 1: y = sigmoid(.) NCHW [N][H][W]; mode 2: NCHW without sigmoid
 //   stats (nullable, mode 0): fwd[0..N) += sum y, fwd[N..2N) += sum y^2
+//   cw (0: C) = row length of w when the stored depth C is padded (channels >= cw multiply zeros)
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
-                       int W, float* y, int mode, double* stats, cudaStream_t s);
+                       int W, float* y, int mode, double* stats, cudaStream_t s, int cw = 0);
 // backward: dy NHWC [H][W][N] (mode 0) or dout NCHW with sigmoid derivative folded in (mode 1: dy = dout*o*(1-o))
 //   dx (optional) plain [H][W][C]; dw[N][C] and db[N] accumulated into fp64 (zeroed by caller)
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
-                       cudaStream_t s);
+                       cudaStream_t s, int cw = 0);
 
 // loss[slot] += mean(m^2 (o - t)^2), dout = 2 m^2 (o - t) / n; mask may be null ([H*W], broadcast over C channels);
 // slot = *it_dev if it_dev != null else 0

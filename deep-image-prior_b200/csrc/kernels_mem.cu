@@ -200,7 +200,7 @@ static void fit_grid(VecGeom& g, Kern kernel, size_t smem) {
 
 // ------------------------------------------------------------------------------------------------ input_pad
 __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict__ noise, float sigma,
-                            float* __restrict__ dst, int C, int H, int W) {
+                            float* __restrict__ dst, int C, int H, int W, int Cs) {
   pdl_enter();
   __shared__ float tile[32][33];
   const int Wp = W + 2;
@@ -212,7 +212,7 @@ __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict
     for (int k = 0; k < 4; ++k) {
       const int c = c0 + ty + 8 * k;
       float val = 0.f;
-      if (xx < Wp && c < C) {
+      if (xx < Wp && c < Cs) {
         const int sx = reflect_idx(xx - 1, W);
         const size_t off = (static_cast<size_t>(c) * H + sy) * W + sx;
         val = z[off];
@@ -230,9 +230,9 @@ __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict
   }
 }
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
-                      cudaStream_t s) {
+                      cudaStream_t s, int c_src) {
   dim3 grid((W + 2 + 31) / 32, H + 2), block(32, 8);
-  launch_k(k_input_pad, dim3(grid), dim3(block), 0, s, 1, z, noise, sigma, dst, C, H, W);
+  launch_k(k_input_pad, dim3(grid), dim3(block), 0, s, 1, z, noise, sigma, dst, C, H, W, c_src > 0 ? c_src : C);
 }
 
 // ------------------------------------------------------------------------------------------------ item loop
@@ -810,11 +810,19 @@ void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bil
   launch_k(k_upadj, dim3(g.blocks), dim3(g.threads), 0, s, 1, D, ld, coff, h, w, C, bilinear, dst, g.VL, g.PPB);
 }
 
+// weight row n of a skinny conv for lanes 4v..4v+3: rows are cw long (cw < C when the stored depth is zero-padded)
+__device__ __forceinline__ float4 skinny_wrow(const float* __restrict__ w, int n, int cw, int v) {
+  if ((cw & 3) == 0) return 4 * v < cw ? ld4(w + n * cw + 4 * v) : f4zero();
+  const float* r = w + n * cw;
+  const int c = 4 * v;
+  return make_float4(c < cw ? r[c] : 0.f, c + 1 < cw ? r[c + 1] : 0.f, c + 2 < cw ? r[c + 2] : 0.f, c + 3 < cw ? r[c + 3] : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------ skinny 1x1 convs
 // VL = C/4 lanes per pixel (power of two <= 32); warp-shuffle reduction over the pixel's lanes.
 __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
                                                     const float* __restrict__ b, int C, int N, int H, int W,
-                                                    float* __restrict__ y, int mode, double* __restrict__ stats) {
+                                                    float* __restrict__ y, int mode, double* __restrict__ stats, int cw) {
   pdl_enter();
   const int VL = C / 4;
   const int PPB = 256 / VL;
@@ -824,7 +832,7 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
   float bv[4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
-    wv[n] = n < N ? ld4(w + n * C + 4 * v) : f4zero();
+    wv[n] = n < N ? skinny_wrow(w, n, cw, v) : f4zero();
     bv[n] = (n < N && b != nullptr) ? b[n] : 0.f;
   }
   float4 s1 = f4zero(), s2 = f4zero();
@@ -867,22 +875,22 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
   }
 }
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
-                       int W, float* y, int mode, double* stats, cudaStream_t s) {
+                       int W, float* y, int mode, double* stats, cudaStream_t s, int cw) {
   const int PPB = 256 / (C / 4);
   long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
   if (nb > 148 * 8) nb = 148 * 8;
   launch_red(k_skinny_fwd, static_cast<int>(nb), 256, 2 * 256 * sizeof(float4) + 2 * 4 * sizeof(double), s, x, ldx, x_rs, w, b, C, N, H, W,
-                  y, mode, stats);
+                  y, mode, stats, cw > 0 ? cw : C);
 }
 
 __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
                              int H, int W, const float* __restrict__ dy, const float* __restrict__ out_nchw, int mode,
-                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB) {
+                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB, int cw) {
   pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const int npix = H * W;
   float4 wv[4];
-  for (int n = 0; n < 4; ++n) wv[n] = n < N ? ld4(w + n * C + 4 * v) : f4zero();
+  for (int n = 0; n < 4; ++n) wv[n] = n < N ? skinny_wrow(w, n, cw, v) : f4zero();
   float4 acc[5] = {f4zero(), f4zero(), f4zero(), f4zero(), f4zero()};  // dw rows 0..3, db (lane v == 0 only)
   struct Item { float4 g, x; };
   item_loop<4>(blockIdx.x * PPB + slot, gridDim.x * PPB, npix,
@@ -927,11 +935,11 @@ __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, con
 }
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,
-                       cudaStream_t s) {
+                       cudaStream_t s, int cw) {
   VecGeom g = vec_geom(C, static_cast<long long>(H) * W);
   fit_grid(g, k_skinny_bwd, red_bytes(g, 5));
   launch_red(k_skinny_bwd, g.blocks, g.threads, red_bytes(g, 5), s, x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db,
-                                                             g.VL, g.PPB);
+                                                             g.VL, g.PPB, cw > 0 ? cw : C);
 }
 
 // ------------------------------------------------------------------------------------------------ MSE loss

@@ -27,6 +27,7 @@ class NetDesc(ctypes.Structure):
         ("upsample_bilinear", ctypes.c_int),
         ("need_sigmoid", ctypes.c_int),
         ("precision", ctypes.c_int),
+        ("upsample_mask", ctypes.c_int),
     ]
 
 
@@ -136,8 +137,14 @@ class Plan:
         if not torch.cuda.is_available():
             raise RuntimeError("dip-b200 needs a CUDA device (sm_100a); none is visible")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, int(bool(bilinear)), 1,
-                            precision)
+        # bilinear: one flag for every scale, or a per-scale sequence (flash-no-flash.ipynb c8)
+        if isinstance(bilinear, (list, tuple)):
+            assert len(bilinear) == num_scales
+            mask = sum(1 << i for i, b in enumerate(bilinear) if b)
+            self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, -1, 1, precision, mask)
+        else:
+            self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, int(bool(bilinear)), 1,
+                                precision, 0)
         self.H, self.W = H, W
         nbytes = L.dip_plan_workspace_bytes(ctypes.byref(self.desc), H, W)
         if nbytes == 0:

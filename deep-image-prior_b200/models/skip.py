@@ -239,13 +239,15 @@ def skip(num_input_channels=2, num_output_channels=3,
         why = "act_fun must be 'LeakyReLU'"
     elif not (need_sigmoid and need_bias and need1x1_up):
         why = 'need_sigmoid, need_bias and need1x1_up must be True'
-    elif len(set(upsample_mode)) != 1 or upsample_mode[0] not in ('bilinear', 'nearest'):
-        why = "upsample_mode must be uniformly 'bilinear' or 'nearest'"
-    elif num_output_channels > 4 or num_input_channels not in (4, 8, 16, 32, 64, 128):
-        why = 'num_output_channels <= 4 and num_input_channels in {4,...,128} (power of two)'
+    elif any(m not in ('bilinear', 'nearest') for m in upsample_mode):
+        why = "upsample_mode must be 'bilinear' or 'nearest' (per scale)"
+    elif not (1 <= num_output_channels <= 4 and 1 <= num_input_channels <= 128):
+        why = 'num_output_channels in 1..4 and num_input_channels in 1..128'
     if why is None:
         net._dip_spec = dict(in_channels=num_input_channels, out_channels=num_output_channels, num_scales=n,
-                             channels=128, skip_channels=num_channels_skip[0], bilinear=upsample_mode[0] == 'bilinear')
+                             channels=128, skip_channels=num_channels_skip[0],
+                             bilinear=(upsample_mode[0] == 'bilinear' if len(set(upsample_mode)) == 1
+                                       else [m == 'bilinear' for m in upsample_mode]))
     else:
         net._dip_why = why
     return net

@@ -28,14 +28,16 @@ enum { DIP_PRECISION_TF32 = 0, /* tcgen05 kind::tf32 convolutions, fp32 accumula
 
 /* Arguments of models.skip(...) that the engine supports (reference: models/skip.py:5-11, models/__init__.py:12-17). */
 typedef struct {
-  int in_channels;       /* num_input_channels (multiple of 4; 32 in every BASELINE config)            */
+  int in_channels;       /* num_input_channels, 1..128 (32 in every BASELINE config; 3 in flash-no-flash)  */
   int out_channels;      /* num_output_channels (<= 4; 3)                                               */
   int num_scales;        /* len(num_channels_down)                                                      */
   int channels;          /* num_channels_down[i] == num_channels_up[i] == 128                           */
-  int skip_channels;     /* num_channels_skip[i] (4)                                                    */
-  int upsample_bilinear; /* upsample_mode: 1 'bilinear', 0 'nearest'                                    */
+  int skip_channels;     /* num_channels_skip[i]: 4, or 128 (inpainting.ipynb kate)                     */
+  int upsample_bilinear; /* upsample_mode: 1 'bilinear', 0 'nearest', -1: per scale, see upsample_mask  */
   int need_sigmoid;      /* 1                                                                           */
   int precision;         /* DIP_PRECISION_*                                                             */
+  int upsample_mask;     /* upsample_bilinear == -1: bit i set = scale i (0 = outermost) is 'bilinear'
+                            (flash-no-flash.ipynb c8: ['nearest','nearest','bilinear','bilinear','bilinear']) */
 } dip_net_desc;
 
 const char* dip_last_error(void);

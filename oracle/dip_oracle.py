@@ -132,7 +132,8 @@ def skip_forward(params, z, cfg, tape=None):
         d = _act(_bn(d, P[pre + "d2_bn.g"], P[pre + "d2_bn.b"]))
         if l < cfg.num_scales - 1:
             d = rec(l + 1, d)
-        if cfg.upsample_mode == "bilinear":
+        mode = cfg.upsample_mode if isinstance(cfg.upsample_mode, str) else cfg.upsample_mode[l]   # per scale: skip.py:81
+        if mode == "bilinear":
             d = F.interpolate(d, scale_factor=2, mode="bilinear", align_corners=False)
         else:
             d = F.interpolate(d, scale_factor=2, mode="nearest")

@@ -61,6 +61,47 @@ def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtyp
     print(name, 'losses', losses)
 
 
+def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.01, masked=False, dtype=torch.float32,
+                threads=8):
+    """Skip-net variants of the other notebooks that use the 128-wide network: flash-no-flash.ipynb c8 (image as input,
+    per-scale upsampling modes) and restoration.ipynb c7 barbara (n_channels=1, masked loss)."""
+    torch.set_num_threads(threads)
+    with ref_harness.reference_modules() as ref:
+        torch.manual_seed(0)
+        net = ref.models.skip(in_depth, out_ch, num_channels_down=[128] * 5, num_channels_up=[128] * 5,
+                              num_channels_skip=[4] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True,
+                              pad='reflection').type(dtype)
+        g = torch.Generator().manual_seed(2)
+        z0 = torch.rand(1, in_depth, H, W, generator=g).type(dtype)          # an image (or noise) as the network input
+        target = torch.rand(1, out_ch, H, W, generator=g).type(dtype)
+        mask = (torch.rand(1, 1, H, W, generator=g) > 0.5).type(dtype) if masked else None
+        gn = torch.Generator().manual_seed(123)
+        mse = torch.nn.MSELoss()
+        params = [p for p in net.parameters()]
+        opt = torch.optim.Adam(params, lr=lr)
+        losses = []
+        for i in range(iters):
+            noise = torch.randn(z0.shape, generator=gn).type(dtype)
+            opt.zero_grad()
+            out = net(z0 + noise * sigma)
+            loss = mse(out * mask, target * mask) if masked else mse(out, target)
+            loss.backward()
+            if i == 0:
+                out0 = out.detach().clone()
+                gnorm0 = np.array([p.grad.double().norm().item() for p in params])
+                g_first = [params[k].grad.detach().clone().numpy() for k in (0, 4)]   # L0 skip conv w, L0 down conv w
+            losses.append(loss.item())
+            opt.step()
+        keys = list(net.state_dict().keys())
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), H=H, W=W, in_depth=in_depth, out_ch=out_ch,
+                        modes=np.array(modes if isinstance(modes, list) else [modes] * 5), iters=iters, sigma=sigma, lr=lr,
+                        masked=masked, losses=np.array(losses), out0=out0.numpy(), gnorm0=gnorm0, g_skip0_w=g_first[0],
+                        g_d1_0_w=g_first[1], dtype=str(dtype), state_keys=np.array(keys))
+    print(name, 'losses', losses)
+
+
+FLASH_MODES = ['nearest', 'nearest', 'bilinear', 'bilinear', 'bilinear']
+
 DOWN_CASES = [  # (tag, ctor kwargs, H, W)
     ('lanczos2_f4', dict(factor=4, kernel_type='lanczos2', phase=0.5, preserve_size=True), 64, 96),
     ('lanczos2_f2', dict(factor=2, kernel_type='lanczos2', phase=0.5, preserve_size=True), 38, 50),
@@ -136,6 +177,11 @@ if __name__ == '__main__':
         run_case('inpaint64x96_nearest_masked_skip128_fp32', 64, 96, 'nearest', 3, sigma=0.03, masked=True,
                  dtype=torch.float32, skip_n11=128)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'variants':   # only the flash-no-flash / restoration fixtures
+        for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
+            run_variant('flash64x96_in3_mixed_' + tag, 64, 96, 3, 3, FLASH_MODES, dtype=dt)
+            run_variant('restore64_out1_masked_' + tag, 64, 64, 32, 1, 'bilinear', masked=True, dtype=dt)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sr':   # only the super-resolution fixtures
         run_downsampler_cases()
         run_sr_case('sr64x96_fp64', 64, 96, 3, torch.float64)
@@ -151,3 +197,6 @@ if __name__ == '__main__':
     run_downsampler_cases()
     run_sr_case('sr64x96_fp64', 64, 96, 3, torch.float64)
     run_sr_case('sr64x96_fp32', 64, 96, 3, torch.float32)
+    for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
+        run_variant('flash64x96_in3_mixed_' + tag, 64, 96, 3, 3, FLASH_MODES, dtype=dt)
+        run_variant('restore64_out1_masked_' + tag, 64, 64, 32, 1, 'bilinear', masked=True, dtype=dt)

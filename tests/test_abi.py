@@ -43,7 +43,7 @@ def test_workspace_query_rejects_unsupported_configurations_with_a_reason():
     assert base > 0
     for desc, H, W, word in [
         (de.NetDesc(32, 3, 5, 128, 8, 1, 1, 0), 512, 512, "num_channels_skip"),      # skip width other than 4 / 128
-        (de.NetDesc(24, 3, 5, 128, 4, 1, 1, 0), 512, 512, "input depth"),            # not a power of two
+        (de.NetDesc(200, 3, 5, 128, 4, 1, 1, 0), 512, 512, "input depth"),           # > 128
         (de.NetDesc(32, 5, 5, 128, 4, 1, 1, 0), 512, 512, "num_output_channels"),
         (de.NetDesc(32, 3, 9, 128, 4, 1, 1, 0), 512, 512, "scales"),
         (de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0), 500, 512, "divisible"),              # 500 % 32 != 0
@@ -58,6 +58,9 @@ def test_workspace_query_rejects_unsupported_configurations_with_a_reason():
     assert 3.5 * base < big < 4.5 * base
     small, _ = q(de.NetDesc(8, 1, 3, 128, 4, 0, 1, 1), 64, 96)
     assert 0 < small < base
+    # flash-no-flash: image (3 channels) as input, per-scale upsampling modes; stored with 4 channels -> smaller than 32
+    flash, _ = q(de.NetDesc(3, 3, 5, 128, 4, -1, 1, 0, 0b11100), 704, 768)
+    assert 0 < flash
 
 
 def test_downsampler_output_size_matches_torch_conv_arithmetic():
