@@ -216,6 +216,7 @@ struct ConvOp {
     const int kp = (wg_w % 32 == 0) ? 32 : 16;
     const int blocks = wg_h * ((wg_w + kp - 1) / kp);
     int ks = 148 / k;
+    if (const char* e = getenv("DIP_WGRAD_KS")) { const int cap = atoi(e); if (cap >= 1 && cap < ks) ks = cap; }   // experiment
     if (ks > blocks) ks = blocks;
     return ks < 1 ? 1 : ks;
   }
@@ -336,6 +337,8 @@ struct ConvOp {
     return 0;
   }
   int run_wgrad(int prec, float* partial, float* dw, cudaStream_t s) {
+    static const bool dbg_skip = getenv("DIP_DBG_SKIP_WGRAD") != nullptr;   // timing diagnostic only: gradients are wrong
+    if (dbg_skip) return 0;
     int ks;
     if (prec == DIP_PRECISION_TF32) {
       TcWgradParams p = wg;
@@ -506,6 +509,9 @@ struct dip_plan {
   std::vector<cudaEvent_t> wev;
   size_t wev_used = 0;
   bool side_on = false;
+  // weight-gradient GEMMs of the outer levels deferred until the main chain is inside the (latency-bound, SM-starved)
+  // deep levels, where a full-GPU tensor-core kernel on the side stream costs the least
+  std::vector<dip::ConvOp*> deferred;
   bool prepacked = false;   // the runner already issued the weight repack of this forward (beside the noise kernel)
   // tables
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
@@ -979,8 +985,25 @@ static GradSrc src_upadj(const float* d, int ld, int bilinear) { GradSrc s{}; s.
 // kernels that fill every SM, so they run one after the other whichever way: the dgrad is enqueued first and the main
 // stream has the higher priority, so that the wgrad overlaps the HBM-bound kernels that follow the dgrad instead of
 // delaying it.  (DIP_WGRAD_FIRST=1: the old order, for A/B runs.)
-static int conv_backward(dip_plan* P, ConvOp& op, bool dgrad, int prec, cudaStream_t s) {
+static int defer_level() {
+  // measured (profiles/r01_matrix_wgrad_schedule.txt): 347.5 it/s without deferral, 352.3 with the level-0/1 wgrads deferred
+  static const int lv = getenv("DIP_DEFER_WGRAD") ? atoi(getenv("DIP_DEFER_WGRAD")) : 2;   // 0: no deferral
+  return lv;
+}
+static int flush_deferred(dip_plan* P, int prec, cudaStream_t s) {
+  if (P->deferred.empty()) return 0;
+  cudaStream_t ws = fork_side(P, s);
+  for (ConvOp* op : P->deferred) DIP_CHECK(op->run_wgrad(prec, P->partial, P->grads[op->p_w], ws));
+  P->deferred.clear();
+  return 0;
+}
+static int conv_backward(dip_plan* P, ConvOp& op, bool dgrad, int prec, cudaStream_t s, int level = 99) {
   static const bool wgrad_first = getenv("DIP_WGRAD_FIRST") != nullptr;
+  if (P->side_on && level < defer_level() && (int)P->lv.size() > defer_level()) {
+    if (dgrad) DIP_CHECK(op.run_dgrad(prec, s));
+    P->deferred.push_back(&op);
+    return 0;
+  }
   cudaStream_t ws = fork_side(P, s);
   if (wgrad_first) DIP_CHECK(op.run_wgrad(prec, P->partial, P->grads[op.p_w], ws));
   if (dgrad) DIP_CHECK(op.run_dgrad(prec, s));
@@ -997,7 +1020,8 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   const int wl = prec == DIP_PRECISION_TF32 ? 2 : 2;
   // 1x1 conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl));
-  DIP_CHECK(conv_backward(P, v.c11, true, prec, s));
+  if (l == defer_level()) DIP_CHECK(flush_deferred(P, prec, s));
+  DIP_CHECK(conv_backward(P, v.c11, true, prec, s, l));
   nl += wl + 1;
   // up conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl));
@@ -1009,7 +1033,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
     DIP_CHECK(v.up_b.run_wgrad(prec, P->partial, P->grads[v.up.p_w], ws));
     nl += 2 * (wl + 1);
   } else {
-    DIP_CHECK(conv_backward(P, v.up, true, prec, s));
+    DIP_CHECK(conv_backward(P, v.up, true, prec, s, l));
     nl += wl + 1;
   }
   // concat BN
@@ -1057,6 +1081,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
 static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   if (!P->bound) return fail("dip_backward: parameters not bound");
   int nl = 0;
+  P->deferred.clear();
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
   P->side_on = getenv("DIP_NO_SIDE") == nullptr;
   Level& v0 = P->lv[0];
@@ -1067,6 +1092,7 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   sh.dwh = P->dw_head; sh.dbh = P->db_head;
   nl += 1;
   DIP_CHECK(bwd_level(P, 0, sh, s, nl));
+  DIP_CHECK(flush_deferred(P, P->desc.precision, s));
   join_side(P, s);
   join_skip(P, s);
   launch_k(k_cvt_table, dim3(P->n_cvt), dim3(128), 0, s, 1, P->d_cvt);
