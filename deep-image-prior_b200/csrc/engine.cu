@@ -1004,6 +1004,13 @@ static int conv_backward(dip_plan* P, ConvOp& op, bool dgrad, int prec, cudaStre
     P->deferred.push_back(&op);
     return 0;
   }
+  static const bool after_dgrad = getenv("DIP_WGRAD_AFTER_DGRAD") != nullptr;
+  if (after_dgrad) {
+    // the wgrad becomes runnable only once its sibling dgrad has finished: it then starts beside the HBM-bound kernels
+    // that follow the dgrad instead of fighting it for the SMs
+    if (dgrad) DIP_CHECK(op.run_dgrad(prec, s));
+    return op.run_wgrad(prec, P->partial, P->grads[op.p_w], fork_side(P, s));
+  }
   cudaStream_t ws = fork_side(P, s);
   if (wgrad_first) DIP_CHECK(op.run_wgrad(prec, P->partial, P->grads[op.p_w], ws));
   if (dgrad) DIP_CHECK(op.run_dgrad(prec, s));
