@@ -546,7 +546,6 @@ static int build_plan(dip_plan* P, Arena& A) {
   if (d.out_channels < 1 || d.out_channels > 4) return fail("dip-b200: num_output_channels must be <= 4");
   if (L < 1 || L > 8) return fail("dip-b200: 1..8 scales supported");
   if (P->H % (1 << L) || P->W % (1 << L)) return fail("dip-b200: H and W must be divisible by 2^num_scales");
-  if (!d.need_sigmoid) return fail("dip-b200: need_sigmoid=False is not supported by the engine (round 1)");
   const int prec = d.precision;
   P->lv.resize(L);
   int pidx = 0;
@@ -664,9 +663,10 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.dRaw_d2 = A.get<float>(hw * 128);
     v.dP_d1 = A.get<float>(hwp * 128);
     v.dRaw_d1 = A.get<float>(hw * 128);
-    v.ZS = l > 0 ? A.get<float>(HW * 128) : nullptr;
-    v.dS = (wide && l > 0) ? A.get<float>(HW * 128) : nullptr;
-    v.dPin = l > 0 ? A.get<float>(HWp * 128) : nullptr;
+    const bool in_grad = d.input_grad != 0;   // level 0 then also needs its input gradient
+    v.ZS = (l > 0 || in_grad) ? A.get<float>(HW * 128) : nullptr;
+    v.dS = ((wide && l > 0) || (in_grad && l == 0)) ? A.get<float>(HW * v.Cin) : nullptr;
+    v.dPin = (l > 0 || in_grad) ? A.get<float>(HWp * v.Cin) : nullptr;
     reg(pf + "Pin", v.Pin, v.H + 2, v.W + 2, v.Cin, v.Cin);
     reg(pf + "raw_s", v.raw_s, v.H, v.W, CS, CS);
     reg(pf + "raw_d1", v.raw_d1, v.h, v.w, 128, 128);
@@ -710,7 +710,8 @@ static int build_plan(dip_plan* P, Arena& A) {
     a.set_shapes();
     a.in = v.Pin; a.in_rows = v.H + 2; a.in_cols = v.W + 2; a.in_ld = v.Cin; a.offx = a.offy = 0;
     a.out = v.raw_d1; a.out_h = v.h; a.out_w = v.w; a.stats = v.bn_d1.fwd;
-    a.has_dgrad = l > 0;
+    a.has_dgrad = l > 0 || d.input_grad != 0;
+    a.dg_ld = v.Cin;   // level 0: stored depth (>= the conv's real input depth)
     a.dg_in = v.ZS; a.dg_in_h = v.H; a.dg_in_w = v.W; a.dg_out = v.dPin; a.dg_out_h = v.H + 2; a.dg_out_w = v.W + 2; a.dg_off = -2;
     a.wg_dy = v.dRaw_d1; a.wg_h = v.h; a.wg_w = v.w;
     // down2: P_d1 -> raw_d2
@@ -744,7 +745,8 @@ static int build_plan(dip_plan* P, Arena& A) {
       k1.set_shapes();
       k1.in = v.Pin; k1.in_rows = v.H + 2; k1.in_cols = v.W + 2; k1.in_ld = v.Cin; k1.offx = k1.offy = 1;
       k1.out = v.raw_s; k1.out_h = v.H; k1.out_w = v.W; k1.stats = v.bn_s.fwd;
-      k1.has_dgrad = l > 0;
+      k1.has_dgrad = l > 0 || d.input_grad != 0;
+      k1.dg_ld = v.Cin;
       k1.dg_in = v.dRaw_s; k1.dg_in_h = v.H; k1.dg_in_w = v.W; k1.dg_out = v.dS; k1.dg_out_h = v.H; k1.dg_out_w = v.W; k1.dg_off = 0;
       k1.wg_dy = v.dRaw_s; k1.wg_h = v.H; k1.wg_w = v.W;
       ops.push_back(&k1);
@@ -787,7 +789,8 @@ static int build_plan(dip_plan* P, Arena& A) {
     DIP_CUDA(cudaStreamCreateWithPriority(&P->sstream, cudaStreamNonBlocking, lo));
   }
   // The zero-stuffed buffers are written at even positions only: clear them once.
-  for (int l = 1; l < L; ++l) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
+  for (int l = 0; l < L; ++l)
+    if (P->lv[l].ZS != nullptr) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
   if (prec == DIP_PRECISION_TF32)
     for (ConvOp* op : P->convs) DIP_CHECK(op->build_tc(P->partial));
   P->pack_max = 0;
@@ -923,7 +926,7 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
     launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s);
   } else {
     // top level: BN + LeakyReLU + RGB head + sigmoid in one pass; the 128-channel activation is never materialised
-    HeadRef hd{P->params[P->p_head_w], P->params[P->p_head_b], P->desc.out_channels, P->out_saved};
+    HeadRef hd{P->params[P->p_head_w], P->params[P->p_head_b], P->desc.out_channels, P->out_saved, P->desc.need_sigmoid != 0};
     launch_bn_act_head(v.raw_v, bn_ref(P, v.bn_v), v.H, v.W, hd, s);
   }
   nl += 6 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
@@ -1056,12 +1059,12 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   if (CS == 128) {
     DIP_CHECK(v.sk.run_wgrad(prec, P->partial, P->grads[v.p_skip_w], fork_side(P, ks)));
     nl += wl;
-    if (l > 0) { DIP_CHECK(v.sk.run_dgrad(prec, ks)); nl += 1; }   // dS, added to the fold of dPin by the level above
+    if (l > 0 || P->desc.input_grad) { DIP_CHECK(v.sk.run_dgrad(prec, ks)); nl += 1; }   // dS, added to the fold of dPin by the level above
   } else {
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
     // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
     launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
-                      nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks, v.Cin_act);
+                      (l == 0 && P->desc.input_grad) ? v.dS : nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks, v.Cin_act);
     nl += 1;
   }
   // deeper branch
@@ -1078,9 +1081,10 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl));
   DIP_CHECK(conv_backward(P, v.d2, true, prec, s));
   nl += wl + 1;
-  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, l > 0 ? v.ZS : nullptr, s, nl));
-  DIP_CHECK(conv_backward(P, v.d1, l > 0, prec, s));
-  nl += wl + (l > 0 ? 1 : 0);
+  const bool d1_dgrad = l > 0 || P->desc.input_grad != 0;
+  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, d1_dgrad ? v.ZS : nullptr, s, nl));
+  DIP_CHECK(conv_backward(P, v.d1, d1_dgrad, prec, s));
+  nl += wl + (d1_dgrad ? 1 : 0);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1094,7 +1098,7 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
   GradSrc sh{};
-  launch_head_dlogit(dout, P->out_saved, P->desc.out_channels, P->H * P->W, P->dl4, s);
+  launch_head_dlogit(dout, P->out_saved, P->desc.out_channels, P->H * P->W, P->dl4, s, P->desc.need_sigmoid != 0);
   sh.kind = 3; sh.dl4 = P->dl4; sh.wh = P->params[P->p_head_w]; sh.nh = P->desc.out_channels;
   sh.dwh = P->dw_head; sh.dbh = P->db_head;
   nl += 1;
@@ -1422,6 +1426,14 @@ int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* 
   for (int i = 0; i < iters; ++i) DIP_CUDA(cudaGraphLaunch(P->gexec, gs));
   DIP_CUDA(cudaEventRecord(P->gev_out, gs));
   DIP_CUDA(cudaStreamWaitEvent(s, P->gev_out, 0));
+  return 0;
+}
+
+int dip_input_grad(dip_plan* P, void* dz, dip_stream_t stream) {
+  if (!P->desc.input_grad) return fail("dip_input_grad: the plan was created without input_grad");
+  Level& v = P->lv[0];
+  launch_input_grad(v.dPin, v.dS, v.Cin, v.Cin_act, v.H, v.W, (float*)dz, (cudaStream_t)stream);
+  DIP_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -85,6 +85,7 @@ struct HeadRef {
   const float* b;      // [K]
   int K;               // <= 4
   float* out;          // NCHW [K][H*W]
+  int sigmoid;         // 1: nn.Sigmoid behind the head (need_sigmoid=True, skip.py:97-98), 0: the logits are the output
 };
 
 // z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
@@ -135,7 +136,12 @@ struct GradSrc {
 };
 
 // dl4[p][k] = dout[k][p] * o[k][p] * (1 - o[k][p]) (k < K, else 0); dout / outv are NCHW [K][npix]
-void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s);
+//   sigmoid = 0 (need_sigmoid=False): dl4[p][k] = dout[k][p]
+void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s, int sigmoid = 1);
+// dL/dz of the network input (OPT_OVER='input', utils/common_utils.py:47-49), torch layout [C][H][W]:
+//   dz[c][i][j] = fold(gp)[i][j][c] + ds[i][j][c]; gp = padded dgrad output of the level-0 stride-2 conv
+//   [(H+2)][(W+2)][ld], ds = input gradient of the level-0 skip conv [H][W][ld] (nullable)
+void launch_input_grad(const float* gp, const float* ds, int ld, int C, int H, int W, float* dz, cudaStream_t s);
 
 // BN(+LeakyReLU) backward. reduce: bwd[0..C) += sum dz, bwd[C..2C) += sum dz*xhat.
 // apply: dx = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)); writes draw plain [H][W][C];

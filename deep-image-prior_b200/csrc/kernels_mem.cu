@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) k_bn_act_head(const float* __restrict__ r
                  }
                  if (lane < head.K) {
                    const float t = (lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3]) + hb;
-                   head.out[static_cast<size_t>(lane) * npix + p] = 1.f / (1.f + expf(-t));
+                   head.out[static_cast<size_t>(lane) * npix + p] = head.sigmoid ? 1.f / (1.f + expf(-t)) : t;
                  }
                });
 }
@@ -564,21 +564,63 @@ struct RedItem {
 typedef RedItem BwdItem;
 // dl4[p] = dout[k][p] * o[k][p] * (1 - o[k][p]) for k < K (else 0): sigmoid' folded into the logit gradient once per pixel
 __global__ void k_head_dlogit(const float* __restrict__ dout, const float* __restrict__ outv, int K, int npix,
-                              float* __restrict__ dl4) {
+                              float* __restrict__ dl4, int sigmoid) {
   pdl_enter();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
     float d[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k = 0; k < K; ++k) {
       const float o = outv[static_cast<size_t>(k) * npix + p];
-      d[k] = dout[static_cast<size_t>(k) * npix + p] * o * (1.f - o);
+      d[k] = dout[static_cast<size_t>(k) * npix + p] * (sigmoid ? o * (1.f - o) : 1.f);
     }
     st4(dl4 + static_cast<size_t>(p) * 4, make_float4(d[0], d[1], d[2], d[3]));
   }
 }
-void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s) {
+void launch_head_dlogit(const float* dout, const float* outv, int K, int npix, float* dl4, cudaStream_t s, int sigmoid) {
   int blocks = (npix + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(k_head_dlogit, dim3(blocks), dim3(256), 0, s, 1, dout, outv, K, npix, dl4);
+  launch_k(k_head_dlogit, dim3(blocks), dim3(256), 0, s, 1, dout, outv, K, npix, dl4, sigmoid);
+}
+
+// ------------------------------------------------------------------------------------------------ input gradient
+// NHWC -> NCHW transpose through a 32 x 32 shared tile (rows of 32 pixels of one image row x 32 channels), with the
+// reflection-pad adjoint of the padded gradient and the skip-conv addend applied while reading.
+__global__ void k_input_grad(const float* __restrict__ gp, const float* __restrict__ ds, int ld, int C, int H, int W,
+                             float* __restrict__ dz) {
+  pdl_enter();
+  __shared__ float tile[32][33];
+  const int i = blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int Wp = W + 2;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int k = 0; k < 4; ++k) {
+      const int j = blockIdx.x * 32 + ty + 8 * k, c = c0 + tx;
+      float val = 0.f;
+      if (j < W && c < C) {
+        int rows[3], cols[3];
+        int nr = 0, nc = 0;
+        rows[nr++] = i + 1;
+        if (i == 1) rows[nr++] = 0;
+        if (i == H - 2) rows[nr++] = H + 1;
+        cols[nc++] = j + 1;
+        if (j == 1) cols[nc++] = 0;
+        if (j == W - 2) cols[nc++] = W + 1;
+        for (int a = 0; a < nr; ++a)
+          for (int b = 0; b < nc; ++b) val += gp[(static_cast<size_t>(rows[a]) * Wp + cols[b]) * ld + c];
+        if (ds != nullptr) val += ds[(static_cast<size_t>(i) * W + j) * ld + c];
+      }
+      tile[ty + 8 * k][tx] = val;   // [pixel][channel]
+    }
+    __syncthreads();
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, j = blockIdx.x * 32 + tx;
+      if (j < W && c < C) dz[(static_cast<size_t>(c) * H + i) * W + j] = tile[tx][ty + 8 * k];
+    }
+    __syncthreads();
+  }
+}
+void launch_input_grad(const float* gp, const float* ds, int ld, int C, int H, int W, float* dz, cudaStream_t s) {
+  dim3 grid((W + 31) / 32, H), block(32, 8);
+  launch_k(k_input_grad, dim3(grid), dim3(block), 0, s, 1, gp, ds, ld, C, H, W, dz);
 }
 template <int KIND>
 __global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,

@@ -28,6 +28,7 @@ class NetDesc(ctypes.Structure):
         ("need_sigmoid", ctypes.c_int),
         ("precision", ctypes.c_int),
         ("upsample_mask", ctypes.c_int),
+        ("input_grad", ctypes.c_int),
     ]
 
 
@@ -41,6 +42,7 @@ ABI_SYMBOLS = [
     "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_plan_set_timing", "dip_plan_get_timing", "dip_plan_get_timing_records", "dip_op_scratch_bytes", "dip_op_conv_fprop",
     "dip_op_conv_dgrad", "dip_op_conv_wgrad",
     "dip_lanczos_down_out_size", "dip_lanczos_down_fwd", "dip_lanczos_down_bwd", "dip_plan_set_downsampler",
+    "dip_input_grad",
 ]
 
 
@@ -104,6 +106,7 @@ def lib():
     L.dip_lanczos_down_fwd.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     L.dip_lanczos_down_bwd.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     L.dip_plan_set_downsampler.argtypes = [vp, ctypes.POINTER(f32), i32, i32, i32]
+    L.dip_input_grad.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -132,7 +135,7 @@ class Plan:
     """A compiled schedule for one skip network at one input size (dip_plan in include/dip.h)."""
 
     def __init__(self, in_channels, out_channels, num_scales, channels, skip_channels, bilinear, H, W,
-                 precision=PRECISION_TF32, device=None):
+                 precision=PRECISION_TF32, device=None, need_sigmoid=True, input_grad=False):
         L = lib()
         if not torch.cuda.is_available():
             raise RuntimeError("dip-b200 needs a CUDA device (sm_100a); none is visible")
@@ -141,10 +144,11 @@ class Plan:
         if isinstance(bilinear, (list, tuple)):
             assert len(bilinear) == num_scales
             mask = sum(1 << i for i, b in enumerate(bilinear) if b)
-            self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, -1, 1, precision, mask)
+            self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, -1, int(bool(need_sigmoid)),
+                                precision, mask, int(bool(input_grad)))
         else:
-            self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, int(bool(bilinear)), 1,
-                                precision, 0)
+            self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, int(bool(bilinear)),
+                                int(bool(need_sigmoid)), precision, 0, int(bool(input_grad)))
         self.H, self.W = H, W
         nbytes = L.dip_plan_workspace_bytes(ctypes.byref(self.desc), H, W)
         if nbytes == 0:
@@ -200,6 +204,13 @@ class Plan:
     def backward(self, dout):
         with torch.cuda.device(self.device):
             check(lib().dip_backward(self.h, _ptr(dout), _stream()))
+
+    def input_grad(self):
+        """dL/d(net_input) of the last backward (plans created with input_grad=True), 1 x C_in x H x W."""
+        dz = torch.empty((1, self.desc.in_channels, self.H, self.W), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().dip_input_grad(self.h, _ptr(dz), _stream()))
+        return dz
 
     def set_downsampler(self, kernel, factor, pad):
         """Loss of the runner is taken on downsampler(out) (dip_plan_set_downsampler); kernel: K x K taps or None."""

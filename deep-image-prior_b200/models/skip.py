@@ -38,12 +38,15 @@ class _EngineFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, z, anchor):
         ctx.net = net
-        return net._engine_forward(z)
+        ctx.want_dz = bool(ctx.needs_input_grad[1])
+        return net._engine_forward(z, want_dz=ctx.want_dz)
 
     @staticmethod
     def backward(ctx, dout):
         ctx.net._engine_backward(dout)
-        return None, None, None
+        # OPT_OVER = 'net,input' (utils/common_utils.py:47-49): the input is a leaf that is optimised too
+        dz = ctx.net._dip_active_plan.input_grad() if ctx.want_dz else None
+        return None, dz, None
 
 
 class SkipNet(nn.Sequential):
@@ -64,13 +67,13 @@ class SkipNet(nn.Sequential):
         self._dip_cache = None
         return super()._apply(fn, *args, **kwargs)
 
-    def _engine_state(self, z):
+    def _engine_state(self, z, want_dz=False):
         """(plan, parameters) for input z; everything derived from the module tree is cached between calls and
         re-validated cheaply (storage of the first / last parameter and of one BatchNorm buffer): after the per-step
         loss read-back of a notebook closure the GPU idles until this returns, so it must cost microseconds."""
         import dip_engine as de
         prec = de.PRECISION_TF32 if self.precision == 'tf32' else de.PRECISION_FP32
-        key = (int(z.shape[2]), int(z.shape[3]), z.device, prec)
+        key = (int(z.shape[2]), int(z.shape[3]), z.device, prec, bool(want_dz))
         c = getattr(self, '_dip_cache', None)
         if c is not None and c['key'] == key:
             ps = c['params']
@@ -83,11 +86,12 @@ class SkipNet(nn.Sequential):
         import dip_engine as de
         spec = self._dip_spec
         H, W = key[0], key[1]
-        pkey = (H, W, str(z.device), prec)
+        pkey = (H, W, str(z.device), prec, key[4])
         plan = self._dip_plans.get(pkey)
         if plan is None:
             plan = de.Plan(spec['in_channels'], spec['out_channels'], spec['num_scales'], spec['channels'],
-                           spec['skip_channels'], spec['bilinear'], H, W, precision=prec, device=z.device)
+                           spec['skip_channels'], spec['bilinear'], H, W, precision=prec, device=z.device,
+                           need_sigmoid=spec['need_sigmoid'], input_grad=key[4])
             self._dip_plans[pkey] = plan
         params = list(self.parameters())
         for p in params:
@@ -113,8 +117,8 @@ class SkipNet(nn.Sequential):
                                bn0=running[0], b0=running[0].data_ptr())
         return plan, params
 
-    def _engine_forward(self, z):
-        plan, _ = self._engine_state(z)
+    def _engine_forward(self, z, want_dz=False):
+        plan, _ = self._engine_state(z, want_dz)
         self._dip_active_plan = plan
         zc = z.detach().contiguous()
         return plan.forward(zc)
@@ -143,9 +147,6 @@ class SkipNet(nn.Sequential):
         if self._dip_spec is not None and x.is_cuda:
             if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != self._dip_spec['in_channels']:
                 raise ValueError("dip-b200: expected input of shape 1 x %d x H x W" % self._dip_spec['in_channels'])
-            if x.requires_grad:
-                raise NotImplementedError("dip-b200: gradients w.r.t. the network input (OPT_OVER='input') are not "
-                                          "computed by the engine (SURVEY.md section 8f)")
             if not torch.is_grad_enabled():
                 return self._engine_forward(x)
             if self._dip_anchor is None or self._dip_anchor.device != x.device:
@@ -237,15 +238,15 @@ def skip(num_input_channels=2, num_output_channels=3,
         why = "downsample_mode must be 'stride'"
     elif act_fun != 'LeakyReLU':
         why = "act_fun must be 'LeakyReLU'"
-    elif not (need_sigmoid and need_bias and need1x1_up):
-        why = 'need_sigmoid, need_bias and need1x1_up must be True'
+    elif not (need_bias and need1x1_up):
+        why = 'need_bias and need1x1_up must be True'
     elif any(m not in ('bilinear', 'nearest') for m in upsample_mode):
         why = "upsample_mode must be 'bilinear' or 'nearest' (per scale)"
     elif not (1 <= num_output_channels <= 4 and 1 <= num_input_channels <= 128):
         why = 'num_output_channels in 1..4 and num_input_channels in 1..128'
     if why is None:
         net._dip_spec = dict(in_channels=num_input_channels, out_channels=num_output_channels, num_scales=n,
-                             channels=128, skip_channels=num_channels_skip[0],
+                             channels=128, skip_channels=num_channels_skip[0], need_sigmoid=bool(need_sigmoid),
                              bilinear=(upsample_mode[0] == 'bilinear' if len(set(upsample_mode)) == 1
                                        else [m == 'bilinear' for m in upsample_mode]))
     else:

@@ -34,10 +34,12 @@ typedef struct {
   int channels;          /* num_channels_down[i] == num_channels_up[i] == 128                           */
   int skip_channels;     /* num_channels_skip[i]: 4, or 128 (inpainting.ipynb kate)                     */
   int upsample_bilinear; /* upsample_mode: 1 'bilinear', 0 'nearest', -1: per scale, see upsample_mask  */
-  int need_sigmoid;      /* 1                                                                           */
+  int need_sigmoid;      /* 1: nn.Sigmoid behind the head (models/skip.py:97-98), 0: none                */
   int precision;         /* DIP_PRECISION_*                                                             */
   int upsample_mask;     /* upsample_bilinear == -1: bit i set = scale i (0 = outermost) is 'bilinear'
                             (flash-no-flash.ipynb c8: ['nearest','nearest','bilinear','bilinear','bilinear']) */
+  int input_grad;        /* 1: dip_backward also prepares dL/d(net_input) for dip_input_grad
+                            (OPT_OVER = 'net,input', utils/common_utils.py:47-49); costs two extra level-0 launches */
 } dip_net_desc;
 
 const char* dip_last_error(void);
@@ -65,6 +67,9 @@ int dip_forward(dip_plan* plan, const void* z, const void* noise, float sigma, v
 /* total_loss.backward() through the network (denoising.ipynb c10:24): dout [C_out][H][W] = dL/d(out).
  * Fills the bound grads[] (overwrite, not accumulate). */
 int dip_backward(dip_plan* plan, const void* dout, dip_stream_t stream);
+/* dL/d(net_input) of the last dip_backward (plans created with input_grad = 1): dz [C_in][H][W], overwritten.
+ * Replaces autograd's gradient of the closure w.r.t. `net_input` when it is optimised (get_params('net,input')). */
+int dip_input_grad(dip_plan* plan, void* dz, dip_stream_t stream);
 
 /* torch.nn.MSELoss()(out*mask, target*mask) and its gradient (denoising.ipynb c8:50,c10:23; inpainting.ipynb c17:17).
  * loss: device double (accumulated: zero it first); dout may be NULL; mask [H*W] or NULL. */

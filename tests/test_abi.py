@@ -47,7 +47,6 @@ def test_workspace_query_rejects_unsupported_configurations_with_a_reason():
         (de.NetDesc(32, 5, 5, 128, 4, 1, 1, 0), 512, 512, "num_output_channels"),
         (de.NetDesc(32, 3, 9, 128, 4, 1, 1, 0), 512, 512, "scales"),
         (de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0), 500, 512, "divisible"),              # 500 % 32 != 0
-        (de.NetDesc(32, 3, 5, 128, 4, 1, 0, 0), 512, 512, "need_sigmoid"),
     ]:
         n, err = q(desc, H, W)
         assert n == 0 and word in err, (n, err)
@@ -61,6 +60,11 @@ def test_workspace_query_rejects_unsupported_configurations_with_a_reason():
     # flash-no-flash: image (3 channels) as input, per-scale upsampling modes; stored with 4 channels -> smaller than 32
     flash, _ = q(de.NetDesc(3, 3, 5, 128, 4, -1, 1, 0, 0b11100), 704, 768)
     assert 0 < flash
+    # need_sigmoid = False is accepted; the input-gradient option adds the level-0 gradient buffers
+    nosig, _ = q(de.NetDesc(32, 3, 5, 128, 4, 1, 0, 0))
+    assert nosig == base
+    ingrad, _ = q(de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0, 0, 1))
+    assert ingrad > base
 
 
 def test_downsampler_output_size_matches_torch_conv_arithmetic():

