@@ -169,7 +169,6 @@ def test_input_gradient_and_no_sigmoid_vs_oracle(cfgargs):
     out = net(zd)
     loss = torch.nn.functional.mse_loss(out, target.cuda())
     loss.backward()
-    assert out.min().item() < 0 or out.max().item() > 1 or True          # logits, not squashed
     assert (out.detach().cpu() - out_ref.detach()).abs().max().item() < 5e-4
     assert abs(loss.item() - loss_ref.item()) < 1e-5
 
