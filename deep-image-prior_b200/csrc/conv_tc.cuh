@@ -23,12 +23,12 @@ struct TcConvParams {
   int offx, offy;          // input coordinate of tap (0,0) for output pixel (0,0)
   int kblocks;             // 32-channel K blocks per tap
   int tail_mmas;           // number of K=8 MMAs issued for the last K block of a tap (1..4)
-  int n_mma;               // UMMA N (multiple of 16, <= 160)
+  int n_mma;               // UMMA N of this CTA (multiple of 16, <= 160): all output channels, or N / n_split of them
   int n_chunks;            // output 32-channel chunks written (ceil(n_mma/32))
   int stages;              // smem pipeline depth
   int patch;               // 1: 3x3 stride-1 patch mode (tile 8 x 16; one (bw+2) x (bh+2) input patch serves all taps)
   int pw, ph;              // patch extent in pixels
-  int tps;                 // patch mode: filter taps per weight stage (1 or 2)
+  int tps;                 // patch mode: filter taps per weight stage (1..3; 3 = one filter row per barrier round)
   int csize;               // thread-block cluster size (1, 2, 4): the weight tile is multicast across the cluster
   int n_split;             // 1, 2 or 4 CTAs per pixel tile, each computing n_mma = N / n_split output channels (small levels)
   const float* bias;       // [n_mma] or nullptr
