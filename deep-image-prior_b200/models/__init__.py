@@ -8,6 +8,8 @@ import torch.nn as nn
 from .common import Concat, GenNoise, Swish, act, bn, conv  # noqa: F401
 from .downsampler import Downsampler, get_kernel  # noqa: F401
 from .skip import SkipNet, allow_torch_execution, skip  # noqa: F401
+from .resnet import ResNet  # noqa: F401  (import shims: the notebooks import these names; building them raises)
+from .unet import UNet  # noqa: F401
 
 
 def get_net(input_depth, NET_TYPE, pad, upsample_mode, n_channels=3, act_fun='LeakyReLU', skip_n33d=128, skip_n33u=128,

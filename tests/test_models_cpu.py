@@ -117,3 +117,21 @@ def test_downsampler_kernel_matches_reference_values():
     taps = k.sum(0)
     want = [-0.001065, -0.009752, -0.020384, -0.014878, 0.024594, 0.098658, 0.183115, 0.239711]
     assert k.shape == (16, 16) and np.allclose(taps[:8], want, atol=1e-6) and np.allclose(taps[8:], want[::-1], atol=1e-6)
+
+
+def test_notebook_import_lines_resolve():
+    """The import cells of the skip-net notebooks (inpainting.ipynb c3, restoration.ipynb c3, super-resolution.ipynb c3,
+    flash-no-flash.ipynb c3) must resolve against this package; out-of-scope builders exist as names and raise when built."""
+    from models import get_net, skip  # noqa: F401
+    from models.downsampler import Downsampler  # noqa: F401
+    from models.resnet import ResNet
+    from models.skip import skip as skip2  # noqa: F401
+    from models.unet import UNet
+    from utils.denoising_utils import get_noisy_image  # noqa: F401
+    from utils.inpainting_utils import get_bernoulli_mask, get_text_mask  # noqa: F401
+    from utils.sr_utils import load_LR_HR_imgs_sr, tv_loss  # noqa: F401
+    for cls in (ResNet, UNet):
+        with pytest.raises(NotImplementedError):
+            cls(32, 3)
+    with pytest.raises(NotImplementedError):
+        get_net(32, "UNet", "reflection", "bilinear")
