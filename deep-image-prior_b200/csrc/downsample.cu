@@ -107,14 +107,13 @@ cudaError_t launch_down_fwd(const float* x, int C, int H, int W, const float* ke
   if (Ho < 1 || Wo < 1) return cudaErrorInvalidValue;
   const size_t smem = down_fwd_smem(K, f);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_down_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    attr_set = smem;
-  }
   dim3 grid((Wo + kDownTile - 1) / kDownTile, (Ho + kDownTile - 1) / kDownTile, C);
   return launch_k(k_down_fwd, grid, dim3(256), smem, s, 1, x, H, W, kern, K, f, pad, y, Ho, Wo);
+}
+
+// function attributes are per device: called from engine_init() once for every device the library is used on
+cudaError_t down_kernels_init() {
+  return cudaFuncSetAttribute(k_down_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 cudaError_t launch_down_bwd(const float* dy, int C, int H, int W, const float* kern, int K, int f, int pad, float* dx,

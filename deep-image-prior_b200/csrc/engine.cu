@@ -41,12 +41,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
-static bool g_inited = false;
+static unsigned long long g_inited_mask = 0;   // one bit per device: function attributes (dynamic smem opt-in) are per device
 
 static int engine_init() {
-  if (g_inited) return 0;
   int dev = 0;
   DIP_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64) return fail("dip-b200: device ordinal >= 64 not supported");
+  if (g_inited_mask & (1ull << dev)) return 0;
   cudaDeviceProp prop;
   DIP_CUDA(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail("dip-b200 requires an sm_100 (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor));
@@ -57,7 +58,8 @@ static int engine_init() {
   if (fn == nullptr || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available from the driver");
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   DIP_CUDA(tc_kernels_init());
-  g_inited = true;
+  DIP_CUDA(down_kernels_init());
+  g_inited_mask |= 1ull << dev;
   return 0;
 }
 
@@ -493,7 +495,17 @@ struct dip_plan {
   static constexpr int kLossRing = 65536;
   double* loss_ring = nullptr;   // [kLossRing] loss slots of the runner when the caller passes no history buffer
   int* it_dev = nullptr;         // [2] device counters: {global Adam step, iteration index of this call}
-  struct GraphKey { const void *z0, *target, *mask, *out, *slots, *adam; float sigma; uint64_t seed; double lr; };
+  // identity of everything the captured step bakes in; compared field by field (the struct has padding).  adam_id is a
+  // process-wide serial number: a new dip_adam allocated at the address of a destroyed one must not match.
+  struct GraphKey {
+    const void *z0 = nullptr, *target = nullptr, *mask = nullptr, *out = nullptr, *slots = nullptr;
+    unsigned long long adam_id = 0, adam_bind = 0;
+    float sigma = 0.f; uint64_t seed = 0; double lr = 0.0;
+    bool operator==(const GraphKey& o) const {
+      return z0 == o.z0 && target == o.target && mask == o.mask && out == o.out && slots == o.slots && adam_id == o.adam_id &&
+             adam_bind == o.adam_bind && sigma == o.sigma && seed == o.seed && lr == o.lr;
+    }
+  };
   GraphKey gkey{};
   cudaGraphExec_t gexec = nullptr;
   // notebook path (dip_forward / dip_backward called once per closure): each is replayed as its own CUDA graph over the
@@ -694,6 +706,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   }
   P->out_saved = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->zbuf = A.get<float>((size_t)P->H * P->W * d.in_channels);
+  reg("zbuf", P->zbuf, d.in_channels, P->H, P->W, P->W);   // torch-layout planes [C][H][W]: the runner's perturbed input
   P->dout = A.get<float>((size_t)P->H * P->W * d.out_channels);
   P->dl4 = A.get<float>((size_t)P->H * P->W * 4);
   P->ds_kern = A.get<float>(dip_plan::kDownMaxK * dip_plan::kDownMaxK);
@@ -1123,7 +1136,11 @@ struct dip_adam {
   float** d_p = nullptr; const float** d_g = nullptr; float** d_m = nullptr; float** d_v = nullptr;
   int* d_blk_tensor = nullptr; int* d_blk_start = nullptr; int* d_numel = nullptr;
   bool bound = false;
+  unsigned long long id = 0;        // unique per dip_adam_create (graph cache key of dip_run_iterations)
+  unsigned long long bind_gen = 0;  // bumped by dip_adam_bind (the captured k_adam reads the tables, not their addresses,
+                                    // but a re-bind after capture must still invalidate nothing else; kept for clarity)
 };
+static unsigned long long g_adam_serial = 0;
 
 static void drop_graphs(dip_plan* P) {
   for (cudaGraphExec_t* g : {&P->gexec, &P->gfwd, &P->gbwd})
@@ -1263,6 +1280,7 @@ int dip_noise_perturb(const void* z0, void* z, float sigma, uint64_t seed, uint6
 
 int dip_lanczos_down_fwd(const void* x, int C, int H, int W, const void* kern, int K, int factor, int pad, void* y,
                          dip_stream_t stream) {
+  DIP_CHECK(engine_init());
   if (K < 1 || factor < 1 || pad < 0) return fail("dip_lanczos_down_fwd: bad K / factor / pad");
   if (down_out_size(H, K, factor, pad) < 1 || down_out_size(W, K, factor, pad) < 1)
     return fail("dip_lanczos_down_fwd: image smaller than the filter");
@@ -1271,6 +1289,7 @@ int dip_lanczos_down_fwd(const void* x, int C, int H, int W, const void* kern, i
 }
 int dip_lanczos_down_bwd(const void* dy, int C, int H, int W, const void* kern, int K, int factor, int pad, void* dx,
                          dip_stream_t stream) {
+  DIP_CHECK(engine_init());
   if (K < 1 || factor < 1 || pad < 0) return fail("dip_lanczos_down_bwd: bad K / factor / pad");
   if (down_out_size(H, K, factor, pad) < 1 || down_out_size(W, K, factor, pad) < 1)
     return fail("dip_lanczos_down_bwd: image smaller than the filter");
@@ -1292,6 +1311,7 @@ int dip_plan_set_downsampler(dip_plan* P, const float* kern_host, int K, int fac
 
 int dip_adam_create(int ntensors, const long long* numel, dip_adam** out) {
   dip_adam* a = new dip_adam();
+  a->id = ++g_adam_serial;
   a->n = ntensors;
   a->numel.assign(numel, numel + ntensors);
   std::vector<int> bt, bs, ne;
@@ -1326,6 +1346,7 @@ int dip_adam_bind(dip_adam* a, void* const* p, void* const* g, void* const* m, v
   DIP_CUDA(cudaMemcpy(a->d_m, m, a->n * sizeof(void*), cudaMemcpyHostToDevice));
   DIP_CUDA(cudaMemcpy(a->d_v, v, a->n * sizeof(void*), cudaMemcpyHostToDevice));
   a->bound = true;
+  a->bind_gen++;
   return 0;
 }
 int dip_adam_step(dip_adam* a, double lr, double beta1, double beta2, double eps, int step, dip_stream_t stream) {
@@ -1405,8 +1426,10 @@ int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* 
   DIP_CUDA(cudaEventRecord(P->gev_in, s));
   DIP_CUDA(cudaStreamWaitEvent(gs, P->gev_in, 0));
   double* slots = loss_hist != nullptr ? loss_hist : P->loss_ring;
-  dip_plan::GraphKey key{z0, target, mask, out, slots, adam, sigma, seed, lr};
-  if (P->gexec == nullptr || memcmp(&key, &P->gkey, sizeof key) != 0) {
+  dip_plan::GraphKey key;
+  key.z0 = z0; key.target = target; key.mask = mask; key.out = out; key.slots = slots;
+  key.adam_id = adam->id; key.adam_bind = adam->bind_gen; key.sigma = sigma; key.seed = seed; key.lr = lr;
+  if (P->gexec == nullptr || !(key == P->gkey)) {
     if (P->gexec != nullptr) { cudaGraphExecDestroy(P->gexec); P->gexec = nullptr; }
     cudaGraph_t graph = nullptr;
     DIP_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));

@@ -188,6 +188,7 @@ void launch_advance(int* it_dev, cudaStream_t s);
 // Downsampler (super-resolution operator, models/downsampler.py:58-71): planes [C][H][W], taps kern[K][K] (device),
 // replication pad `pad`, stride f; output planes [C][Ho][Wo] with Ho = down_out_size(H, K, f, pad).   (downsample.cu)
 int down_out_size(int n, int K, int f, int pad);
+cudaError_t down_kernels_init();   // per-device function attributes (dynamic shared memory opt-in)
 cudaError_t launch_down_fwd(const float* x, int C, int H, int W, const float* kern, int K, int f, int pad, float* y,
                             cudaStream_t s);
 // adjoint: dy [C][Ho][Wo] -> dx [C][H][W] (every element written)

@@ -1,14 +1,15 @@
 """`from models import *` surface of the reference (reference: models/__init__.py:1-32): skip, get_net, nn.
 
-Round-1 scope: the skip network family is the hot path.  The other builders of the reference
-(ResNet, UNet, texture_nets) are outside the accelerated path and not provided yet; asking for them raises.
+The skip network family is the accelerated hot path.  ResNet and UNet keep the reference's
+builder API as ordinary torch modules (stock torch ops, never accelerated: SURVEY.md 8f.4); texture_nets (py2-era code
+that does not run under py3 in the reference either, models/texture_nets.py:11-13) is not provided.
 """
 import torch.nn as nn
 
 from .common import Concat, GenNoise, Swish, act, bn, conv  # noqa: F401
 from .downsampler import Downsampler, get_kernel  # noqa: F401
 from .skip import SkipNet, allow_torch_execution, skip  # noqa: F401
-from .resnet import ResNet  # noqa: F401  (import shims: the notebooks import these names; building them raises)
+from .resnet import ResNet  # noqa: F401
 from .unet import UNet  # noqa: F401
 
 
@@ -23,7 +24,14 @@ def get_net(input_depth, NET_TYPE, pad, upsample_mode, n_channels=3, act_fun='Le
     if NET_TYPE == 'identity':
         assert input_depth == 3
         return nn.Sequential()
-    if NET_TYPE in ('ResNet', 'UNet', 'texture_nets'):
-        raise NotImplementedError("dip-b200: NET_TYPE=%r is outside the accelerated hot path (SURVEY.md section 8f) and "
-                                  "is not provided in this round" % NET_TYPE)
+    if NET_TYPE == 'ResNet':
+        # same positional call as the reference (models/__init__.py:9-11, marked TODO there: act_fun receives
+        # nn.BatchNorm2d and the construction raises TypeError in the reference too)
+        return ResNet(input_depth, 3, 10, 16, 1, nn.BatchNorm2d, False)
+    if NET_TYPE == 'UNet':
+        return UNet(num_input_channels=input_depth, num_output_channels=3, feature_scale=4, more_layers=0, concat_x=False,
+                    upsample_mode=upsample_mode, pad=pad, norm_layer=nn.BatchNorm2d, need_sigmoid=True, need_bias=True)
+    if NET_TYPE == 'texture_nets':
+        raise NotImplementedError("dip-b200: NET_TYPE='texture_nets' is not provided (the reference's builder does not run "
+                                  "under python 3: models/texture_nets.py:11-13 passes float paddings)")
     assert False, 'unknown NET_TYPE ' + str(NET_TYPE)

@@ -105,6 +105,9 @@ class Downsampler(nn.Module):
             if input.dtype != torch.float32 or self.downsampler_.weight.device != input.device:
                 raise RuntimeError("dip-b200: Downsampler needs float32 CUDA tensors on the module's device "
                                    "(downsampler.type(torch.cuda.FloatTensor))")
+            if input.dim() != 4 or input.shape[1] != self.downsampler_.weight.shape[0]:
+                raise ValueError("dip-b200: Downsampler built for %d planes got an input of shape %s"
+                                 % (self.downsampler_.weight.shape[0], tuple(input.shape)))
             kern = self.downsampler_.weight.detach()[0, 0]
             return _DownFn.apply(input, kern, self.factor, self.pad)
         from .skip import _ALLOW_TORCH

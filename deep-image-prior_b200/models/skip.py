@@ -39,13 +39,24 @@ class _EngineFn(torch.autograd.Function):
     def forward(ctx, net, z, anchor):
         ctx.net = net
         ctx.want_dz = bool(ctx.needs_input_grad[1])
-        return net._engine_forward(z, want_dz=ctx.want_dz)
+        out = net._engine_forward(z, want_dz=ctx.want_dz)
+        # the saved activations / BatchNorm statistics live in the plan's workspace, one set per plan: remember which
+        # forward they belong to (any later forward on the same network overwrites them)
+        ctx.plan = net._dip_active_plan
+        ctx.generation = net._dip_generation
+        return out
 
     @staticmethod
     def backward(ctx, dout):
-        ctx.net._engine_backward(dout)
+        net = ctx.net
+        if net._dip_generation != ctx.generation or net._dip_active_plan is not ctx.plan:
+            raise RuntimeError(
+                "dip-b200: backward() of a forward pass whose saved activations were overwritten by a later forward of "
+                "the same network (the engine keeps ONE set of activations per network: call backward() before the next "
+                "net(...) -- torch.no_grad() previews included -- or use a second network object)")
+        net._engine_backward(dout)
         # OPT_OVER = 'net,input' (utils/common_utils.py:47-49): the input is a leaf that is optimised too
-        dz = ctx.net._dip_active_plan.input_grad() if ctx.want_dz else None
+        dz = ctx.plan.input_grad() if ctx.want_dz else None
         return None, dz, None
 
 
@@ -59,6 +70,8 @@ class SkipNet(nn.Sequential):
         self._dip_plans = {}
         self._dip_grad_arena = None
         self._dip_anchor = None
+        self._dip_generation = 0     # bumped by every engine forward (guards backward against stale activations)
+        self._dip_active_plan = None
         self.precision = 'tf32'      # 'tf32' (tcgen05 tensor cores, default) | 'fp32' (exact CUDA-core parity mode)
 
     # ---- engine plumbing -------------------------------------------------------------------------------------
@@ -120,6 +133,7 @@ class SkipNet(nn.Sequential):
     def _engine_forward(self, z, want_dz=False):
         plan, _ = self._engine_state(z, want_dz)
         self._dip_active_plan = plan
+        self._dip_generation += 1
         zc = z.detach().contiguous()
         return plan.forward(zc)
 
@@ -147,6 +161,15 @@ class SkipNet(nn.Sequential):
         if self._dip_spec is not None and x.is_cuda:
             if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != self._dip_spec['in_channels']:
                 raise ValueError("dip-b200: expected input of shape 1 x %d x H x W" % self._dip_spec['in_channels'])
+            if x.dtype != torch.float32:
+                # torch would raise a dtype mismatch against the float32 weights (e.g. get_noise(..., 'meshgrid')
+                # without .type(dtype) is float64); the engine reads raw fp32 storage, so it must refuse as well
+                raise RuntimeError("dip-b200: expected a float32 input, got %s (use .type(torch.cuda.FloatTensor))" % x.dtype)
+            if not self.training:
+                # nothing in the reference ever calls .eval(); the engine only implements the
+                # training-mode BatchNorm (batch statistics + running-stat update)
+                raise NotImplementedError("dip-b200: the engine runs BatchNorm in training mode only (net.eval() is not "
+                                          "supported; models.allow_torch_execution(True) + CPU tensors runs stock torch)")
             if not torch.is_grad_enabled():
                 return self._engine_forward(x)
             if self._dip_anchor is None or self._dip_anchor.device != x.device:

@@ -170,7 +170,119 @@ def run_sr_case(name, H, W, iters, dtype, factor=4, sigma=0.03, lr=0.01, threads
     print(name, 'losses', losses)
 
 
+def _bn_state(net):
+    """running_mean / running_var / num_batches_tracked of every BatchNorm, in state_dict order, concatenated."""
+    sd = net.state_dict()
+    rm = np.concatenate([sd[k].numpy().ravel() for k in sd if k.endswith('running_mean')])
+    rv = np.concatenate([sd[k].numpy().ravel() for k in sd if k.endswith('running_var')])
+    nbt = np.array([float(sd[k]) for k in sd if k.endswith('num_batches_tracked')])
+    return rm.copy(), rv.copy(), nbt
+
+
+def run_baseline_case(kind, threads=8, iters=2):
+    """One-/two-step fixtures of the UNMODIFIED reference at the BASELINE.json shapes, on the reference's own data
+    (committed copies under tests/golden/data): 'denoise512' (denoising.ipynb c4-c10, F16 512x512, sigma 25),
+    'inpaint512' (inpainting.ipynb c5-c17, kate 512x512 + mask, skip=128, nearest), 'sr_zebra' (super-resolution.ipynb
+    c5-c10, zebra 384x576 -> 96x144, Lanczos-2 x4), 'sr1024' (BASELINE wording 256 -> 1024: synthetic LR target).
+    Full tensors at these sizes are too big for fixtures: the network output is stored on a stride-4 grid together with
+    its first two moments and the loss; gradients as per-tensor norms / sums plus slices."""
+    import importlib
+    torch.set_num_threads(threads)
+    dtype = torch.float32
+    data = os.path.join(HERE, 'data')
+    with ref_harness.reference_modules() as ref:
+        cu, models = ref.common_utils, ref.models
+        mask = None
+        ds = None
+        extra = {}
+        if kind == 'denoise512':
+            img_pil = cu.crop_image(cu.get_image(os.path.join(data, 'F16_GT.png'), -1)[0], d=32)
+            img_np = cu.pil_to_np(img_pil)
+            np.random.seed(0)
+            _, noisy_np = ref.denoising_utils.get_noisy_image(img_np, 25 / 255.)
+            target = cu.np_to_torch(noisy_np).type(dtype)
+            H, W = img_np.shape[1:]
+            sigma = 1. / 30
+            torch.manual_seed(0)
+            net = models.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                                 upsample_mode='bilinear').type(dtype)
+            extra['target_sum'] = float(target.double().sum())
+        elif kind == 'inpaint512':
+            img_pil, _ = cu.get_image(os.path.join(data, 'kate.png'), -1)
+            mask_pil, _ = cu.get_image(os.path.join(data, 'kate_mask.png'), -1)
+            mask_pil = cu.crop_image(mask_pil, 64)
+            img_pil = cu.crop_image(img_pil, 64)
+            img_np, mask_np = cu.pil_to_np(img_pil), cu.pil_to_np(mask_pil)
+            target = cu.np_to_torch(img_np).type(dtype)
+            mask = cu.np_to_torch(mask_np).type(dtype)
+            H, W = img_np.shape[1:]
+            sigma = 0.03
+            torch.manual_seed(0)
+            net = models.skip(32, img_np.shape[0], num_channels_down=[128] * 5, num_channels_up=[128] * 5,
+                              num_channels_skip=[128] * 5, filter_size_up=3, filter_size_down=3, upsample_mode='nearest',
+                              filter_skip_size=1, need_sigmoid=True, need_bias=True, pad='reflection',
+                              act_fun='LeakyReLU').type(dtype)
+            extra['mask_sum'] = float(mask.double().sum())
+        elif kind in ('sr_zebra', 'sr1024'):
+            sru = importlib.import_module('utils.sr_utils')
+            dsm = importlib.import_module('models.downsampler')
+            if kind == 'sr_zebra':
+                imgs = sru.load_LR_HR_imgs_sr(os.path.join(data, 'zebra_GT.png'), -1, 4, 'CROP')
+                target = cu.np_to_torch(imgs['LR_np']).type(dtype)
+                H, W = imgs['HR_pil'].size[1], imgs['HR_pil'].size[0]
+            else:
+                H = W = 1024
+                g = torch.Generator().manual_seed(2)
+                target = torch.rand(1, 3, H // 4, W // 4, generator=g).type(dtype)
+            sigma = 0.03
+            torch.manual_seed(0)
+            net = models.get_net(32, 'skip', 'reflection', skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                                 upsample_mode='bilinear').type(dtype)
+            ds = dsm.Downsampler(n_planes=3, factor=4, kernel_type='lanczos2', phase=0.5, preserve_size=True).type(dtype)
+            extra['target_sum'] = float(target.double().sum())
+        else:
+            raise ValueError(kind)
+        torch.manual_seed(1)
+        z0 = cu.get_noise(32, 'noise', (H, W)).type(dtype).detach()
+        gn = torch.Generator().manual_seed(123)
+        mse = torch.nn.MSELoss()
+        params = cu.get_params('net', net, z0)
+        opt = torch.optim.Adam(params, lr=0.01)
+        losses = []
+        for i in range(iters):
+            noise = torch.randn(z0.shape, generator=gn).type(dtype)
+            opt.zero_grad()
+            out = net(z0 + noise * sigma)
+            o = ds(out) if ds is not None else out
+            loss = mse(o * mask, target * mask) if mask is not None else mse(o, target)
+            loss.backward()
+            if i == 0:
+                out0 = out.detach().clone()
+                gnorm0 = np.array([p.grad.double().norm().item() for p in params])
+                gsum0 = np.array([p.grad.double().sum().item() for p in params])
+                g_head_w = params[-2].grad.detach().clone().numpy()
+                g_up0_w_slice = params[-10].grad.detach()[:4, :8].clone().numpy()      # L0.up.w[:4,:8]
+                g_d2_4_slice = params[4 * 12 + 8].grad.detach()[:4, :8].clone().numpy()  # L4.d2.w[:4,:8] (deepest level)
+                g_skip0_w = params[0].grad.detach().clone().numpy()
+                rm1, rv1, nbt1 = _bn_state(net)
+            losses.append(loss.item())
+            opt.step()
+        pnorm = np.array([p.detach().double().norm().item() for p in params])
+        rm, rv, nbt = _bn_state(net)
+    np.savez_compressed(os.path.join(HERE, 'baseline_' + kind + '_fp32.npz'), H=H, W=W, iters=iters, sigma=sigma, lr=0.01,
+                        losses=np.array(losses), out0_sub=out0.numpy()[:, :, ::4, ::4].astype(np.float32),
+                        out0_mean=out0.double().mean().item(), out0_sq=(out0.double() ** 2).mean().item(),
+                        gnorm0=gnorm0, gsum0=gsum0, g_head_w=g_head_w, g_up0_w_slice=g_up0_w_slice,
+                        g_d2_4_slice=g_d2_4_slice, g_skip0_w=g_skip0_w, pnorm=pnorm, rm1=rm1, rv1=rv1, nbt1=nbt1, rm=rm,
+                        rv=rv, nbt=nbt, **extra)
+    print(kind, H, W, 'losses', losses)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'baseline':   # BASELINE-shape fixtures on the reference's data
+        for kind in (sys.argv[2:] or ['denoise512', 'inpaint512', 'sr_zebra', 'sr1024']):
+            run_baseline_case(kind, threads=int(os.environ.get('DIP_GOLD_THREADS', '8')))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'inpaint':   # only the inpainting (skip=128) fixtures
         run_case('inpaint64x96_nearest_masked_skip128_fp64', 64, 96, 'nearest', 3, sigma=0.03, masked=True,
                  dtype=torch.float64, skip_n11=128)

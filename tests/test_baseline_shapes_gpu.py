@@ -1,0 +1,236 @@
+"""Network-level parity at the BASELINE.json shapes (the configurations bench.py times), on the reference's own data:
+
+  denoise512  denoising.ipynb c4-c10       F16 512x512, sigma 25, skip[128x5] cs=4 bilinear           (configs 1/2/5)
+  inpaint512  inpainting.ipynb c5-c17      kate 512x512 + mask, skip=128 nearest, masked MSE           (config 4)
+  sr_zebra    super-resolution.ipynb c5-10 zebra 384x576 -> 96x144, Lanczos-2 x4 in the loss           (config 3, real pair)
+  sr1024      BASELINE wording 256 -> 1024 synthetic LR target, same operator                          (config 3)
+
+One closure step, engine (through the C ABI) vs (a) the CPU oracle evaluated live on the same inputs -- every pre-BN
+activation of every level, the output, the loss, every gradient -- and (b) the fixtures generated from the UNMODIFIED
+reference (tests/golden/make_golden.py baseline -> tests/golden/baseline_*_fp32.npz).  The oracle itself is checked
+against the same fixtures here (and in tests/test_oracle.py for the cases that fit the CPU suite).
+
+Tiers: fp32 = exact-fp32 CUDA-core convs, tight; tf32 = tensor-core path (the benchmarked one), whose gradient error
+is required to be like cuDNN-TF32's on the same graph (the reference's own GPU arithmetic, comparator only).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dip_oracle as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+DATA = os.path.join(GOLD, "data")
+
+FWD_TOL = {"fp32": 1e-4, "tf32": 2e-2}
+RAW_TOL = {"fp32": 2e-4, "tf32": 3e-2}
+GRAD_TOL = {"fp32": 3e-2}
+LOSS_TOL = {"fp32": 2e-6, "tf32": 1e-3}
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def load_case(kind):
+    """Inputs built with THIS repo's task utilities (the mirrors of utils/*.py) from the committed copies of the
+    reference's images; the fixture's checksums prove they equal what the reference built."""
+    from utils import common_utils as cu
+    from utils.denoising_utils import get_noisy_image
+    from utils.sr_utils import load_LR_HR_imgs_sr
+    g = np.load(os.path.join(GOLD, "baseline_%s_fp32.npz" % kind))
+    mask = down = None
+    cs, mode = 4, "bilinear"
+    if kind == "denoise512":
+        img_np = cu.pil_to_np(cu.crop_image(cu.get_image(os.path.join(DATA, "F16_GT.png"), -1)[0], d=32))
+        np.random.seed(0)
+        target = cu.np_to_torch(get_noisy_image(img_np, 25 / 255.)[1])
+    elif kind == "inpaint512":
+        img_pil = cu.crop_image(cu.get_image(os.path.join(DATA, "kate.png"), -1)[0], 64)
+        mask_pil = cu.crop_image(cu.get_image(os.path.join(DATA, "kate_mask.png"), -1)[0], 64)
+        target = cu.np_to_torch(cu.pil_to_np(img_pil))
+        mask = cu.np_to_torch(cu.pil_to_np(mask_pil))
+        assert abs(float(mask.double().sum()) - float(g["mask_sum"])) < 1e-3
+        cs, mode = 128, "nearest"
+    else:
+        if kind == "sr_zebra":
+            imgs = load_LR_HR_imgs_sr(os.path.join(DATA, "zebra_GT.png"), -1, 4, "CROP")
+            target = cu.np_to_torch(imgs["LR_np"])
+        else:
+            gg = torch.Generator().manual_seed(2)
+            target = torch.rand(1, 3, 256, 256, generator=gg)
+        kern = O.down_kernel(4, "lanczos2", 0.5)
+        down = (torch.from_numpy(kern).float(), 4, O.down_pad(kern.shape[0], 4))
+    if "target_sum" in g:
+        assert abs(float(target.double().sum()) - float(g["target_sum"])) < 1e-2, "inputs differ from the reference's"
+    H, W = int(g["H"]), int(g["W"])
+    cfg = O.SkipConfig(upsample_mode=mode, skip_channels=cs)
+    params = O.init_params(cfg, seed=0)
+    z0 = O.get_noise(32, (H, W), seed=1)
+    noise = torch.randn(z0.shape, generator=torch.Generator().manual_seed(123))
+    return dict(g=g, H=H, W=W, cfg=cfg, params=params, z0=z0, noise=noise, sigma=float(g["sigma"]), target=target.float(),
+                mask=mask, down=down)
+
+
+_ORACLE = {}
+
+
+def oracle_step(kind):
+    """One oracle step (cached across the precision parameters): tape of activations, output, loss, gradients."""
+    if kind in _ORACLE:
+        return _ORACLE[kind]
+    _ORACLE.clear()     # one case at a time: a 1024^2 tape is ~10 GB of host memory
+    c = load_case(kind)
+    tape = {}
+    z = c["z0"] + c["noise"] * c["sigma"]
+    out = O.skip_forward(c["params"], z, c["cfg"], tape=tape)
+    o = out if c["down"] is None else O.downsample(out, *c["down"])
+    loss = O.mse_loss(o, c["target"], c["mask"])
+    grads = torch.autograd.grad(loss, c["params"])
+    c.update(tape={k: v.detach() for k, v in tape.items() if "raw" in k}, out=out.detach(), loss=loss.item(), grads=grads)
+    # the oracle against the reference-generated fixture at this shape
+    g = c["g"]
+    assert abs(c["loss"] - float(g["losses"][0])) < 2e-6 * max(1.0, abs(float(g["losses"][0]))) + 1e-7
+    assert np.abs(c["out"].numpy()[:, :, ::4, ::4] - g["out0_sub"]).max() < 2e-5
+    gn = np.array([x.double().norm().item() for x in grads])
+    big = g["gnorm0"] > 1e-4 * g["gnorm0"].max()
+    assert np.abs(gn[big] / g["gnorm0"][big] - 1).max() < 3e-2   # LeakyReLU-flip floor between two fp32 CPU runs
+    _ORACLE[kind] = c
+    return c
+
+
+def engine_step(c, prec):
+    import dip_engine as de
+    cfg, H, W = c["cfg"], c["H"], c["W"]
+    plan = de.Plan(32, 3, cfg.num_scales, 128, cfg.skip_channels, cfg.upsample_mode == "bilinear", H, W,
+                   precision=de.PRECISION_TF32 if prec == "tf32" else de.PRECISION_FP32)
+    dparams = [p.detach().cuda().contiguous() for p in c["params"]]
+    dgrads = [torch.zeros_like(p) for p in dparams]
+    plan.bind(dparams, dgrads)
+    out = plan.forward(c["z0"].cuda(), noise=c["noise"].cuda(), sigma=c["sigma"])
+    L = de.lib()
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    target = c["target"].cuda().contiguous()
+    mask = None if c["mask"] is None else c["mask"].cuda().contiguous()
+    if c["down"] is None:
+        dout = torch.empty_like(out)
+        de.check(L.dip_loss_mse(out.data_ptr(), target.data_ptr(), None if mask is None else mask.data_ptr(), 3, H * W,
+                                loss.data_ptr(), dout.data_ptr(), None))
+    else:
+        kern, f, pad = c["down"]
+        kern = kern.cuda().contiguous()
+        lr = de.lanczos_down_fwd(out, kern, f, pad)
+        dlr = torch.empty_like(lr)
+        de.check(L.dip_loss_mse(lr.data_ptr(), target.data_ptr(), None, 3, lr.shape[2] * lr.shape[3], loss.data_ptr(),
+                                dlr.data_ptr(), None))
+        dout = de.lanczos_down_bwd(dlr, kern, f, pad, H, W)
+    plan.backward(dout)
+    torch.cuda.synchronize()
+    return plan, out, loss.item(), dgrads
+
+
+def cudnn_tf32_grads(c):
+    """The reference's own GPU arithmetic: the same graph on torch-CUDA with cuDNN's default TF32 convolutions."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        pc = [p.detach().cuda().requires_grad_(True) for p in c["params"]]
+        z = (c["z0"] + c["noise"] * c["sigma"]).cuda()
+        out = O.skip_forward(pc, z, c["cfg"])
+        if c["down"] is not None:
+            kern, f, pad = c["down"]
+            x = torch.nn.functional.pad(out, (pad,) * 4, mode="replicate")
+            w = torch.zeros(3, 3, *kern.shape, device="cuda")
+            for i in range(3):
+                w[i, i] = kern.cuda()
+            o = torch.nn.functional.conv2d(x, w, stride=f)
+        else:
+            o = out
+        m = None if c["mask"] is None else c["mask"].cuda()
+        loss = O.mse_loss(o, c["target"].cuda(), m)
+        return [x.detach().cpu() for x in torch.autograd.grad(loss, pc)], out.detach().cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("kind", ["denoise512", "inpaint512", "sr_zebra", "sr1024"])
+def test_one_step_at_baseline_shape(kind, prec):
+    c = oracle_step(kind)
+    plan, out, loss, dgrads = engine_step(c, prec)
+    cfg, g = c["cfg"], c["g"]
+    # (1) every pre-BN activation, level by level
+    for l in range(cfg.num_scales):
+        for nm in ("raw_s", "raw_d1", "raw_d2", "raw_u", "raw_v"):
+            key = "L%d.%s" % (l, nm)
+            e = rel(plan.buffer(key), c["tape"][key][0].permute(1, 2, 0))
+            assert e < RAW_TOL[prec], (key, e)
+    # (2) output and loss: vs the oracle and vs the reference fixture
+    assert (out.cpu() - c["out"]).abs().max().item() < FWD_TOL[prec]
+    assert np.abs(out.cpu().numpy()[:, :, ::4, ::4] - g["out0_sub"]).max() < FWD_TOL[prec]
+    assert abs(out.double().mean().item() - float(g["out0_mean"])) < FWD_TOL[prec] * 0.1
+    assert abs(loss - c["loss"]) < LOSS_TOL[prec] and abs(loss - float(g["losses"][0])) < LOSS_TOL[prec]
+    # (3) gradients
+    names = [n for n, _ in O.param_layout(cfg)]
+    gmax = max(x.norm().item() for x in c["grads"])
+    if prec == "fp32":
+        worst = ("", 0.0)
+        for name, gd, gr in zip(names, dgrads, c["grads"]):
+            if gr.norm().item() < 1e-5 * gmax:
+                assert gd.norm().item() < 1e-4 * gmax, name   # mathematically-zero gradients: rounding noise only
+                continue
+            e = rel(gd, gr)
+            worst = max(worst, (name, e), key=lambda t: t[1])
+        assert worst[1] < GRAD_TOL["fp32"], worst
+        gn = np.array([x.double().norm().item() for x in dgrads])
+        big = g["gnorm0"] > 1e-4 * g["gnorm0"].max()
+        assert np.abs(gn[big] / g["gnorm0"][big] - 1).max() < GRAD_TOL["fp32"]
+        assert rel(dgrads[-2], torch.from_numpy(g["g_head_w"])) < GRAD_TOL["fp32"]
+        assert rel(dgrads[-10][:4, :8], torch.from_numpy(g["g_up0_w_slice"])) < GRAD_TOL["fp32"]
+        assert rel(dgrads[4 * 12 + 8][:4, :8], torch.from_numpy(g["g_d2_4_slice"])) < 2 * GRAD_TOL["fp32"]
+    else:
+        gc, out_c = cudnn_tf32_grads(c)
+        e_out_ours = (out.cpu() - c["out"]).abs().max().item()
+        e_out_cudnn = (out_c - c["out"]).abs().max().item()
+        assert e_out_ours < 3.0 * e_out_cudnn + 2e-3, (e_out_ours, e_out_cudnn)
+        e_ours, e_cudnn = [], []
+        for name, gd, gcu, gr in zip(names, dgrads, gc, c["grads"]):
+            if gr.norm().item() < 1e-4 * gmax:
+                continue
+            eo, ec = rel(gd, gr), rel(gcu, gr)
+            assert eo < 3.0 * ec + 0.08, (name, eo, ec)
+            e_ours.append(eo)
+            e_cudnn.append(ec)
+        assert np.median(e_ours) < 1.5 * np.median(e_cudnn) + 0.01, (np.median(e_ours), np.median(e_cudnn))
+    del plan
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_running_stats_at_512_vs_reference_fixture(prec):
+    """BatchNorm running_mean / running_var / num_batches_tracked of ALL 30 layers after the first forward of the F16
+    denoising configuration through the module API, vs the unmodified reference (fixture keys rm1 / rv1 / nbt1)."""
+    import models
+    c = load_case("denoise512")
+    g = c["g"]
+    dtype = torch.cuda.FloatTensor
+    torch.manual_seed(0)
+    net = models.get_net(32, "skip", "reflection", skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                         upsample_mode="bilinear").type(dtype)
+    net.precision = prec
+    with torch.no_grad():
+        net((c["z0"] + c["noise"] * c["sigma"]).type(dtype))
+    torch.cuda.synchronize()
+    sd = net.state_dict()
+    rm = np.concatenate([sd[k].cpu().numpy().ravel() for k in sd if k.endswith("running_mean")])
+    rv = np.concatenate([sd[k].cpu().numpy().ravel() for k in sd if k.endswith("running_var")])
+    nbt = np.array([float(sd[k]) for k in sd if k.endswith("num_batches_tracked")])
+    assert rm.shape == g["rm1"].shape and np.all(nbt == g["nbt1"]) and np.all(nbt == 1)
+    tol = 1e-5 if prec == "fp32" else 2e-3
+    assert np.abs(rm - g["rm1"]).max() < tol * max(1.0, np.abs(g["rm1"]).max()), np.abs(rm - g["rm1"]).max()
+    assert np.abs(rv / g["rv1"] - 1).max() < (1e-4 if prec == "fp32" else 2e-2), np.abs(rv / g["rv1"] - 1).max()

@@ -1,0 +1,186 @@
+"""The device noise generator of the benchmarked runner (k_noise: Philox4x32-10 + Box-Muller; replaces
+`noise.normal_()` of denoising.ipynb c10:12-13), BatchNorm running statistics vs stock torch, and the misuse guards of
+the module API."""
+import copy
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _perturb(z0, sigma, seed, offset):
+    import dip_engine as de
+    z = torch.empty_like(z0)
+    de.check(de.lib().dip_noise_perturb(z0.data_ptr(), z.data_ptr(), float(sigma), int(seed), int(offset), z0.numel(), None))
+    torch.cuda.synchronize()
+    return z
+
+
+def test_noise_moments_and_streams():
+    n = 1 << 23
+    z0 = torch.zeros(n, device="cuda")
+    a = _perturb(z0, 1.0, 1234, 0).double()
+    # N(0,1): standard errors for n = 8.4 M samples are 3.5e-4 (mean), 4.9e-4 (variance), 8.5e-4 (skew), 1.7e-3 (kurtosis)
+    m, v = a.mean().item(), a.var().item()
+    sk = ((a - m) ** 3).mean().item() / v ** 1.5
+    ku = ((a - m) ** 4).mean().item() / v ** 2
+    assert abs(m) < 2e-3 and abs(v - 1) < 3e-3 and abs(sk) < 5e-3 and abs(ku - 3) < 1e-2, (m, v, sk, ku)
+    for s, p in ((1.0, 0.682689), (2.0, 0.954500), (3.0, 0.997300)):    # tail mass
+        assert abs((a.abs() < s).double().mean().item() - p) < 1e-3
+    assert a.abs().max().item() > 4.5          # the tails are populated (no clipping of the uniforms)
+    assert torch.isfinite(a).all()
+    # neighbouring outputs (the Box-Muller cos/sin pair, the two pairs of one Philox block) are uncorrelated
+    for lag in (1, 2, 3, 4):
+        assert abs((a[:-lag] * a[lag:]).mean().item()) < 2e-3
+    # determinism; a different iteration offset or seed is an independent stream
+    assert torch.equal(_perturb(z0, 1.0, 1234, 0).double(), a)
+    for b in (_perturb(z0, 1.0, 1234, 1).double(), _perturb(z0, 1.0, 1235, 0).double()):
+        assert not torch.equal(a, b)
+        assert abs((a * b).mean().item()) < 2e-3 and abs(b.var().item() - 1) < 3e-3
+    # z = z0 + sigma * n, elementwise
+    z0r = torch.rand(n, device="cuda")
+    zz = _perturb(z0r, 1.0 / 30, 1234, 0)
+    assert torch.allclose(zz, z0r + a.float() / 30, atol=1e-6)
+
+
+def test_runner_uses_a_fresh_stream_every_iteration():
+    """dip_run_iterations: iteration i of the run draws stream `adam step count + i` of (seed): the perturbed input left
+    in the plan's staging buffer after k iterations equals dip_noise_perturb(offset = k - 1), across calls too."""
+    import dip_engine as de
+    H = W = 64
+    cfg = O.SkipConfig()
+    params = O.init_params(cfg, seed=0)
+    plan = de.Plan(32, 3, 5, 128, 4, True, H, W)
+    dparams = [p.detach().cuda().contiguous() for p in params]
+    dgrads = [torch.zeros_like(p) for p in dparams]
+    plan.bind(dparams, dgrads)
+    for p, gbuf in zip(dparams, dgrads):
+        p.grad = gbuf
+    adam = de.FusedAdam(dparams, lr=0.01)
+    adam._bind(dgrads)
+    z0 = O.get_noise(32, (H, W), seed=1).cuda()
+    target = torch.rand(1, 3, H, W, device="cuda")
+    seen = []
+    done = 0
+    for iters in (1, 2, 3):
+        de.run_iterations(plan, adam, z0, target, None, 1. / 30, 99, iters, 0.01)
+        torch.cuda.synchronize()
+        done += iters
+        zb = plan.buffer("zbuf").reshape(-1)
+        want = _perturb(z0.reshape(-1), 1. / 30, 99, done - 1)
+        assert torch.equal(zb, want), (iters, (zb - want).abs().max().item())
+        seen.append(zb.clone())
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    assert adam.step_count == 6
+
+
+@pytest.mark.parametrize("cs,mode", [(4, "bilinear"), (128, "nearest")])
+def test_running_stats_match_stock_torch(cs, mode):
+    """running_mean / running_var / num_batches_tracked of every BatchNorm (incl. the channel-rotated concat BN) after
+    1 and 3 forwards vs the same module tree executed by stock torch on the CPU (momentum 0.1, unbiased variance)."""
+    import models
+    H, W = 64, 96
+    torch.manual_seed(0)
+    net = models.skip(32, 3, num_channels_down=[128] * 5, num_channels_up=[128] * 5, num_channels_skip=[cs] * 5,
+                      upsample_mode=mode, need_sigmoid=True, need_bias=True, pad="reflection", act_fun="LeakyReLU")
+    ref = copy.deepcopy(net)
+    net = net.type(torch.cuda.FloatTensor)
+    net.precision = "fp32"
+    g = torch.Generator().manual_seed(5)
+    zs = [torch.rand(1, 32, H, W, generator=g) * 0.1 for _ in range(3)]
+    models.allow_torch_execution(True)
+    try:
+        for i, z in enumerate(zs):
+            with torch.no_grad():
+                ref(z)
+                net(z.cuda())
+            torch.cuda.synchronize()
+            if i in (0, 2):
+                sr, sn = ref.state_dict(), net.state_dict()
+                for k in sr:
+                    if k.endswith("running_mean") or k.endswith("running_var"):
+                        assert torch.allclose(sn[k].cpu(), sr[k], rtol=2e-4, atol=2e-6), (k, (sn[k].cpu() - sr[k]).abs().max())
+                    elif k.endswith("num_batches_tracked"):
+                        assert float(sn[k]) == float(sr[k]) == i + 1
+    finally:
+        models.allow_torch_execution(False)
+
+
+def _net64():
+    import models
+    torch.manual_seed(0)
+    return models.get_net(32, "skip", "reflection", skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                          upsample_mode="bilinear").type(torch.cuda.FloatTensor)
+
+
+def test_backward_of_an_overwritten_forward_raises():
+    net = _net64()
+    z = torch.rand(1, 32, 64, 64, device="cuda") * 0.1
+    out1 = net(z)
+    out2 = net(z * 0.5)                     # overwrites the activations saved for out1
+    with pytest.raises(RuntimeError, match="overwritten"):
+        out1.sum().backward()
+    out2.sum().backward()                   # the latest forward is fine
+    out3 = net(z)
+    with torch.no_grad():
+        net(z)                              # a no_grad preview between forward and backward is the same hazard
+    with pytest.raises(RuntimeError, match="overwritten"):
+        out3.sum().backward()
+    # different spatial size = different plan: the first plan's activations are intact but it is no longer the active one
+    out4 = net(z)
+    net(torch.rand(1, 32, 64, 96, device="cuda"))
+    with pytest.raises(RuntimeError, match="overwritten"):
+        out4.sum().backward()
+
+
+def test_wrong_dtype_eval_mode_and_plane_count_raise():
+    import models
+    net = _net64()
+    z = torch.rand(1, 32, 64, 64, device="cuda")
+    with pytest.raises(RuntimeError, match="float32"):
+        net(z.double())
+    with pytest.raises(RuntimeError, match="float32"):
+        net(z.half())
+    net.eval()
+    with pytest.raises(NotImplementedError, match="training mode"):
+        net(z)
+    net.train()
+    net(z)
+    ds = models.Downsampler(n_planes=3, factor=4, kernel_type="lanczos2", phase=0.5, preserve_size=True).type(torch.cuda.FloatTensor)
+    with pytest.raises(ValueError, match="planes"):
+        ds(torch.rand(1, 4, 64, 64, device="cuda"))
+
+
+def test_new_adam_after_destroy_is_not_served_a_stale_graph():
+    """dip_run_iterations caches one captured step per plan; a second optimiser (next image of a per-rank shard) must get
+    its own capture even if the allocator hands it the address of the destroyed one."""
+    import dip_engine as de
+    H = W = 64
+    cfg = O.SkipConfig()
+    plan = de.Plan(32, 3, 5, 128, 4, True, H, W)
+    z0 = O.get_noise(32, (H, W), seed=1).cuda()
+    target = torch.rand(1, 3, H, W, device="cuda")
+    finals = []
+    for image in range(3):
+        params = O.init_params(cfg, seed=0)
+        dparams = [p.detach().cuda().contiguous() for p in params]
+        dgrads = [torch.zeros_like(p) for p in dparams]
+        plan.bind(dparams, dgrads)
+        for p, gbuf in zip(dparams, dgrads):
+            p.grad = gbuf
+        adam = de.FusedAdam(dparams, lr=0.01)
+        adam._bind(dgrads)
+        before = [p.clone() for p in dparams]
+        hist = torch.zeros(4, dtype=torch.float64, device="cuda")
+        de.run_iterations(plan, adam, z0, target, None, 1. / 30, 7, 4, 0.01, loss_hist=hist)
+        torch.cuda.synchronize()
+        moved = sum(float((a - b).abs().sum()) for a, b in zip(before, dparams))
+        assert moved > 0, "parameters of image %d were never updated (stale graph)" % image
+        finals.append(hist.cpu().numpy().copy())
+        del adam
+    assert np.allclose(finals[0], finals[1], rtol=1e-3) and np.allclose(finals[0], finals[2], rtol=1e-3)
