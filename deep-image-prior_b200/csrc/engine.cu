@@ -154,6 +154,17 @@ struct TimeScope {
   ~TimeScope() { if (t) { size_t e1 = t->get(s); t->recs.push_back({cls, flops, e0, e1}); } }
 };
 
+// HBM-bound launches are recorded as class 16 + 8 * kernel id + sub-kind; the "flops" field of the record then carries the
+// launch's ALGORITHMIC bytes (unique elements its contract reads + writes, x 4 B) -- bench.py's HBM rooflines.
+enum HbmId { H_INPUT_PAD = 0, H_NOISE, H_SKINNY_FWD, H_BN_ACT_WRITE, H_BN_ACT_HEAD, H_CAT_STATS, H_CAT_WRITE, H_BN_BWD_REDUCE,
+             H_BN_BWD_APPLY, H_CAT_BWD_REDUCE, H_CAT_BWD_APPLY, H_UPADJ, H_SKINNY_BWD, H_MSE, H_ADAM, H_HEAD_DLOGIT, H_DOWN_FWD,
+             H_DOWN_BWD, H_PACK, H_WGRAD_REDUCE };
+#define HBM_T(timer, id, sub, bytes, s, stmt)                                              \
+  do {                                                                                     \
+    TimeScope _ts((timer), 16 + 8 * (int)(id) + (int)(sub), (double)(bytes), (s));         \
+    stmt;                                                                                  \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------ conv op
 // Filter taps per weight stage of the patch-mode convs: a barrier round costs the MMA-issuing thread a fixed ~0.2 us, so a
 // whole filter row (3 taps = 12 MMAs) per round when the stages fit, else 2 (env DIP_TPS overrides).
@@ -356,7 +367,8 @@ struct ConvOp {
       a.partial = partial; a.c_pad = c_pad; a.ksplits = ks = simt_ksplits;
       launch_simt_wgrad(a, s);
     }
-    launch_wgrad_reduce(partial, ks, N, C, k, k, rot, c_pad, dw, s, Ctot, coff);
+    HBM_T(timer, H_WGRAD_REDUCE, 0, ((double)ks + 1.0) * k * k * 128.0 * c_pad * sizeof(float), s,
+          launch_wgrad_reduce(partial, ks, N, C, k, k, rot, c_pad, dw, s, Ctot, coff));
     DIP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -915,32 +927,41 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
       DIP_CHECK(v.sk.run_fprop(prec, P->params[v.p_skip_b], ks));
       nl += prec == DIP_PRECISION_FP32 ? 2 : 1;
     } else {
-      launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
-                        v.bn_s.fwd, ks, v.Cin_act);
+      HBM_T(&P->timer, H_SKINNY_FWD, 0, (double)v.H * v.W * (v.Cin_act + CS) * sizeof(float), ks,
+            launch_skinny_fwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s, 0,
+                              v.bn_s.fwd, ks, v.Cin_act));
       nl += 1;
     }
   }
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
-  launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, v.P_d1, 128, 1, 1, s);
+  HBM_T(&P->timer, H_BN_ACT_WRITE, 1, 128.0 * ((double)v.h * v.w + (double)(v.h + 2) * (v.w + 2)) * sizeof(float), s,
+        launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, v.P_d1, 128, 1, 1, s));
   DIP_CHECK(v.d2.run_fprop(prec, P->params[v.d2.p_b], s));
-  launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, v.P_d2, 128, last ? 0 : 1, 1, s);
+  HBM_T(&P->timer, H_BN_ACT_WRITE, last ? 0 : 1,
+        128.0 * ((double)v.h * v.w + (last ? (double)v.h * v.w : (double)(v.h + 2) * (v.w + 2))) * sizeof(float), s,
+        launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, v.P_d2, 128, last ? 0 : 1, 1, s));
   nl += 4 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
   if (!last) DIP_CHECK(fwd_level(P, l + 1, s, nl));
   // upsample + concat + BN + pad
   join_skip(P, s);
   CatArgs ca = cat_args(P, v, level_usrc(P, l));
-  launch_cat_stats(ca, v.bn_cat.fwd, s);
-  launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s);
+  const double cat_in = (128.0 * v.h * v.w + (double)CS * v.H * v.W) * sizeof(float);
+  HBM_T(&P->timer, H_CAT_STATS, v.bilinear, cat_in, s, launch_cat_stats(ca, v.bn_cat.fwd, s));
+  HBM_T(&P->timer, H_CAT_WRITE, v.bilinear, cat_in + (128.0 + CS) * (v.H + 2) * (v.W + 2) * sizeof(float), s,
+        launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s));
   DIP_CHECK(v.up.run_fprop(prec, P->params[v.up.p_b], s));
-  launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, v.A_u, 128, 0, 1, s);
+  HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * 128 * v.H * v.W * sizeof(float), s,
+        launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, v.A_u, 128, 0, 1, s));
   DIP_CHECK(v.c11.run_fprop(prec, P->params[v.c11.p_b], s));
   if (l > 0) {
-    launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s);
+    HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * 128 * v.H * v.W * sizeof(float), s,
+          launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s));
   } else {
     // top level: BN + LeakyReLU + RGB head + sigmoid in one pass; the 128-channel activation is never materialised
     HeadRef hd{P->params[P->p_head_w], P->params[P->p_head_b], P->desc.out_channels, P->out_saved, P->desc.need_sigmoid != 0};
-    launch_bn_act_head(v.raw_v, bn_ref(P, v.bn_v), v.H, v.W, hd, s);
+    HBM_T(&P->timer, H_BN_ACT_HEAD, 0, (128.0 + P->desc.out_channels) * v.H * v.W * sizeof(float), s,
+          launch_bn_act_head(v.raw_v, bn_ref(P, v.bn_v), v.H, v.W, hd, s));
   }
   nl += 6 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
   DIP_CUDA(cudaGetLastError());
@@ -950,7 +971,10 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
 // one table-driven launch repacks the weights of all wide convs (OIHW -> per-tap K-major fprop / dgrad operands)
 static void plan_pack(dip_plan* P, cudaStream_t s) {
   dim3 grid((unsigned)((P->pack_max + 255) / 256 < 64 ? (P->pack_max + 255) / 256 : 64), P->n_pack);
-  launch_k(k_pack_table, dim3(grid), dim3(256), 0, s, 1, P->d_pack);
+  double bytes = 0;
+  for (ConvOp* op : P->convs)
+    bytes += ((double)op->N * op->C * op->k * op->k + (op->do_fprop ? (double)op->wp_f_elems() : 0.0) + (op->has_dgrad ? (double)op->wp_d_elems() : 0.0)) * sizeof(float);
+  HBM_T(&P->timer, H_PACK, 0, bytes, s, launch_k(k_pack_table, dim3(grid), dim3(256), 0, s, 1, P->d_pack));
 }
 
 static int plan_forward(dip_plan* P, const float* z, const float* noise, float sigma, float* out, cudaStream_t s) {
@@ -963,7 +987,9 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
   if (!P->prepacked) plan_pack(P, fork_side(P, s));   // weight repack runs beside the input transform
   P->prepacked = false;
   Level& v0 = P->lv[0];
-  launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act);
+  HBM_T(&P->timer, H_INPUT_PAD, noise != nullptr,
+        ((noise != nullptr ? 2.0 : 1.0) * v0.Cin_act * v0.H * v0.W + (double)v0.Cin * (v0.H + 2) * (v0.W + 2)) * sizeof(float), s,
+        launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act));
   join_side(P, s);
   nl += 3;
   DIP_CHECK(fwd_level(P, 0, s, nl));
@@ -980,13 +1006,17 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
 static int bn_bwd(dip_plan* P, const float* raw, int ld_raw, BnLayer& b, int act, GradSrc src, int H, int W, float* draw,
                   float* zs, cudaStream_t s, int& nl) {
   BnRef r = bn_ref(P, b);
-  launch_bn_bwd_reduce(raw, ld_raw, r, act, src, H, W, b.bwd, s);
-  {
-    // timing class 3 (bench.py's HBM roofline): the apply pass with a plain gradient source; algorithmic bytes =
-    // read raw + read gradient + write the input gradient (unique elements of the kernel's contract)
-    TimeScope ts(&P->timer, src.kind == 0 && zs == nullptr ? 3 : 4, 3.0 * H * W * b.C * sizeof(float), s);
-    launch_bn_bwd_apply(raw, ld_raw, r, act, src, H, W, b.bwd, draw, zs, b.dbias, s);
-  }
+  // algorithmic bytes: raw + the gradient source as the kernel's contract names it (plain [H][W][C]; fold: the padded
+  // dgrad output (+ the 4-channel skip-branch gradient / the plain addend); upsample adjoint: the 2H x 2W gradient; head:
+  // the 4 logit gradients per pixel), + the written input gradient (and its zero-stuffed copy) for the apply pass
+  const double px = (double)H * W, C4 = b.C * sizeof(float);
+  double gsrc = px * C4;
+  if (src.kind == 1) gsrc = (double)(H + 2) * (W + 2) * C4 + (src.ds != nullptr ? px * 4 * sizeof(float) : 0.0) + (src.add != nullptr ? px * C4 : 0.0);
+  else if (src.kind == 2) gsrc = 4.0 * px * C4;
+  else if (src.kind == 3) gsrc = px * 4 * sizeof(float);
+  HBM_T(&P->timer, H_BN_BWD_REDUCE, src.kind, px * C4 + gsrc, s, launch_bn_bwd_reduce(raw, ld_raw, r, act, src, H, W, b.bwd, s));
+  HBM_T(&P->timer, H_BN_BWD_APPLY, src.kind + (zs != nullptr ? 4 : 0), px * C4 + gsrc + px * C4 * (zs != nullptr ? 2.0 : 1.0), s,
+        launch_bn_bwd_apply(raw, ld_raw, r, act, src, H, W, b.bwd, draw, zs, b.dbias, s));
   nl += 2;
   return 0;
 }
@@ -1061,12 +1091,15 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   }
   // concat BN
   BnRef rc = bn_ref(P, v.bn_cat);
-  launch_cat_bwd_reduce(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, s);
-  launch_cat_bwd_apply(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, v.dCat, s);
+  const double catb = ((double)v.H * v.W + (double)(v.H + 2) * (v.W + 2)) * CC * sizeof(float);   // stored BN output + padded gradient
+  HBM_T(&P->timer, H_CAT_BWD_REDUCE, 0, catb, s, launch_cat_bwd_reduce(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, s));
+  HBM_T(&P->timer, H_CAT_BWD_APPLY, 0, catb + (double)v.H * v.W * CC * sizeof(float), s,
+        launch_cat_bwd_apply(v.P_cat, rc, v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, v.dCat, s));
   // skip branch (on the skip stream: independent of the deeper levels; the level above joins before it reads dRaw_s / dS)
   cudaStream_t ks = fork_skip(P, s);
   // gradient w.r.t. the low-resolution tensor that was upsampled into this concat (adjoint of x2 upsampling), once
-  launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp, s);
+  HBM_T(&P->timer, H_UPADJ, v.bilinear, 128.0 * ((double)v.H * v.W + (double)v.h * v.w) * sizeof(float), s,
+        launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp, s));
   nl += 3;
   DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl));
   if (CS == 128) {
@@ -1076,8 +1109,9 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   } else {
     const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
     // weight gradient only: the input gradient of this conv is folded into the BN backward of the level above
-    launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
-                      (l == 0 && P->desc.input_grad) ? v.dS : nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks, v.Cin_act);
+    HBM_T(&P->timer, H_SKINNY_BWD, 0, (double)v.H * v.W * (v.Cin_act + CS) * sizeof(float), ks,
+          launch_skinny_bwd(pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0,
+                            (l == 0 && P->desc.input_grad) ? v.dS : nullptr, v.dw_s, nullptr /*bias grad comes from the BN backward*/, ks, v.Cin_act));
     nl += 1;
   }
   // deeper branch
@@ -1111,7 +1145,8 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
   GradSrc sh{};
-  launch_head_dlogit(dout, P->out_saved, P->desc.out_channels, P->H * P->W, P->dl4, s, P->desc.need_sigmoid != 0);
+  HBM_T(&P->timer, H_HEAD_DLOGIT, 0, (2.0 * P->desc.out_channels + 4.0) * P->H * P->W * sizeof(float), s,
+        launch_head_dlogit(dout, P->out_saved, P->desc.out_channels, P->H * P->W, P->dl4, s, P->desc.need_sigmoid != 0));
   sh.kind = 3; sh.dl4 = P->dl4; sh.wh = P->params[P->p_head_w]; sh.nh = P->desc.out_channels;
   sh.dwh = P->dw_head; sh.dbh = P->db_head;
   nl += 1;
@@ -1374,7 +1409,7 @@ static int run_body(dip_plan* P, dip_adam* adam, const float* z0, const float* t
     P->prepacked = true;
   }
   if (sigma > 0.f) {
-    launch_noise(z0, P->zbuf, sigma, seed, (uint64_t)step_base, it_dev, nz, s);
+    HBM_T(&P->timer, H_NOISE, 0, 2.0 * nz * sizeof(float), s, launch_noise(z0, P->zbuf, sigma, seed, (uint64_t)step_base, it_dev, nz, s));
     zin = P->zbuf;
   }
   DIP_CHECK(plan_forward(P, zin, nullptr, 0.f, out, s));
@@ -1383,16 +1418,22 @@ static int run_body(dip_plan* P, dip_adam* adam, const float* z0, const float* t
     // super-resolution: loss on the downsampled output (super-resolution.ipynb c10:8-11); the operator's adjoint
     // turns the low-resolution loss gradient into dL/d(out)
     const int co = P->desc.out_channels;
-    DIP_CUDA(launch_down_fwd(P->out_saved, co, P->H, P->W, P->ds_kern, P->ds_K, P->ds_f, P->ds_pad, P->ds_y, s));
+    HBM_T(&P->timer, H_DOWN_FWD, 0, (double)co * ((double)P->H * P->W + (double)P->ds_Ho * P->ds_Wo) * sizeof(float), s,
+          DIP_CUDA(launch_down_fwd(P->out_saved, co, P->H, P->W, P->ds_kern, P->ds_K, P->ds_f, P->ds_pad, P->ds_y, s)));
     launch_mse(P->ds_y, target, mask, co, P->ds_Ho * P->ds_Wo, loss_slot, P->ds_dy, slot_idx, s);
-    DIP_CUDA(launch_down_bwd(P->ds_dy, co, P->H, P->W, P->ds_kern, P->ds_K, P->ds_f, P->ds_pad, P->dout, s));
+    HBM_T(&P->timer, H_DOWN_BWD, 0, (double)co * ((double)P->H * P->W + (double)P->ds_Ho * P->ds_Wo) * sizeof(float), s,
+          DIP_CUDA(launch_down_bwd(P->ds_dy, co, P->H, P->W, P->ds_kern, P->ds_K, P->ds_f, P->ds_pad, P->dout, s)));
   } else {
-    launch_mse(P->out_saved, target, mask, P->desc.out_channels, hw, loss_slot, P->dout, slot_idx, s);
+    HBM_T(&P->timer, H_MSE, mask != nullptr, (3.0 * P->desc.out_channels + (mask != nullptr ? 1.0 : 0.0)) * hw * sizeof(float), s,
+          launch_mse(P->out_saved, target, mask, P->desc.out_channels, hw, loss_slot, P->dout, slot_idx, s));
   }
   DIP_CHECK(plan_backward(P, P->dout, s));
   if (!adam->bound) return fail("dip_run_iterations: adam not bound");
   AdamTable t{adam->d_p, adam->d_g, adam->d_m, adam->d_v, adam->d_blk_tensor, adam->d_blk_start, adam->d_numel, adam->nblocks};
-  launch_adam(t, lr, 0.9, 0.999, 1e-8, step_base + 1, it_dev, s);
+  {
+    double np_ = 0; for (long long n : adam->numel) np_ += (double)n;
+    HBM_T(&P->timer, H_ADAM, 0, 7.0 * np_ * sizeof(float), s, launch_adam(t, lr, 0.9, 0.999, 1e-8, step_base + 1, it_dev, s));
+  }
   if (it_dev != nullptr) launch_advance(it_dev, s);
   DIP_CUDA(cudaGetLastError());
   return 0;
@@ -1478,7 +1519,7 @@ int dip_plan_get_timing(dip_plan* plan, double* ms3, double* flops3, int* launch
     DIP_CUDA(cudaEventSynchronize(plan->timer.pool[r.e1]));
     float ms = 0.f;
     DIP_CUDA(cudaEventElapsedTime(&ms, plan->timer.pool[r.e0], plan->timer.pool[r.e1]));
-    if (r.cls > 2) continue;   // classes 3+ (HBM-bound kernels) are reported through dip_plan_get_timing_records only
+    if (r.cls > 2) continue;   // HBM-bound kernels (class >= 16) are reported through dip_plan_get_timing_records only
     ms3[r.cls] += ms; flops3[r.cls] += r.flops; launches3[r.cls] += 1;
   }
   plan->timer.reset();

@@ -117,6 +117,8 @@ def run_full_budget(prec):
     return rows, rec, refs
 
 
+@pytest.mark.skipif(not all(os.path.exists(os.path.join(GOLD, "f16_full_t%d.npz" % t)) for t in (4, 3)),
+                    reason="full-budget reference fixtures not generated yet (tests/golden/make_f16_full.py)")
 @pytest.mark.parametrize("prec", ["tf32"])
 def test_f16_2000_iterations_vs_reference_runs(prec):
     rows, rec, refs = run_full_budget(prec)
