@@ -243,7 +243,14 @@ def run_ours(args):
     import dip_engine as de
     import multi_gpu as mg
     import models
-    from utils.common_utils import get_params, optimize
+    import contextlib
+    import io
+    from utils.common_utils import get_params
+    from utils.common_utils import optimize as _optimize
+
+    def optimize(*a):                       # utils.optimize prints "Starting optimization with ADAM" like the reference does:
+        with contextlib.redirect_stdout(io.StringIO()):   # stdout must stay the one JSON line
+            _optimize(*a)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -331,13 +338,38 @@ def run_ours(args):
 
     # ---- 4. e2e: utils.optimize() with the notebook closure, host input + loss read-back in the timed region --------
     z_pinned = z0_h.pin_memory()
-    net_input_saved = torch.empty_like(z0)
     noise = z0.detach().clone()
     last = {"loss": 0.0}
+    # every step's input crosses PCIe inside the timed region (33.5 MB, ~0.6 ms): the copy for step i+1 is issued on a copy
+    # stream while step i computes (double-buffered device input), as any input pipeline would do
+    zbuf = [torch.empty_like(z0), torch.empty_like(z0)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    pipe = {"i": 0}
+
+    def prefetch(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])                # the step that last read this buffer has finished
+            zbuf[b].copy_(z_pinned, non_blocking=True)         # H2D: the step's input
+            ready[b].record(copy_stream)
+
+    def pipe_reset():
+        torch.cuda.synchronize()
+        for b in range(2):
+            consumed[b].record()
+        pipe["i"] = 0
+        prefetch(0)
 
     def lean_closure():                      # denoising.ipynb c10:8-24 without the logging
-        net_input_saved.copy_(z_pinned, non_blocking=True)                    # H2D: the step's input (33.5 MB)
-        net_input = net_input_saved + (noise.normal_() * SIGMA_REG)           # c10:12-13, device RNG
+        i = pipe["i"]
+        b = i % 2
+        torch.cuda.current_stream().wait_event(ready[b])
+        net_input = zbuf[b] + (noise.normal_() * SIGMA_REG)                   # c10:12-13, device RNG
+        consumed[b].record()
+        prefetch(i + 1)
+        pipe["i"] = i + 1
         out = net(net_input)
         total_loss = mse(out, target)
         total_loss.backward()
@@ -345,8 +377,13 @@ def run_ours(args):
         return total_loss
 
     e2e_steps = max(args.steps, 200)
+    pipe_reset()
     optimize("adam", get_params("net", net, z0), lean_closure, LR, 5)
-    e2e_ms, _ = timed(lambda: optimize("adam", get_params("net", net, z0), lean_closure, LR, e2e_steps))
+
+    def e2e_run():
+        prefetch(pipe["i"])          # (re-issued inside the timed region: the first step's H2D is timed too)
+        optimize("adam", get_params("net", net, z0), lean_closure, LR, e2e_steps)
+    e2e_ms, _ = timed(e2e_run)
     e2e_value = mg.aggregate_rate(e2e_steps, e2e_ms / 1000.0, world)
 
     # verbatim closure of denoising.ipynb c10: EMA, three PSNR read-backs, last_net snapshot

@@ -547,8 +547,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
       tc_fence_after();
     }
     for (int s = 0; s < p.kw; ++s) {
+      if (p.atomic && blk1 <= blk0) break;   // nothing accumulated by this CTA
       const int tap = r * p.kw + s;
-      float* dst = p.partial + ((static_cast<size_t>(ks) * (p.kh * p.kw) + tap) * 128 + n) * c_pad;
+      float* dst = p.partial + ((static_cast<size_t>(p.atomic ? 0 : ks) * (p.kh * p.kw) + tap) * 128 + n) * c_pad;
       for (int j = 0; j < p.c_chunks; ++j) {
         uint32_t v[32];
         if (blk1 > blk0) {
@@ -557,6 +558,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = 0u;
+        }
+        if (p.atomic) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            red_add_v4(dst + j * 32 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                       __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+          continue;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {

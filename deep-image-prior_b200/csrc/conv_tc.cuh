@@ -43,11 +43,14 @@ struct TcConvParams {
 // Weight-gradient GEMM:  dW[tap][n][c] = sum_{pixels} dY[pixel][n] * X[pixel (+) tap][c]
 //   dY : NHWC fp32 [H][W][128] through a 3-D map (128, W, H)
 //   X  : conv input through the same 5-D view as in TcConvParams
-//   out: fp32 partials [ksplit][tap][128][c_pad]  (deterministic split-K; reduced by a follow-up kernel)
+//   out: atomic = 1 (engine): every split-K CTA adds its tile into ONE fp32 accumulator [tap][128][c_pad] with vector
+//        reductions at the L2 (red.global.add.v4.f32; the 0.6 MB accumulator never leaves the L2) -- no partials in
+//        HBM, no reduction kernel;  atomic = 0: deterministic partials [ksplit][tap][128][c_pad] + follow-up reduce
 struct TcWgradParams {
   CUtensorMap tmY;
   CUtensorMap tmX;
-  float* partial;          // [ksplits][kh*kw][128][c_pad]
+  float* partial;          // atomic: [kh*kw][128][c_pad] accumulator (zeroed by the caller); else [ksplits][kh*kw][128][c_pad]
+  int atomic;
   int kh, kw, stride, offx, offy;
   int px_blocks_x;         // W / kp
   int px_blocks;           // total pixel blocks = H * px_blocks_x

@@ -205,6 +205,7 @@ struct ConvOp {
   float* out = nullptr; int out_h = 0, out_w = 0;
   double* stats = nullptr;
   float* wp_f = nullptr; float* wp_d = nullptr;
+  float* wacc = nullptr;   // plan-owned weight-gradient accumulator [tap][128][c_pad] (tensor-core path; zeroed once per backward)
   // dgrad: dg_in [dg_in_h][dg_in_w][128] -> dg_out [dg_out_h][dg_out_w][C]
   bool has_dgrad = false;
   const float* dg_in = nullptr; int dg_in_h = 0, dg_in_w = 0;
@@ -225,6 +226,7 @@ struct ConvOp {
   }
   size_t wp_f_elems() const { return (size_t)k * k * N * c_pad; }
   size_t wp_d_elems() const { return (size_t)k * k * crows * 128; }
+  size_t wacc_elems() const { return (size_t)k * k * 128 * c_pad; }
   int tc_ksplits() const {
     const int kp = (wg_w % 32 == 0) ? 32 : 16;
     const int blocks = wg_h * ((wg_w + kp - 1) / kp);
@@ -234,7 +236,7 @@ struct ConvOp {
     return ks < 1 ? 1 : ks;
   }
   size_t partial_elems(int prec) const {
-    const int ks = prec == DIP_PRECISION_TF32 ? tc_ksplits() : simt_ksplits;
+    const int ks = prec == DIP_PRECISION_TF32 ? 1 : simt_ksplits;   // tensor-core path: one accumulator (atomic split-K)
     return (size_t)ks * k * k * 128 * c_pad;
   }
 
@@ -354,11 +356,21 @@ struct ConvOp {
     if (dbg_skip) return 0;
     int ks;
     if (prec == DIP_PRECISION_TF32) {
+      // split-K CTAs add their tiles into one accumulator with vector reductions at the L2.  Plan-owned accumulator
+      // (wacc): zeroed by one memset per backward, unpacked to OIHW by one table kernel at the end of the backward pass.
+      // Single-op entry points: zero + launch + unpack here.
       TcWgradParams p = wg;
-      p.partial = partial;
-      ks = p.ksplits;
-      TimeScope ts(timer, 2, alg_flops(), s);
-      DIP_CUDA(tc_wgrad_launch(p, s));
+      p.atomic = 1;
+      p.partial = wacc != nullptr ? wacc : partial;
+      if (wacc == nullptr) DIP_CUDA(cudaMemsetAsync(partial, 0, wacc_elems() * sizeof(float), s));
+      {
+        TimeScope ts(timer, 2, alg_flops(), s);
+        DIP_CUDA(tc_wgrad_launch(p, s));
+      }
+      if (wacc != nullptr) return 0;
+      launch_wgrad_reduce(partial, 1, N, C, k, k, rot, c_pad, dw, s, Ctot, coff);
+      DIP_CUDA(cudaGetLastError());
+      return 0;
     } else {
       SimtWgradArgs a{};
       a.dY = wg_dy; a.h = wg_h; a.w = wg_w;
@@ -400,6 +412,20 @@ __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
       if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
       e.dst_d[j] = v;
     }
+  }
+}
+// accumulators [tap][128][c_pad] of all tensor-core weight gradients -> OIHW gradients (one launch per backward pass)
+struct UnpackEntry {
+  const float* acc; float* dw;
+  int N, C, taps, rot, c_pad, Ctot, coff;
+};
+__global__ void k_wgrad_unpack_table(const UnpackEntry* __restrict__ tab) {
+  pdl_enter();
+  const UnpackEntry e = tab[blockIdx.y];
+  const int total = e.N * e.C * e.taps;   // dw elements this entry owns: (n, engine channel c, tap)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % e.taps, c = (i / e.taps) % e.C, n = i / (e.taps * e.C);
+    e.dw[((size_t)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * e.taps + tap] = e.acc[((size_t)tap * 128 + n) * e.c_pad + c];
   }
 }
 struct CvtEntry {
@@ -536,10 +562,13 @@ struct dip_plan {
   // weight-gradient GEMMs of the outer levels deferred until the main chain is inside the (latency-bound, SM-starved)
   // deep levels, where a full-GPU tensor-core kernel on the side stream costs the least
   std::vector<dip::ConvOp*> deferred;
+  // runner: the input perturbation is generated inside the level-0 input transform (k_noise_pad) -- set around plan_forward
+  struct { bool on = false; const float* z0 = nullptr; float sigma = 0.f; uint64_t seed = 0, offset = 0; const int* it_dev = nullptr; } fnoise;
   bool prepacked = false;   // the runner already issued the weight repack of this forward (beside the noise kernel)
   // tables
-  PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr;
-  int n_pack = 0, n_cvt = 0, n_run = 0;
+  PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr; UnpackEntry* d_unpack = nullptr;
+  int n_pack = 0, n_cvt = 0, n_run = 0, n_unpack = 0;
+  float* wacc_base = nullptr; size_t wacc_bytes = 0;   // all weight-gradient accumulators, contiguous
   long long pack_max = 0;
   bool bound = false;
   int nbt_is_float = 0;
@@ -797,6 +826,17 @@ static int build_plan(dip_plan* P, Arena& A) {
     }
   }
   P->partial = A.get<float>(partial_max);
+  // weight-gradient accumulators of the tensor-core path: one per conv, contiguous (a single memset per backward)
+  P->n_unpack = 0;
+  if (prec == DIP_PRECISION_TF32) {
+    size_t tot = 0;
+    for (ConvOp* op : P->convs) if (op->do_wgrad) { tot += (op->wacc_elems() + 63) & ~size_t(63); P->n_unpack++; }
+    P->wacc_base = A.get<float>(tot);
+    P->wacc_bytes = tot * sizeof(float);
+    size_t off = 0;
+    for (ConvOp* op : P->convs) if (op->do_wgrad) { op->wacc = P->wacc_base ? P->wacc_base + off : nullptr; off += (op->wacc_elems() + 63) & ~size_t(63); }
+  }
+  P->d_unpack = A.get<UnpackEntry>(P->n_unpack > 0 ? P->n_unpack : 1);
   P->n_pack = (int)P->convs.size();
   P->n_cvt = (int)P->bns.size() * 3 + L + 2;
   P->n_run = (int)P->bns.size();
@@ -836,6 +876,15 @@ static int upload_tables(dip_plan* P) {
     pk.push_back(e);
   }
   DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
+  if (P->n_unpack > 0) {
+    std::vector<UnpackEntry> up;
+    for (ConvOp* op : P->convs) {
+      if (!op->do_wgrad || op->wacc == nullptr) continue;
+      up.push_back(UnpackEntry{op->wacc, P->grads[op->p_w], op->N, op->C, op->k * op->k, op->rot, op->c_pad, op->Ctot, op->coff});
+    }
+    if ((int)up.size() != P->n_unpack) return fail("internal: unpack table size mismatch");
+    DIP_CUDA(cudaMemcpy(P->d_unpack, up.data(), up.size() * sizeof(UnpackEntry), cudaMemcpyHostToDevice));
+  }
   std::vector<CvtEntry> cv;
   for (BnLayer* b : P->bns) {
     cv.push_back(CvtEntry{b->bwd + b->C * kAccS, P->grads[b->p_gamma], b->C, b->rot});  // dgamma = sum dz*xhat
@@ -987,9 +1036,14 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
   if (!P->prepacked) plan_pack(P, fork_side(P, s));   // weight repack runs beside the input transform
   P->prepacked = false;
   Level& v0 = P->lv[0];
-  HBM_T(&P->timer, H_INPUT_PAD, noise != nullptr,
-        ((noise != nullptr ? 2.0 : 1.0) * v0.Cin_act * v0.H * v0.W + (double)v0.Cin * (v0.H + 2) * (v0.W + 2)) * sizeof(float), s,
-        launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act));
+  if (P->fnoise.on)
+    HBM_T(&P->timer, H_NOISE, 1, ((double)v0.Cin_act * v0.H * v0.W + (double)v0.Cin * (v0.H + 2) * (v0.W + 2)) * sizeof(float), s,
+          launch_noise_pad(P->fnoise.z0, P->fnoise.sigma, P->fnoise.seed, P->fnoise.offset, P->fnoise.it_dev, v0.Pin, v0.Cin,
+                           v0.H, v0.W, v0.Cin_act, s));
+  else
+    HBM_T(&P->timer, H_INPUT_PAD, noise != nullptr,
+          ((noise != nullptr ? 2.0 : 1.0) * v0.Cin_act * v0.H * v0.W + (double)v0.Cin * (v0.H + 2) * (v0.W + 2)) * sizeof(float), s,
+          launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act));
   join_side(P, s);
   nl += 3;
   DIP_CHECK(fwd_level(P, 0, s, nl));
@@ -1070,7 +1124,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   const int CS = P->desc.skip_channels;
   const int CC = 128 + CS;
   const bool last = l == (int)P->lv.size() - 1;
-  const int wl = prec == DIP_PRECISION_TF32 ? 2 : 2;
+  const int wl = prec == DIP_PRECISION_TF32 ? 1 : 2;   // tensor-core wgrads accumulate in place (no per-conv reduction launch)
   // 1x1 conv + BN + LReLU
   DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl));
   if (l == defer_level()) DIP_CHECK(flush_deferred(P, prec, s));
@@ -1141,6 +1195,7 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   int nl = 0;
   P->deferred.clear();
   DIP_CUDA(cudaMemsetAsync(P->acc_bwd, 0, P->acc_bwd_n * sizeof(double), s));
+  if (P->n_unpack > 0) DIP_CUDA(cudaMemsetAsync(P->wacc_base, 0, P->wacc_bytes, s));
   P->side_on = getenv("DIP_NO_SIDE") == nullptr;
   Level& v0 = P->lv[0];
   // RGB head backward (sigmoid', dgrad 3->128, wgrad, bias grad) is fused into the BN backward of the last stage
@@ -1156,6 +1211,11 @@ static int plan_backward(dip_plan* P, const float* dout, cudaStream_t s) {
   join_skip(P, s);
   launch_k(k_cvt_table, dim3(P->n_cvt), dim3(128), 0, s, 1, P->d_cvt);
   nl += 1;
+  if (P->n_unpack > 0) {
+    HBM_T(&P->timer, H_WGRAD_REDUCE, 1, 2.0 * (double)P->wacc_bytes, s,
+          launch_k(k_wgrad_unpack_table, dim3(64, P->n_unpack), dim3(256), 0, s, 1, P->d_unpack));
+    nl += 2;   // + the accumulator memset
+  }
   DIP_CUDA(cudaGetLastError());
   P->launches_bwd = nl;
   return 0;
@@ -1408,11 +1468,17 @@ static int run_body(dip_plan* P, dip_adam* adam, const float* z0, const float* t
     plan_pack(P, fork_side(P, s));
     P->prepacked = true;
   }
-  if (sigma > 0.f) {
+  static const bool split_noise = getenv("DIP_SPLIT_NOISE") != nullptr;   // A/B switch: separate k_noise + k_input_pad launches
+  if (sigma > 0.f && (split_noise || P->W % 4 != 0)) {
     HBM_T(&P->timer, H_NOISE, 0, 2.0 * nz * sizeof(float), s, launch_noise(z0, P->zbuf, sigma, seed, (uint64_t)step_base, it_dev, nz, s));
     zin = P->zbuf;
+  } else if (sigma > 0.f) {
+    P->fnoise.on = true; P->fnoise.z0 = z0; P->fnoise.sigma = sigma; P->fnoise.seed = seed; P->fnoise.offset = (uint64_t)step_base;
+    P->fnoise.it_dev = it_dev;
   }
-  DIP_CHECK(plan_forward(P, zin, nullptr, 0.f, out, s));
+  const int frc = plan_forward(P, zin, nullptr, 0.f, out, s);
+  P->fnoise.on = false;
+  DIP_CHECK(frc);
   const int* slot_idx = it_dev != nullptr ? it_dev + 1 : nullptr;
   if (P->ds_K > 0) {
     // super-resolution: loss on the downsampled output (super-resolution.ipynb c10:8-11); the operator's adjoint

@@ -182,6 +182,10 @@ void launch_mse(const float* out, const float* target, const float* mask, int C,
 // stream = offset + *it_dev)
 void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, size_t n,
                   cudaStream_t s);
+// runner input in one pass: dst (reflection-padded NHWC [(H+2)][(W+2)][C]) = pad(z0 + sigma * N(0,1)), the same Philox stream
+// as launch_noise (W % 4 == 0); channels >= c_src of the stored depth C are written as zeros
+void launch_noise_pad(const float* z0, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, float* dst, int C, int H,
+                      int W, int c_src, cudaStream_t s);
 // it_dev[0] += 1, it_dev[1] += 1 (step / iteration counters of the graph-captured runner)
 void launch_advance(int* it_dev, cudaStream_t s);
 

@@ -224,6 +224,11 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
       : "memory");
 }
 
+// fp32 vector reduction to global memory (sm_90+): 4 consecutive floats, performed at the L2, no return value
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -112,8 +112,11 @@ def test_one_step_at_baseline_shape(kind, prec):
     if prec == "fp32":
         worst = ("", 0.0)
         for name, gd, gr in zip(names, dgrads, c["grads"]):
-            if gr.norm().item() < 1e-5 * gmax:
-                assert gd.norm().item() < 1e-4 * gmax, name   # mathematically-zero gradients: rounding noise only
+            dead = (name.endswith(".b") and "_bn" not in name and not name.startswith("head")) or name.endswith("cat_bn.b")
+            if dead or gr.norm().item() < 1e-5 * gmax:
+                # mathematically-zero gradients (a conv bias / the concat-BN shift in front of a BatchNorm): rounding noise
+                # in the reference too, whatever its size there -- only "small" can be asserted
+                assert gd.norm().item() < 1e-3 * gmax and gr.norm().item() < 1e-3 * gmax, name
                 continue
             e = rel(gd, gr)
             worst = max(worst, (name, e), key=lambda t: t[1])
@@ -131,7 +134,8 @@ def test_one_step_at_baseline_shape(kind, prec):
         assert e_out_ours < 3.0 * e_out_cudnn + 2e-3, (e_out_ours, e_out_cudnn)
         e_ours, e_cudnn = [], []
         for name, gd, gcu, gr in zip(names, dgrads, gc, c["grads"]):
-            if gr.norm().item() < 1e-4 * gmax:
+            dead = (name.endswith(".b") and "_bn" not in name and not name.startswith("head")) or name.endswith("cat_bn.b")
+            if dead or gr.norm().item() < 1e-4 * gmax:
                 continue
             eo, ec = rel(gd, gr), rel(gcu, gr)
             assert eo < 3.0 * ec + 0.08, (name, eo, ec)

@@ -49,8 +49,9 @@ def test_noise_moments_and_streams():
 
 
 def test_runner_uses_a_fresh_stream_every_iteration():
-    """dip_run_iterations: iteration i of the run draws stream `adam step count + i` of (seed): the perturbed input left
-    in the plan's staging buffer after k iterations equals dip_noise_perturb(offset = k - 1), across calls too."""
+    """dip_run_iterations: iteration i of the run draws stream `adam step count + i` of (seed): the perturbed, reflection-
+    padded level-0 input left in the plan after k iterations equals pad(dip_noise_perturb(offset = k - 1)), across calls
+    too (the runner generates the noise inside its input transform, k_noise_pad: same Philox stream as k_noise)."""
     import dip_engine as de
     H = W = 64
     cfg = O.SkipConfig()
@@ -71,10 +72,11 @@ def test_runner_uses_a_fresh_stream_every_iteration():
         de.run_iterations(plan, adam, z0, target, None, 1. / 30, 99, iters, 0.01)
         torch.cuda.synchronize()
         done += iters
-        zb = plan.buffer("zbuf").reshape(-1)
-        want = _perturb(z0.reshape(-1), 1. / 30, 99, done - 1)
-        assert torch.equal(zb, want), (iters, (zb - want).abs().max().item())
-        seen.append(zb.clone())
+        pin = plan.buffer("L0.Pin")                                   # (H+2, W+2, C) NHWC, reflection padded
+        want = _perturb(z0.reshape(-1), 1. / 30, 99, done - 1).reshape(32, H, W)
+        wantp = torch.nn.functional.pad(want[None], (1, 1, 1, 1), mode="reflect")[0].permute(1, 2, 0)
+        assert torch.equal(pin, wantp), (iters, (pin - wantp).abs().max().item())
+        seen.append(pin.clone())
     assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
     assert adam.step_count == 6
 
