@@ -359,95 +359,65 @@ __device__ __forceinline__ CatLane cat_lane(const CatArgs& a, int v) {
   l.bs = bn_coef<1>(a.bn_s, l.is_up ? -1 : v - a.Cu / 4);
   return l;
 }
-// Strip of `n` (<= kCatSeg) consecutive source pixels (si, sj0 .. sj0+n-1) of U; f(sj, q) receives the 4 pre-BN concat
-// values q[0..3] at output pixels (2si,2sj), (2si,2sj+1), (2si+1,2sj), (2si+1,2sj+1).  Bilinear (align_corners=False:
-// weights 1/4, 3/4, edge clamp) is separable: a column of U is interpolated vertically ONCE into its two output rows
-// (top / bottom) and kept in registers while the window slides right -> 3 loads per source pixel instead of 9.
-static constexpr int kCatSeg = 8;
-template <class F>
-__device__ __forceinline__ void cat_strip(const CatArgs& a, const CatLane& l, int v, int si, int sj0, int n, F f) {
+// out[0..3] = pre-BN concat values at (2si,2sj), (2si,2sj+1), (2si+1,2sj), (2si+1,2sj+1)
+__device__ __forceinline__ void cat_quad(const CatArgs& a, const CatLane& l, int si, int sj, int v, float4 (&out)[4]) {
   const int h = a.H >> 1, w = a.W >> 1;
-  float4 q[4];
-  if (l.is_up && a.bilinear) {
+  if (l.is_up) {
     const float* base = a.U + 4 * v;
-    const float* p0 = base + static_cast<size_t>(max(si - 1, 0)) * w * a.Cu;
-    const float* p1 = base + static_cast<size_t>(si) * w * a.Cu;
-    const float* p2 = base + static_cast<size_t>(min(si + 1, h - 1)) * w * a.Cu;
-    float4 tL, bL, tC, bC, tR, bR;
-    auto column = [&](int j, float4& top, float4& bot) {
-      const size_t o = static_cast<size_t>(j) * a.Cu;
-      const float4 n0 = ld4(p0 + o), n1 = ld4(p1 + o), n2 = ld4(p2 + o);
-      const float4 mid = f4fma(0.75f, n1, f4zero());
-      top = f4fma(0.25f, n0, mid);
-      bot = f4fma(0.25f, n2, mid);
-    };
-    column(max(sj0 - 1, 0), tL, bL);
-    column(sj0, tC, bC);
-#pragma unroll
-    for (int t = 0; t < kCatSeg; ++t) {
-      if (t < n) {
-        const int sj = sj0 + t;
-        column(min(sj + 1, w - 1), tR, bR);
-        const float4 mt = f4fma(0.75f, tC, f4zero()), mb = f4fma(0.75f, bC, f4zero());
-        q[0] = f4fma(0.25f, tL, mt);
-        q[1] = f4fma(0.25f, tR, mt);
-        q[2] = f4fma(0.25f, bL, mb);
-        q[3] = f4fma(0.25f, bR, mb);
-        f(sj, q);
-        tL = tC; bL = bC; tC = tR; bC = bR;
-      }
+    if (!a.bilinear) {
+      const float4 c = ld4(base + (static_cast<size_t>(si) * w + sj) * a.Cu);
+      out[0] = out[1] = out[2] = out[3] = c;
+      return;
     }
-  } else if (l.is_up) {
-    const float* p1 = a.U + 4 * v + static_cast<size_t>(si) * w * a.Cu;
+    const int r0 = max(si - 1, 0), r2 = min(si + 1, h - 1);
+    const int c0 = max(sj - 1, 0), c2 = min(sj + 1, w - 1);
+    const int rr[3] = {r0, si, r2};
+    float4 hl[3], hr[3];
 #pragma unroll
-    for (int t = 0; t < kCatSeg; ++t) {
-      if (t < n) {
-        q[0] = q[1] = q[2] = q[3] = ld4(p1 + static_cast<size_t>(sj0 + t) * a.Cu);
-        f(sj0 + t, q);
-      }
+    for (int q = 0; q < 3; ++q) {
+      const float* rowp = base + static_cast<size_t>(rr[q]) * w * a.Cu;
+      const float4 n0 = ld4(rowp + static_cast<size_t>(c0) * a.Cu);
+      const float4 n1 = ld4(rowp + static_cast<size_t>(sj) * a.Cu);
+      const float4 n2 = ld4(rowp + static_cast<size_t>(c2) * a.Cu);
+      hl[q] = f4fma(0.25f, n0, f4fma(0.75f, n1, f4zero()));
+      hr[q] = f4fma(0.25f, n2, f4fma(0.75f, n1, f4zero()));
     }
+    out[0] = f4fma(0.25f, hl[0], f4fma(0.75f, hl[1], f4zero()));
+    out[1] = f4fma(0.25f, hr[0], f4fma(0.75f, hr[1], f4zero()));
+    out[2] = f4fma(0.25f, hl[2], f4fma(0.75f, hl[1], f4zero()));
+    out[3] = f4fma(0.25f, hr[2], f4fma(0.75f, hr[1], f4zero()));
   } else {
     const float* base = a.raw_s + 4 * (v - a.Cu / 4);
 #pragma unroll
-    for (int t = 0; t < kCatSeg; ++t) {
-      if (t < n) {
-        const int sj = sj0 + t;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = 2 * si + (e >> 1), j = 2 * sj + (e & 1);
-          q[e] = lrelu4(bn_apply(l.bs, ld4(base + (static_cast<size_t>(i) * a.W + j) * a.Cs)));
-        }
-        f(sj, q);
-      }
+    for (int q = 0; q < 4; ++q) {
+      const int i = 2 * si + (q >> 1), j = 2 * sj + (q & 1);
+      out[q] = lrelu4(bn_apply(l.bs, ld4(base + (static_cast<size_t>(i) * a.W + j) * a.Cs)));
     }
   }
 }
-// work items of the concat kernels: (source row, segment of kCatSeg source pixels)
-__device__ __forceinline__ int cat_items(const CatArgs& a) { return (a.H >> 1) * (((a.W >> 1) + kCatSeg - 1) / kCatSeg); }
 
 __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
   pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
-  const int w = a.W >> 1, segs = (w + kCatSeg - 1) / kCatSeg, nitems = cat_items(a);
+  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   float4 acc[2] = {f4zero(), f4zero()};
-  for (int it = blockIdx.x * PPB + slot; it < nitems; it += gridDim.x * PPB) {
-    const int si = it / segs, sj0 = (it - si * segs) * kCatSeg;
-    cat_strip(a, l, v, si, sj0, min(kCatSeg, w - sj0), [&](int, const float4 (&q)[4]) {
+  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+    const int si = p / w, sj = p - si * w;
+    float4 q[4];
+    cat_quad(a, l, si, sj, v, q);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc[0] = f4add(acc[0], q[e]);
-        acc[1] = f4mla(q[e], q[e], acc[1]);
-      }
-    });
+    for (int e = 0; e < 4; ++e) {
+      acc[0] = f4add(acc[0], q[e]);
+      acc[1] = f4mla(q[e], q[e], acc[1]);
+    }
   }
   double* const dst[2] = {fwd, fwd + (a.Cu + a.Cs) * kAccS};
   const int wid[2] = {a.Cu + a.Cs, a.Cu + a.Cs};
   block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
-static long long cat_nitems(const CatArgs& a) { return static_cast<long long>(a.H / 2) * ((a.W / 2 + kCatSeg - 1) / kCatSeg); }
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, cat_nitems(a));
+  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_stats, red_bytes(g, 2));
   launch_red(k_cat_stats, g.blocks, g.threads, red_bytes(g, 2), s, a, fwd_cat, g.VL, g.PPB);
 }
@@ -472,42 +442,32 @@ __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, in
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const Bn4 cf = bn_coef<0>(bn_cat, v);
-  const int w = a.W >> 1, segs = (w + kCatSeg - 1) / kCatSeg, nitems = cat_items(a);
+  const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   const int ld = a.Cu + a.Cs;
-  for (int it = blockIdx.x * PPB + slot; it < nitems; it += gridDim.x * PPB) {
-    const int si = it / segs, sj0 = (it - si * segs) * kCatSeg;
-    cat_strip(a, l, v, si, sj0, min(kCatSeg, w - sj0), [&](int sj, const float4 (&q)[4]) {
+  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+    const int si = p / w, sj = p - si * w;
+    float4 q[4];
+    cat_quad(a, l, si, sj, v, q);
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]));
-    });
+    for (int e = 0; e < 4; ++e)
+      store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]));
   }
 }
 void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
-  VecGeom g = vec_geom(a.Cu + a.Cs, cat_nitems(a));
+  VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_write, 0);
   launch_k(k_cat_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, a, bn_cat, dst, g.VL, g.PPB);
 }
 
 // ------------------------------------------------------------------------------------------------ gradient sources
-__device__ __forceinline__ float4 fold_interior(const float* __restrict__ gp, int ld, int coff, int W, int i, int j, int v);
-__device__ __forceinline__ float4 fold_finish(const float* __restrict__ gp, int ld, int coff, int H, int W, int i, int j, int v,
-                                              float4 r);
 // fold: adjoint of ReflectionPad2d(1). Interior (i,j) <- padded (i+1,j+1) plus mirrored halo rows/cols.
 __device__ __forceinline__ float4 fold_read(const float* __restrict__ gp, int ld, int coff, int H, int W, int i, int j,
                                             int v) {
-  return fold_finish(gp, ld, coff, H, W, i, j, v, fold_interior(gp, ld, coff, W, i, j, v));
-}
-// The two halves of fold_read: the unconditional interior load belongs in the LOAD phase of item_loop (no branch, so the
-// loads of all items in flight are issued back to back); the mirrored halo positions -- only the one-pixel ring next to
-// the border has any -- are added when the item is consumed.
-__device__ __forceinline__ float4 fold_interior(const float* __restrict__ gp, int ld, int coff, int W, int i, int j, int v) {
-  return ld4(gp + coff + 4 * v + (static_cast<size_t>(i + 1) * (W + 2) + (j + 1)) * ld);
-}
-__device__ __forceinline__ float4 fold_finish(const float* __restrict__ gp, int ld, int coff, int H, int W, int i, int j, int v,
-                                              float4 r) {
   const int Wp = W + 2;
   const float* base = gp + coff + 4 * v;
+  // the interior load is unconditional (issued at once, so several items' loads are in flight together); only the
+  // one-pixel ring next to the border has mirrored halo positions to add
+  float4 r = ld4(base + (static_cast<size_t>(i + 1) * Wp + (j + 1)) * ld);
   if (i == 1 || i == H - 2 || j == 1 || j == W - 2) {
     int rows[3], cols[3];
     int nr = 0, nc = 0;
@@ -570,21 +530,25 @@ __device__ __forceinline__ SrcRegs src_regs(const GradSrc& s, int C, int v) {
   }
   return r;
 }
-// Gradient w.r.t. the BN(+act) output at pixel p = (i, j), in two halves (see item_loop): grad_load issues the loads of the
-// item (no branches, no arithmetic on loaded values), grad_finish turns them into the gradient when the item is consumed.
-struct RedItem {
-  float4 x, g, d;  // raw conv output; gradient source as loaded; kind 1: skip-branch gradients (ds) or plain addend
-};
-typedef RedItem BwdItem;
+// gradient w.r.t. the BN(+act) output at pixel p = (i, j); dl (kind 3) returns the head's logit gradients
 template <int KIND>
-__device__ __forceinline__ void grad_load(const GradSrc& s, int H, int W, int p, int i, int j, int v, RedItem& it) {
-  if (KIND == 0) it.g = ld4(s.g + static_cast<size_t>(p) * s.ld + s.coff + 4 * v);
-  else if (KIND == 1) {
-    it.g = fold_interior(s.g, s.ld, s.coff, W, i, j, v);
-    if (s.ds != nullptr) it.d = ld4(s.ds + static_cast<size_t>(p) * 4);  // n2 == 4
-    else if (s.add != nullptr) it.d = ld4(s.add + static_cast<size_t>(p) * s.ld_add + 4 * v);
-  } else if (KIND == 2) it.g = upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
-  else it.g = ld4(s.dl4 + static_cast<size_t>(p) * 4);  // the 4 logit gradients of the pixel (k_head_dlogit)
+__device__ __forceinline__ float4 grad_read(const GradSrc& s, const SrcRegs& sr, int H, int W, int p, int i, int j, int v) {
+  if (KIND == 0) return ld4(s.g + static_cast<size_t>(p) * s.ld + s.coff + 4 * v);
+  if (KIND == 1) {
+    float4 r = fold_read(s.g, s.ld, s.coff, H, W, i, j, v);
+    if (s.ds != nullptr) {
+      const float4 d = ld4(s.ds + static_cast<size_t>(p) * 4);  // n2 == 4
+      r = f4fma(d.x, sr.w[0], r);
+      r = f4fma(d.y, sr.w[1], r);
+      r = f4fma(d.z, sr.w[2], r);
+      r = f4fma(d.w, sr.w[3], r);
+    }
+    if (s.add != nullptr) r = f4add(r, ld4(s.add + static_cast<size_t>(p) * s.ld_add + 4 * v));
+    return r;
+  }
+  if (KIND == 2) return upadj_read(s.g, s.ld, s.coff, H, W, i, j, v, s.bilinear);
+  // KIND == 3: the item carries the 4 logit gradients of the pixel (k_head_dlogit); head_grad() expands them when consumed
+  return ld4(s.dl4 + static_cast<size_t>(p) * 4);
 }
 // head source: gradient w.r.t. the last activation = sum_k dl[k] * w_head[k][c]
 __device__ __forceinline__ float4 head_grad(const SrcRegs& sr, float4 d) {
@@ -595,28 +559,16 @@ __device__ __forceinline__ float4 head_grad(const SrcRegs& sr, float4 d) {
   r = f4fma(d.w, sr.w[3], r);
   return r;
 }
-template <int KIND>
-__device__ __forceinline__ float4 grad_finish(const GradSrc& s, const SrcRegs& sr, int H, int W, int i, int j, int v,
-                                              const RedItem& it) {
-  if (KIND == 1) {
-    float4 r = fold_finish(s.g, s.ld, s.coff, H, W, i, j, v, it.g);
-    if (s.ds != nullptr) {   // + the input gradient of the next level's 1x1 skip conv, computed on the fly
-      r = f4fma(it.d.x, sr.w[0], r);
-      r = f4fma(it.d.y, sr.w[1], r);
-      r = f4fma(it.d.z, sr.w[2], r);
-      r = f4fma(it.d.w, sr.w[3], r);
-    } else if (s.add != nullptr) r = f4add(r, it.d);
-    return r;
-  }
-  if (KIND == 3) return head_grad(sr, it.g);
-  return it.g;
-}
 __device__ __forceinline__ float4 lrelu_bwd4(float4 y, float4 g) {
   return make_float4(y.x > 0.f ? g.x : kLreluSlope * g.x, y.y > 0.f ? g.y : kLreluSlope * g.y,
                      y.z > 0.f ? g.z : kLreluSlope * g.z, y.w > 0.f ? g.w : kLreluSlope * g.w);
 }
 
 // ------------------------------------------------------------------------------------------------ BN(+LReLU) backward
+struct RedItem {
+  float4 x, g;  // raw conv output, gradient w.r.t. the BN(+act) output (head source: the pixel's logit gradients)
+};
+typedef RedItem BwdItem;
 // dl4[p] = dout[k][p] * o[k][p] * (1 - o[k][p]) for k < K (else 0): sigmoid' folded into the logit gradient once per pixel
 __global__ void k_head_dlogit(const float* __restrict__ dout, const float* __restrict__ outv, int K, int npix,
                               float* __restrict__ dl4, int sigmoid) {
@@ -691,12 +643,11 @@ __global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bw
         RedItem it;
         const int i = p / W, j = p - i * W;
         it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-        grad_load<KIND>(src, H, W, p, i, j, v, it);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v);
         return it;
       },
-      [&](int p, const RedItem& it) {
-        const int i = p / W, j = p - i * W;
-        float4 dz = grad_finish<KIND>(src, sr, H, W, i, j, v, it);
+      [&](int, const RedItem& it) {
+        float4 dz = KIND == 3 ? head_grad(sr, it.g) : it.g;
         if (act) dz = lrelu_bwd4(bn_apply(cf, it.x), dz);
         acc[0] = f4add(acc[0], dz);
         acc[1] = f4mla(dz, bn_xhat(cf, it.x), acc[1]);
@@ -742,11 +693,11 @@ __global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const f
         BwdItem it;
         const int i = p / W, j = p - i * W;
         it.x = ld4(raw + static_cast<size_t>(p) * ld_raw + 4 * v);
-        grad_load<KIND>(src, H, W, p, i, j, v, it);
+        it.g = grad_read<KIND>(src, sr, H, W, p, i, j, v);
         return it;
       },
       [&](int p, const BwdItem& it) {
-        float4 dz = grad_finish<KIND>(src, sr, H, W, p / W, p - (p / W) * W, v, it);
+        float4 dz = KIND == 3 ? head_grad(sr, it.g) : it.g;
         const float4 y = bn_apply(cf, it.x);
         if constexpr (KIND == 3) {
           const float4 u = act ? lrelu4(y) : y;
@@ -838,14 +789,12 @@ __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict_
                  RedItem it;
                  const int i = p / W, j = p - i * W;
                  it.x = ld4(pcat + (static_cast<size_t>(i + 1) * Wp + (j + 1)) * ld + 4 * v);
-                 it.g = fold_interior(gp, ld, 0, W, i, j, v);
+                 it.g = fold_read(gp, ld, 0, H, W, i, j, v);
                  return it;
                },
-               [&](int p, const RedItem& it) {
-                 const int i = p / W, j = p - i * W;
-                 const float4 g = fold_finish(gp, ld, 0, H, W, i, j, v, it.g);
-                 acc[0] = f4add(acc[0], g);
-                 acc[1] = f4mla(g, cat_xhat(cf, it.x), acc[1]);
+               [&](int, const RedItem& it) {
+                 acc[0] = f4add(acc[0], it.g);
+                 acc[1] = f4mla(it.g, cat_xhat(cf, it.x), acc[1]);
                });
   double* const dst[2] = {bwd, bwd + bn_cat.C * kAccS};
   const int wid[2] = {bn_cat.C, bn_cat.C};
@@ -872,18 +821,16 @@ __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__
                  RedItem it;
                  const int i = p / W, j = p - i * W;
                  it.x = ld4(pcat + (static_cast<size_t>(i + 1) * Wp + (j + 1)) * ld + 4 * v);
-                 it.g = fold_interior(gp, ld, 0, W, i, j, v);
+                 it.g = fold_read(gp, ld, 0, H, W, i, j, v);
                  return it;
                },
                [&](int p, const RedItem& it) {
-                 const int i = p / W, j = p - i * W;
-                 const float4 g = fold_finish(gp, ld, 0, H, W, i, j, v, it.g);
                  const float4 xh = cat_xhat(cf, it.x);
                  float4 dx;
-                 dx.x = cf.scale.x * (g.x - m1.x - xh.x * m2.x);
-                 dx.y = cf.scale.y * (g.y - m1.y - xh.y * m2.y);
-                 dx.z = cf.scale.z * (g.z - m1.z - xh.z * m2.z);
-                 dx.w = cf.scale.w * (g.w - m1.w - xh.w * m2.w);
+                 dx.x = cf.scale.x * (it.g.x - m1.x - xh.x * m2.x);
+                 dx.y = cf.scale.y * (it.g.y - m1.y - xh.y * m2.y);
+                 dx.z = cf.scale.z * (it.g.z - m1.z - xh.z * m2.z);
+                 dx.w = cf.scale.w * (it.g.w - m1.w - xh.w * m2.w);
                  st4(dcat + static_cast<size_t>(p) * C + 4 * v, dx);
                });
 }
@@ -938,46 +885,33 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
     bv[n] = (n < N && b != nullptr) ? b[n] : 0.f;
   }
   float4 s1 = f4zero(), s2 = f4zero();
-  // every thread runs the same number of trips so that the shuffles stay warp-convergent; U pixels per lane group and trip,
-  // all loads issued before the first dot product (one dependent load per trip left these kernels latency-bound)
-  constexpr int U = 4;
-  const int per_trip = gridDim.x * PPB * U;
-  const int trips = (npix + per_trip - 1) / per_trip;
+  // every thread runs the same number of trips so that the shuffles stay warp-convergent
+  const int trips = (npix + gridDim.x * PPB - 1) / (gridDim.x * PPB);
   for (int t = 0; t < trips; ++t) {
-    const int pbase = (t * gridDim.x + blockIdx.x) * PPB * U + slot;
-    float4 xv[U];
+    const int p = (t * gridDim.x + blockIdx.x) * PPB + slot;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < npix) {
+      const int i = p / W, j = p - i * W;
+      const float4 xv = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = pbase + u * PPB;
-      xv[u] = f4zero();
-      if (p < npix) {
-        const int i = p / W, j = p - i * W;
-        xv[u] = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
-      }
+      for (int n = 0; n < 4; ++n) acc[n] = f4dot(xv, wv[n]);
     }
+    for (int o = VL >> 1; o > 0; o >>= 1) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = pbase + u * PPB;
-      float acc[4];
+      for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    }
+    if (p < npix && v == 0) {
+      float o4[4];
 #pragma unroll
-      for (int n = 0; n < 4; ++n) acc[n] = f4dot(xv[u], wv[n]);
-      for (int o = VL >> 1; o > 0; o >>= 1) {
-#pragma unroll
-        for (int n = 0; n < 4; ++n) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-      }
-      if (p < npix && v == 0) {
-        float o4[4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) o4[n] = n < N ? acc[n] + bv[n] : 0.f;
-        if (mode == 0) {
-          if (N == 4) st4(y + static_cast<size_t>(p) * 4, make_float4(o4[0], o4[1], o4[2], o4[3]));
-          else for (int n = 0; n < N; ++n) y[static_cast<size_t>(p) * N + n] = o4[n];
-          const float4 ov = make_float4(o4[0], o4[1], o4[2], o4[3]);
-          s1 = f4add(s1, ov);
-          s2 = f4mla(ov, ov, s2);
-        } else {
-          for (int n = 0; n < N; ++n) y[static_cast<size_t>(n) * npix + p] = (mode == 1) ? 1.f / (1.f + expf(-o4[n])) : o4[n];
-        }
+      for (int n = 0; n < 4; ++n) o4[n] = n < N ? acc[n] + bv[n] : 0.f;
+      if (mode == 0) {
+        if (N == 4) st4(y + static_cast<size_t>(p) * 4, make_float4(o4[0], o4[1], o4[2], o4[3]));
+        else for (int n = 0; n < N; ++n) y[static_cast<size_t>(p) * N + n] = o4[n];
+        const float4 ov = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        s1 = f4add(s1, ov);
+        s2 = f4mla(ov, ov, s2);
+      } else {
+        for (int n = 0; n < N; ++n) y[static_cast<size_t>(n) * npix + p] = (mode == 1) ? 1.f / (1.f + expf(-o4[n])) : o4[n];
       }
     }
   }
@@ -992,7 +926,7 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
                        int W, float* y, int mode, double* stats, cudaStream_t s, int cw) {
   const int PPB = 256 / (C / 4);
-  long long nb = (static_cast<long long>(H) * W + 4 * PPB - 1) / (4 * PPB);   // 4 pixels per lane group and trip
+  long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
   if (nb > 148 * 8) nb = 148 * 8;
   launch_red(k_skinny_fwd, static_cast<int>(nb), 256, 2 * 256 * sizeof(float4) + 2 * 4 * sizeof(double), s, x, ldx, x_rs, w, b, C, N, H, W,
                   y, mode, stats, cw > 0 ? cw : C);
