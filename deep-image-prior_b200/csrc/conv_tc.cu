@@ -54,11 +54,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   uint8_t* patch_base = smem;
   uint8_t* stage_base = smem + 2 * patch_alloc;
   uint8_t* staging = stage_base + p.stages * stage_bytes;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(staging + p.n_chunks * kChunkBytes);
+  const int pair = p.pair;                                  // two tiles per iteration (see TcConvParams::pair)
+  const int stg_chunks = pair ? 2 : p.n_chunks;             // pair mode stores a tile in two 64-channel halves
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(staging + stg_chunks * kChunkBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_x * p.tiles_y;
+  const int num_tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y;   // pair mode: work items are tile pairs
   const int kb_per_tile = p.kh * p.kw * p.kblocks;
   // Cluster of `csize` CTAs: every CTA works on its own tile, all of them walk the identical (tap, k-block) sequence, and
   // each CTA fetches 1/csize of the weight tile and multicasts it to the whole cluster (weights are the same for all
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   const int tile_stride = gridDim.x / n_split;
   const int n_iters = (num_tiles + tile_stride - 1) / tile_stride;
   const int tile0 = n_split > 1 ? blockIdx.x / n_split : (blockIdx.x / csize) * csize + crank;  // first tile; stride tile_stride
-  const uint32_t acc_cols = (p.n_mma + 31) & ~31;  // column stride between the two accumulators
+  const uint32_t tile_cols = (p.n_mma + 31) & ~31;              // TMEM columns of one tile's accumulator
+  const uint32_t acc_cols = pair ? 2 * tile_cols : tile_cols;   // column stride between the two accumulator buffers
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       for (int it = 0; it < n_iters; ++it) {
         const int tile = tile0 + it * tile_stride;
         const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-        const int x0 = tx * p.bw, y0 = ty * p.bh;
+        const int x0 = tx * p.bw, y0 = ty * p.bh * (pair ? 2 : 1);
         if (p.patch) {
           // 3x3 stride-1: ONE (bw+2) x (bh+2) input patch per 32-channel block serves all nine taps (the MMA warp
           // addresses tap (r,s) as the same patch shifted by r*pw+s rows); only the weight tiles stream per tap.
@@ -226,6 +229,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           // by scripts/exp_desc_shift.py), so a tap is just an address offset into the patch.
           const uint32_t ahi = desc_hi(p.pw * 128, 2);
           const uint32_t row_step = static_cast<uint32_t>(p.pw) * 8;  // one patch row, in 16-byte units
+          const uint32_t pair_off = row_step * static_cast<uint32_t>(p.bh);   // second tile of a pair: bh patch rows further down
+          const uint32_t tmem_d1 = tmem_d + tile_cols;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&ctl->a_full[ab], aphase);
             tc_fence_after();
@@ -257,13 +262,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                         mma_tf32_lohi(tmem_d, a_lo[t] + 2, ahi, bt + 2, bhi, idesc, 1u);
                         mma_tf32_lohi(tmem_d, a_lo[t] + 4, ahi, bt + 4, bhi, idesc, 1u);
                         mma_tf32_lohi(tmem_d, a_lo[t] + 6, ahi, bt + 6, bhi, idesc, 1u);
+                        if (pair) {   // same weight tile, the lower tile of the pair
+                          const uint32_t a1 = a_lo[t] + pair_off;
+                          mma_tf32_lohi(tmem_d1, a1, ahi, bt, bhi, idesc, t == 0 ? accf : 1u);
+                          mma_tf32_lohi(tmem_d1, a1 + 2, ahi, bt + 2, bhi, idesc, 1u);
+                          mma_tf32_lohi(tmem_d1, a1 + 4, ahi, bt + 4, bhi, idesc, 1u);
+                          mma_tf32_lohi(tmem_d1, a1 + 6, ahi, bt + 6, bhi, idesc, 1u);
+                        }
                       }
                     }
                   } else {
                     for (int t = 0; t < nt; ++t)
-                      for (int k = 0; k < nmma; ++k)
+                      for (int k = 0; k < nmma; ++k) {
                         mma_tf32_lohi(tmem_d, a_lo[t] + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi, idesc,
                                       (t | k) > 0 ? 1u : accf);
+                        if (pair)
+                          mma_tf32_lohi(tmem_d1, a_lo[t] + pair_off + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi,
+                                        idesc, (t | k) > 0 ? 1u : accf);
+                      }
                   }
                 }
                 if (!(p.dbg_flags & 64)) {
@@ -324,6 +340,94 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     uint32_t acc_phase = 0;
     double stat_s1 = 0.0, stat_s2 = 0.0;
     const int bw_shift = 31 - __clz(p.bw);  // tile widths are powers of two
+    if (pair) {
+      // ------------------------------------------------------------------ pair mode (n_mma == 128, n_split == 1)
+      // Per iteration: two tiles (upper / lower) x two 64-channel halves.  A half = 2 chunks of the staging buffer: TMEM ->
+      // (+bias) -> swizzled smem -> TMA store; BN statistics of those 64 channels are taken from the staged copy by 128
+      // threads = 64 channels x 2 row halves.  A thread therefore owns two channels (one per half) of one row half.
+      double ps1[2] = {0.0, 0.0}, ps2[2] = {0.0, 0.0};
+      const int cl = et & 63, rh = et >> 6;
+      for (int it = 0; it < n_iters; ++it) {
+        const int tile = tile0 + it * tile_stride;
+        const int tx = tile % p.tiles_x, typ = tile / p.tiles_x;
+        const int x0 = tx * p.bw;
+        mbar_wait(&ctl->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        for (int sub = 0; sub < 2; ++sub) {
+          const int y0 = (2 * typ + sub) * p.bh;
+          const uint32_t taddr = tmem_base + acc * acc_cols + sub * tile_cols + (static_cast<uint32_t>(ew * 32) << 16);
+          for (int half = 0; half < 2; ++half) {
+            if (et == 0) tma_store_wait_read0();   // the previous half's TMA store has finished reading the staging buffer
+            named_bar_sync(1, 128);                // (and every thread is past its statistics pass over it)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = half * 2 + jj;
+              uint32_t v[32];
+              tmem_ld_32x32(taddr + j * 32, v);
+              tmem_ld_wait();
+              uint8_t* rowp = staging + jj * kChunkBytes + row * 128;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 o;
+                o.x = __uint_as_float(v[q * 4 + 0]) + ctl->bias[j * 32 + q * 4 + 0];
+                o.y = __uint_as_float(v[q * 4 + 1]) + ctl->bias[j * 32 + q * 4 + 1];
+                o.z = __uint_as_float(v[q * 4 + 2]) + ctl->bias[j * 32 + q * 4 + 2];
+                o.w = __uint_as_float(v[q * 4 + 3]) + ctl->bias[j * 32 + q * 4 + 3];
+                *reinterpret_cast<float4*>(rowp + ((q ^ (row & 7)) << 4)) = o;
+              }
+            }
+            if (sub == 1 && half == 1) {   // both accumulators of this buffer drained -> back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (et == 0) {
+              for (int jj = 0; jj < 2; ++jj) tma_store_3d(&p.tmD, staging + jj * kChunkBytes, (half * 2 + jj) * 32, x0, y0);
+              tma_store_commit();
+            }
+            if (p.stats != nullptr) {
+              const int jj = cl >> 5, q = (cl & 31) >> 2, e = cl & 3;
+              const uint8_t* cb = staging + jj * kChunkBytes + e * 4;
+              float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+              const int m0 = rh * 64;
+              if (x0 + p.bw <= p.out_w && y0 + p.bh <= p.out_h) {
+#pragma unroll 8
+                for (int m = m0; m < m0 + 64; m += 2) {
+                  const float x = *reinterpret_cast<const float*>(cb + m * 128 + ((q ^ (m & 7)) << 4));
+                  const float y = *reinterpret_cast<const float*>(cb + (m + 1) * 128 + ((q ^ ((m + 1) & 7)) << 4));
+                  a0 += x; b0 = fmaf(x, x, b0);
+                  a1 += y; b1 = fmaf(y, y, b1);
+                }
+              } else {
+                for (int m = m0; m < m0 + 64; ++m) {
+                  const int py = m >> bw_shift, px = m & (p.bw - 1);
+                  if (x0 + px < p.out_w && y0 + py < p.out_h) {
+                    const float x = *reinterpret_cast<const float*>(cb + m * 128 + ((q ^ (m & 7)) << 4));
+                    a0 += x; b0 = fmaf(x, x, b0);
+                  }
+                }
+              }
+              ps1[half] += static_cast<double>(a0 + a1);
+              ps2[half] += static_cast<double>(b0 + b1);
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (p.stats != nullptr) {
+        const int rep = (blockIdx.x % kAccR) * kAccLine;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c = half * 64 + cl;
+          if (c < p.stats_ld) {
+            atomicAdd(&p.stats[c * kAccStride + rep], ps1[half]);
+            atomicAdd(&p.stats[(p.stats_ld + c) * kAccStride + rep], ps2[half]);
+          }
+        }
+      }
+    } else
     for (int it = 0; it < n_iters; ++it) {
       const int tile = tile0 + it * tile_stride;
       const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -395,7 +499,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.stats != nullptr && et < p.n_mma && n_off + et < p.stats_ld) {
+    if (!pair && p.stats != nullptr && et < p.n_mma && n_off + et < p.stats_ld) {
       const int rep = (blockIdx.x % kAccR) * kAccLine;
       atomicAdd(&p.stats[(n_off + et) * kAccStride + rep], stat_s1);
       atomicAdd(&p.stats[(p.stats_ld + n_off + et) * kAccStride + rep], stat_s2);
@@ -590,8 +694,8 @@ size_t tc_conv_smem_bytes(const TcConvParams& p) {
   const size_t b_bytes = (static_cast<size_t>(p.n_mma) * 128 + 1023) & ~size_t(1023);
   const size_t patch = p.patch ? ((static_cast<size_t>(p.pw) * p.ph * 128 + 1023) & ~size_t(1023)) : 0;
   const size_t tps = p.patch ? (p.tps < 1 ? 1 : p.tps) : 1;
-  return 1024 + 2 * patch + p.stages * ((p.patch ? 0 : kABytes) + tps * b_bytes) + static_cast<size_t>(p.n_chunks) * kChunkBytes +
-         sizeof(SmemCtl);
+  return 1024 + 2 * patch + p.stages * ((p.patch ? 0 : kABytes) + tps * b_bytes) +
+         static_cast<size_t>(p.pair ? 2 : p.n_chunks) * kChunkBytes + sizeof(SmemCtl);
 }
 size_t tc_wgrad_smem_bytes(const TcWgradParams& p) {
   const size_t chunk = static_cast<size_t>(p.kp) * 128;
@@ -606,8 +710,9 @@ cudaError_t tc_kernels_init() {
 }
 
 cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
-  const int tiles = p.tiles_x * p.tiles_y;
+  const int tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y;
   const int cs = p.csize < 1 ? 1 : p.csize;
+  if (p.pair && (!p.patch || cs != 1 || p.n_split > 1 || p.n_mma != 128)) return cudaErrorInvalidValue;
   int grid = (tiles + cs - 1) / cs * cs;
   const int cap = num_sms / cs * cs;
   if (grid > cap) grid = cap;

@@ -30,6 +30,9 @@ struct TcConvParams {
   int pw, ph;              // patch extent in pixels
   int tps;                 // patch mode: filter taps per weight stage (1..3; 3 = one filter row per barrier round)
   int csize;               // thread-block cluster size (1, 2, 4): the weight tile is multicast across the cluster
+  int pair;                // patch mode, n_mma == 128: every CTA iteration computes TWO vertically adjacent tiles from one
+                           // (bw+2) x (2*bh+2) input patch and ONE stream of weight tiles (two accumulators per TMEM buffer):
+                           // half the L2->SM weight traffic and half the barrier rounds per FLOP
   int n_split;             // 1, 2 or 4 CTAs per pixel tile, each computing n_mma = N / n_split output channels (small levels)
   const float* bias;       // [n_mma] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr

@@ -34,6 +34,7 @@ CASES = [
     (128, 3, 1, 256, 256, 0),     # >= 2 waves of tiles: cluster multicast of the weight tile
     (132, 3, 1, 200, 312, 4),
     (128, 1, 1, 256, 512, 0),
+    (128, 3, 1, 270, 150, 0),     # tile-pair mode (>= 2 x 148 tiles of 8 x 16) with ragged right / bottom tiles and an odd tile-row count
 ]
 
 
@@ -66,7 +67,7 @@ def test_fprop(case, prec):
 
 @pytest.mark.parametrize("prec", [1, 0])
 @pytest.mark.parametrize("case", [(128, 3, 32, 32, 0), (132, 3, 32, 32, 4), (128, 1, 32, 32, 0), (128, 3, 10, 20, 0),
-                                  (132, 3, 2, 2, 4), (128, 3, 64, 128, 0), (128, 3, 254, 254, 0), (132, 3, 200, 312, 4)])
+                                  (132, 3, 2, 2, 4), (128, 3, 64, 128, 0), (128, 3, 254, 254, 0), (132, 3, 200, 312, 4), (128, 3, 268, 148, 0)])
 def test_dgrad(case, prec):
     import dip_engine as de
     C, k, h, w_, rot = case
