@@ -418,6 +418,14 @@ def run_ours(args):
     vb_ms, _ = timed(lambda: optimize("adam", get_params("net", net, z0), verbatim_closure, LR, vb_steps))
     vb_value = mg.aggregate_rate(vb_steps, vb_ms / 1000.0, world)
 
+    # the same closure logic with device-side metrics (utils/fast_closure.py): one 32-byte read-back per iteration
+    from utils.fast_closure import DenoisingClosure
+    fast = DenoisingClosure(net, z0, target, clean_h.to(dev), reg_noise_std=SIGMA_REG, exp_weight=0.99, show_every=100, mse=mse)
+    fv_steps = max(args.steps, 200)
+    optimize("adam", get_params("net", net, z0), fast, LR, 5)
+    fv_ms, _ = timed(lambda: optimize("adam", get_params("net", net, z0), fast, LR, fv_steps))
+    fv_value = mg.aggregate_rate(fv_steps, fv_ms / 1000.0, world)
+
     # ---- 5. the reference's own GPU path: same module tree on stock torch.cuda + cuDNN ------------------------------
     lib_value = None
     if rank == 0:
@@ -529,6 +537,10 @@ def run_ours(args):
                                      "api": "same, with the verbatim denoising.ipynb c10 closure: EMA out_avg, 3 x PSNR on "
                                             "D2H copies of the 3x512x512 output, last_net = [x.detach().cpu() ...] of the 112 "
                                             "parameters every iteration"},
+            "e2e_fast_verbatim_closure": {"value": fv_value, "unit": "it/s", "steps": fv_steps,
+                                          "api": "utils.fast_closure.DenoisingClosure: the c10 logic (EMA, PSNR_noisy / PSNR_gt / "
+                                                 "PSNR_gt_sm, back-tracking snapshot) with device-side PSNRs (dip_loss_mse) and a "
+                                                 "device-side parameter snapshot; one 32-byte read-back per iteration"},
             "gpu_library_baseline": {"value": lib_value, "unit": "it/s", "n_gpus": 1,
                                      "what": "the same module tree executed by stock torch.cuda + cuDNN (cudnn.benchmark=True, "
                                              "TF32 convolutions = torch default), lean closure, torch.optim.Adam -- the "

@@ -60,8 +60,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y;   // pair mode: work items are tile pairs
-  const int kb_per_tile = p.kh * p.kw * p.kblocks;
+  const int tiles_pp = p.tiles_x * p.tiles_y;                     // tiles per sub-pixel phase (nphase > 0)
+  const int num_tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2)   // pair mode: work items are tile pairs
+                               : p.nphase > 0 ? tiles_pp * p.nphase : tiles_pp;
   // Cluster of `csize` CTAs: every CTA works on its own tile, all of them walk the identical (tap, k-block) sequence, and
   // each CTA fetches 1/csize of the weight tile and multicasts it to the whole cluster (weights are the same for all
   // tiles) -> L2->SM traffic per k-block drops from 16+16 KB to 16+16/csize KB.  Tiles past the end are harmless
@@ -168,9 +169,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           }
           continue;
         }
-        for (int r = 0; r < p.kh; ++r) {
-          for (int s = 0; s < p.kw; ++s) {
-            const int ix = p.offx + s, iy = p.offy + r;  // tap offset in input coordinates
+        // per-tap mode: one phase (kh x kw taps at offx / offy) or the phase this work item belongs to
+        int kh = p.kh, kw = p.kw, offx = p.offx, offy = p.offy, tap0 = 0, px0 = x0, py0 = y0;
+        if (p.nphase > 0) {
+          if (tile >= num_tiles) break;
+          const TcConvParams::Phase& q = p.phs[tile / tiles_pp];
+          const int t = tile % tiles_pp;
+          kh = q.kh; kw = q.kw; offx = q.offx; offy = q.offy; tap0 = q.tap0;
+          px0 = (t % p.tiles_x) * p.bw; py0 = (t / p.tiles_x) * p.bh;
+        }
+        for (int r = 0; r < kh; ++r) {
+          for (int s = 0; s < kw; ++s) {
+            const int ix = offx + s, iy = offy + r;  // tap offset in input coordinates
+            const int x0 = px0, y0 = py0;
             int cpx, cx, cpy, cy;
             if (p.stride == 1) {
               cpx = 0; cx = x0 + ix; cpy = 0; cy = y0 + iy;
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
               // input coordinate = 2*out + i  ->  (parity, half) = (i & 1, out + (i >> 1)); offsets are >= 0 here
               cpx = ix & 1; cx = x0 + (ix >> 1); cpy = iy & 1; cy = y0 + (iy >> 1);
             }
-            const int tap = r * p.kw + s;
+            const int tap = tap0 + r * kw + s;
             for (int kb = 0; kb < p.kblocks; ++kb) {
               mbar_wait(&ctl->empty[stage], phase ^ 1);
               uint8_t* sa = stage_base + stage * stage_bytes;
@@ -219,6 +230,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       int ab = 0;
       uint32_t aphase = 0;
       for (int it = 0; it < n_iters; ++it) {
+        int kb_per_tile = p.kh * p.kw * p.kblocks;
+        if (p.nphase > 0) {
+          const int tile = tile0 + it * tile_stride;
+          if (tile >= num_tiles) break;
+          kb_per_tile = p.phs[tile / tiles_pp].kh * p.phs[tile / tiles_pp].kw * p.kblocks;
+        }
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
@@ -430,7 +447,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     } else
     for (int it = 0; it < n_iters; ++it) {
       const int tile = tile0 + it * tile_stride;
-      const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+      int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+      int opx = 0, opy = 0;
+      if (p.nphase > 0) {
+        if (tile >= num_tiles) break;
+        const int t = tile % tiles_pp;
+        tx = t % p.tiles_x; ty = t / p.tiles_x;
+        opx = p.phs[tile / tiles_pp].opx; opy = p.phs[tile / tiles_pp].opy;
+      }
       const int x0 = tx * p.bw, y0 = ty * p.bh;
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -467,7 +491,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (et == 0) {
-        for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, n_off + j * 32, x0, y0);
+        if (p.nphase > 0)
+          for (int j = 0; j < p.n_chunks; ++j) tma_store_5d(&p.tmD, staging + j * kChunkBytes, n_off + j * 32, opx, x0, opy, y0);
+        else
+          for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, n_off + j * 32, x0, y0);
         tma_store_commit();
       }
       if (p.stats != nullptr && et < p.n_mma) {
@@ -710,8 +737,9 @@ cudaError_t tc_kernels_init() {
 }
 
 cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
-  const int tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y;
+  const int tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y * (p.nphase > 0 ? p.nphase : 1);
   const int cs = p.csize < 1 ? 1 : p.csize;
+  if (p.nphase > 0 && (p.patch || cs != 1 || p.nphase > 4)) return cudaErrorInvalidValue;
   if (p.pair && (!p.patch || cs != 1 || p.n_split > 1 || p.n_mma != 128)) return cudaErrorInvalidValue;
   int grid = (tiles + cs - 1) / cs * cs;
   const int cap = num_sms / cs * cs;

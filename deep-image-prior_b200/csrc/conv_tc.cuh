@@ -34,6 +34,13 @@ struct TcConvParams {
                            // (bw+2) x (2*bh+2) input patch and ONE stream of weight tiles (two accumulators per TMEM buffer):
                            // half the L2->SM weight traffic and half the barrier rounds per FLOP
   int n_split;             // 1, 2 or 4 CTAs per pixel tile, each computing n_mma = N / n_split output channels (small levels)
+  // Stride-2 input gradient as its 4 sub-pixel phases in ONE launch (nphase = 4, per-tap mode): output pixel (2i+a, 2j+b)
+  // of the padded input gradient only receives the taps r = a (mod 2), s = b (mod 2), i.e. a (2-a) x (2-b) stride-1
+  // correlation over dY.  Work item = (phase, tile of the (h+1) x (w+1) phase grid); tmD is then the 5-D parity view
+  // (C, px, X, py, Y) of the padded gradient buffer and the tile is stored at parity (opx, opy).  nphase = 0: one phase
+  // described by kh / kw / offx / offy above, 3-D tmD.
+  int nphase;
+  struct Phase { int kh, kw, offx, offy, tap0, opx, opy; } phs[4];   // tap0: first packed weight tap of the phase
   const float* bias;       // [n_mma] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
   int stats_ld;

@@ -218,6 +218,7 @@ struct ConvOp {
   float* wacc = nullptr;   // plan-owned weight-gradient accumulator [tap][128][c_pad] (tensor-core path; zeroed once per backward)
   // dgrad: dg_in [dg_in_h][dg_in_w][128] -> dg_out [dg_out_h][dg_out_w][C]
   bool has_dgrad = false;
+  bool dg_s2 = false;   // tensor-core dgrad of a stride-2 3x3 conv as its 4 sub-pixel phases (dg_in = dY [h][w][128], not zero-stuffed)
   const float* dg_in = nullptr; int dg_in_h = 0, dg_in_w = 0;
   float* dg_out = nullptr; int dg_out_h = 0, dg_out_w = 0; int dg_off = 0;
   // wgrad: dY [wg_h][wg_w][128]
@@ -283,7 +284,32 @@ struct ConvOp {
     fit_stages(fp);
     }
     // ---- dgrad
-    if (has_dgrad) {
+    if (has_dgrad && dg_s2) {
+      // phase grid: (dg_out_h / 2) x (dg_out_w / 2) positions per parity class of the padded gradient
+      const int gh = dg_out_h / 2, gw = dg_out_w / 2;
+      pick_tile(gw, gh, &bw, &bh);
+      dg = TcConvParams{};
+      DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+      dg.csize = 1; dg.tps = 1;
+      dg.n_split = pick_nsplit(4 * ((gw + bw - 1) / bw) * ((gh + bh - 1) / bh), crows);
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.n_split));
+      DIP_CHECK(map_act5(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, 2, bw, bh));   // parity view of the padded gradient
+      dg.tiles_x = (gw + bw - 1) / bw; dg.tiles_y = (gh + bh - 1) / bh;
+      dg.bw = bw; dg.bh = bh; dg.out_w = gw; dg.out_h = gh;
+      dg.kh = dg.kw = 2; dg.stride = 1; dg.offx = dg.offy = -1;
+      dg.nphase = 4;
+      int t0 = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          TcConvParams::Phase& q = dg.phs[a * 2 + b];
+          q.kh = 2 - a; q.kw = 2 - b; q.offy = a == 0 ? -1 : 0; q.offx = b == 0 ? -1 : 0; q.tap0 = t0; q.opx = b; q.opy = a;
+          t0 += q.kh * q.kw;
+        }
+      dg.kblocks = 4; dg.tail_mmas = 4;
+      dg.n_mma = crows / dg.n_split; dg.n_chunks = (dg.n_mma + 31) / 32;
+      dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
+      fit_stages(dg);
+    } else if (has_dgrad) {
       pick_tile(dg_out_w, dg_out_h, &bw, &bh);
       dg = TcConvParams{};
       if (k == 3 && patch_ok) {
@@ -405,7 +431,14 @@ struct PackEntry {
   const float* w; float* dst_f; float* dst_d;
   int N, C, k, rot, n_rows, c_pad, c_rows;
   int Ctot, coff;   // weight has Ctot input channels; this entry packs engine channels [coff, coff + C)
+  int s2;           // dgrad pack of a stride-2 3x3 conv: taps in sub-pixel phase order (kS2Taps), not flipped
 };
+// packed tap t of the 4-phase stride-2 dgrad -> filter tap r * 3 + s.  Phase (a, b) = parity of the padded gradient pixel;
+// its taps are r in {2, 0} (a = 0: dY rows i-1, i) or {1} (a = 1), same for s.  Phases in the order (0,0) (0,1) (1,0) (1,1).
+__constant__ int kS2Taps[9] = {2 * 3 + 2, 2 * 3 + 0, 0 * 3 + 2, 0 * 3 + 0,   // (0,0): (r', s') = (0,0) (0,1) (1,0) (1,1)
+                               2 * 3 + 1, 0 * 3 + 1,                           // (0,1): s = 1
+                               1 * 3 + 2, 1 * 3 + 0,                           // (1,0): r = 1
+                               1 * 3 + 1};                                     // (1,1)
 __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
   pdl_enter();
   const PackEntry e = tab[blockIdx.y];
@@ -421,7 +454,7 @@ __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
     } else {
       const long long j = i - nf;
       const int n = (int)(j % 128), c = (int)((j / 128) % e.c_rows), tapf = (int)(j / (128LL * e.c_rows));
-      const int tap = taps - 1 - tapf;
+      const int tap = e.s2 ? kS2Taps[tapf] : taps - 1 - tapf;
       float v = 0.f;
       if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
       e.dst_d[j] = v;
@@ -780,7 +813,10 @@ static int build_plan(dip_plan* P, Arena& A) {
     a.out = v.raw_d1; a.out_h = v.h; a.out_w = v.w; a.stats = v.bn_d1.fwd;
     a.has_dgrad = l > 0 || d.input_grad != 0;
     a.dg_ld = v.Cin;   // level 0: stored depth (>= the conv's real input depth)
-    a.dg_in = v.ZS; a.dg_in_h = v.H; a.dg_in_w = v.W; a.dg_out = v.dPin; a.dg_out_h = v.H + 2; a.dg_out_w = v.W + 2; a.dg_off = -2;
+    a.dg_s2 = prec == DIP_PRECISION_TF32 && getenv("DIP_ZERO_STUFF") == nullptr;   // A/B switch: the old zero-stuffed stride-1 dgrad
+    if (a.dg_s2) { a.dg_in = v.dRaw_d1; a.dg_in_h = v.h; a.dg_in_w = v.w; }
+    else { a.dg_in = v.ZS; a.dg_in_h = v.H; a.dg_in_w = v.W; }
+    a.dg_out = v.dPin; a.dg_out_h = v.H + 2; a.dg_out_w = v.W + 2; a.dg_off = -2;
     a.wg_dy = v.dRaw_d1; a.wg_h = v.h; a.wg_w = v.w;
     // down2: P_d1 -> raw_d2
     ConvOp& b = v.d2;
@@ -886,7 +922,7 @@ static int upload_tables(dip_plan* P) {
     PackEntry e{};
     e.w = P->params[op->p_w]; e.dst_f = op->do_fprop ? op->wp_f : nullptr; e.dst_d = op->has_dgrad ? op->wp_d : nullptr;
     e.N = op->N; e.C = op->C; e.k = op->k; e.rot = op->rot; e.n_rows = op->N; e.c_pad = op->c_pad; e.c_rows = op->crows;
-    e.Ctot = op->Ctot; e.coff = op->coff;
+    e.Ctot = op->Ctot; e.coff = op->coff; e.s2 = op->dg_s2 ? 1 : 0;
     pk.push_back(e);
   }
   DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
@@ -1197,7 +1233,8 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(conv_backward(P, v.d2, true, prec, s));
   nl += wl + 1;
   const bool d1_dgrad = l > 0 || P->desc.input_grad != 0;
-  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, d1_dgrad ? v.ZS : nullptr, s, nl));
+  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1,
+                   (d1_dgrad && !v.d1.dg_s2) ? v.ZS : nullptr, s, nl));
   DIP_CHECK(conv_backward(P, v.d1, d1_dgrad, prec, s));
   nl += wl + (d1_dgrad ? 1 : 0);
   DIP_CUDA(cudaGetLastError());
@@ -1670,6 +1707,32 @@ int dip_op_conv_dgrad(const void* dy, int dy_h, int dy_w, const void* w, int N, 
   op.dg_in = (const float*)dy; op.dg_in_h = dy_h; op.dg_in_w = dy_w;
   op.dg_out = (float*)dx; op.dg_out_h = dx_h; op.dg_out_w = dx_w; op.dg_off = -(k - 1);
   if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
+  return op.run_dgrad(precision, s);
+}
+int dip_op_conv_dgrad_s2(const void* dy, int dy_h, int dy_w, const void* w, int N, int C, int rot, void* dx, int precision,
+                         void* scratch, dip_stream_t stream) {
+  DIP_CHECK(engine_init());
+  if (precision != DIP_PRECISION_TF32) return fail("dip_op_conv_dgrad_s2: tensor-core path only (the exact-fp32 mode zero-stuffs)");
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvOp op;
+  if (N != 128) return fail("dip_op_conv_dgrad_s2: N must be 128");
+  if (C % 4 != 0 || C > 160) return fail("dip_op_conv_dgrad_s2: C must be a multiple of 4 and <= 160");
+  op.N = N; op.C = C; op.k = 3; op.stride = 2; op.rot = rot;
+  op.set_shapes();
+  op.wp_f = (float*)scratch;
+  op.wp_d = (float*)scratch + ((op.wp_f_elems() + 63) & ~size_t(63));
+  // one-entry pack table in the scratch area behind the packed weights
+  PackEntry e{};
+  e.w = (const float*)w; e.dst_f = nullptr; e.dst_d = op.wp_d; e.N = N; e.C = C; e.k = 3; e.rot = rot; e.n_rows = N;
+  e.c_pad = op.c_pad; e.c_rows = op.crows; e.Ctot = C; e.coff = 0; e.s2 = 1;
+  PackEntry* d_e = reinterpret_cast<PackEntry*>(op.wp_d + ((op.wp_d_elems() + 63) & ~size_t(63)));
+  DIP_CUDA(cudaMemcpyAsync(d_e, &e, sizeof e, cudaMemcpyHostToDevice, s));
+  launch_k(k_pack_table, dim3(64, 1), dim3(256), 0, s, 1, (const PackEntry*)d_e);
+  op.do_fprop = false; op.do_wgrad = false;
+  op.has_dgrad = true; op.dg_s2 = true;
+  op.dg_in = (const float*)dy; op.dg_in_h = dy_h; op.dg_in_w = dy_w;
+  op.dg_out = (float*)dx; op.dg_out_h = 2 * dy_h + 2; op.dg_out_w = 2 * dy_w + 2; op.dg_off = -2;
+  DIP_CHECK(op.build_tc(nullptr));
   return op.run_dgrad(precision, s);
 }
 int dip_op_conv_wgrad(const void* dy, int dy_h, int dy_w, const void* a, int a_h, int a_w, int a_c, int N, int C, int k, int stride,

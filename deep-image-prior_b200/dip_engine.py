@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "dip_plan_num_params", "dip_plan_num_bn", "dip_plan_param_numel", "dip_plan_bind", "dip_forward", "dip_backward",
     "dip_loss_mse", "dip_noise_perturb", "dip_adam_create", "dip_adam_destroy", "dip_adam_bind", "dip_adam_step",
     "dip_run_iterations", "dip_plan_buffer", "dip_plan_num_launches", "dip_plan_set_timing", "dip_plan_get_timing", "dip_plan_get_timing_records", "dip_op_scratch_bytes", "dip_op_conv_fprop",
-    "dip_op_conv_dgrad", "dip_op_conv_wgrad",
+    "dip_op_conv_dgrad", "dip_op_conv_wgrad", "dip_op_conv_dgrad_s2",
     "dip_lanczos_down_out_size", "dip_lanczos_down_fwd", "dip_lanczos_down_bwd", "dip_plan_set_downsampler",
     "dip_input_grad",
 ]
@@ -101,6 +101,7 @@ def lib():
     L.dip_op_conv_fprop.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32,
                                     vp, vp]
     L.dip_op_conv_dgrad.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    L.dip_op_conv_dgrad_s2.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, i32, vp, vp]
     L.dip_op_conv_wgrad.argtypes = [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, vp]
     L.dip_lanczos_down_out_size.argtypes = [i32, i32, i32, i32]
     L.dip_lanczos_down_fwd.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
@@ -378,6 +379,17 @@ def op_conv_dgrad(dy_nhwc, w, k, dx_h, dx_w, rot=0, precision=PRECISION_TF32):
     dx = torch.empty((dx_h, dx_w, C), dtype=torch.float32, device=dy_nhwc.device)
     check(lib().dip_op_conv_dgrad(_ptr(dy_nhwc), dy_h, dy_w, _ptr(w), N, C, k, rot, _ptr(dx), dx_h, dx_w, precision,
                                   _ptr(_get_scratch(dy_nhwc.device)), _stream()))
+    return dx
+
+
+def op_conv_dgrad_s2(dy_nhwc, w, rot=0, precision=PRECISION_TF32):
+    """Input gradient of a 3x3 stride-2 conv (4 sub-pixel phases): dy [h][w][128] -> dx [(2h+2)][(2w+2)][C]."""
+    dy_h, dy_w, n = dy_nhwc.shape
+    N, C = w.shape[0], w.shape[1]
+    assert n == N
+    dx = torch.full((2 * dy_h + 2, 2 * dy_w + 2, C), float("nan"), dtype=torch.float32, device=dy_nhwc.device)
+    check(lib().dip_op_conv_dgrad_s2(_ptr(dy_nhwc), dy_h, dy_w, _ptr(w), N, C, rot, _ptr(dx), precision,
+                                     _ptr(_get_scratch(dy_nhwc.device)), _stream()))
     return dx
 
 

@@ -100,3 +100,22 @@ def test_wgrad(case, prec):
     torch.cuda.synchronize()
     err = rel_err(dw, ref)
     assert err < TOL[prec]
+
+
+@pytest.mark.parametrize("case", [(128, 16, 16), (128, 64, 64), (128, 129, 128), (32, 40, 24), (128, 9, 13), (128, 2, 2)])
+def test_dgrad_stride2_phases(case):
+    """Input gradient of the 3x3 stride-2 convs as four sub-pixel phase GEMMs in one launch (no zero-stuffing), vs
+    conv_transpose2d(stride=2) in fp64.  dx is the padded (2h+2) x (2w+2) gradient: the transposed conv covers
+    (2h+1) x (2w+1), the last row / column receive no tap and must come out as exact zeros (never left unwritten)."""
+    import dip_engine as de
+    C, h, w_ = case
+    g = torch.Generator().manual_seed(4)
+    dy = torch.randn(128, h, w_, generator=g)
+    w = torch.randn(128, C, 3, 3, generator=g) / (128 * 9) ** 0.5
+    ref = F.conv_transpose2d(dy[None].double(), w.double(), stride=2)[0]          # C x (2h+1) x (2w+1)
+    dx = de.op_conv_dgrad_s2(nhwc(dy).cuda(), w.cuda())
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx).all(), "part of the padded gradient was never written"
+    got = dx.permute(2, 0, 1).cpu()
+    assert rel_err(got[:, :2 * h + 1, :2 * w_ + 1], ref) < TOL[0]
+    assert got[:, 2 * h + 1, :].abs().max() == 0 and got[:, :, 2 * w_ + 1].abs().max() == 0

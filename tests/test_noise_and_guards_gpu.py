@@ -189,3 +189,62 @@ def test_new_adam_after_destroy_is_not_served_a_stale_graph():
     # floating-point atomics, so the summation order differs run to run, and the trajectory is chaotic: SURVEY.md 7.4)
     for f in finals[1:]:
         assert np.allclose(finals[0][:2], f[:2], rtol=1e-4) and np.allclose(finals[0], f, rtol=0.1)
+
+
+def test_fast_denoising_closure_matches_the_verbatim_one():
+    """utils.fast_closure.DenoisingClosure = denoising.ipynb c10 with device-side metrics: same losses / PSNRs / EMA as
+    the verbatim closure (host-side compare_psnr on D2H copies) on the same perturbation stream, and its device-side
+    parameter snapshot restores like the notebook's CPU copy does."""
+    from utils.common_utils import get_params, optimize
+    from utils.fast_closure import DenoisingClosure, psnr_device
+    H = W = 64
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(1, 3, H, W, generator=g).cuda()
+    noisy = (img + 0.1 * torch.randn(1, 3, H, W, generator=g).cuda()).clamp(0, 1)
+    z = (torch.rand(1, 32, H, W, generator=g) * 0.1).cuda()
+
+    def np_psnr(a, b):
+        return 10 * np.log10(1.0 / np.mean((a.astype(np.float64) - b) ** 2))
+
+    assert abs(psnr_device(img, noisy).item() - np_psnr(img.cpu().numpy(), noisy.cpu().numpy())) < 1e-4
+
+    # verbatim closure (c10:8-33), 4 iterations
+    net = _net64()
+    net.precision = "fp32"
+    mse = torch.nn.MSELoss()
+    torch.manual_seed(11)
+    noise = z.clone()
+    st = {"out_avg": None}
+    ref = []
+
+    def closure():
+        net_input = z + (noise.normal_() * (1. / 30))
+        out = net(net_input)
+        st["out_avg"] = out.detach() if st["out_avg"] is None else st["out_avg"] * 0.99 + out.detach() * 0.01
+        total_loss = mse(out, noisy)
+        total_loss.backward()
+        o = out.detach().cpu().numpy()[0]
+        ref.append((total_loss.item(), np_psnr(noisy.cpu().numpy()[0], o), np_psnr(img.cpu().numpy()[0], o),
+                    np_psnr(img.cpu().numpy()[0], st["out_avg"].cpu().numpy()[0])))
+        return total_loss
+    optimize("adam", get_params("net", net, z), closure, 0.01, 4)
+
+    net2 = _net64()
+    net2.precision = "fp32"
+    torch.manual_seed(11)
+    fast = DenoisingClosure(net2, z, noisy, img, reg_noise_std=1. / 30, exp_weight=0.99, show_every=100, mse=mse)
+    optimize("adam", get_params("net", net2, z), fast, 0.01, 4)
+    got, want = np.array(fast.history), np.array(ref)
+    assert np.allclose(got[:2], want[:2], rtol=1e-4, atol=1e-4), (got[:2], want[:2])      # identical state for two iterations
+    assert np.allclose(got, want, rtol=0.05, atol=0.05)                                     # then the usual fp drift
+    assert torch.allclose(fast.out_avg, st["out_avg"], atol=5e-2)
+    # snapshot / restore on the device
+    assert fast.snapshot.valid and fast.i == 4
+    before = [p.detach().clone() for p in net2.parameters()]
+    with torch.no_grad():
+        for p in net2.parameters():
+            p.add_(1.0)
+    fast.snapshot.restore()
+    # the snapshot holds the parameters as they were when the closure of the last iteration ran (before its Adam step)
+    assert all(torch.isfinite(p).all() for p in net2.parameters())
+    assert sum(float((a - b).abs().max()) for a, b in zip(before, net2.parameters())) < 112 * 0.011
