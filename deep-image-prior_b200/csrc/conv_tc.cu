@@ -25,8 +25,8 @@ static constexpr int kAccStride = kAccS;  // fp64 accumulators: kAccR replicas x
 struct SmemCtl {
   uint64_t full[8];
   uint64_t empty[8];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[4];   // one per TMEM accumulator buffer: 2 (single tiles, double-buffered), 4 or 3 (tile pairs)
+  uint64_t tmem_empty[4];
   uint64_t a_full[2];    // patch mode: input patch buffers
   uint64_t a_empty[2];
   uint32_t tmem_base;
@@ -48,15 +48,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   const int b_bytes = p.n_mma * 128;
   // per-tap mode: stage = [A tile 16 KB][B tile]; patch mode: two input patches up front, stages hold B tiles only
   const int patch_bytes = p.patch ? p.pw * p.ph * 128 : 0;
-  const int patch_alloc = (patch_bytes + 1023) & ~1023;
+  const int patch_alloc = (patch_bytes + 127) & ~127;
   const int tps = p.patch ? p.tps : 1;  // filter taps per B stage (patch mode)
   const int stage_bytes = (p.patch ? 0 : kABytes) + ((tps * b_bytes + 1023) & ~1023);
-  uint8_t* patch_base = smem;
-  uint8_t* stage_base = smem + 2 * patch_alloc;
+  // layout: [weight (+A) stages | epilogue staging | 2 input patches | control].  Stages and staging are 1024-byte aligned
+  // (swizzle atoms); the patches only need 128 bytes: TMA and UMMA both swizzle on absolute smem address bits.
+  uint8_t* stage_base = smem;
   uint8_t* staging = stage_base + p.stages * stage_bytes;
   const int pair = p.pair;                                  // two tiles per iteration (see TcConvParams::pair)
-  const int stg_chunks = pair ? 2 : p.n_chunks;             // pair mode stores a tile in two 64-channel halves
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(staging + stg_chunks * kChunkBytes);
+  const int stg_chunks = pair ? 2 : p.n_chunks;             // pair mode stores a tile 64 channels at a time
+  uint8_t* patch_base = staging + stg_chunks * kChunkBytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(patch_base + 2 * patch_alloc);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,7 +83,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   const int n_iters = (num_tiles + tile_stride - 1) / tile_stride;
   const int tile0 = n_split > 1 ? blockIdx.x / n_split : (blockIdx.x / csize) * csize + crank;  // first tile; stride tile_stride
   const uint32_t tile_cols = (p.n_mma + 31) & ~31;              // TMEM columns of one tile's accumulator
-  const uint32_t acc_cols = pair ? 2 * tile_cols : tile_cols;   // column stride between the two accumulator buffers
+  const uint32_t acc_cols = tile_cols;                          // column stride between accumulator buffers
+  // pair mode: accumulator buffers are handed out per TILE in round-robin order -- 4 buffers of 128 columns (two pairs in
+  // flight), or 3 of 160 (the 132-channel dgrad: the upper tile of the next pair reuses the buffer the epilogue drains first)
+  const int nbuf = pair ? (tile_cols * 4 <= 512 ? 4 : 3) : 2;
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
@@ -94,16 +99,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       mbar_init(&ctl->full[i], 1);
       mbar_init(&ctl->empty[i], csize);  // released by the MMA warp of every CTA that multicasts into this stage
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&ctl->tmem_full[i], 1);
       mbar_init(&ctl->tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->a_full[i], 1);
       mbar_init(&ctl->a_empty[i], 1);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&ctl->tmem_base, tmem_cols_pow2(2 * acc_cols));
+    tmem_alloc(&ctl->tmem_base, tmem_cols_pow2(nbuf * acc_cols));
     tmem_relinquish();
   }
   pdl_wait();  // everything above is independent of the previous kernel's results
@@ -236,9 +243,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           if (tile >= num_tiles) break;
           kb_per_tile = p.phs[tile / tiles_pp].kh * p.phs[tile / tiles_pp].kw * p.kblocks;
         }
-        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        // accumulator buffers of this iteration: single tiles alternate between two; a pair takes the next two of nbuf
+        const int g0 = 2 * it;
+        const int b0 = pair ? g0 % nbuf : acc, b1 = (g0 + 1) % nbuf;
+        if (pair) {
+          mbar_wait(&ctl->tmem_empty[b0], (((g0 / nbuf) & 1) ^ 1));
+          mbar_wait(&ctl->tmem_empty[b1], ((((g0 + 1) / nbuf) & 1) ^ 1));
+        } else {
+          mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        }
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * acc_cols;
+        const uint32_t tmem_d = tmem_base + b0 * acc_cols;
         uint32_t accf = 0;  // 0 for the first MMA of the tile (overwrite), 1 afterwards
         if (p.patch) {
           // tile row ty = 8 consecutive patch pixels starting at ((ty + r) * pw + sx): 8-row groups pw*128 B apart.  The
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           const uint32_t ahi = desc_hi(p.pw * 128, 2);
           const uint32_t row_step = static_cast<uint32_t>(p.pw) * 8;  // one patch row, in 16-byte units
           const uint32_t pair_off = row_step * static_cast<uint32_t>(p.bh);   // second tile of a pair: bh patch rows further down
-          const uint32_t tmem_d1 = tmem_d + tile_cols;
+          const uint32_t tmem_d1 = tmem_base + b1 * acc_cols;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(&ctl->a_full[ab], aphase);
             tc_fence_after();
@@ -343,7 +358,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        if (elect_one()) tc_commit(&ctl->tmem_full[acc]);
+        if (elect_one()) {
+          tc_commit(&ctl->tmem_full[b0]);
+          if (pair) tc_commit(&ctl->tmem_full[b1]);
+        }
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -368,17 +386,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
         const int tile = tile0 + it * tile_stride;
         const int tx = tile % p.tiles_x, typ = tile / p.tiles_x;
         const int x0 = tx * p.bw;
-        mbar_wait(&ctl->tmem_full[acc], acc_phase);
-        tc_fence_after();
+        const int n_rounds = (p.n_chunks + 1) / 2;   // 64 channels per staging round
         for (int sub = 0; sub < 2; ++sub) {
+          const int g = 2 * it + sub, buf = g % nbuf;
+          mbar_wait(&ctl->tmem_full[buf], (g / nbuf) & 1);
+          tc_fence_after();
           const int y0 = (2 * typ + sub) * p.bh;
-          const uint32_t taddr = tmem_base + acc * acc_cols + sub * tile_cols + (static_cast<uint32_t>(ew * 32) << 16);
-          for (int half = 0; half < 2; ++half) {
+          const uint32_t taddr = tmem_base + buf * acc_cols + (static_cast<uint32_t>(ew * 32) << 16);
+          for (int half = 0; half < n_rounds; ++half) {
             if (et == 0) tma_store_wait_read0();   // the previous half's TMA store has finished reading the staging buffer
             named_bar_sync(1, 128);                // (and every thread is past its statistics pass over it)
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = half * 2 + jj;
+              if (j >= p.n_chunks) break;
               uint32_t v[32];
               tmem_ld_32x32(taddr + j * 32, v);
               tmem_ld_wait();
@@ -393,18 +414,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                 *reinterpret_cast<float4*>(rowp + ((q ^ (row & 7)) << 4)) = o;
               }
             }
-            if (sub == 1 && half == 1) {   // both accumulators of this buffer drained -> back to the MMA warp
+            if (half == n_rounds - 1) {   // this tile's accumulator is drained -> its buffer goes back to the MMA warp
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+              if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
             }
             fence_proxy_async_smem();
             named_bar_sync(1, 128);
             if (et == 0) {
-              for (int jj = 0; jj < 2; ++jj) tma_store_3d(&p.tmD, staging + jj * kChunkBytes, (half * 2 + jj) * 32, x0, y0);
+              for (int jj = 0; jj < 2 && half * 2 + jj < p.n_chunks; ++jj)
+                tma_store_3d(&p.tmD, staging + jj * kChunkBytes, (half * 2 + jj) * 32, x0, y0);
               tma_store_commit();
             }
-            if (p.stats != nullptr) {
+            if (p.stats != nullptr) {   // n_mma == 128 only (two rounds): the launcher rejects statistics on wider tiles
               const int jj = cl >> 5, q = (cl & 31) >> 2, e = cl & 3;
               const uint8_t* cb = staging + jj * kChunkBytes + e * 4;
               float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
@@ -426,12 +448,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                   }
                 }
               }
-              ps1[half] += static_cast<double>(a0 + a1);
-              ps2[half] += static_cast<double>(b0 + b1);
+              ps1[half & 1] += static_cast<double>(a0 + a1);
+              ps2[half & 1] += static_cast<double>(b0 + b1);
             }
           }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (p.stats != nullptr) {
         const int rep = (blockIdx.x % kAccR) * kAccLine;
@@ -539,7 +560,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   if (csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols_pow2(2 * acc_cols));
+    tmem_dealloc(tmem_base, tmem_cols_pow2(nbuf * acc_cols));
   }
 }
 
@@ -719,7 +740,7 @@ static constexpr size_t kMaxSmem = 232448;  // 227 KB
 
 size_t tc_conv_smem_bytes(const TcConvParams& p) {
   const size_t b_bytes = (static_cast<size_t>(p.n_mma) * 128 + 1023) & ~size_t(1023);
-  const size_t patch = p.patch ? ((static_cast<size_t>(p.pw) * p.ph * 128 + 1023) & ~size_t(1023)) : 0;
+  const size_t patch = p.patch ? ((static_cast<size_t>(p.pw) * p.ph * 128 + 127) & ~size_t(127)) : 0;
   const size_t tps = p.patch ? (p.tps < 1 ? 1 : p.tps) : 1;
   return 1024 + 2 * patch + p.stages * ((p.patch ? 0 : kABytes) + tps * b_bytes) +
          static_cast<size_t>(p.pair ? 2 : p.n_chunks) * kChunkBytes + sizeof(SmemCtl);
@@ -740,7 +761,8 @@ cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
   const int tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y * (p.nphase > 0 ? p.nphase : 1);
   const int cs = p.csize < 1 ? 1 : p.csize;
   if (p.nphase > 0 && (p.patch || cs != 1 || p.nphase > 4)) return cudaErrorInvalidValue;
-  if (p.pair && (!p.patch || cs != 1 || p.n_split > 1 || p.n_mma != 128)) return cudaErrorInvalidValue;
+  if (p.pair && (!p.patch || cs != 1 || p.n_split > 1 || p.n_mma > 160 || (p.n_mma != 128 && p.stats != nullptr)))
+    return cudaErrorInvalidValue;
   int grid = (tiles + cs - 1) / cs * cs;
   const int cap = num_sms / cs * cs;
   if (grid > cap) grid = cap;

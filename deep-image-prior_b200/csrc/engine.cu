@@ -180,12 +180,12 @@ static int pick_nsplit(int tiles, int n_rows) {
   while (sp * 2 <= mx && tiles * sp * 2 <= 148 && n_rows % (32 * sp * 2) == 0) sp *= 2;
   return sp;
 }
-// Tile pairs (TcConvParams::pair): 128 output channels only (2 tiles x 2 buffers x 128 columns = the whole TMEM), and only when
+// Tile pairs (TcConvParams::pair): 128 output channels (4 accumulators of 128 TMEM columns) or 144 (3 of 160), and only when
 // the wave quantisation does not eat the gain: a pair iteration costs ~1.6 single-tile iterations (measured on the level-0
 // 3x3 conv: 184.8 -> 145.9 us), so pair when ceil(pairs / SMs) * 1.6 < ceil(tiles / SMs)   (tiles_y = rows of 8 x 16 tiles)
 static int pick_pair(int tiles_x, int tiles_y, int n_rows) {
   static const bool off = getenv("DIP_NO_PAIR") != nullptr;
-  if (off || n_rows != 128) return 0;
+  if (off || (n_rows != 128 && n_rows != 144)) return 0;   // 144: the 132-channel dgrad (three rotating accumulators, no statistics)
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   const int tiles = tiles_x * tiles_y, pairs = tiles_x * ((tiles_y + 1) / 2);
   return ((pairs + sms - 1) / sms) * 16 < ((tiles + sms - 1) / sms) * 10 ? 1 : 0;
