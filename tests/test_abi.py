@@ -74,3 +74,20 @@ def test_downsampler_output_size_matches_torch_conv_arithmetic():
                          (15, 16, 4, 0)]:
         want = (n + 2 * pad - K) // f + 1 if n + 2 * pad >= K else 0
         assert L.dip_lanczos_down_out_size(n, K, f, pad) == want == de.down_out_size(n, K, f, pad)
+
+
+def test_integration_md_stub_matches_the_header_struct():
+    """INTEGRATION.md section 2 shows the ctypes binding a reference maintainer adds: its NetDesc must have exactly the
+    fields of dip_net_desc in include/dip.h, in order (a shorter struct makes the library read past it)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "dip.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} dip_net_desc;", hdr, re.S).group(1)
+    header_fields = re.findall(r"^\s*int\s+(\w+);", body, re.M)
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    stub = re.search(r"class NetDesc\(ctypes.Structure\):.*?_fields_ = \[(.*?)\]\n", doc, re.S).group(1)
+    stub_fields = re.findall(r'"(\w+)"', stub)
+    import dip_engine as de
+    assert header_fields == stub_fields == [n for n, _ in de.NetDesc._fields_] and len(header_fields) == 10
+    ctor = re.search(r"desc = NetDesc\((.*?)\)\s+#", doc).group(1)
+    assert len([x for x in ctor.split(",") if x.strip()]) == len(header_fields)
