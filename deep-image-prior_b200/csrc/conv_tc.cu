@@ -41,8 +41,15 @@ __device__ __forceinline__ uint32_t tmem_cols_pow2(uint32_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------ fprop / dgrad
-__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+// Body of the conv kernel.  DEEP = false: the stand-alone launch (tc_conv_kernel).  DEEP = true: one PHASE of the persistent
+// deep-level kernel (deep.cu): `p` is a shared-memory copy of the scalars, `pm` the parameter block in global memory whose
+// tensor maps TMA reads; TMEM (512 columns) is allocated once by the caller and handed in as tmem_pre; the CTA-local
+// barriers are re-initialised here (every barrier of the previous phase has completed all its phases by then); CTAs
+// beyond the grid the stand-alone launch would have used (p.vgrid) sit the phase out.
+template <bool DEEP>
+__device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConvParams* pm, uint8_t* smem_raw, uint32_t tmem_pre) {
+  const int grid_x = DEEP ? p.vgrid : static_cast<int>(gridDim.x);
+  if (DEEP && static_cast<int>(blockIdx.x) >= grid_x) return;
   // 1024-byte alignment is required by the 128B swizzle atoms.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.n_mma * 128;
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   const int n_part = blockIdx.x % n_split;
   const int n_off = n_part * p.n_mma;             // first output channel of this CTA
   const int n_total = p.n_mma * n_split;          // rows per tap of the packed weights
-  const int tile_stride = gridDim.x / n_split;
+  const int tile_stride = grid_x / n_split;
   const int n_iters = (num_tiles + tile_stride - 1) / tile_stride;
   const int tile0 = n_split > 1 ? blockIdx.x / n_split : (blockIdx.x / csize) * csize + crank;  // first tile; stride tile_stride
   const uint32_t tile_cols = (p.n_mma + 31) & ~31;              // TMEM columns of one tile's accumulator
@@ -88,11 +95,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   // flight), or 3 of 160 (the 132-channel dgrad: the upper tile of the next pair reuses the buffer the epilogue drains first)
   const int nbuf = pair ? (tile_cols * 4 <= 512 ? 4 : 3) : 2;
 
-  pdl_trigger();
+  if (!DEEP) pdl_trigger();
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
-    tma_prefetch_desc(&p.tmD);
+    tma_prefetch_desc(&pm->tmA);
+    tma_prefetch_desc(&pm->tmB);
+    tma_prefetch_desc(&pm->tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -109,11 +116,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (!DEEP && warp == 2) {
     tmem_alloc(&ctl->tmem_base, tmem_cols_pow2(nbuf * acc_cols));
     tmem_relinquish();
   }
-  pdl_wait();  // everything above is independent of the previous kernel's results
+  if (!DEEP) pdl_wait();  // everything above is independent of the previous kernel's results
   if (warp == 3) {
     for (int i = lane; i < 160; i += 32) ctl->bias[i] = (p.bias != nullptr && i < p.n_mma) ? p.bias[n_off + i] : 0.f;
   }
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast / remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_base = DEEP ? tmem_pre : ctl->tmem_base;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
               if (p.dbg_flags & 1) mbar_arrive(&ctl->a_full[ab]);
               else {
                 mbar_expect_tx(&ctl->a_full[ab], patch_bytes);
-                tma_load_5d(patch_base + ab * patch_alloc, &p.tmA, &ctl->a_full[ab], kb * 32, 0, x0 + p.offx, 0, y0 + p.offy);
+                tma_load_5d(patch_base + ab * patch_alloc, &pm->tmA, &ctl->a_full[ab], kb * 32, 0, x0 + p.offx, 0, y0 + p.offy);
               }
             }
             __syncwarp();
@@ -163,9 +170,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                   mbar_expect_tx(&ctl->full[stage], tps * b_bytes);
                   if (csize == 1) {
                     for (int t = 0; t < tps; ++t)
-                      tma_load_2d(sb + t * b_bytes, &p.tmB, &ctl->full[stage], kb * 32, (tap + t) * n_total + n_off);
+                      tma_load_2d(sb + t * b_bytes, &pm->tmB, &ctl->full[stage], kb * 32, (tap + t) * n_total + n_off);
                   } else {
-                    tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                    tma_load_2d_mc(sb + crank * b_rows * 128, &pm->tmB, &ctl->full[stage], kb * 32,
                                    tap * p.n_mma + crank * b_rows, cmask);
                   }
                 }
@@ -205,10 +212,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
                 const bool ldA = !(p.dbg_flags & 1), ldB = !(p.dbg_flags & 2);
                 if (ldA || ldB) mbar_expect_tx(&ctl->full[stage], (ldA ? kABytes : 0) + (ldB ? b_bytes : 0));
                 else mbar_arrive(&ctl->full[stage]);
-                if (ldA) tma_load_5d(sa, &p.tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
+                if (ldA) tma_load_5d(sa, &pm->tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
                 if (ldB) {
-                  if (csize == 1) tma_load_2d(sb, &p.tmB, &ctl->full[stage], kb * 32, tap * n_total + n_off);
-                  else tma_load_2d_mc(sb + crank * b_rows * 128, &p.tmB, &ctl->full[stage], kb * 32,
+                  if (csize == 1) tma_load_2d(sb, &pm->tmB, &ctl->full[stage], kb * 32, tap * n_total + n_off);
+                  else tma_load_2d_mc(sb + crank * b_rows * 128, &pm->tmB, &ctl->full[stage], kb * 32,
                                       tap * p.n_mma + crank * b_rows, cmask);
                 }
               }
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
             named_bar_sync(1, 128);
             if (et == 0) {
               for (int jj = 0; jj < 2 && half * 2 + jj < p.n_chunks; ++jj)
-                tma_store_3d(&p.tmD, staging + jj * kChunkBytes, (half * 2 + jj) * 32, x0, y0);
+                tma_store_3d(&pm->tmD, staging + jj * kChunkBytes, (half * 2 + jj) * 32, x0, y0);
               tma_store_commit();
             }
             if (p.stats != nullptr) {   // n_mma == 128 only (two rounds): the launcher rejects statistics on wider tiles
@@ -513,9 +520,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       named_bar_sync(1, 128);
       if (et == 0) {
         if (p.nphase > 0)
-          for (int j = 0; j < p.n_chunks; ++j) tma_store_5d(&p.tmD, staging + j * kChunkBytes, n_off + j * 32, opx, x0, opy, y0);
+          for (int j = 0; j < p.n_chunks; ++j) tma_store_5d(&pm->tmD, staging + j * kChunkBytes, n_off + j * 32, opx, x0, opy, y0);
         else
-          for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&p.tmD, staging + j * kChunkBytes, n_off + j * 32, x0, y0);
+          for (int j = 0; j < p.n_chunks; ++j) tma_store_3d(&pm->tmD, staging + j * kChunkBytes, n_off + j * 32, x0, y0);
         tma_store_commit();
       }
       if (p.stats != nullptr && et < p.n_mma) {
@@ -558,10 +565,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (csize > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
-  if (warp == 2) {
+  if (!DEEP && warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols_pow2(nbuf * acc_cols));
   }
+}
+__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_constant__ TcConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  tc_conv_body<false>(p, &p, smem_raw, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -572,8 +583,9 @@ struct SmemCtlW {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+template <bool DEEP>
+__device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWgradParams* pm, uint8_t* smem_raw, uint32_t tmem_pre) {
+  if (DEEP && static_cast<int>(blockIdx.x) >= p.kh * p.ksplits) return;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int chunk_bytes = p.kp * 128;                          // kp pixel rows x 32 channels
   const int y_bytes = 4 * chunk_bytes;                         // dY: 128 channels
@@ -595,10 +607,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   const int blk0 = static_cast<int>((static_cast<long long>(p.px_blocks) * ks) / p.ksplits);
   const int blk1 = static_cast<int>((static_cast<long long>(p.px_blocks) * (ks + 1)) / p.ksplits);
 
-  pdl_trigger();
+  if (!DEEP) pdl_trigger();
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmY);
-    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&pm->tmY);
+    tma_prefetch_desc(&pm->tmX);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -609,14 +621,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&ctl->tmem_base, ncols);
-    tmem_relinquish();
+    if (!DEEP) {
+      tmem_alloc(&ctl->tmem_base, ncols);
+      tmem_relinquish();
+    }
   }
-  pdl_wait();
+  if (!DEEP) pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_base = DEEP ? tmem_pre : ctl->tmem_base;
 
   if (warp == 0) {
     {
@@ -629,11 +643,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         uint8_t* sy = smem + stage * stage_bytes;
         if (elect_one()) {
         mbar_expect_tx(&ctl->full[stage], stage_tx);
-        for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * chunk_bytes, &p.tmY, &ctl->full[stage], j * 32, x0, y);
+        for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * chunk_bytes, &pm->tmY, &ctl->full[stage], j * 32, x0, y);
         if (p.xshare) {
           uint8_t* sx = sy + y_bytes;
           for (int j = 0; j < p.c_chunks; ++j)
-            tma_load_5d(sx + j * xchunk, &p.tmX, &ctl->full[stage], j * 32, 0, x0 + p.offx, 0, y + p.offy + r);
+            tma_load_5d(sx + j * xchunk, &pm->tmX, &ctl->full[stage], j * 32, 0, x0 + p.offx, 0, y + p.offy + r);
         } else
         for (int s = 0; s < p.kw; ++s) {
           const int ix = p.offx + s, iy = p.offy + r;
@@ -645,7 +659,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
           }
           uint8_t* sx = sy + y_bytes + s * x_bytes;
           for (int j = 0; j < p.c_chunks; ++j)
-            tma_load_5d(sx + j * chunk_bytes, &p.tmX, &ctl->full[stage], j * 32, cpx, cx, cpy, cy);
+            tma_load_5d(sx + j * chunk_bytes, &pm->tmX, &ctl->full[stage], j * 32, cpx, cx, cpy, cy);
         }
         }
         __syncwarp();
@@ -731,8 +745,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, ncols);
+    if (!DEEP) tmem_dealloc(tmem_base, ncols);
   }
+}
+__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  tc_wgrad_body<false>(p, &p, smem_raw, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -773,6 +791,12 @@ cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
   const size_t smem = tc_conv_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
   return launch_k(tc_conv_kernel, dim3(grid), dim3(kNumThreads), smem, s, cs, p);
+}
+// grid the stand-alone launch uses (the persistent deep-level kernel runs the same CTA -> tile mapping on its first vgrid CTAs)
+int tc_conv_grid(const TcConvParams& p, int num_sms) {
+  const int tiles = p.pair ? p.tiles_x * ((p.tiles_y + 1) / 2) : p.tiles_x * p.tiles_y * (p.nphase > 0 ? p.nphase : 1);
+  if (p.n_split > 1) return tiles * p.n_split;
+  return tiles < num_sms ? tiles : num_sms;
 }
 
 cudaError_t tc_wgrad_launch(const TcWgradParams& p, cudaStream_t s) {

@@ -15,6 +15,7 @@
 
 #include "../../include/dip.h"
 #include "conv_tc.cuh"
+#include "deep.cuh"
 #include "kernels.cuh"
 
 namespace dip {
@@ -59,6 +60,7 @@ static int engine_init() {
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   DIP_CUDA(tc_kernels_init());
   DIP_CUDA(down_kernels_init());
+  DIP_CUDA(deep_kernels_init());
   g_inited_mask |= 1ull << dev;
   return 0;
 }
@@ -190,11 +192,11 @@ static int pick_pair(int tiles_x, int tiles_y, int n_rows) {
   const int tiles = tiles_x * tiles_y, pairs = tiles_x * ((tiles_y + 1) / 2);
   return ((pairs + sms - 1) / sms) * 16 < ((tiles + sms - 1) / sms) * 10 ? 1 : 0;
 }
-static void fit_stages(TcConvParams& p) {
+static void fit_stages(TcConvParams& p, size_t budget = 232448) {
   for (;;) {
     p.stages = 6;
-    while (tc_conv_smem_bytes(p) > 232448 && p.stages > 2) p.stages--;
-    if (tc_conv_smem_bytes(p) <= 232448 || p.tps <= 1) return;
+    while (tc_conv_smem_bytes(p) > budget && p.stages > 2) p.stages--;
+    if (tc_conv_smem_bytes(p) <= budget || p.tps <= 1) return;
     p.tps--;  // two stages of 3 taps do not fit (wide dgrad tiles): fall back to 2 taps per stage
   }
 }
@@ -616,6 +618,11 @@ struct dip_plan {
   PackEntry* d_pack = nullptr; CvtEntry* d_cvt = nullptr; RunEntry* d_run = nullptr; UnpackEntry* d_unpack = nullptr;
   int n_pack = 0, n_cvt = 0, n_run = 0, n_unpack = 0;
   float* wacc_base = nullptr; size_t wacc_bytes = 0;   // all weight-gradient accumulators, contiguous
+  // persistent deep-level kernel (deep.cu): levels >= deep_from run as one launch per pass
+  static constexpr int kDeepMaxOps = 96;
+  DeepOp* d_deep_fwd = nullptr; DeepOp* d_deep_bwd = nullptr;
+  int n_deep_fwd = 0, n_deep_bwd = 0, deep_grid = 0, deep_from = 2;
+  unsigned* deep_bar = nullptr;
   long long pack_max = 0;
   bool bound = false;
   int nbt_is_float = 0;
@@ -887,6 +894,11 @@ static int build_plan(dip_plan* P, Arena& A) {
     for (ConvOp* op : P->convs) if (op->do_wgrad) { op->wacc = P->wacc_base ? P->wacc_base + off : nullptr; off += (op->wacc_elems() + 63) & ~size_t(63); }
   }
   P->d_unpack = A.get<UnpackEntry>(P->n_unpack > 0 ? P->n_unpack : 1);
+  P->d_deep_fwd = A.get<DeepOp>(dip_plan::kDeepMaxOps);
+  P->d_deep_bwd = A.get<DeepOp>(2 * dip_plan::kDeepMaxOps);
+  P->deep_bar = A.get<unsigned>(64);
+  if (const char* e = getenv("DIP_DEEP_FROM")) P->deep_from = atoi(e);
+  if (P->deep_from < 1) P->deep_from = 1;
   P->n_pack = (int)P->convs.size();
   P->n_cvt = (int)P->bns.size() * 3 + L + 2;
   P->n_run = (int)P->bns.size();
@@ -1013,6 +1025,17 @@ static const float* level_usrc(const dip_plan* P, int l) {
   return l == L - 1 ? P->lv[l].P_d2 : P->lv[l + 1].U;
 }
 
+// The persistent deep-level kernel (deep.cu) replaces the launches of levels >= deep_from (tensor-core precision, no
+// per-launch timers).  OPT-IN (DIP_DEEP=1): parity-green (tests/test_engine_gpu.py::test_deep_kernel_matches_launches) but
+// measured SLOWER than the launches it replaces on B200 -- forward 382 us vs 340 us, backward 745 us vs ~700 us of kernel time
+// (ncu), 314 vs 378 it/s end to end: the small kernels are bounded by their own prologue + a few memory round trips, not by
+// launch gaps, and one 256-thread CTA per SM (255 registers: the conv code lives in the same kernel) has an eighth of the
+// loads in flight that the stand-alone kernels have.  See DESIGN.md section 10.
+static bool deep_on(const dip_plan* P) {
+  const char* e = getenv("DIP_DEEP");   // read per call: the test switches it inside one process
+  return e != nullptr && e[0] == '1' && P->desc.precision == DIP_PRECISION_TF32 && !P->timer.on && P->n_deep_fwd > 0 &&
+         (int)P->lv.size() > P->deep_from;
+}
 static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   Level& v = P->lv[l];
   const int prec = P->desc.precision;
@@ -1041,7 +1064,15 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
         128.0 * ((double)v.h * v.w + (last ? (double)v.h * v.w : (double)(v.h + 2) * (v.w + 2))) * sizeof(float), s,
         launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, v.P_d2, 128, last ? 0 : 1, 1, s));
   nl += 4 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
-  if (!last) DIP_CHECK(fwd_level(P, l + 1, s, nl));
+  if (!last) {
+    if (deep_on(P) && l + 1 == P->deep_from) {
+      // every level below this one: ONE persistent launch (deep.cu) instead of ~13 launches per level
+      DIP_CUDA(launch_deep(P->d_deep_fwd, P->n_deep_fwd, P->deep_bar, P->deep_grid, s));
+      nl += 2;
+    } else {
+      DIP_CHECK(fwd_level(P, l + 1, s, nl));
+    }
+  }
   // upsample + concat + BN + pad
   join_skip(P, s);
   CatArgs ca = cat_args(P, v, level_usrc(P, l));
@@ -1221,7 +1252,13 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   // deeper branch
   GradSrc src_d2;
   if (!last) {
-    DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), s, nl));
+    if (deep_on(P) && P->n_deep_bwd > 0 && l + 1 == P->deep_from) {
+      if (P->deep_from >= defer_level()) DIP_CHECK(flush_deferred(P, prec, s));   // outer-level wgrads run beside the deep kernel
+      DIP_CUDA(launch_deep(P->d_deep_bwd, P->n_deep_bwd, P->deep_bar + 16, P->deep_grid, s));
+      nl += 2;
+    } else {
+      DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), s, nl));
+    }
     join_skip(P, s);   // the next level's skip-branch gradients (dRaw_s / dS) feed the BN backward below
     Level& n = P->lv[l + 1];
     if (CS == 128) { src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = 128; }
@@ -1238,6 +1275,171 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(conv_backward(P, v.d1, d1_dgrad, prec, s));
   nl += wl + (d1_dgrad ? 1 : 0);
   DIP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ deep-level op lists
+static void vec_lanes(int C, int* VL, int* PPB) { *VL = C / 4; *PPB = 256 / *VL; if (*PPB < 1) *PPB = 1; }
+static DeepOp deep_conv(dip_plan* P, const TcConvParams& src, const float* bias, double* stats, int sync = 1) {
+  DeepOp o;
+  o.type = DO_CONV; o.sync = sync;
+  o.u.conv = src;
+  o.u.conv.bias = bias;
+  o.u.conv.stats = stats;
+  fit_stages(o.u.conv, deep_dyn_smem());
+  o.u.conv.vgrid = tc_conv_grid(o.u.conv, g_num_sms);
+  if (o.u.conv.vgrid > P->deep_grid) P->deep_grid = o.u.conv.vgrid;
+  return o;
+}
+static DeepOp deep_bn_act_write(dip_plan* P, const float* raw, const BnLayer& b, int H, int W, float* dst, int pad) {
+  DeepOp o;
+  o.type = DO_BN_ACT_WRITE;
+  vec_lanes(b.C, &o.VL, &o.PPB);
+  o.u.bnw = DeepBnActWrite{raw, b.C, bn_ref(P, b), H, W, dst, b.C, pad, 1};
+  return o;
+}
+static void deep_fwd_level(dip_plan* P, int l, std::vector<DeepOp>& ops) {
+  Level& v = P->lv[l];
+  const int CS = P->desc.skip_channels;
+  const bool last = l == (int)P->lv.size() - 1;
+  const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
+  // skip branch (independent of the deeper branch until the concat: no barrier behind it)
+  if (CS == 128) {
+    ops.push_back(deep_conv(P, v.sk.fp, P->params[v.p_skip_b], v.bn_s.fwd, 0));
+  } else {
+    DeepOp o;
+    o.type = DO_SKINNY_FWD; o.sync = 0;
+    o.u.skf = DeepSkinnyFwd{pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], P->params[v.p_skip_b], v.Cin, CS, v.H, v.W, v.raw_s,
+                            0, v.bn_s.fwd, v.Cin_act};
+    ops.push_back(o);
+  }
+  ops.push_back(deep_conv(P, v.d1.fp, P->params[v.d1.p_b], v.bn_d1.fwd));
+  ops.push_back(deep_bn_act_write(P, v.raw_d1, v.bn_d1, v.h, v.w, v.P_d1, 1));
+  ops.push_back(deep_conv(P, v.d2.fp, P->params[v.d2.p_b], v.bn_d2.fwd));
+  ops.push_back(deep_bn_act_write(P, v.raw_d2, v.bn_d2, v.h, v.w, v.P_d2, last ? 0 : 1));
+  if (!last) deep_fwd_level(P, l + 1, ops);
+  {
+    DeepOp o;
+    o.type = DO_CAT_STATS;
+    vec_lanes(128 + CS, &o.VL, &o.PPB);
+    o.u.cat = DeepCat{cat_args(P, v, level_usrc(P, l)), v.bn_cat.fwd, bn_ref(P, v.bn_cat), v.P_cat};
+    ops.push_back(o);
+    o.type = DO_CAT_WRITE;
+    ops.push_back(o);
+  }
+  ops.push_back(deep_conv(P, v.up.fp, P->params[v.up.p_b], v.bn_u.fwd));
+  {
+    DeepOp o = deep_bn_act_write(P, v.raw_u, v.bn_u, v.H, v.W, v.A_u, 0);
+    ops.push_back(o);
+  }
+  ops.push_back(deep_conv(P, v.c11.fp, P->params[v.c11.p_b], v.bn_v.fwd));
+  ops.push_back(deep_bn_act_write(P, v.raw_v, v.bn_v, v.H, v.W, v.U, 0));
+}
+static void deep_bn_bwd(dip_plan* P, const float* raw, int ld_raw, BnLayer& b, GradSrc src, int H, int W, float* draw,
+                        std::vector<DeepOp>& ops, int sync_last = 1) {
+  DeepOp o;
+  o.type = DO_BN_BWD_REDUCE;
+  vec_lanes(b.C, &o.VL, &o.PPB);
+  o.u.bnb = DeepBnBwd{raw, ld_raw, bn_ref(P, b), 1, src, H, W, b.bwd, draw, nullptr, b.dbias};
+  ops.push_back(o);
+  o.type = DO_BN_BWD_APPLY; o.sync = sync_last;
+  ops.push_back(o);
+}
+static DeepOp deep_wgrad(dip_plan* P, const ConvOp& op, int sync = 1) {
+  DeepOp o;
+  o.type = DO_WGRAD; o.sync = sync;
+  o.u.wg = op.wg;
+  o.u.wg.atomic = 1;
+  o.u.wg.partial = op.wacc;
+  const int cap = P->deep_grid / op.k;   // kh * ksplits CTAs must fit the deep grid
+  if (o.u.wg.ksplits > cap) o.u.wg.ksplits = cap;
+  while (tc_wgrad_smem_bytes(o.u.wg) > deep_dyn_smem() && o.u.wg.stages > 1) o.u.wg.stages--;
+  return o;
+}
+static void deep_bwd_level(dip_plan* P, int l, GradSrc src_v, std::vector<DeepOp>& ops) {
+  Level& v = P->lv[l];
+  const int CS = P->desc.skip_channels, CC = 128 + CS;
+  const bool last = l == (int)P->lv.size() - 1;
+  // 1x1 conv + BN + LReLU
+  deep_bn_bwd(P, v.raw_v, 128, v.bn_v, src_v, v.H, v.W, v.dRaw_v, ops);
+  ops.push_back(deep_conv(P, v.c11.dg, nullptr, nullptr, 0));
+  ops.push_back(deep_wgrad(P, v.c11));
+  // up conv + BN + LReLU
+  deep_bn_bwd(P, v.raw_u, 128, v.bn_u, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, ops);
+  if (CS == 128) {
+    ops.push_back(deep_conv(P, v.up_a.dg, nullptr, nullptr, 0));
+    ops.push_back(deep_conv(P, v.up_b.dg, nullptr, nullptr, 0));
+    ops.push_back(deep_wgrad(P, v.up_a, 0));
+    ops.push_back(deep_wgrad(P, v.up_b));
+  } else {
+    ops.push_back(deep_conv(P, v.up.dg, nullptr, nullptr, 0));
+    ops.push_back(deep_wgrad(P, v.up));
+  }
+  // concat BN
+  {
+    DeepOp o;
+    o.type = DO_CAT_BWD_REDUCE;
+    vec_lanes(CC, &o.VL, &o.PPB);
+    o.u.catb = DeepCatBwd{v.P_cat, bn_ref(P, v.bn_cat), v.dP_cat, CC, v.H, v.W, v.bn_cat.bwd, v.dCat};
+    ops.push_back(o);
+    o.type = DO_CAT_BWD_APPLY;
+    ops.push_back(o);
+  }
+  {
+    DeepOp o;   // adjoint of the x2 upsampling; the skip-branch ops behind it only read dCat as well: no barrier
+    o.type = DO_UPADJ; o.sync = 0;
+    vec_lanes(128, &o.VL, &o.PPB);
+    o.u.up = DeepUpadj{v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp};
+    ops.push_back(o);
+  }
+  // skip branch
+  deep_bn_bwd(P, v.raw_s, CS, v.bn_s, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, ops);
+  if (CS == 128) {
+    ops.push_back(deep_conv(P, v.sk.dg, nullptr, nullptr, 0));   // dS (levels > 0 always need it)
+    ops.push_back(deep_wgrad(P, v.sk));
+  } else {
+    const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
+    DeepOp o;
+    o.type = DO_SKINNY_BWD; o.sync = 1;
+    vec_lanes(v.Cin, &o.VL, &o.PPB);
+    o.u.skb = DeepSkinnyBwd{pin_interior, v.Cin, v.W + 2, P->params[v.p_skip_w], v.Cin, CS, v.H, v.W, v.dRaw_s, nullptr, 0, nullptr,
+                            v.dw_s, nullptr, v.Cin_act};
+    ops.push_back(o);
+  }
+  // deeper branch
+  GradSrc src_d2;
+  if (!last) {
+    deep_bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), ops);
+    Level& n = P->lv[l + 1];
+    if (CS == 128) { src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = 128; }
+    else src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
+  } else {
+    src_d2 = src_plain(v.dUp, 128, 0);
+  }
+  deep_bn_bwd(P, v.raw_d2, 128, v.bn_d2, src_d2, v.h, v.w, v.dRaw_d2, ops);
+  ops.push_back(deep_conv(P, v.d2.dg, nullptr, nullptr, 0));
+  ops.push_back(deep_wgrad(P, v.d2));
+  deep_bn_bwd(P, v.raw_d1, 128, v.bn_d1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1, ops);
+  ops.push_back(deep_conv(P, v.d1.dg, nullptr, nullptr, 0));     // 4-phase stride-2 input gradient -> dPin
+  ops.push_back(deep_wgrad(P, v.d1));
+}
+static int build_deep_ops(dip_plan* P) {
+  P->n_deep_fwd = P->n_deep_bwd = 0;
+  P->deep_grid = 128 < g_num_sms ? 128 : g_num_sms;
+  if (P->desc.precision != DIP_PRECISION_TF32 || (int)P->lv.size() <= P->deep_from) return 0;
+  std::vector<DeepOp> fwd;
+  deep_fwd_level(P, P->deep_from, fwd);
+  if ((int)fwd.size() > dip_plan::kDeepMaxOps) return fail("internal: deep forward op list too long");
+  DIP_CUDA(cudaMemcpy(P->d_deep_fwd, fwd.data(), fwd.size() * sizeof(DeepOp), cudaMemcpyHostToDevice));
+  P->n_deep_fwd = (int)fwd.size();
+  if (getenv("DIP_NO_DEEP_BWD") == nullptr && P->lv[P->deep_from].d1.dg_s2) {
+    std::vector<DeepOp> bwd;
+    deep_bwd_level(P, P->deep_from, src_plain(P->lv[P->deep_from - 1].dUp, 128, 0), bwd);
+    if ((int)bwd.size() > 2 * dip_plan::kDeepMaxOps) return fail("internal: deep backward op list too long");
+    DIP_CUDA(cudaMemcpy(P->d_deep_bwd, bwd.data(), bwd.size() * sizeof(DeepOp), cudaMemcpyHostToDevice));
+    P->n_deep_bwd = (int)bwd.size();
+  }
+  if (P->deep_grid > g_num_sms) P->deep_grid = g_num_sms;
   return 0;
 }
 
@@ -1387,6 +1589,7 @@ int dip_plan_bind(dip_plan* P, void* const* params, void* const* grads, void* co
   P->running.clear();
   if (bn_running != nullptr) P->running.assign(bn_running, bn_running + 3 * P->bns.size());
   DIP_CHECK(upload_tables(P));
+  DIP_CHECK(build_deep_ops(P));
   P->bound = true;
   return 0;
 }

@@ -154,8 +154,10 @@ __device__ __forceinline__ void block_reduce_atomic(float4 (&acc)[K], int VL, in
   } else {
     nparts = PPB;
     part = tid / VL;
+    if (part < nparts) {   // (a 256-thread block of the persistent deep-level kernel has idle threads when VL * PPB < 256)
 #pragma unroll
-    for (int k = 0; k < K; ++k) red_smem[(k * nparts + part) * VL + (tid % VL)] = acc[k];
+      for (int k = 0; k < K; ++k) red_smem[(k * nparts + part) * VL + (tid % VL)] = acc[k];
+    }
   }
   __syncthreads();
   // one (k, v) pair per thread (K <= PPB always): the column is summed in fp64 and added to the global accumulators
@@ -278,10 +280,9 @@ void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, 
 }
 
 // ------------------------------------------------------------------------------------------------ bn_act_write
-__global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
+__device__ __forceinline__ void d_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
                                                       float* __restrict__ dst, int ld_out, int pad, int act, int VL,
                                                       int PPB) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
@@ -297,6 +298,12 @@ __global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ 
                  if (act) y = lrelu4(y);
                  st4(dst + static_cast<size_t>(p) * ld_out + 4 * v, y);
                });
+}
+__global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
+                                                      float* __restrict__ dst, int ld_out, int pad, int act, int VL,
+                                                      int PPB) {
+  pdl_enter();
+  d_bn_act_write(raw, ld_in, bn, H, W, dst, ld_out, pad, act, VL, PPB);
 }
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
                          int act, cudaStream_t s) {
@@ -396,13 +403,12 @@ __device__ __forceinline__ void cat_quad(const CatArgs& a, const CatLane& l, int
   }
 }
 
-__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
-  pdl_enter();
+__device__ __forceinline__ void d_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   float4 acc[2] = {f4zero(), f4zero()};
-  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+  for (int p = slot < PPB ? blockIdx.x * PPB + slot : nsrc; p < nsrc; p += gridDim.x * PPB) {
     const int si = p / w, sj = p - si * w;
     float4 q[4];
     cat_quad(a, l, si, sj, v, q);
@@ -415,6 +421,10 @@ __global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB
   double* const dst[2] = {fwd, fwd + (a.Cu + a.Cs) * kAccS};
   const int wid[2] = {a.Cu + a.Cs, a.Cu + a.Cs};
   block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
+}
+__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
+  pdl_enter();
+  d_cat_stats(a, fwd, VL, PPB);
 }
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
@@ -437,14 +447,13 @@ __device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld,
     for (int c = 0; c < nc; ++c) st4(dst + (static_cast<size_t>(rows[r]) * Wp + cols[c]) * ld + 4 * v, val);
 }
 
-__global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
-  pdl_enter();
+__device__ __forceinline__ void d_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const Bn4 cf = bn_coef<0>(bn_cat, v);
   const int w = a.W >> 1, nsrc = (a.H >> 1) * w;
   const int ld = a.Cu + a.Cs;
-  for (int p = blockIdx.x * PPB + slot; p < nsrc; p += gridDim.x * PPB) {
+  for (int p = slot < PPB ? blockIdx.x * PPB + slot : nsrc; p < nsrc; p += gridDim.x * PPB) {
     const int si = p / w, sj = p - si * w;
     float4 q[4];
     cat_quad(a, l, si, sj, v, q);
@@ -452,6 +461,10 @@ __global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, in
     for (int e = 0; e < 4; ++e)
       store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]));
   }
+}
+__global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
+  pdl_enter();
+  d_cat_write(a, bn_cat, dst, VL, PPB);
 }
 void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
@@ -695,9 +708,8 @@ void launch_input_grad(const float* gp, const float* ds, int ld, int C, int H, i
   launch_k(k_input_grad, dim3(grid), dim3(block), 0, s, 1, gp, ds, ld, C, H, W, dz);
 }
 template <int KIND>
-__global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+__device__ __forceinline__ void d_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                        int H, int W, double* __restrict__ bwd, int VL, int PPB) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
@@ -732,6 +744,12 @@ __global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bw
   const int wid[2] = {bn.C, bn.C};
   block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
+template <int KIND>
+__global__ void __launch_bounds__(256, (KIND == 0 || KIND == 2) ? 3 : 2) k_bn_bwd_reduce(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+                                                       int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+  pdl_enter();
+  d_bn_bwd_reduce<KIND>(raw, ld_raw, bn, act, src, H, W, bwd, VL, PPB);
+}
 void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
                           cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
@@ -749,10 +767,9 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
 // apply pass; for the head source (KIND 3) it also accumulates the head's own gradients:
 //   dW_head[k][c] += dl[k] * act(bn(raw))[c],  db_head[k] += dl[k]
 template <int KIND>
-__global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+__device__ __forceinline__ void d_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                       int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
                                                       float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
@@ -828,6 +845,13 @@ __global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const f
     block_reduce_atomic<K>(acc, VL, PPB, dst, wid);
   }
 }
+template <int KIND>
+__global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
+                                                      int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
+                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
+  pdl_enter();
+  d_bn_bwd_apply<KIND>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, VL, PPB);
+}
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
                          const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
@@ -871,16 +895,15 @@ __device__ __forceinline__ float4 cat_xhat(const CatBwdCoef& c, float4 y) {
   return make_float4((y.x - c.beta.x) * c.inv_gamma.x, (y.y - c.beta.y) * c.inv_gamma.y, (y.z - c.beta.z) * c.inv_gamma.z,
                      (y.w - c.beta.w) * c.inv_gamma.w);
 }
-__global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
+__device__ __forceinline__ void d_cat_bwd_reduce(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
                                                         int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int Wp = W + 2;
   float4 acc[2] = {f4zero(), f4zero()};
   // (the row-segment loop of the BN backward kernels was measured SLOWER here: 53.6 -> 65.9 us at 512x512 -- with 33 lanes
   // per pixel a unit is only 14 pixels and these two kernels already run at 5.2 - 6.1 TB/s)
-  item_loop<DIP_U_CATBWD>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+  item_loop<DIP_U_CATBWD>(slot < PPB ? blockIdx.x * PPB + slot : H * W, gridDim.x * PPB, H * W,
                [&](int p) {
                  RedItem it;
                  const int i = p / W, j = p - i * W;
@@ -896,23 +919,27 @@ __global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict_
   const int wid[2] = {bn_cat.C, bn_cat.C};
   block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
+__global__ void __launch_bounds__(256) k_cat_bwd_reduce(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
+                                                        int ld, int H, int W, double* __restrict__ bwd, int VL, int PPB) {
+  pdl_enter();
+  d_cat_bwd_reduce(pcat, bn_cat, gp, ld, H, W, bwd, VL, PPB);
+}
 void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, double* bwd,
                            cudaStream_t s) {
   VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
   fit_grid(g, k_cat_bwd_reduce, red_bytes(g, 2));
   launch_red(k_cat_bwd_reduce, g.blocks, g.threads, red_bytes(g, 2), s, pcat, bn_cat, gp, ld, H, W, bwd, g.VL, g.PPB);
 }
-__global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
+__device__ __forceinline__ void d_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
                                                        int ld, int H, int W, const double* __restrict__ bwd,
                                                        float* __restrict__ dcat, int VL, int PPB) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatBwdCoef cf = cat_bwd_coef(bn_cat, v);
   const int C = bn_cat.C;
   const int Wp = W + 2;
   float4 m1, m2;
   bwd_means<0>(bwd, C, bn_cat.inv_n, v, m1, m2);
-  item_loop<DIP_U_CATBWD>(blockIdx.x * PPB + slot, gridDim.x * PPB, H * W,
+  item_loop<DIP_U_CATBWD>(slot < PPB ? blockIdx.x * PPB + slot : H * W, gridDim.x * PPB, H * W,
                [&](int p) {
                  RedItem it;
                  const int i = p / W, j = p - i * W;
@@ -930,6 +957,12 @@ __global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__
                  st4(dcat + static_cast<size_t>(p) * C + 4 * v, dx);
                });
 }
+__global__ void __launch_bounds__(256) k_cat_bwd_apply(const float* __restrict__ pcat, BnRef bn_cat, const float* __restrict__ gp,
+                                                       int ld, int H, int W, const double* __restrict__ bwd,
+                                                       float* __restrict__ dcat, int VL, int PPB) {
+  pdl_enter();
+  d_cat_bwd_apply(pcat, bn_cat, gp, ld, H, W, bwd, dcat, VL, PPB);
+}
 void launch_cat_bwd_apply(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, const double* bwd,
                           float* dcat, cudaStream_t s) {
   VecGeom g = vec_geom(bn_cat.C, static_cast<long long>(H) * W);
@@ -938,9 +971,8 @@ void launch_cat_bwd_apply(const float* pcat, BnRef bn_cat, const float* gp, int 
 }
 
 // Adjoint of the x2 upsampling, materialised once: dst[h][w][C] <- D[2h][2w][ld] (channels coff..coff+C)
-__global__ void __launch_bounds__(256) k_upadj(const float* __restrict__ D, int ld, int coff, int h, int w, int C, int bilinear,
+__device__ __forceinline__ void d_upadj(const float* __restrict__ D, int ld, int coff, int h, int w, int C, int bilinear,
                                                float* __restrict__ dst, int VL, int PPB) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   item_loop<1>(blockIdx.x * PPB + slot, gridDim.x * PPB, h * w,
                [&](int p) {
@@ -948,6 +980,11 @@ __global__ void __launch_bounds__(256) k_upadj(const float* __restrict__ D, int 
                  return upadj_read(D, ld, coff, h, w, i, j, v, bilinear);
                },
                [&](int p, float4 g) { st4(dst + static_cast<size_t>(p) * C + 4 * v, g); });
+}
+__global__ void __launch_bounds__(256) k_upadj(const float* __restrict__ D, int ld, int coff, int h, int w, int C, int bilinear,
+                                               float* __restrict__ dst, int VL, int PPB) {
+  pdl_enter();
+  d_upadj(D, ld, coff, h, w, C, bilinear, dst, VL, PPB);
 }
 void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bilinear, float* dst, cudaStream_t s) {
   VecGeom g = vec_geom(C, static_cast<long long>(h) * w);
@@ -965,10 +1002,9 @@ __device__ __forceinline__ float4 skinny_wrow(const float* __restrict__ w, int n
 
 // ------------------------------------------------------------------------------------------------ skinny 1x1 convs
 // VL = C/4 lanes per pixel (power of two <= 32); warp-shuffle reduction over the pixel's lanes.
-__global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
+__device__ __forceinline__ void d_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
                                                     const float* __restrict__ b, int C, int N, int H, int W,
                                                     float* __restrict__ y, int mode, double* __restrict__ stats, int cw) {
-  pdl_enter();
   const int VL = C / 4;
   const int PPB = 256 / VL;
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
@@ -1019,6 +1055,12 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
     block_reduce_atomic<2>(acc2, 1, 256, dst, wid);
   }
 }
+__global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
+                                                    const float* __restrict__ b, int C, int N, int H, int W,
+                                                    float* __restrict__ y, int mode, double* __restrict__ stats, int cw) {
+  pdl_enter();
+  d_skinny_fwd(x, ldx, x_rs, w, b, C, N, H, W, y, mode, stats, cw);
+}
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
                        int W, float* y, int mode, double* stats, cudaStream_t s, int cw) {
   const int PPB = 256 / (C / 4);
@@ -1028,10 +1070,9 @@ void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const 
                   y, mode, stats, cw > 0 ? cw : C);
 }
 
-__global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
+__device__ __forceinline__ void d_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
                              int H, int W, const float* __restrict__ dy, const float* __restrict__ out_nchw, int mode,
                              float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB, int cw) {
-  pdl_enter();
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const int npix = H * W;
   float4 wv[4];
@@ -1077,6 +1118,12 @@ __global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, con
                           N > 3 ? dw + 3 * C * kAccS : nullptr, db};
   const int wid[5] = {C, C, C, C, N};  // acc[4] (bias gradient) lives on lanes v == 0 only
   block_reduce_atomic<5>(acc, VL, PPB, dst, wid);
+}
+__global__ void k_skinny_bwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w, int C, int N,
+                             int H, int W, const float* __restrict__ dy, const float* __restrict__ out_nchw, int mode,
+                             float* __restrict__ dx, double* __restrict__ dw, double* __restrict__ db, int VL, int PPB, int cw) {
+  pdl_enter();
+  d_skinny_bwd(x, ldx, x_rs, w, C, N, H, W, dy, out_nchw, mode, dx, dw, db, VL, PPB, cw);
 }
 void launch_skinny_bwd(const float* x, int ldx, int x_rs, const float* w, int C, int N, int H, int W,
                        const float* dy, const float* out_nchw, int mode, float* dx, double* dw, double* db,

@@ -331,3 +331,29 @@ def test_inpainting_closure_through_modules_vs_golden(prec):
     assert (np.median(dev) if prec == "tf32" else dev.max()) < (0.1 if prec == "tf32" else GRAD_TOL[prec]), dev.max()
     optimize("adam", params, closure, float(g["lr"]), 2)           # keeps running (3 iterations like the fixture)
     assert np.isfinite(losses).all() and abs(losses[1] - float(g["losses"][1])) < 2e-2
+
+
+def test_deep_kernel_matches_launches():
+    """DIP_DEEP=1: levels >= 2 run as ONE persistent kernel per pass (deep.cu: op list + grid-wide barriers, the same device
+    code as the stand-alone kernels).  It must reproduce the launch-by-launch path: outputs, every gradient, and a few runner
+    iterations.  (Opt-in: measured slower than the launches it replaces)"""
+    import dip_engine as de
+    H, W = 64, 96
+    cfg, params, z0, target, _ = make_problem(H, W, "bilinear")
+    res = {}
+    for mode in ("launches", "deep"):
+        if mode == "deep":
+            os.environ["DIP_DEEP"] = "1"
+        try:
+            plan, dparams, dgrads = make_engine(cfg, params, H, W, "tf32")     # graphs are captured per plan
+            out = plan.forward(z0.cuda())
+            dout = (2.0 * (out - target.cuda()) / out.numel()).contiguous()
+            plan.backward(dout)
+            torch.cuda.synchronize()
+            res[mode] = (out.clone(), [g.clone() for g in dgrads], plan.num_launches())
+        finally:
+            os.environ.pop("DIP_DEEP", None)
+    assert res["deep"][2][0] < res["launches"][2][0] - 20 and res["deep"][2][1] < res["launches"][2][1] - 40   # launches saved
+    assert torch.allclose(res["deep"][0], res["launches"][0], rtol=0, atol=1e-6)
+    for a, b in zip(res["deep"][1], res["launches"][1]):
+        assert rel(a, b) < 1e-3 or b.norm().item() < 1e-6      # split-K atomics: summation order differs run to run
