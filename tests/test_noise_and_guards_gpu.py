@@ -248,3 +248,28 @@ def test_fast_denoising_closure_matches_the_verbatim_one():
     # the snapshot holds the parameters as they were when the closure of the last iteration ran (before its Adam step)
     assert all(torch.isfinite(p).all() for p in net2.parameters())
     assert sum(float((a - b).abs().max()) for a, b in zip(before, net2.parameters())) < 112 * 0.011
+
+
+def test_optimize_lbfgs_branch_on_the_engine():
+    """utils.optimize('LBFGS', ...) (reference: utils/common_utils.py:208-221): 100 Adam warm-up steps at lr 1e-3 (fused
+    Adam on the engine), then torch.optim.LBFGS driving the same closure -- the network, loss gradient and parameter updates
+    all go through the engine module (LBFGS itself is stock torch: SURVEY.md 8f.4 keeps it outside the accelerated path)."""
+    from utils.common_utils import get_params, optimize
+    net = _net64()
+    g = torch.Generator().manual_seed(9)
+    z = (torch.rand(1, 32, 64, 64, generator=g) * 0.1).cuda()
+    target = torch.rand(1, 3, 64, 64, generator=g).cuda()
+    mse = torch.nn.MSELoss()
+    losses = []
+
+    def closure():
+        out = net(z)
+        loss = mse(out, target)
+        loss.backward()
+        losses.append(loss.item())
+        return loss
+
+    optimize("LBFGS", get_params("net", net, z), closure, 0.01, 8)
+    assert len(losses) >= 100 + 8 and np.isfinite(losses).all()
+    assert np.mean(losses[95:100]) < losses[0]                 # the Adam warm-up made progress
+    assert min(losses[100:]) < np.mean(losses[95:100])         # and LBFGS went further down
