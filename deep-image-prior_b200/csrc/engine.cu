@@ -643,7 +643,9 @@ static int build_plan(dip_plan* P, Arena& A) {
   const dip_net_desc& d = P->desc;
   const int L = d.num_scales, CH = d.channels, CS = d.skip_channels;
   if (CH != 128) return fail("dip-b200: only num_channels_down == num_channels_up == 128 is supported by the engine");
-  if (CS != 4 && CS != 128) return fail("dip-b200: num_channels_skip must be 4 or 128");
+  if (CS != 0 && CS != 4 && CS != 128) return fail("dip-b200: num_channels_skip must be 0, 4 or 128");
+  const int ps = CS > 0 ? 4 : 0;   // parameters of the skip branch (conv w, b, BN gamma, beta): absent for num_channels_skip = 0
+                                   // (inpainting.ipynb c14:11-16 "vase": models/skip.py:50-53 then adds `deeper` alone, no Concat)
   const bool wide = CS == 128;   // skip branch on the tensor cores, 256-channel concat
   if (d.in_channels < 1 || d.in_channels > 128) return fail("dip-b200: input depth must be in [1,128]");
   // level-0 activations are stored with the input depth rounded up to a power of two >= 4 (zero channels); the conv
@@ -660,7 +662,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   std::vector<int> pre(L), post(L);
   {
     int idx = 0;
-    for (int l = 0; l < L; ++l) { pre[l] = idx; idx += 12; }
+    for (int l = 0; l < L; ++l) { pre[l] = idx; idx += 8 + ps; }
     for (int l = L - 1; l >= 0; --l) { post[l] = idx; idx += 10; }
     P->p_head_w = idx; P->p_head_b = idx + 1;
     pidx = idx + 2;
@@ -681,17 +683,22 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.bilinear = d.upsample_bilinear < 0 ? (d.upsample_mask >> l) & 1 : (d.upsample_bilinear != 0);
     const int b0 = pre[l], b1 = post[l];
     // skip conv 1x1 Cin -> CS
-    v.p_skip_w = b0; v.p_skip_b = b0 + 1;
-    P->numel[b0] = (long long)CS * v.Cin_act; P->numel[b0 + 1] = CS;
-    bn_init(v.bn_s, CS, 0, v.H * v.W, b0 + 2, b0 + 1);
+    if (CS > 0) {
+      v.p_skip_w = b0; v.p_skip_b = b0 + 1;
+      P->numel[b0] = (long long)CS * v.Cin_act; P->numel[b0 + 1] = CS;
+      bn_init(v.bn_s, CS, 0, v.H * v.W, b0 + 2, b0 + 1);
+    } else {
+      v.p_skip_w = v.p_skip_b = -1;
+      v.bn_s = BnLayer{};
+    }
     // down1 3x3 s2
-    v.d1.C = v.Cin_act; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + 4; v.d1.p_b = b0 + 5;
-    P->numel[b0 + 4] = 128LL * v.Cin_act * 9; P->numel[b0 + 5] = 128;
-    bn_init(v.bn_d1, 128, 0, v.h * v.w, b0 + 6, b0 + 5);
+    v.d1.C = v.Cin_act; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + ps; v.d1.p_b = b0 + ps + 1;
+    P->numel[b0 + ps] = 128LL * v.Cin_act * 9; P->numel[b0 + ps + 1] = 128;
+    bn_init(v.bn_d1, 128, 0, v.h * v.w, b0 + ps + 2, b0 + ps + 1);
     // down2 3x3
-    v.d2.C = 128; v.d2.k = 3; v.d2.stride = 1; v.d2.p_w = b0 + 8; v.d2.p_b = b0 + 9;
-    P->numel[b0 + 8] = 128LL * 128 * 9; P->numel[b0 + 9] = 128;
-    bn_init(v.bn_d2, 128, 0, v.h * v.w, b0 + 10, b0 + 9);
+    v.d2.C = 128; v.d2.k = 3; v.d2.stride = 1; v.d2.p_w = b0 + ps + 4; v.d2.p_b = b0 + ps + 5;
+    P->numel[b0 + ps + 4] = 128LL * 128 * 9; P->numel[b0 + ps + 5] = 128;
+    bn_init(v.bn_d2, 128, 0, v.h * v.w, b0 + ps + 6, b0 + ps + 5);
     // concat BN (torch channel order [skip | up], engine order [up | skip])
     bn_init(v.bn_cat, 128 + CS, CS, v.H * v.W, b1 + 0, -1);
     // up 3x3 (128+CS) -> 128
@@ -717,7 +724,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   // BN order (running-stat table) follows state_dict order: skip, d1, d2, <deeper>, cat, up, 1x1
   {
     std::vector<BnLayer*> a, b;
-    for (int l = 0; l < L; ++l) { a.push_back(&P->lv[l].bn_s); a.push_back(&P->lv[l].bn_d1); a.push_back(&P->lv[l].bn_d2); }
+    for (int l = 0; l < L; ++l) { if (CS > 0) a.push_back(&P->lv[l].bn_s); a.push_back(&P->lv[l].bn_d1); a.push_back(&P->lv[l].bn_d2); }
     for (int l = L - 1; l >= 0; --l) { a.push_back(&P->lv[l].bn_cat); a.push_back(&P->lv[l].bn_u); a.push_back(&P->lv[l].bn_v); }
     P->bns = a;
     for (size_t i = 0; i < P->bns.size(); ++i) P->bns[i]->idx = (int)i;
@@ -956,7 +963,7 @@ static int upload_tables(dip_plan* P) {
   }
   for (size_t l = 0; l < P->lv.size(); ++l) {
     // skip=128: the skip conv's weight gradient comes from the tensor-core wgrad, not from fp64 accumulators
-    if (P->desc.skip_channels == 128) cv.push_back(CvtEntry{P->lv[l].dw_s, nullptr, 0, 0});
+    if (P->desc.skip_channels == 128 || P->desc.skip_channels == 0) cv.push_back(CvtEntry{P->lv[l].dw_s, nullptr, 0, 0});
     else cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0,
                                P->lv[l].Cin_act, P->lv[l].Cin});   // accumulator rows hold the stored depth
   }
@@ -1016,7 +1023,9 @@ static void join_skip(dip_plan* P, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ forward
 static CatArgs cat_args(const dip_plan* P, const Level& v, const float* Usrc) {
   CatArgs a;
-  a.U = Usrc; a.raw_s = v.raw_s; a.bn_s = bn_ref(P, v.bn_s);
+  a.U = Usrc; a.raw_s = v.raw_s;
+  if (P->desc.skip_channels > 0) a.bn_s = bn_ref(P, v.bn_s);
+  else a.bn_s = BnRef{nullptr, nullptr, nullptr, 0, 0, 0.f};   // num_channels_skip = 0: the "concat" is the upsampled tensor alone
   a.Cu = 128; a.Cs = P->desc.skip_channels; a.H = v.H; a.W = v.W; a.bilinear = v.bilinear;
   return a;
 }
@@ -1043,7 +1052,7 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   const bool last = l == (int)P->lv.size() - 1;
   const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
   // skip branch: 1x1 conv Cin -> CS (+ statistics); independent of the deeper branch until the concat -> skip stream
-  {
+  if (CS > 0) {
     cudaStream_t ks = fork_skip(P, s);
     if (CS == 128) {
       DIP_CHECK(v.sk.run_fprop(prec, P->params[v.p_skip_b], ks));
@@ -1074,7 +1083,7 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
     }
   }
   // upsample + concat + BN + pad
-  join_skip(P, s);
+  if (CS > 0) join_skip(P, s);
   CatArgs ca = cat_args(P, v, level_usrc(P, l));
   const double cat_in = (128.0 * v.h * v.w + (double)CS * v.H * v.W) * sizeof(float);
   HBM_T(&P->timer, H_CAT_STATS, v.bilinear, cat_in, s, launch_cat_stats(ca, v.bn_cat.fwd, s));
@@ -1236,8 +1245,10 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   HBM_T(&P->timer, H_UPADJ, v.bilinear, 128.0 * ((double)v.H * v.W + (double)v.h * v.w) * sizeof(float), s,
         launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp, s));
   nl += 3;
-  DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl));
-  if (CS == 128) {
+  if (CS > 0) DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl));
+  if (CS == 0) {
+    // no skip branch (models/skip.py:50-53 with num_channels_skip = 0)
+  } else if (CS == 128) {
     DIP_CHECK(v.sk.run_wgrad(prec, P->partial, P->grads[v.p_skip_w], fork_side(P, ks)));
     nl += wl;
     if (l > 0 || P->desc.input_grad) { DIP_CHECK(v.sk.run_dgrad(prec, ks)); nl += 1; }   // dS, added to the fold of dPin by the level above
@@ -1262,6 +1273,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
     join_skip(P, s);   // the next level's skip-branch gradients (dRaw_s / dS) feed the BN backward below
     Level& n = P->lv[l + 1];
     if (CS == 128) { src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = 128; }
+    else if (CS == 0) src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0);
     else src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
   } else {
     src_d2 = src_plain(v.dUp, 128, 0);
@@ -1426,7 +1438,7 @@ static void deep_bwd_level(dip_plan* P, int l, GradSrc src_v, std::vector<DeepOp
 static int build_deep_ops(dip_plan* P) {
   P->n_deep_fwd = P->n_deep_bwd = 0;
   P->deep_grid = 128 < g_num_sms ? 128 : g_num_sms;
-  if (P->desc.precision != DIP_PRECISION_TF32 || (int)P->lv.size() <= P->deep_from) return 0;
+  if (P->desc.precision != DIP_PRECISION_TF32 || (int)P->lv.size() <= P->deep_from || P->desc.skip_channels == 0) return 0;
   std::vector<DeepOp> fwd;
   deep_fwd_level(P, P->deep_from, fwd);
   if ((int)fwd.size() > dip_plan::kDeepMaxOps) return fail("internal: deep forward op list too long");
@@ -1816,7 +1828,7 @@ int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* 
 int dip_input_grad(dip_plan* P, void* dz, dip_stream_t stream) {
   if (!P->desc.input_grad) return fail("dip_input_grad: the plan was created without input_grad");
   Level& v = P->lv[0];
-  launch_input_grad(v.dPin, v.dS, v.Cin, v.Cin_act, v.H, v.W, (float*)dz, (cudaStream_t)stream);
+  launch_input_grad(v.dPin, P->desc.skip_channels > 0 ? v.dS : nullptr, v.Cin, v.Cin_act, v.H, v.W, (float*)dz, (cudaStream_t)stream);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }

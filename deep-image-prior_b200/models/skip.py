@@ -251,8 +251,8 @@ def skip(num_input_channels=2, num_output_channels=3,
     chans = set(num_channels_down) | set(num_channels_up)
     if chans != {128}:
         why = 'num_channels_down/up must all be 128'
-    elif set(num_channels_skip) not in ({4}, {128}):
-        why = 'num_channels_skip must all be 4 or all be 128'
+    elif set(num_channels_skip) not in ({0}, {4}, {128}):
+        why = 'num_channels_skip must all be 0, all be 4 or all be 128'
     elif set(filter_size_down) != {3} or set(filter_size_up) != {3} or filter_skip_size != 1:
         why = 'filter sizes must be 3/3/1'
     elif pad != 'reflection':

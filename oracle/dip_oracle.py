@@ -48,8 +48,9 @@ def param_layout(cfg):
     pre, post = [], []
     for l in range(L):
         cin = cfg.in_channels if l == 0 else C
-        pre.append([("L%d.skip.w" % l, (S, cin, 1, 1)), ("L%d.skip.b" % l, (S,)),
-                    ("L%d.skip_bn.g" % l, (S,)), ("L%d.skip_bn.b" % l, (S,)),
+        sk = [("L%d.skip.w" % l, (S, cin, 1, 1)), ("L%d.skip.b" % l, (S,)),
+              ("L%d.skip_bn.g" % l, (S,)), ("L%d.skip_bn.b" % l, (S,))] if S > 0 else []   # num_channels_skip = 0: no skip branch
+        pre.append(sk + [
                     ("L%d.d1.w" % l, (C, cin, 3, 3)), ("L%d.d1.b" % l, (C,)),
                     ("L%d.d1_bn.g" % l, (C,)), ("L%d.d1_bn.b" % l, (C,)),
                     ("L%d.d2.w" % l, (C, C, 3, 3)), ("L%d.d2.b" % l, (C,)),
@@ -79,6 +80,8 @@ def init_params(cfg, seed=None, dtype=torch.float32):
         cin = cfg.in_channels if l == 0 else C
         for name, (o, i, k) in (("skip", (S, cin, 1)), ("d1", (C, cin, 3)), ("d2", (C, C, 3)), ("up", (C, C + S, 3)),
                                 ("c11", (C, C, 1))):
+            if o == 0:
+                continue   # models/skip.py:57-60: the skip conv is only constructed (and only draws from the RNG) when it has channels
             m = nn.Conv2d(i, o, k)  # torch default init: kaiming_uniform(a=sqrt(5)) + bias U(+-1/sqrt(fan_in))
             vals["L%d.%s.w" % (l, name)] = m.weight.detach()
             vals["L%d.%s.b" % (l, name)] = m.bias.detach()
@@ -118,10 +121,12 @@ def skip_forward(params, z, cfg, tape=None):
 
     def rec(l, x):
         pre = "L%d." % l
-        s = _conv(x, P[pre + "skip.w"], P[pre + "skip.b"])
-        if tape is not None:
-            tape[pre + "raw_s"] = s
-        s = _act(_bn(s, P[pre + "skip_bn.g"], P[pre + "skip_bn.b"]))
+        s = None
+        if cfg.skip_channels > 0:
+            s = _conv(x, P[pre + "skip.w"], P[pre + "skip.b"])
+            if tape is not None:
+                tape[pre + "raw_s"] = s
+            s = _act(_bn(s, P[pre + "skip_bn.g"], P[pre + "skip_bn.b"]))
         d = _conv(x, P[pre + "d1.w"], P[pre + "d1.b"], stride=2)
         if tape is not None:
             tape[pre + "raw_d1"] = d
@@ -137,7 +142,7 @@ def skip_forward(params, z, cfg, tape=None):
             d = F.interpolate(d, scale_factor=2, mode="bilinear", align_corners=False)
         else:
             d = F.interpolate(d, scale_factor=2, mode="nearest")
-        c = torch.cat([s, d], dim=1)  # Concat: skip channels first (models/common.py:19-39)
+        c = torch.cat([s, d], dim=1) if s is not None else d  # Concat: skip channels first (models/common.py:19-39); skip.py:50-53
         if tape is not None:
             tape[pre + "cat"] = c
         c = _bn(c, P[pre + "cat_bn.g"], P[pre + "cat_bn.b"])

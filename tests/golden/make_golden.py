@@ -62,17 +62,19 @@ def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtyp
 
 
 def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.01, masked=False, dtype=torch.float32,
-                threads=8):
+                threads=8, skip_ch=4, meshgrid=False):
     """Skip-net variants of the other notebooks that use the 128-wide network: flash-no-flash.ipynb c8 (image as input,
     per-scale upsampling modes) and restoration.ipynb c7 barbara (n_channels=1, masked loss)."""
     torch.set_num_threads(threads)
     with ref_harness.reference_modules() as ref:
         torch.manual_seed(0)
         net = ref.models.skip(in_depth, out_ch, num_channels_down=[128] * 5, num_channels_up=[128] * 5,
-                              num_channels_skip=[4] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True,
+                              num_channels_skip=[skip_ch] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True,
                               pad='reflection').type(dtype)
         g = torch.Generator().manual_seed(2)
         z0 = torch.rand(1, in_depth, H, W, generator=g).type(dtype)          # an image (or noise) as the network input
+        if meshgrid:   # inpainting.ipynb c14:1-16 (vase): INPUT = 'meshgrid', input_depth = 2 (utils/common_utils.py:145-149)
+            z0 = ref.common_utils.get_noise(in_depth, 'meshgrid', (H, W)).type(dtype)
         target = torch.rand(1, out_ch, H, W, generator=g).type(dtype)
         mask = (torch.rand(1, 1, H, W, generator=g) > 0.5).type(dtype) if masked else None
         gn = torch.Generator().manual_seed(123)
@@ -89,14 +91,14 @@ def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.0
             if i == 0:
                 out0 = out.detach().clone()
                 gnorm0 = np.array([p.grad.double().norm().item() for p in params])
-                g_first = [params[k].grad.detach().clone().numpy() for k in (0, 4)]   # L0 skip conv w, L0 down conv w
+                g_first = [params[k].grad.detach().clone().numpy() for k in (0, 4 if skip_ch else 0)]   # L0 skip conv w (if any), L0 down conv w
             losses.append(loss.item())
             opt.step()
         keys = list(net.state_dict().keys())
     np.savez_compressed(os.path.join(HERE, name + '.npz'), H=H, W=W, in_depth=in_depth, out_ch=out_ch,
                         modes=np.array(modes if isinstance(modes, list) else [modes] * 5), iters=iters, sigma=sigma, lr=lr,
                         masked=masked, losses=np.array(losses), out0=out0.numpy(), gnorm0=gnorm0, g_skip0_w=g_first[0],
-                        g_d1_0_w=g_first[1], dtype=str(dtype), state_keys=np.array(keys))
+                        g_d1_0_w=g_first[1], dtype=str(dtype), state_keys=np.array(keys), skip_ch=skip_ch, z0=z0.numpy())
     print(name, 'losses', losses)
 
 
@@ -293,6 +295,10 @@ if __name__ == '__main__':
         for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
             run_variant('flash64x96_in3_mixed_' + tag, 64, 96, 3, 3, FLASH_MODES, dtype=dt)
             run_variant('restore64_out1_masked_' + tag, 64, 64, 32, 1, 'bilinear', masked=True, dtype=dt)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'vase':   # inpainting.ipynb "vase": num_channels_skip = 0, meshgrid input, nearest
+        for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
+            run_variant('vase64x96_in2_skip0_masked_' + tag, 64, 96, 2, 3, 'nearest', masked=True, dtype=dt, skip_ch=0, meshgrid=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sr':   # only the super-resolution fixtures
         run_downsampler_cases()

@@ -81,3 +81,17 @@ def test_flash_no_flash_notebook_runs_unchanged():
     loss = _losses(ns["__stdout__"], r"Loss ([0-9.]+)")
     assert len(loss) == 30 and loss[-1] < loss[0]
     assert ns["out_np"].shape == (3, 704, 768)
+
+
+@needs_ref
+def test_inpainting_notebook_vase_branch_runs_unchanged():
+    """inpainting.ipynb with the "Fig 6" vase image selected (the user edit of cell 5: img_path / mask_path): meshgrid input of
+    depth 2, skip(..., num_channels_skip=[0]*5, upsample_mode='nearest') -- no skip branches, no Concat -- 320x320."""
+    torch.manual_seed(0)
+    ns = run_notebook(os.path.join(REF, "inpainting.ipynb"),
+                      dict(PLOT=False, num_iter=30, img_path="data/inpainting/vase.png", mask_path="data/inpainting/vase_mask.png"))
+    _assert_engine_net(ns["net"])
+    assert ns["net"]._dip_spec["skip_channels"] == 0 and ns["net"]._dip_spec["in_channels"] == 2 and ns["INPUT"] == "meshgrid"
+    loss = _losses(ns["__stdout__"], r"Loss ([0-9.]+)")
+    assert len(loss) == 30 and loss[-1] < 0.7 * loss[0]
+    assert ns["out_np"].shape == (3, 320, 320)

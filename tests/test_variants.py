@@ -1,6 +1,7 @@
 """Skip-net variants of the other notebooks that use the 128-wide network: flash-no-flash.ipynb c8
 (3-channel image as the network input, per-scale upsampling modes) and restoration.ipynb c7 barbara (n_channels = 1,
-masked loss).  Fixtures from the unmodified reference: tests/golden/make_golden.py `variants`."""
+masked loss), and inpainting.ipynb c14:1-16 "vase" (num_channels_skip = 0: no skip branch / no Concat, meshgrid input of depth
+2, nearest upsampling, masked loss).  Fixtures from the unmodified reference: tests/golden/make_golden.py `variants` / `vase`."""
 import os
 
 import numpy as np
@@ -10,15 +11,21 @@ import torch
 from oracle import dip_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["flash64x96_in3_mixed", "restore64_out1_masked"]
+CASES = ["flash64x96_in3_mixed", "restore64_out1_masked", "vase64x96_in2_skip0_masked"]
+
+
+def skip_ch(g):
+    return int(g["skip_ch"]) if "skip_ch" in g else 4
 
 
 def setup(g, dtype):
     H, W = int(g["H"]), int(g["W"])
     modes = [str(m) for m in g["modes"]]
-    cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes)
+    cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skip_ch(g))
     gen = torch.Generator().manual_seed(2)
     z0 = torch.rand(1, cfg.in_channels, H, W, generator=gen).to(dtype)
+    if "z0" in g:   # the vase fixture's meshgrid input (the generator draws above stay, so target / mask match the fixture's)
+        z0 = torch.from_numpy(g["z0"]).to(dtype)
     target = torch.rand(1, cfg.out_channels, H, W, generator=gen).to(dtype)
     mask = (torch.rand(1, 1, H, W, generator=gen) > 0.5).to(dtype) if bool(g["masked"]) else None
     gn = torch.Generator().manual_seed(123)
@@ -44,7 +51,7 @@ def test_oracle_matches_reference_golden_fp64(case):
     big = g["gnorm0"] > 1e-9
     assert np.allclose(gn[big], g["gnorm0"][big], rtol=1e-6)
     assert np.allclose(rec["grads0"][0].numpy(), g["g_skip0_w"], rtol=1e-6, atol=1e-12)
-    assert np.allclose(rec["grads0"][4].numpy(), g["g_d1_0_w"], rtol=1e-6, atol=1e-12)
+    assert np.allclose(rec["grads0"][4 if skip_ch(g) else 0].numpy(), g["g_d1_0_w"], rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -54,13 +61,14 @@ def test_module_tree_matches_reference_and_is_accelerated(case):
     modes = [str(m) for m in g["modes"]]
     torch.manual_seed(0)
     net = models.skip(int(g["in_depth"]), int(g["out_ch"]), num_channels_down=[128] * 5, num_channels_up=[128] * 5,
-                      num_channels_skip=[4] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True, pad="reflection")
+                      num_channels_skip=[skip_ch(g)] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True, pad="reflection")
     assert list(net.state_dict().keys()) == [str(k) for k in g["state_keys"]]
     spec = net._dip_spec
     assert spec is not None and spec["in_channels"] == int(g["in_depth"]) and spec["out_channels"] == int(g["out_ch"])
     if len(set(modes)) > 1:
         assert spec["bilinear"] == [m == "bilinear" for m in modes]
-    cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes)
+    cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skip_ch(g))
+    assert spec["skip_channels"] == skip_ch(g)
     for a, b in zip(net.parameters(), O.init_params(cfg, seed=0)):
         assert a.shape == b.shape and torch.equal(a.detach(), b.detach())
 
@@ -77,8 +85,8 @@ def test_engine_matches_reference_golden(case, prec):
     dtype = torch.cuda.FloatTensor
     torch.manual_seed(0)
     net = models.skip(cfg.in_channels, cfg.out_channels, num_channels_down=[128] * 5, num_channels_up=[128] * 5,
-                      num_channels_skip=[4] * 5, upsample_mode=list(cfg.upsample_mode), need_sigmoid=True, need_bias=True,
-                      pad="reflection").type(dtype)
+                      num_channels_skip=[cfg.skip_channels] * 5, upsample_mode=list(cfg.upsample_mode), need_sigmoid=True,
+                      need_bias=True, pad="reflection").type(dtype)
     net.precision = prec
     z0d, tgt = z0.type(dtype), target.type(dtype)
     md = mask.type(dtype) if mask is not None else None
@@ -109,7 +117,7 @@ def test_engine_matches_reference_golden(case, prec):
         return ((a - b).norm() / (b.norm() + 1e-30)).item()
     # the two level-0 convs that read the (zero-padded) input: 1x1 skip conv (CUDA-core path) and 3x3 stride-2 conv
     assert rel(params[0].grad, g["g_skip0_w"]) < (3e-2 if prec == "fp32" else 0.3)
-    assert rel(params[4].grad, g["g_d1_0_w"]) < (3e-2 if prec == "fp32" else 0.3)
+    assert rel(params[4 if cfg.skip_channels else 0].grad, g["g_d1_0_w"]) < (3e-2 if prec == "fp32" else 0.3)
     optimize("adam", params, closure, float(g["lr"]), 2)
     assert np.isfinite(losses).all() and abs(losses[1] - float(g["losses"][1])) < 2e-2
 
@@ -142,7 +150,8 @@ def test_runner_with_odd_input_depth():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfgargs", [dict(), dict(in_channels=3), dict(skip_channels=128, upsample_mode="nearest")])
+@pytest.mark.parametrize("cfgargs", [dict(), dict(in_channels=3), dict(skip_channels=128, upsample_mode="nearest"),
+                                     dict(skip_channels=0, in_channels=2, upsample_mode="nearest")])
 def test_input_gradient_and_no_sigmoid_vs_oracle(cfgargs):
     """OPT_OVER = 'net,input' (utils/common_utils.py:47-49: the input tensor is optimised too) and need_sigmoid=False
     (models/skip.py:97): dL/d(net_input), the output and the weight gradients vs autograd of the oracle, exact-fp32 mode."""
