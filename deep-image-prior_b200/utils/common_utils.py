@@ -50,22 +50,33 @@ def get_params(opt_over, net, net_input, downsampler=None):
 
 
 def get_image_grid(images_np, nrow=8):
-    grid = torchvision.utils.make_grid([torch.from_numpy(x) for x in images_np], nrow)
-    return grid.numpy()
+    """C x H x W arrays tiled into one C x H' x W' array, `nrow` images per row, 2-pixel black gutters (what the reference
+    gets from torchvision.utils.make_grid, utils/common_utils.py:55-60; a single image comes back as it is)."""
+    imgs = [np.asarray(x) for x in images_np]
+    if len(imgs) == 1:
+        return imgs[0]
+    gap = 2
+    c, h, w = imgs[0].shape
+    cols = min(nrow, len(imgs))
+    rows = -(-len(imgs) // cols)
+    canvas = np.zeros((c, rows * (h + gap) + gap, cols * (w + gap) + gap), dtype=imgs[0].dtype)
+    for k, im in enumerate(imgs):
+        top, left = (k // cols) * (h + gap) + gap, (k % cols) * (w + gap) + gap
+        canvas[:, top:top + h, left:left + w] = im
+    return canvas
 
 
 def plot_image_grid(images_np, nrow=8, factor=1, interpolation='lanczos'):
-    """Shows images in a grid (display only; no-op without matplotlib) (reference: :67-87)."""
-    n_channels = max(x.shape[0] for x in images_np)
-    assert n_channels in (1, 3), "images should have 1 or 3 channels"
-    images_np = [x if x.shape[0] == n_channels else np.concatenate([x, x, x], axis=0) for x in images_np]
-    grid = get_image_grid(images_np, nrow)
+    """Display helper of the notebooks (reference: utils/common_utils.py:62-87): grey images are promoted to 3 channels when
+    mixed with colour ones, the tiled grid is shown with matplotlib when it is installed, and returned either way."""
+    depth = max(im.shape[0] for im in images_np)
+    assert depth in (1, 3), "images should have 1 or 3 channels"
+    tiles = [im if im.shape[0] == depth else np.repeat(im, 3, axis=0) for im in images_np]
+    grid = get_image_grid(tiles, nrow)
     if plt is not None:
-        plt.figure(figsize=(len(images_np) + factor, 12 + factor))
-        if images_np[0].shape[0] == 1:
-            plt.imshow(grid[0], cmap='gray', interpolation=interpolation)
-        else:
-            plt.imshow(grid.transpose(1, 2, 0), interpolation=interpolation)
+        plt.figure(figsize=(len(tiles) + factor, 12 + factor))
+        shown = grid[0] if depth == 1 else np.moveaxis(grid, 0, -1)
+        plt.imshow(shown, interpolation=interpolation, **({'cmap': 'gray'} if depth == 1 else {}))
         plt.show()
     return grid
 

@@ -97,3 +97,17 @@ def test_inpainting_utils_equal_live_reference():
     assert np.array_equal(mine, theirs)
     if have_font:
         assert np.array_equal(np.array(ours.get_text_mask(img)), t_theirs)
+
+
+def test_image_grid_matches_torchvision_make_grid():
+    """get_image_grid (used by plot_image_grid, which the notebooks call unconditionally in a few cells) tiles like
+    torchvision.utils.make_grid does for the reference (utils/common_utils.py:55-60), without needing torchvision."""
+    torchvision = pytest.importorskip("torchvision")
+    from utils.common_utils import get_image_grid, plot_image_grid
+    rng = np.random.RandomState(0)
+    for n, nrow in ((1, 8), (2, 3), (5, 3), (4, 4), (7, 2)):
+        ims = [rng.rand(3, 5, 7).astype(np.float32) for _ in range(n)]
+        ref = torchvision.utils.make_grid([torch.from_numpy(x) for x in ims], nrow).numpy()
+        assert np.array_equal(get_image_grid(ims, nrow), ref)
+    mixed = plot_image_grid([rng.rand(3, 4, 4).astype(np.float32), rng.rand(1, 4, 4).astype(np.float32)], 3, 11)
+    assert mixed.shape == (3, 8, 14)
