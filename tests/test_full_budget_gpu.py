@@ -137,8 +137,88 @@ def test_f16_2000_iterations_vs_reference_runs(prec):
     assert np.abs(mine - ref).max() < 1.0, np.abs(mine - ref).max()
 
 
+def run_sr_full_budget(prec):
+    """super-resolution.ipynb c5-c11 on the zebra pair (x4, 576x384 -> 144x96), 2000 iterations, through the modules
+    (net + models.Downsampler on the engine's stencil kernels) and utils.optimize(), same perturbation stream as the fixtures."""
+    import models
+    from utils import common_utils as cu
+    from utils.sr_utils import load_LR_HR_imgs_sr
+    refs = [np.load(os.path.join(GOLD, "sr_full_t%d.npz" % t)) for t in (4, 3)]
+    iters = int(refs[0]["iters"])
+    dtype = torch.cuda.FloatTensor
+    imgs = load_LR_HR_imgs_sr(os.path.join(GOLD, "data", "zebra_GT.png"), -1, 4, "CROP")
+    reg_noise_std, LR = 0.03, 0.01
+    torch.manual_seed(1)
+    net_input = cu.get_noise(32, "noise", (imgs["HR_pil"].size[1], imgs["HR_pil"].size[0])).type(dtype).detach()
+    torch.manual_seed(0)
+    net = models.get_net(32, "skip", "reflection", skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                         upsample_mode="bilinear").type(dtype)
+    net.precision = prec
+    mse = torch.nn.MSELoss().type(dtype)
+    img_LR_var = cu.np_to_torch(imgs["LR_np"]).type(dtype)
+    downsampler = models.Downsampler(n_planes=3, factor=4, kernel_type="lanczos2", phase=0.5, preserve_size=True).type(dtype)
+    net_input_saved = net_input.detach().clone()
+    q = queue.Queue(maxsize=4)
+
+    def producer():
+        gen = torch.Generator().manual_seed(123)
+        buf = torch.empty(net_input.shape)
+        for _ in range(iters):
+            q.put(buf.normal_(generator=gen).clone().pin_memory())
+    threading.Thread(target=producer, daemon=True).start()
+    rec = dict(loss=[], psnr_LR=[], psnr_HR=[])
+
+    def closure():   # super-resolution.ipynb c10
+        ni = net_input_saved + (q.get().cuda(non_blocking=True) * reg_noise_std)
+        out_HR = net(ni)
+        out_LR = downsampler(out_HR)
+        total_loss = mse(out_LR, img_LR_var)
+        total_loss.backward()
+        rec["loss"].append(total_loss.item())
+        rec["psnr_LR"].append(_psnr(imgs["LR_np"], cu.torch_to_np(out_LR)))
+        rec["psnr_HR"].append(_psnr(imgs["HR_np"], cu.torch_to_np(out_HR)))
+        return total_loss
+
+    cu.optimize("adam", cu.get_params("net", net, net_input), closure, LR, iters)
+    torch.cuda.synchronize()
+    rows = {}
+    for key in ("psnr_LR", "psnr_HR"):
+        t = lambda x: float(np.mean(np.asarray(x)[-50:]))   # noqa: E731  (single iterations jitter by ~0.1 dB)
+        ra, rb, mine = t(refs[0][key]), t(refs[1][key]), t(rec[key])
+        rows[key] = dict(tail50_engine=mine, tail50_ref_t4=ra, tail50_ref_t3=rb, ref_spread=abs(ra - rb),
+                         diff_vs_ref_mean=mine - 0.5 * (ra + rb), last_engine=float(rec[key][-1]),
+                         last_ref_t4=float(refs[0][key][-1]), last_ref_t3=float(refs[1][key][-1]))
+    rows["precision"], rows["iters"] = prec, iters
+    rows["first_losses"] = dict(engine=rec["loss"][:3], ref_t4=refs[0]["loss"][:3].tolist(), ref_t3=refs[1]["loss"][:3].tolist())
+    print("\nFULL-BUDGET SR zebra x4 (%s, %d iterations): %s" % (prec, iters, json.dumps(rows, indent=1)))
+    try:
+        os.makedirs(os.path.join(os.path.dirname(HERE), "gpurun_out"), exist_ok=True)
+        json.dump(rows, open(os.path.join(os.path.dirname(HERE), "gpurun_out", "full_budget_sr_%s.json" % prec), "w"), indent=1)
+    except OSError:
+        pass
+    return rows, rec, refs
+
+
+@pytest.mark.skipif(not all(os.path.exists(os.path.join(GOLD, "sr_full_t%d.npz" % t)) for t in (4, 3)),
+                    reason="SR full-budget reference fixtures not generated (tests/golden/make_sr_full.py)")
+def test_sr_zebra_2000_iterations_vs_reference_runs():
+    """BASELINE config 3 at its full budget (the real zebra pair): end-of-run PSNR_HR / PSNR_LR (means over the last 50
+    iterations) of the engine vs two runs of the unmodified reference; same acceptance band as the denoising test."""
+    rows, rec, refs = run_sr_full_budget("tf32")
+    assert abs(rec["loss"][0] - float(refs[0]["loss"][0])) < 1e-3
+    for key in ("psnr_LR", "psnr_HR"):
+        r = rows[key]
+        assert abs(r["diff_vs_ref_mean"]) < max(3.0 * r["ref_spread"], 0.5), (key, r)
+    mine = np.asarray(rec["psnr_HR"])[200::100]
+    ref = 0.5 * (refs[0]["psnr_HR"][200::100] + refs[1]["psnr_HR"][200::100])
+    assert np.abs(mine - ref).max() < 1.0, np.abs(mine - ref).max()
+
+
 if __name__ == "__main__":   # python tests/test_full_budget_gpu.py fp32   (ad-hoc run of the exact-fp32 tier)
     import sys
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, os.path.join(os.path.dirname(HERE), "deep-image-prior_b200"))
-    run_full_budget(sys.argv[1] if len(sys.argv) > 1 else "tf32")
+    if len(sys.argv) > 2 and sys.argv[2] == "sr":
+        run_sr_full_budget(sys.argv[1])
+    else:
+        run_full_budget(sys.argv[1] if len(sys.argv) > 1 else "tf32")
