@@ -28,6 +28,12 @@ namespace dip {
 #ifndef DIP_U_CATBWD
 #define DIP_U_CATBWD 2
 #endif
+#ifndef DIP_U_HEAD
+#define DIP_U_HEAD 4       // pixels in flight per warp of the fused BN + RGB head kernel
+#endif
+#ifndef DIP_CAT_MINBLOCKS
+#define DIP_CAT_MINBLOCKS 4   // __launch_bounds__ min blocks per SM of the concat kernels (register cap 64: level-0 k_cat_write 62 -> 49.5 us; 5 spills)
+#endif
 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(256) k_bn_act_head(const float* __restrict__ r
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = k < head.K ? ld4(head.w + k * 128 + 4 * lane) : f4zero();
   const float hbk = ((lane >> 3) & 3) < head.K ? head.b[(lane >> 3) & 3] : 0.f;   // bias of the output this lane ends up with
-  item_loop<4>(blockIdx.x * 8 + wslot, gridDim.x * 8, npix,
+  item_loop<DIP_U_HEAD>(blockIdx.x * 8 + wslot, gridDim.x * 8, npix,
                [&](int p) { return ld4(raw + static_cast<size_t>(p) * 128 + 4 * lane); },
                [&](int p, float4 x) {
                  const float4 y = lrelu4(bn_apply(cf, x));
@@ -422,7 +428,7 @@ __device__ __forceinline__ void d_cat_stats(CatArgs a, double* __restrict__ fwd,
   const int wid[2] = {a.Cu + a.Cs, a.Cu + a.Cs};
   block_reduce_atomic<2>(acc, VL, PPB, dst, wid);
 }
-__global__ void k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
+__global__ void __launch_bounds__(256, DIP_CAT_MINBLOCKS) k_cat_stats(CatArgs a, double* __restrict__ fwd, int VL, int PPB) {
   pdl_enter();
   d_cat_stats(a, fwd, VL, PPB);
 }
@@ -462,7 +468,7 @@ __device__ __forceinline__ void d_cat_write(CatArgs a, BnRef bn_cat, float* __re
       store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]));
   }
 }
-__global__ void k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
+__global__ void __launch_bounds__(256, DIP_CAT_MINBLOCKS) k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
   pdl_enter();
   d_cat_write(a, bn_cat, dst, VL, PPB);
 }
