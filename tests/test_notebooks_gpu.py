@@ -95,3 +95,16 @@ def test_inpainting_notebook_vase_branch_runs_unchanged():
     loss = _losses(ns["__stdout__"], r"Loss ([0-9.]+)")
     assert len(loss) == 30 and loss[-1] < 0.7 * loss[0]
     assert ns["out_np"].shape == (3, 320, 320)
+
+
+@needs_ref
+def test_super_resolution_notebook_factor_8():
+    """super-resolution.ipynb with the user edit `factor = 8` of cell 3 (c7:16-18: num_iter 4000, reg_noise_std 0.05): the
+    32 x 32 Lanczos-2 downsampler (models/downsampler.py:14-17) in the loss, LR target 72 x 48."""
+    torch.manual_seed(0)
+    ns = run_notebook(os.path.join(REF, "super-resolution.ipynb"), dict(PLOT=False, factor=8, num_iter=30))
+    _assert_engine_net(ns["net"])
+    assert ns["downsampler"].kernel.shape == (32, 32) and ns["reg_noise_std"] == 0.05
+    assert tuple(ns["img_LR_var"].shape[2:]) == (48, 72)
+    hist = np.array(ns["psnr_history"])
+    assert hist.shape == (30, 2) and hist[-1, 0] > hist[0, 0] + 1
