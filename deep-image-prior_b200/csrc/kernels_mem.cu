@@ -1008,7 +1008,7 @@ __device__ __forceinline__ float4 skinny_wrow(const float* __restrict__ w, int n
 
 // ------------------------------------------------------------------------------------------------ skinny 1x1 convs
 // VL = C/4 lanes per pixel (power of two <= 32); warp-shuffle reduction over the pixel's lanes.
-__device__ __forceinline__ void d_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
+__device__ __forceinline__ void d_skinny_fwd_narrow(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
                                                     const float* __restrict__ b, int C, int N, int H, int W,
                                                     float* __restrict__ y, int mode, double* __restrict__ stats, int cw) {
   const int VL = C / 4;
@@ -1061,6 +1061,80 @@ __device__ __forceinline__ void d_skinny_fwd(const float* __restrict__ x, int ld
     block_reduce_atomic<2>(acc2, 1, 256, dst, wid);
   }
 }
+// Wide inputs (G = C/4 = 8, 16 or 32 lanes per pixel): a lane group takes U = G/4 CONSECUTIVE pixels per trip, forms the
+// 4 x U partial dot products of its 4 channels, and all 4U = G values are reduced over the group with a value-halving butterfly
+// (G - 1 shuffles per U pixels instead of 4 * log2(G) per pixel: 7 vs 24 for C = 32, 31 vs 160 for C = 128).  Afterwards lane l
+// of the group holds output n = l / U of pixel u = l % U, so a group's 4U outputs are 4U consecutive floats of y.
+template <int G>
+__device__ __forceinline__ void d_skinny_fwd_wide(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
+                                                  const float* __restrict__ b, int N, int H, int W, float* __restrict__ y,
+                                                  double* __restrict__ stats, int cw) {
+  constexpr int U = G / 4;
+  const int v = threadIdx.x % G, grp = threadIdx.x / G;
+  const int groups = blockDim.x / G;                 // groups per block; a block covers groups * U = 64 pixels per trip
+  const int npix = H * W;
+  float4 wv[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) wv[n] = n < N ? skinny_wrow(w, n, cw, v) : f4zero();
+  const int my_n = v / U, my_u = v % U;              // what this lane owns after the butterfly
+  const float my_b = (my_n < N && b != nullptr) ? b[my_n] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  const int per_trip = gridDim.x * groups * U;
+  const int trips = (npix + per_trip - 1) / per_trip;   // the same for every thread: the shuffles stay warp-convergent
+  for (int t = 0; t < trips; ++t) {
+    const int p0 = ((t * gridDim.x + blockIdx.x) * groups + grp) * U;
+    float4 xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u;
+      xv[u] = f4zero();
+      if (p < npix) {
+        const int i = p / W, j = p - i * W;
+        xv[u] = ld4(x + (static_cast<size_t>(i) * x_rs + j) * ldx + 4 * v);
+      }
+    }
+    float vals[4 * U];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int u = 0; u < U; ++u) vals[n * U + u] = f4dot(xv[u], wv[n]);
+    // value-halving butterfly: after the step with offset o, a lane keeps the half of its values selected by its bit o
+#pragma unroll
+    for (int o = G / 2, cnt = 2 * U; o >= 1; o >>= 1, cnt >>= 1) {   // cnt = values kept after this step
+      const bool up = (v & o) != 0;
+#pragma unroll
+      for (int k = 0; k < cnt; ++k) {
+        const float lo = vals[k], hi = vals[k + cnt];
+        vals[k] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, o);
+      }
+    }
+    const int p = p0 + my_u;
+    if (p < npix && my_n < N) {
+      const float o = vals[0] + my_b;
+      y[static_cast<size_t>(p) * N + my_n] = o;
+      s1 += o;
+      s2 = fmaf(o, o, s2);
+    }
+  }
+  if (stats != nullptr) {
+    float4 acc2[2] = {f4zero(), f4zero()};
+    float* a1 = reinterpret_cast<float*>(&acc2[0]);
+    float* a2 = reinterpret_cast<float*>(&acc2[1]);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { a1[n] = my_n == n ? s1 : 0.f; a2[n] = my_n == n ? s2 : 0.f; }
+    double* const dst[2] = {stats, stats + N * kAccS};
+    const int wid[2] = {N, N};
+    block_reduce_atomic<2>(acc2, 1, 256, dst, wid);
+  }
+}
+__device__ __forceinline__ void d_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
+                                             const float* __restrict__ b, int C, int N, int H, int W, float* __restrict__ y,
+                                             int mode, double* __restrict__ stats, int cw) {
+  if (mode == 0 && C == 128) d_skinny_fwd_wide<32>(x, ldx, x_rs, w, b, N, H, W, y, stats, cw);
+  else if (mode == 0 && C == 64) d_skinny_fwd_wide<16>(x, ldx, x_rs, w, b, N, H, W, y, stats, cw);
+  else if (mode == 0 && C == 32) d_skinny_fwd_wide<8>(x, ldx, x_rs, w, b, N, H, W, y, stats, cw);
+  else d_skinny_fwd_narrow(x, ldx, x_rs, w, b, C, N, H, W, y, mode, stats, cw);
+}
 __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x, int ldx, int x_rs, const float* __restrict__ w,
                                                     const float* __restrict__ b, int C, int N, int H, int W,
                                                     float* __restrict__ y, int mode, double* __restrict__ stats, int cw) {
@@ -1069,7 +1143,7 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const float* __restrict__ x,
 }
 void launch_skinny_fwd(const float* x, int ldx, int x_rs, const float* w, const float* b, int C, int N, int H,
                        int W, float* y, int mode, double* stats, cudaStream_t s, int cw) {
-  const int PPB = 256 / (C / 4);
+  const int PPB = C >= 32 ? 64 : 256 / (C / 4);   // pixels per block and trip (wide path: 64 whatever the depth)
   long long nb = (static_cast<long long>(H) * W + PPB - 1) / PPB;
   if (nb > 148 * 8) nb = 148 * 8;
   launch_red(k_skinny_fwd, static_cast<int>(nb), 256, 2 * 256 * sizeof(float4) + 2 * 4 * sizeof(double), s, x, ldx, x_rs, w, b, C, N, H, W,
