@@ -655,6 +655,9 @@ static int build_plan(dip_plan* P, Arena& A) {
   if (d.out_channels < 1 || d.out_channels > 4) return fail("dip-b200: num_output_channels must be <= 4");
   if (L < 1 || L > 8) return fail("dip-b200: 1..8 scales supported");
   if (P->H % (1 << L) || P->W % (1 << L)) return fail("dip-b200: H and W must be divisible by 2^num_scales");
+  if ((P->H >> L) < 2 || (P->W >> L) < 2)
+    return fail("dip-b200: H and W must be at least 2 * 2^num_scales (ReflectionPad2d(1) in front of the deepest 3x3 conv needs 2 "
+                "pixels per side: torch raises for the reference's network as well)");
   const int prec = d.precision;
   P->lv.resize(L);
   int pidx = 0;

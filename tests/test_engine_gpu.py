@@ -82,7 +82,6 @@ def check_tf32_gradients_like_cudnn(cfg, params, z0, target, dgrads, names):
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("shape_mode", [(64, 64, "bilinear", 4), (96, 64, "nearest", 4), (64, 128, "bilinear", 4),
                                         (64, 96, "nearest", 128), (128, 64, "bilinear", 128),
-                                        (32, 64, "bilinear", 4),      # smallest size torch accepts: the deepest BatchNorm sees 1 x 2 pixels
                                         (64, 32, "nearest", 0)])      # num_channels_skip = 0 (no skip branches)
 def test_forward_backward_vs_oracle(shape_mode, prec):
     H, W, mode, cs = shape_mode   # cs = 128: the inpainting configuration (BASELINE config 4: skip=128, 256-channel concat)
@@ -359,3 +358,12 @@ def test_deep_kernel_matches_launches():
     assert torch.allclose(res["deep"][0], res["launches"][0], rtol=0, atol=1e-6)
     for a, b in zip(res["deep"][1], res["launches"][1]):
         assert rel(a, b) < 1e-3 or b.norm().item() < 1e-6      # split-K atomics: summation order differs run to run
+
+
+def test_too_small_an_image_is_refused_like_torch_refuses_it():
+    """32 x 64 with 5 scales: the deepest 3x3 conv would reflection-pad a 1 x 2 map; torch raises for the reference's network
+    ('Padding size should be less than the corresponding input dimension'), the engine refuses the plan."""
+    import dip_engine as de
+    with pytest.raises(NotImplementedError, match="at least"):
+        de.Plan(32, 3, 5, 128, 4, True, 32, 64)
+    de.Plan(32, 3, 5, 128, 4, True, 64, 64)   # the smallest legal size
