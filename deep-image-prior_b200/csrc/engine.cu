@@ -245,6 +245,10 @@ struct ConvOp {
     const int blocks = wg_h * ((wg_w + kp - 1) / kp);
     int ks = 148 / k;
     if (const char* e = getenv("DIP_WGRAD_KS")) { const int cap = atoi(e); if (cap >= 1 && cap < ks) ks = cap; }   // experiment
+    // every split-K CTA adds a whole [3 taps][128][c_pad] slab to the accumulator with L2 reductions: at the deep levels a CTA
+    // with one or two pixel blocks costs more in reductions than in MMAs, so a CTA gets at least `minblk` pixel blocks
+    static const int minblk = getenv("DIP_WGRAD_MINBLK") ? atoi(getenv("DIP_WGRAD_MINBLK")) : 1;
+    if (minblk > 1 && ks > blocks / minblk) ks = blocks / minblk;
     if (ks > blocks) ks = blocks;
     return ks < 1 ? 1 : ks;
   }

@@ -82,7 +82,7 @@ def check_tf32_gradients_like_cudnn(cfg, params, z0, target, dgrads, names):
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("shape_mode", [(64, 64, "bilinear", 4), (96, 64, "nearest", 4), (64, 128, "bilinear", 4),
                                         (64, 96, "nearest", 128), (128, 64, "bilinear", 128),
-                                        (64, 32, "nearest", 0)])      # num_channels_skip = 0 (no skip branches)
+                                        (64, 96, "nearest", 0)])      # num_channels_skip = 0 (no skip branches)
 def test_forward_backward_vs_oracle(shape_mode, prec):
     H, W, mode, cs = shape_mode   # cs = 128: the inpainting configuration (BASELINE config 4: skip=128, 256-channel concat)
     cfg, params, z0, target, _ = make_problem(H, W, mode, skip_channels=cs)
