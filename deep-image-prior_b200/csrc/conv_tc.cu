@@ -46,8 +46,12 @@ __device__ __forceinline__ uint32_t tmem_cols_pow2(uint32_t n) {
 // tensor maps TMA reads; TMEM (512 columns) is allocated once by the caller and handed in as tmem_pre; the CTA-local
 // barriers are re-initialised here (every barrier of the previous phase has completed all its phases by then); CTAs
 // beyond the grid the stand-alone launch would have used (p.vgrid) sit the phase out.
-template <bool DEEP>
+// BF16 = true: operands are bf16 (kind::f16, K = 16 per MMA).  The BYTE geometry is unchanged -- an operand row is still
+// 128 bytes, now 64 channels, and one MMA still advances 32 bytes along K -- so a "k block" is 64 channels, p.kblocks /
+// p.tail_mmas count those, and only the channel coordinate of the TMA boxes and the instruction kind differ.
+template <bool DEEP, bool BF16 = false>
 __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConvParams* pm, uint8_t* smem_raw, uint32_t tmem_pre) {
+  constexpr int KE = BF16 ? 64 : 32;   // channels per 128-byte operand row
   const int grid_x = DEEP ? p.vgrid : static_cast<int>(gridDim.x);
   if (DEEP && static_cast<int>(blockIdx.x) >= grid_x) return;
   // 1024-byte alignment is required by the 128B swizzle atoms.
@@ -154,7 +158,7 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
               if (p.dbg_flags & 1) mbar_arrive(&ctl->a_full[ab]);
               else {
                 mbar_expect_tx(&ctl->a_full[ab], patch_bytes);
-                tma_load_5d(patch_base + ab * patch_alloc, &pm->tmA, &ctl->a_full[ab], kb * 32, 0, x0 + p.offx, 0, y0 + p.offy);
+                tma_load_5d(patch_base + ab * patch_alloc, &pm->tmA, &ctl->a_full[ab], kb * KE, 0, x0 + p.offx, 0, y0 + p.offy);
               }
             }
             __syncwarp();
@@ -170,9 +174,9 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
                   mbar_expect_tx(&ctl->full[stage], tps * b_bytes);
                   if (csize == 1) {
                     for (int t = 0; t < tps; ++t)
-                      tma_load_2d(sb + t * b_bytes, &pm->tmB, &ctl->full[stage], kb * 32, (tap + t) * n_total + n_off);
+                      tma_load_2d(sb + t * b_bytes, &pm->tmB, &ctl->full[stage], kb * KE, (tap + t) * n_total + n_off);
                   } else {
-                    tma_load_2d_mc(sb + crank * b_rows * 128, &pm->tmB, &ctl->full[stage], kb * 32,
+                    tma_load_2d_mc(sb + crank * b_rows * 128, &pm->tmB, &ctl->full[stage], kb * KE,
                                    tap * p.n_mma + crank * b_rows, cmask);
                   }
                 }
@@ -212,10 +216,10 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
                 const bool ldA = !(p.dbg_flags & 1), ldB = !(p.dbg_flags & 2);
                 if (ldA || ldB) mbar_expect_tx(&ctl->full[stage], (ldA ? kABytes : 0) + (ldB ? b_bytes : 0));
                 else mbar_arrive(&ctl->full[stage]);
-                if (ldA) tma_load_5d(sa, &pm->tmA, &ctl->full[stage], kb * 32, cpx, cx, cpy, cy);
+                if (ldA) tma_load_5d(sa, &pm->tmA, &ctl->full[stage], kb * KE, cpx, cx, cpy, cy);
                 if (ldB) {
-                  if (csize == 1) tma_load_2d(sb, &pm->tmB, &ctl->full[stage], kb * 32, tap * n_total + n_off);
-                  else tma_load_2d_mc(sb + crank * b_rows * 128, &pm->tmB, &ctl->full[stage], kb * 32,
+                  if (csize == 1) tma_load_2d(sb, &pm->tmB, &ctl->full[stage], kb * KE, tap * n_total + n_off);
+                  else tma_load_2d_mc(sb + crank * b_rows * 128, &pm->tmB, &ctl->full[stage], kb * KE,
                                       tap * p.n_mma + crank * b_rows, cmask);
                 }
               }
@@ -232,7 +236,7 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
     // few cycles), so the loop is kept minimal: descriptors are (lo, hi) 32-bit pairs, K advances by adding 2 to lo.
     // All 32 lanes run the (warp-uniform) loop; one elected lane issues the MMAs and the commits.
     {
-      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_mma, 0, 0);
+      const uint32_t idesc = BF16 ? make_idesc_bf16(kTileM, p.n_mma, 0, 0) : make_idesc_tf32(kTileM, p.n_mma, 0, 0);
       const uint32_t bhi = desc_hi(1024, 2);
       const uint32_t stage_lo0 = desc_lo(smem_u32(stage_base) + (p.patch ? 0 : kABytes), 16);
       const uint32_t stage_lo_step = static_cast<uint32_t>(stage_bytes) >> 4;
@@ -297,26 +301,26 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
                     for (int t = 0; t < 3; ++t) {
                       if (t < nt) {
                         const uint32_t bt = b_lo + t * tap_lo_step;
-                        mma_tf32_lohi(tmem_d, a_lo[t], ahi, bt, bhi, idesc, t == 0 ? accf : 1u);
-                        mma_tf32_lohi(tmem_d, a_lo[t] + 2, ahi, bt + 2, bhi, idesc, 1u);
-                        mma_tf32_lohi(tmem_d, a_lo[t] + 4, ahi, bt + 4, bhi, idesc, 1u);
-                        mma_tf32_lohi(tmem_d, a_lo[t] + 6, ahi, bt + 6, bhi, idesc, 1u);
+                        mma_lohi<BF16>(tmem_d, a_lo[t], ahi, bt, bhi, idesc, t == 0 ? accf : 1u);
+                        mma_lohi<BF16>(tmem_d, a_lo[t] + 2, ahi, bt + 2, bhi, idesc, 1u);
+                        mma_lohi<BF16>(tmem_d, a_lo[t] + 4, ahi, bt + 4, bhi, idesc, 1u);
+                        mma_lohi<BF16>(tmem_d, a_lo[t] + 6, ahi, bt + 6, bhi, idesc, 1u);
                         if (pair) {   // same weight tile, the lower tile of the pair
                           const uint32_t a1 = a_lo[t] + pair_off;
-                          mma_tf32_lohi(tmem_d1, a1, ahi, bt, bhi, idesc, t == 0 ? accf : 1u);
-                          mma_tf32_lohi(tmem_d1, a1 + 2, ahi, bt + 2, bhi, idesc, 1u);
-                          mma_tf32_lohi(tmem_d1, a1 + 4, ahi, bt + 4, bhi, idesc, 1u);
-                          mma_tf32_lohi(tmem_d1, a1 + 6, ahi, bt + 6, bhi, idesc, 1u);
+                          mma_lohi<BF16>(tmem_d1, a1, ahi, bt, bhi, idesc, t == 0 ? accf : 1u);
+                          mma_lohi<BF16>(tmem_d1, a1 + 2, ahi, bt + 2, bhi, idesc, 1u);
+                          mma_lohi<BF16>(tmem_d1, a1 + 4, ahi, bt + 4, bhi, idesc, 1u);
+                          mma_lohi<BF16>(tmem_d1, a1 + 6, ahi, bt + 6, bhi, idesc, 1u);
                         }
                       }
                     }
                   } else {
                     for (int t = 0; t < nt; ++t)
                       for (int k = 0; k < nmma; ++k) {
-                        mma_tf32_lohi(tmem_d, a_lo[t] + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi, idesc,
+                        mma_lohi<BF16>(tmem_d, a_lo[t] + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi, idesc,
                                       (t | k) > 0 ? 1u : accf);
                         if (pair)
-                          mma_tf32_lohi(tmem_d1, a_lo[t] + pair_off + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi,
+                          mma_lohi<BF16>(tmem_d1, a_lo[t] + pair_off + 2 * (k & 3), ahi, b_lo + t * tap_lo_step + 2 * (k & 3), bhi,
                                         idesc, (t | k) > 0 ? 1u : accf);
                       }
                   }
@@ -348,13 +352,13 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
               if (!skip_mma || accf == 0) {
                 if (nmma == 4) {
                   // K-major SW128: 8-row groups are 1024 B apart; advancing K by 8 fp32 = +32 B inside the swizzle atom
-                  mma_tf32_lohi(tmem_d, a_lo, ahi, b_lo, bhi, idesc, accf);
-                  mma_tf32_lohi(tmem_d, a_lo + 2, ahi, b_lo + 2, bhi, idesc, 1u);
-                  mma_tf32_lohi(tmem_d, a_lo + 4, ahi, b_lo + 4, bhi, idesc, 1u);
-                  mma_tf32_lohi(tmem_d, a_lo + 6, ahi, b_lo + 6, bhi, idesc, 1u);
+                  mma_lohi<BF16>(tmem_d, a_lo, ahi, b_lo, bhi, idesc, accf);
+                  mma_lohi<BF16>(tmem_d, a_lo + 2, ahi, b_lo + 2, bhi, idesc, 1u);
+                  mma_lohi<BF16>(tmem_d, a_lo + 4, ahi, b_lo + 4, bhi, idesc, 1u);
+                  mma_lohi<BF16>(tmem_d, a_lo + 6, ahi, b_lo + 6, bhi, idesc, 1u);
                 } else {
                   for (int k = 0; k < nmma; ++k)
-                    mma_tf32_lohi(tmem_d, a_lo + 2 * k, ahi, b_lo + 2 * k, bhi, idesc, k > 0 ? 1u : accf);
+                    mma_lohi<BF16>(tmem_d, a_lo + 2 * k, ahi, b_lo + 2 * k, bhi, idesc, k > 0 ? 1u : accf);
                 }
               }
               // frees this smem stage (in every CTA that multicasts into it) once the MMAs above have read it
@@ -574,6 +578,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   tc_conv_body<false>(p, &p, smem_raw, 0u);
 }
+__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel_bf16(const __grid_constant__ TcConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  tc_conv_body<false, true>(p, &p, smem_raw, 0u);
+}
 
 // ------------------------------------------------------------------------------------------------ wgrad
 struct SmemCtlW {
@@ -583,12 +591,16 @@ struct SmemCtlW {
   uint32_t tmem_base;
 };
 
-template <bool DEEP>
+// BF16 = true: dY and X are bf16; a chunk is 64 channels x kp pixel rows of 128 bytes in the standard 128-byte swizzle
+// (16-byte atoms: MN-major 16-bit operands need no 32-byte-atom layout), K = 16 pixels per MMA.
+template <bool DEEP, bool BF16 = false>
 __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWgradParams* pm, uint8_t* smem_raw, uint32_t tmem_pre) {
   if (DEEP && static_cast<int>(blockIdx.x) >= p.kh * p.ksplits) return;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int chunk_bytes = p.kp * 128;                          // kp pixel rows x 32 channels
-  const int y_bytes = 4 * chunk_bytes;                         // dY: 128 channels
+  constexpr int KE = BF16 ? 64 : 32;                           // channels per 128-byte row
+  constexpr int YCH = 128 / KE;                                // chunks of dY (128 channels)
+  const int chunk_bytes = p.kp * 128;                          // kp pixel rows x KE channels
+  const int y_bytes = YCH * chunk_bytes;                       // dY: 128 channels
   // X operand: per tap column its own kp-pixel tile, or (xshare: stride 1) ONE (kp + kw - 1)-pixel tile that all tap
   // columns read through row-shifted descriptors (swizzling is a function of the absolute smem address)
   const int xrows = p.xshare ? p.kp + p.kw - 1 : p.kp;
@@ -602,7 +614,7 @@ __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWg
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x / p.ksplits;   // filter row handled by this CTA
   const int ks = blockIdx.x % p.ksplits;  // split-K index
-  const int c_pad = p.c_chunks * 32;
+  const int c_pad = p.n_cols > 0 ? p.n_cols : p.c_chunks * 32;   // UMMA N = accumulator columns per tap = row stride of the output
   const uint32_t ncols = tmem_cols_pow2(p.kw * c_pad);
   const int blk0 = static_cast<int>((static_cast<long long>(p.px_blocks) * ks) / p.ksplits);
   const int blk1 = static_cast<int>((static_cast<long long>(p.px_blocks) * (ks + 1)) / p.ksplits);
@@ -643,11 +655,11 @@ __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWg
         uint8_t* sy = smem + stage * stage_bytes;
         if (elect_one()) {
         mbar_expect_tx(&ctl->full[stage], stage_tx);
-        for (int j = 0; j < 4; ++j) tma_load_3d(sy + j * chunk_bytes, &pm->tmY, &ctl->full[stage], j * 32, x0, y);
+        for (int j = 0; j < YCH; ++j) tma_load_3d(sy + j * chunk_bytes, &pm->tmY, &ctl->full[stage], j * KE, x0, y);
         if (p.xshare) {
           uint8_t* sx = sy + y_bytes;
           for (int j = 0; j < p.c_chunks; ++j)
-            tma_load_5d(sx + j * xchunk, &pm->tmX, &ctl->full[stage], j * 32, 0, x0 + p.offx, 0, y + p.offy + r);
+            tma_load_5d(sx + j * xchunk, &pm->tmX, &ctl->full[stage], j * KE, 0, x0 + p.offx, 0, y + p.offy + r);
         } else
         for (int s = 0; s < p.kw; ++s) {
           const int ix = p.offx + s, iy = p.offy + r;
@@ -659,7 +671,7 @@ __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWg
           }
           uint8_t* sx = sy + y_bytes + s * x_bytes;
           for (int j = 0; j < p.c_chunks; ++j)
-            tma_load_5d(sx + j * chunk_bytes, &pm->tmX, &ctl->full[stage], j * 32, cpx, cx, cpy, cy);
+            tma_load_5d(sx + j * chunk_bytes, &pm->tmX, &ctl->full[stage], j * KE, cpx, cx, cpy, cy);
         }
         }
         __syncwarp();
@@ -669,17 +681,19 @@ __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWg
   } else if (warp == 1) {
     {
       // A = dY (M = 128 output channels), B = X (N = c_pad input channels); both MN-major, K = pixels.
-      const uint32_t idesc = make_idesc_tf32(128, c_pad, 1, 1);
+      const uint32_t idesc = BF16 ? make_idesc_bf16(128, c_pad, 1, 1) : make_idesc_tf32(128, c_pad, 1, 1);
       // MN-major tf32 must use the 32-byte-atom 128B swizzle: 32-channel chunks are LBO = chunk_bytes apart,
       // 4-pixel K atoms are SBO = 512 B apart; one K=8 MMA consumes 8 pixel rows = 1024 B (lo += 64).
-      const uint32_t hi = desc_hi(512, 1);
+      // bf16: standard 128B swizzle, 8-pixel K groups SBO = 1024 B apart, one K=16 MMA consumes 16 pixel rows = 2048 B
+      const uint32_t hi = BF16 ? desc_hi(1024, 2) : desc_hi(512, 1);
+      constexpr uint32_t kstep = BF16 ? 128u : 64u;
       const uint32_t y_lo0 = desc_lo(smem_u32(smem), chunk_bytes);
       const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
       // X descriptor: LBO = its own chunk stride; per tap column either the next tile or +1 pixel row (128 B)
       const uint32_t x_off = ((static_cast<uint32_t>(y_bytes) >> 4) + ((static_cast<uint32_t>(xchunk) >> 4) << 16)) -
                              ((static_cast<uint32_t>(chunk_bytes) >> 4) << 16);
       const uint32_t x_step = p.xshare ? 8u : (static_cast<uint32_t>(x_bytes) >> 4);
-      const int nk = p.kp / 8;
+      const int nk = p.kp / (BF16 ? 16 : 8);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accf = 0;
@@ -691,8 +705,8 @@ __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWg
           uint32_t x_lo = y_lo + x_off;
           uint32_t td = tmem_base;
           for (int s = 0; s < p.kw; ++s) {
-            mma_tf32_lohi(td, y_lo, hi, x_lo, hi, idesc, accf);
-            for (int k = 1; k < nk; ++k) mma_tf32_lohi(td, y_lo + 64 * k, hi, x_lo + 64 * k, hi, idesc, 1u);
+            mma_lohi<BF16>(td, y_lo, hi, x_lo, hi, idesc, accf);
+            for (int k = 1; k < nk; ++k) mma_lohi<BF16>(td, y_lo + kstep * k, hi, x_lo + kstep * k, hi, idesc, 1u);
             x_lo += x_step;
             td += c_pad;
           }
@@ -716,7 +730,7 @@ __device__ __forceinline__ void tc_wgrad_body(const TcWgradParams& p, const TcWg
       if (p.atomic && blk1 <= blk0) break;   // nothing accumulated by this CTA
       const int tap = r * p.kw + s;
       float* dst = p.partial + ((static_cast<size_t>(p.atomic ? 0 : ks) * (p.kh * p.kw) + tap) * 128 + n) * c_pad;
-      for (int j = 0; j < p.c_chunks; ++j) {
+      for (int j = 0; j < c_pad / 32; ++j) {
         uint32_t v[32];
         if (blk1 > blk0) {
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * c_pad + j * 32, v);
@@ -752,6 +766,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   tc_wgrad_body<false>(p, &p, smem_raw, 0u);
 }
+__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel_bf16(const __grid_constant__ TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  tc_wgrad_body<false, true>(p, &p, smem_raw, 0u);
+}
 
 // ------------------------------------------------------------------------------------------------ host side
 static constexpr size_t kMaxSmem = 232448;  // 227 KB
@@ -766,11 +784,15 @@ size_t tc_conv_smem_bytes(const TcConvParams& p) {
 size_t tc_wgrad_smem_bytes(const TcWgradParams& p) {
   const size_t chunk = static_cast<size_t>(p.kp) * 128;
   const size_t xchunk = p.xshare ? ((static_cast<size_t>(p.kp + p.kw - 1) * 128 + 1023) & ~size_t(1023)) : chunk;
-  return 1024 + p.stages * (4 * chunk + static_cast<size_t>(p.xshare ? 1 : p.kw) * p.c_chunks * xchunk) + sizeof(SmemCtlW);
+  return 1024 + p.stages * ((p.bf16 ? 2 : 4) * chunk + static_cast<size_t>(p.xshare ? 1 : p.kw) * p.c_chunks * xchunk) + sizeof(SmemCtlW);
 }
 
 cudaError_t tc_kernels_init() {
   cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(tc_conv_kernel_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(tc_wgrad_kernel_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
 }
@@ -790,7 +812,7 @@ cudaError_t tc_conv_launch(const TcConvParams& p, int num_sms, cudaStream_t s) {
   }
   const size_t smem = tc_conv_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
-  return launch_k(tc_conv_kernel, dim3(grid), dim3(kNumThreads), smem, s, cs, p);
+  return launch_k(p.bf16 ? tc_conv_kernel_bf16 : tc_conv_kernel, dim3(grid), dim3(kNumThreads), smem, s, cs, p);
 }
 // grid the stand-alone launch uses (the persistent deep-level kernel runs the same CTA -> tile mapping on its first vgrid CTAs)
 int tc_conv_grid(const TcConvParams& p, int num_sms) {
@@ -802,7 +824,7 @@ int tc_conv_grid(const TcConvParams& p, int num_sms) {
 cudaError_t tc_wgrad_launch(const TcWgradParams& p, cudaStream_t s) {
   const size_t smem = tc_wgrad_smem_bytes(p);
   if (smem > kMaxSmem) return cudaErrorInvalidValue;
-  return launch_k(tc_wgrad_kernel, dim3(p.kh * p.ksplits), dim3(kNumThreads), smem, s, 1, p);
+  return launch_k(p.bf16 ? tc_wgrad_kernel_bf16 : tc_wgrad_kernel, dim3(p.kh * p.ksplits), dim3(kNumThreads), smem, s, 1, p);
 }
 
 }  // namespace dip

@@ -21,8 +21,9 @@ struct TcConvParams {
   int kh, kw;              // filter taps
   int stride;              // 1 or 2 (spatial stride of A reads)
   int offx, offy;          // input coordinate of tap (0,0) for output pixel (0,0)
-  int kblocks;             // 32-channel K blocks per tap
-  int tail_mmas;           // number of K=8 MMAs issued for the last K block of a tap (1..4)
+  int bf16;                // 1: bf16 operands (kind::f16): A / Wp are bf16, a K block is 64 channels (still 128 bytes), K = 16 per MMA
+  int kblocks;             // K blocks (128-byte operand rows: 32 fp32 or 64 bf16 channels) per tap
+  int tail_mmas;           // number of MMAs (K = 8 fp32 / 16 bf16 channels) issued for the last K block of a tap (1..4)
   int n_mma;               // UMMA N of this CTA (multiple of 16, <= 160): all output channels, or N / n_split of them
   int n_chunks;            // output 32-channel chunks written (ceil(n_mma/32))
   int stages;              // smem pipeline depth
@@ -66,7 +67,9 @@ struct TcWgradParams {
   int px_blocks_x;         // W / kp
   int px_blocks;           // total pixel blocks = H * px_blocks_x
   int kp;                  // pixels per K block (box width): 16 or 32
-  int c_chunks;            // 32-channel chunks of X (c_pad = 32*c_chunks)
+  int bf16;                // 1: dY / X are bf16 (chunks of 64 channels, standard 128B swizzle, K = 16 pixels per MMA)
+  int c_chunks;            // 128-byte channel chunks of X (32 fp32 / 64 bf16 channels each)
+  int n_cols;              // UMMA N = accumulator columns per tap = row stride of `partial` (0: 32 * c_chunks)
   int xshare;              // 1: stride-1 taps of a filter row share one (kp + kw - 1)-pixel X tile
   int ksplits;             // CTAs per tap row
   int stages;

@@ -2,6 +2,7 @@
 // libdip.so (include/dip.h).  Replaces the execution of the reference's skip network
 // (models/skip.py:41-100, module tree interpreted by torch.nn.Sequential) + autograd backward + Adam.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -65,10 +66,12 @@ static int engine_init() {
   return 0;
 }
 
+static bool is_tc(int prec) { return prec == DIP_PRECISION_TF32 || prec == DIP_PRECISION_BF16; }   // tensor-core paths
+
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box, bool atom32 = false) {
+                      const cuuint32_t* box, bool atom32 = false, bool bf16 = false) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+  CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_b, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -82,9 +85,10 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   return 0;
 }
 // activation [rows][cols][ld] (c valid channels) as the 5-D view (C, px, X, py, Y) used by the conv kernels
-static int map_act5(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int stride, int bw, int bh,
-                    bool atom32 = false) {
-  const cuuint64_t e = sizeof(float);
+// bf16 = true: the tensor holds bf16 (ld in elements); a box row is still 128 bytes = 64 channels
+static int map_act5(CUtensorMap* m, const void* base, int rows, int cols, int ld, int c, int stride, int bw, int bh,
+                    bool atom32 = false, bool bf16 = false) {
+  const cuuint64_t e = bf16 ? 2 : sizeof(float);
   cuuint64_t dims[5], str[4];
   if (stride == 1) {
     dims[0] = c; dims[1] = 1; dims[2] = cols; dims[3] = 1; dims[4] = rows;
@@ -93,22 +97,23 @@ static int map_act5(CUtensorMap* m, const float* base, int rows, int cols, int l
     dims[0] = c; dims[1] = 2; dims[2] = cols / 2; dims[3] = 2; dims[4] = rows / 2;
     str[0] = ld * e; str[1] = 2 * ld * e; str[2] = (cuuint64_t)cols * ld * e; str[3] = 2 * (cuuint64_t)cols * ld * e;
   }
-  cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)bh};
-  return encode_map(m, base, 5, dims, str, box, atom32);
+  cuuint32_t box[5] = {bf16 ? 64u : 32u, 1, (cuuint32_t)bw, 1, (cuuint32_t)bh};
+  return encode_map(m, base, 5, dims, str, box, atom32, bf16);
 }
-static int map_act3(CUtensorMap* m, const float* base, int rows, int cols, int ld, int c, int bw, int bh, bool atom32 = false) {
-  const cuuint64_t e = sizeof(float);
+static int map_act3(CUtensorMap* m, const void* base, int rows, int cols, int ld, int c, int bw, int bh, bool atom32 = false,
+                    bool bf16 = false) {
+  const cuuint64_t e = bf16 ? 2 : sizeof(float);
   cuuint64_t dims[3] = {(cuuint64_t)c, (cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t str[2] = {ld * e, (cuuint64_t)cols * ld * e};
-  cuuint32_t box[3] = {32, (cuuint32_t)bw, (cuuint32_t)bh};
-  return encode_map(m, base, 3, dims, str, box, atom32);
+  cuuint32_t box[3] = {bf16 ? 64u : 32u, (cuuint32_t)bw, (cuuint32_t)bh};
+  return encode_map(m, base, 3, dims, str, box, atom32, bf16);
 }
-static int map_w2(CUtensorMap* m, const float* base, int rows_total, int kcols, int box_rows) {
-  const cuuint64_t e = sizeof(float);
+static int map_w2(CUtensorMap* m, const void* base, int rows_total, int kcols, int box_rows, bool bf16 = false) {
+  const cuuint64_t e = bf16 ? 2 : sizeof(float);
   cuuint64_t dims[2] = {(cuuint64_t)kcols, (cuuint64_t)rows_total};
   cuuint64_t str[1] = {kcols * e};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  return encode_map(m, base, 2, dims, str, box);
+  cuuint32_t box[2] = {bf16 ? 64u : 32u, (cuuint32_t)box_rows};
+  return encode_map(m, base, 2, dims, str, box, false, bf16);
 }
 
 static void pick_tile(int w, int h, int* bw, int* bh) {
@@ -212,6 +217,13 @@ struct ConvOp {
   int dg_ld = 0;   // channel stride of dg_out (0: C)
   int c_pad = 0;   // fprop K extent per tap (multiple of 32)
   int crows = 0;   // dgrad UMMA N (input channels rounded to 16)
+  // precision mode bf16: the tensor-core kernels read bf16 twins of the conv input / of dY (written by the producer kernels
+  // next to -- or instead of -- the fp32 tensors) and bf16 weight packs; outputs and accumulators stay fp32
+  bool bf16 = false;
+  int c_pad16 = 0;                                   // fprop K extent per tap in bf16 (multiple of 64)
+  const uint16_t* in16 = nullptr; int in_ld16 = 0;   // twin of `in`
+  const uint16_t* dg_in16 = nullptr;                 // twin of dg_in (ld 128)
+  const uint16_t* wg_dy16 = nullptr;                 // twin of wg_dy (ld 128)
   // forward
   const float* in = nullptr; int in_rows = 0, in_cols = 0, in_ld = 0; int offx = 0, offy = 0;
   float* out = nullptr; int out_h = 0, out_w = 0;
@@ -233,6 +245,7 @@ struct ConvOp {
 
   void set_shapes() {
     c_pad = round_up(C, 32);
+    c_pad16 = round_up(C, 64);
     crows = round_up(C, 16);
     if (Ctot == 0) Ctot = C;
     if (dg_ld == 0) dg_ld = C;
@@ -240,8 +253,11 @@ struct ConvOp {
   size_t wp_f_elems() const { return (size_t)k * k * N * c_pad; }
   size_t wp_d_elems() const { return (size_t)k * k * crows * 128; }
   size_t wacc_elems() const { return (size_t)k * k * 128 * c_pad; }
+  // pixels per K block of the weight-gradient GEMM (TMA box width).  bf16 halves the bytes per pixel and doubles K per MMA:
+  // 64-pixel blocks keep 12 MMAs per barrier round
+  int wg_kp() const { return (bf16 && wg_w % 64 == 0) ? 64 : (wg_w % 32 == 0) ? 32 : 16; }
   int tc_ksplits() const {
-    const int kp = (wg_w % 32 == 0) ? 32 : 16;
+    const int kp = wg_kp();
     const int blocks = wg_h * ((wg_w + kp - 1) / kp);
     int ks = 148 / k;
     if (const char* e = getenv("DIP_WGRAD_KS")) { const int cap = atoi(e); if (cap >= 1 && cap < ks) ks = cap; }   // experiment
@@ -253,7 +269,7 @@ struct ConvOp {
     return ks < 1 ? 1 : ks;
   }
   size_t partial_elems(int prec) const {
-    const int ks = prec == DIP_PRECISION_TF32 ? 1 : simt_ksplits;   // tensor-core path: one accumulator (atomic split-K)
+    const int ks = is_tc(prec) ? 1 : simt_ksplits;   // tensor-core path: one accumulator (atomic split-K)
     return (size_t)ks * k * k * 128 * c_pad;
   }
 
@@ -270,21 +286,24 @@ struct ConvOp {
       fp.patch = 1; fp.pw = bw + 2; fp.ph = bh + 2;
       fp.pair = pick_pair((out_w + bw - 1) / bw, (out_h + bh - 1) / bh, N);
       if (fp.pair) fp.ph = 2 * bh + 2;
-      DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, 1, fp.pw, fp.ph));
+      DIP_CHECK(bf16 ? map_act5(&fp.tmA, in16, in_rows, in_cols, in_ld16, C, 1, fp.pw, fp.ph, false, true)
+                     : map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, 1, fp.pw, fp.ph));
     } else {
-      DIP_CHECK(map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
+      DIP_CHECK(bf16 ? map_act5(&fp.tmA, in16, in_rows, in_cols, in_ld16, C, stride, bw, bh, false, true)
+                     : map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
     }
     if (do_fprop) {
     fp.csize = fp.pair ? 1 : pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
     fp.tps = (fp.patch && fp.csize == 1) ? pick_tps() : 1;
     fp.n_split = fp.pair ? 1 : fp.csize == 1 ? pick_nsplit(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N) : 1;
-    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, c_pad, N / fp.csize / fp.n_split));
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, bf16 ? c_pad16 : c_pad, N / fp.csize / fp.n_split, bf16));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
     fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
     fp.kh = fp.kw = k; fp.stride = stride; fp.offx = offx; fp.offy = offy;
-    fp.kblocks = c_pad / 32;
-    fp.tail_mmas = (C % 32 == 0) ? 4 : (C % 32 + 7) / 8;
+    fp.bf16 = bf16 ? 1 : 0;
+    fp.kblocks = bf16 ? c_pad16 / 64 : c_pad / 32;
+    fp.tail_mmas = bf16 ? ((C % 64 == 0) ? 4 : (C % 64 + 15) / 16) : ((C % 32 == 0) ? 4 : (C % 32 + 7) / 8);
     fp.n_mma = N / fp.n_split; fp.n_chunks = fp.n_mma / 32;
     fp.bias = nullptr; fp.stats = stats; fp.stats_ld = N;
     fit_stages(fp);
@@ -295,10 +314,11 @@ struct ConvOp {
       const int gh = dg_out_h / 2, gw = dg_out_w / 2;
       pick_tile(gw, gh, &bw, &bh);
       dg = TcConvParams{};
-      DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+      DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, 128, 128, 1, bw, bh, false, true)
+                     : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
       dg.csize = 1; dg.tps = 1;
       dg.n_split = pick_nsplit(4 * ((gw + bw - 1) / bw) * ((gh + bh - 1) / bh), crows);
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.n_split));
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.n_split, bf16));
       DIP_CHECK(map_act5(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, 2, bw, bh));   // parity view of the padded gradient
       dg.tiles_x = (gw + bw - 1) / bw; dg.tiles_y = (gh + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = gw; dg.out_h = gh;
@@ -311,7 +331,8 @@ struct ConvOp {
           q.kh = 2 - a; q.kw = 2 - b; q.offy = a == 0 ? -1 : 0; q.offx = b == 0 ? -1 : 0; q.tap0 = t0; q.opx = b; q.opy = a;
           t0 += q.kh * q.kw;
         }
-      dg.kblocks = 4; dg.tail_mmas = 4;
+      dg.bf16 = bf16 ? 1 : 0;
+      dg.kblocks = bf16 ? 2 : 4; dg.tail_mmas = 4;
       dg.n_mma = crows / dg.n_split; dg.n_chunks = (dg.n_mma + 31) / 32;
       dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
       fit_stages(dg);
@@ -323,19 +344,22 @@ struct ConvOp {
         dg.patch = 1; dg.pw = bw + 2; dg.ph = bh + 2;
         dg.pair = pick_pair((dg_out_w + bw - 1) / bw, (dg_out_h + bh - 1) / bh, crows);
         if (dg.pair) dg.ph = 2 * bh + 2;
-        DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, dg.pw, dg.ph));
+        DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, 128, 128, 1, dg.pw, dg.ph, false, true)
+                       : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, dg.pw, dg.ph));
       } else {
-        DIP_CHECK(map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+        DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, 128, 128, 1, bw, bh, false, true)
+                       : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
       }
       dg.csize = dg.pair ? 1 : pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
       dg.tps = (dg.patch && dg.csize == 1) ? pick_tps() : 1;
       dg.n_split = dg.pair ? 1 : dg.csize == 1 ? pick_nsplit(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows) : 1;
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize / dg.n_split));
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize / dg.n_split, bf16));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
       dg.kh = dg.kw = k; dg.stride = 1; dg.offx = dg.offy = dg_off;
-      dg.kblocks = 4; dg.tail_mmas = 4;
+      dg.bf16 = bf16 ? 1 : 0;
+      dg.kblocks = bf16 ? 2 : 4; dg.tail_mmas = 4;
       dg.n_mma = crows / dg.n_split; dg.n_chunks = (dg.n_mma + 31) / 32;
       dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
       fit_stages(dg);
@@ -343,15 +367,22 @@ struct ConvOp {
     // ---- wgrad
     wg = TcWgradParams{};
     if (!do_wgrad) return 0;
-    wg.kp = (wg_w % 32 == 0) ? 32 : 16;
-    DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1, true));
+    wg.kp = wg_kp();
+    wg.bf16 = bf16 ? 1 : 0;
     wg.xshare = (stride == 1 && k == 3 && getenv("DIP_NO_XSHARE") == nullptr) ? 1 : 0;
-    DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.xshare ? wg.kp + k - 1 : wg.kp, 1, true));
+    if (bf16) {
+      DIP_CHECK(map_act3(&wg.tmY, wg_dy16, wg_h, wg_w, 128, 128, wg.kp, 1, false, true));
+      DIP_CHECK(map_act5(&wg.tmX, in16, in_rows, in_cols, in_ld16, C, stride, wg.xshare ? wg.kp + k - 1 : wg.kp, 1, false, true));
+    } else {
+      DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1, true));
+      DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.xshare ? wg.kp + k - 1 : wg.kp, 1, true));
+    }
     wg.partial = partial;
     wg.kh = wg.kw = k; wg.stride = stride; wg.offx = offx; wg.offy = offy;
     wg.px_blocks_x = (wg_w + wg.kp - 1) / wg.kp;
     wg.px_blocks = wg_h * wg.px_blocks_x;
-    wg.c_chunks = c_pad / 32;
+    wg.c_chunks = bf16 ? c_pad16 / 64 : c_pad / 32;
+    wg.n_cols = c_pad;
     wg.ksplits = tc_ksplits();
     wg.stages = 6;
     while (tc_wgrad_smem_bytes(wg) > 232448 && wg.stages > 1) wg.stages--;
@@ -360,7 +391,7 @@ struct ConvOp {
   }
 
   int run_fprop(int prec, const float* bias, cudaStream_t s) {
-    if (prec == DIP_PRECISION_TF32) {
+    if (is_tc(prec)) {
       TcConvParams p = fp;
       p.bias = bias;
       if (const char* e = getenv("DIP_DBG_SHIFT")) p.dbg_shift = atoi(e);
@@ -383,7 +414,7 @@ struct ConvOp {
     return 0;
   }
   int run_dgrad(int prec, cudaStream_t s) {
-    if (prec == DIP_PRECISION_TF32) {
+    if (is_tc(prec)) {
       TimeScope ts(timer, 1, alg_flops(), s);
       DIP_CUDA(tc_conv_launch(dg, g_num_sms, s));
     } else {
@@ -401,7 +432,7 @@ struct ConvOp {
     static const bool dbg_skip = getenv("DIP_DBG_SKIP_WGRAD") != nullptr;   // timing diagnostic only: gradients are wrong
     if (dbg_skip) return 0;
     int ks;
-    if (prec == DIP_PRECISION_TF32) {
+    if (is_tc(prec)) {
       // split-K CTAs add their tiles into one accumulator with vector reductions at the L2.  Plan-owned accumulator
       // (wacc): zeroed by one memset per backward, unpacked to OIHW by one table kernel at the end of the backward pass.
       // Single-op entry points: zero + launch + unpack here.
@@ -438,6 +469,8 @@ struct PackEntry {
   int N, C, k, rot, n_rows, c_pad, c_rows;
   int Ctot, coff;   // weight has Ctot input channels; this entry packs engine channels [coff, coff + C)
   int s2;           // dgrad pack of a stride-2 3x3 conv: taps in sub-pixel phase order (kS2Taps), not flipped
+  int bf16;         // packs hold bf16 (same buffers); the fprop pack then has rows of c_pad16 (multiple of 64) channels
+  int c_pad16;
 };
 // packed tap t of the 4-phase stride-2 dgrad -> filter tap r * 3 + s.  Phase (a, b) = parity of the padded gradient pixel;
 // its taps are r in {2, 0} (a = 0: dY rows i-1, i) or {1} (a = 1), same for s.  Phases in the order (0,0) (0,1) (1,0) (1,1).
@@ -449,21 +482,24 @@ __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
   pdl_enter();
   const PackEntry e = tab[blockIdx.y];
   const int taps = e.k * e.k;
-  const long long nf = e.dst_f != nullptr ? (long long)taps * e.n_rows * e.c_pad : 0;
+  const int c_pad = e.bf16 ? e.c_pad16 : e.c_pad;
+  __nv_bfloat16* const f16 = reinterpret_cast<__nv_bfloat16*>(e.dst_f);
+  __nv_bfloat16* const d16 = reinterpret_cast<__nv_bfloat16*>(e.dst_d);
+  const long long nf = e.dst_f != nullptr ? (long long)taps * e.n_rows * c_pad : 0;
   const long long nd = e.dst_d != nullptr ? (long long)taps * e.c_rows * 128 : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (long long)gridDim.x * blockDim.x) {
     if (i < nf) {
-      const int c = (int)(i % e.c_pad), n = (int)((i / e.c_pad) % e.n_rows), tap = (int)(i / ((long long)e.c_pad * e.n_rows));
+      const int c = (int)(i % c_pad), n = (int)((i / c_pad) % e.n_rows), tap = (int)(i / ((long long)c_pad * e.n_rows));
       float v = 0.f;
       if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
-      e.dst_f[i] = v;
+      if (e.bf16) f16[i] = __float2bfloat16_rn(v); else e.dst_f[i] = v;
     } else {
       const long long j = i - nf;
       const int n = (int)(j % 128), c = (int)((j / 128) % e.c_rows), tapf = (int)(j / (128LL * e.c_rows));
       const int tap = e.s2 ? kS2Taps[tapf] : taps - 1 - tapf;
       float v = 0.f;
       if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
-      e.dst_d[j] = v;
+      if (e.bf16) d16[j] = __float2bfloat16_rn(v); else e.dst_d[j] = v;
     }
   }
 }
@@ -540,6 +576,10 @@ struct Level {
   int Cin_act;           // depth of the conv weights that read it (differs at level 0 for input depths like 3)
   int bilinear;          // x2 upsampling into this level: 1 bilinear, 0 nearest (skip.py:81, upsample_mode[i])
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
+  // bf16 twins (precision mode bf16; ld = the fp32 tensor's depth rounded up to 8)
+  uint16_t *Pin16 = nullptr, *P_d1_16 = nullptr, *P_d2_16 = nullptr, *P_cat16 = nullptr, *A_u16 = nullptr;
+  uint16_t *dRaw_v16 = nullptr, *dRaw_u16 = nullptr, *dRaw_d2_16 = nullptr, *dRaw_d1_16 = nullptr, *dRaw_s16 = nullptr;
+  int Pin_ld16 = 0, cat_ld16 = 0;
   float *dUp;  // [h][w][128] adjoint of the upsampling applied to dCat
   float *dS;   // skip=128: [H][W][Cin] input gradient of the (tensor-core) skip conv, levels > 0
   float *dRaw_v, *dA_u, *dRaw_u, *dP_cat, *dCat, *dRaw_s, *dRaw_d2, *dP_d1, *dRaw_d1, *ZS, *dPin;
@@ -663,6 +703,8 @@ static int build_plan(dip_plan* P, Arena& A) {
     return fail("dip-b200: H and W must be at least 2 * 2^num_scales (ReflectionPad2d(1) in front of the deepest 3x3 conv needs 2 "
                 "pixels per side: torch raises for the reference's network as well)");
   const int prec = d.precision;
+  if (prec != DIP_PRECISION_TF32 && prec != DIP_PRECISION_FP32 && prec != DIP_PRECISION_BF16) return fail("dip-b200: unknown precision");
+  const bool bf = prec == DIP_PRECISION_BF16;
   P->lv.resize(L);
   int pidx = 0;
   // parameter slots in net.parameters() order: assigned recursively (pre-order part, then post-order part)
@@ -788,6 +830,19 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.ZS = (l > 0 || in_grad) ? A.get<float>(HW * 128) : nullptr;
     v.dS = ((wide && l > 0) || (in_grad && l == 0)) ? A.get<float>(HW * v.Cin) : nullptr;
     v.dPin = (l > 0 || in_grad) ? A.get<float>(HWp * v.Cin) : nullptr;
+    if (bf) {
+      v.Pin_ld16 = round_up(v.Cin, 8); v.cat_ld16 = round_up(128 + CS, 8);
+      if (l == 0) v.Pin16 = A.get<uint16_t>(HWp * v.Pin_ld16); else v.Pin16 = P->lv[l - 1].P_d2_16;
+      v.P_d1_16 = A.get<uint16_t>(hwp * 128);
+      v.P_d2_16 = last ? nullptr : A.get<uint16_t>(hwp * 128);
+      v.P_cat16 = A.get<uint16_t>(HWp * v.cat_ld16);
+      v.A_u16 = A.get<uint16_t>(HW * 128);
+      v.dRaw_v16 = A.get<uint16_t>(HW * 128);
+      v.dRaw_u16 = A.get<uint16_t>(HW * 128);
+      v.dRaw_d2_16 = A.get<uint16_t>(hw * 128);
+      v.dRaw_d1_16 = A.get<uint16_t>(hw * 128);
+      v.dRaw_s16 = wide ? A.get<uint16_t>(HW * 128) : nullptr;
+    }
     reg(pf + "Pin", v.Pin, v.H + 2, v.W + 2, v.Cin, v.Cin);
     reg(pf + "raw_s", v.raw_s, v.H, v.W, CS, CS);
     reg(pf + "raw_d1", v.raw_d1, v.h, v.w, 128, 128);
@@ -834,11 +889,12 @@ static int build_plan(dip_plan* P, Arena& A) {
     a.out = v.raw_d1; a.out_h = v.h; a.out_w = v.w; a.stats = v.bn_d1.fwd;
     a.has_dgrad = l > 0 || d.input_grad != 0;
     a.dg_ld = v.Cin;   // level 0: stored depth (>= the conv's real input depth)
-    a.dg_s2 = prec == DIP_PRECISION_TF32 && getenv("DIP_ZERO_STUFF") == nullptr;   // A/B switch: the old zero-stuffed stride-1 dgrad
+    a.dg_s2 = bf || (prec == DIP_PRECISION_TF32 && getenv("DIP_ZERO_STUFF") == nullptr);   // A/B switch: the old zero-stuffed stride-1 dgrad
     if (a.dg_s2) { a.dg_in = v.dRaw_d1; a.dg_in_h = v.h; a.dg_in_w = v.w; }
     else { a.dg_in = v.ZS; a.dg_in_h = v.H; a.dg_in_w = v.W; }
     a.dg_out = v.dPin; a.dg_out_h = v.H + 2; a.dg_out_w = v.W + 2; a.dg_off = -2;
     a.wg_dy = v.dRaw_d1; a.wg_h = v.h; a.wg_w = v.w;
+    a.in16 = v.Pin16; a.in_ld16 = v.Pin_ld16; a.dg_in16 = v.dRaw_d1_16; a.wg_dy16 = v.dRaw_d1_16;
     // down2: P_d1 -> raw_d2
     ConvOp& b = v.d2;
     b.set_shapes();
@@ -847,6 +903,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     b.has_dgrad = true;
     b.dg_in = v.dRaw_d2; b.dg_in_h = v.h; b.dg_in_w = v.w; b.dg_out = v.dP_d1; b.dg_out_h = v.h + 2; b.dg_out_w = v.w + 2; b.dg_off = -2;
     b.wg_dy = v.dRaw_d2; b.wg_h = v.h; b.wg_w = v.w;
+    b.in16 = v.P_d1_16; b.in_ld16 = 128; b.dg_in16 = v.dRaw_d2_16; b.wg_dy16 = v.dRaw_d2_16;
     // up: P_cat -> raw_u
     ConvOp& c = v.up;
     c.set_shapes();
@@ -855,6 +912,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     c.has_dgrad = !wide;
     c.dg_in = v.dRaw_u; c.dg_in_h = v.H; c.dg_in_w = v.W; c.dg_out = v.dP_cat; c.dg_out_h = v.H + 2; c.dg_out_w = v.W + 2; c.dg_off = -2;
     c.wg_dy = v.dRaw_u; c.wg_h = v.H; c.wg_w = v.W;
+    c.in16 = v.P_cat16; c.in_ld16 = v.cat_ld16; c.dg_in16 = v.dRaw_u16; c.wg_dy16 = v.dRaw_u16;
     // 1x1: A_u -> raw_v
     ConvOp& e = v.c11;
     e.set_shapes();
@@ -863,6 +921,7 @@ static int build_plan(dip_plan* P, Arena& A) {
     e.has_dgrad = true;
     e.dg_in = v.dRaw_v; e.dg_in_h = v.H; e.dg_in_w = v.W; e.dg_out = v.dA_u; e.dg_out_h = v.H; e.dg_out_w = v.W; e.dg_off = 0;
     e.wg_dy = v.dRaw_v; e.wg_h = v.H; e.wg_w = v.W;
+    e.in16 = v.A_u16; e.in_ld16 = 128; e.dg_in16 = v.dRaw_v16; e.wg_dy16 = v.dRaw_v16;
     std::vector<ConvOp*> ops = {&a, &b, &c, &e};
     if (wide) {
       // skip conv 1x1 on the interior of the padded level input
@@ -874,6 +933,7 @@ static int build_plan(dip_plan* P, Arena& A) {
       k1.dg_ld = v.Cin;
       k1.dg_in = v.dRaw_s; k1.dg_in_h = v.H; k1.dg_in_w = v.W; k1.dg_out = v.dS; k1.dg_out_h = v.H; k1.dg_out_w = v.W; k1.dg_off = 0;
       k1.wg_dy = v.dRaw_s; k1.wg_h = v.H; k1.wg_w = v.W;
+      k1.in16 = v.Pin16; k1.in_ld16 = v.Pin_ld16; k1.dg_in16 = v.dRaw_s16; k1.wg_dy16 = v.dRaw_s16;
       ops.push_back(&k1);
       for (ConvOp* h : {&v.up_a, &v.up_b}) {
         h->set_shapes();
@@ -883,6 +943,7 @@ static int build_plan(dip_plan* P, Arena& A) {
         h->dg_in = v.dRaw_u; h->dg_in_h = v.H; h->dg_in_w = v.W;
         h->dg_out = v.dP_cat + h->coff; h->dg_out_h = v.H + 2; h->dg_out_w = v.W + 2; h->dg_off = -2;
         h->wg_dy = v.dRaw_u; h->wg_h = v.H; h->wg_w = v.W;
+        h->in16 = v.P_cat16 != nullptr ? v.P_cat16 + h->coff : nullptr; h->in_ld16 = v.cat_ld16; h->dg_in16 = v.dRaw_u16; h->wg_dy16 = v.dRaw_u16;
         ops.push_back(h);
       }
     }
@@ -890,6 +951,7 @@ static int build_plan(dip_plan* P, Arena& A) {
       op->wp_f = op->do_fprop ? A.get<float>(op->wp_f_elems()) : nullptr;
       op->wp_d = op->has_dgrad ? A.get<float>(op->wp_d_elems()) : nullptr;
       op->simt_ksplits = op->wg_h < 64 ? op->wg_h : 64;
+      op->bf16 = bf;
       op->timer = &P->timer;
       const size_t pe = op->do_wgrad ? op->partial_elems(prec) : 0;
       if (pe > partial_max) partial_max = pe;
@@ -899,7 +961,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   P->partial = A.get<float>(partial_max);
   // weight-gradient accumulators of the tensor-core path: one per conv, contiguous (a single memset per backward)
   P->n_unpack = 0;
-  if (prec == DIP_PRECISION_TF32) {
+  if (is_tc(prec)) {
     size_t tot = 0;
     for (ConvOp* op : P->convs) if (op->do_wgrad) { tot += (op->wacc_elems() + 63) & ~size_t(63); P->n_unpack++; }
     P->wacc_base = A.get<float>(tot);
@@ -932,7 +994,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   // The zero-stuffed buffers are written at even positions only: clear them once.
   for (int l = 0; l < L; ++l)
     if (P->lv[l].ZS != nullptr) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
-  if (prec == DIP_PRECISION_TF32)
+  if (is_tc(prec))
     for (ConvOp* op : P->convs) DIP_CHECK(op->build_tc(P->partial));
   P->pack_max = 0;
   for (ConvOp* op : P->convs) {
@@ -949,6 +1011,7 @@ static int upload_tables(dip_plan* P) {
     e.w = P->params[op->p_w]; e.dst_f = op->do_fprop ? op->wp_f : nullptr; e.dst_d = op->has_dgrad ? op->wp_d : nullptr;
     e.N = op->N; e.C = op->C; e.k = op->k; e.rot = op->rot; e.n_rows = op->N; e.c_pad = op->c_pad; e.c_rows = op->crows;
     e.Ctot = op->Ctot; e.coff = op->coff; e.s2 = op->dg_s2 ? 1 : 0;
+    e.bf16 = op->bf16 ? 1 : 0; e.c_pad16 = op->c_pad16;
     pk.push_back(e);
   }
   DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
@@ -1058,6 +1121,8 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   const int CS = P->desc.skip_channels;
   const bool last = l == (int)P->lv.size() - 1;
   const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
+  // precision mode bf16: conv inputs are written as bf16 twins; the fp32 tensor is dropped where only convolutions read it
+  const bool bf = prec == DIP_PRECISION_BF16;
   // skip branch: 1x1 conv Cin -> CS (+ statistics); independent of the deeper branch until the concat -> skip stream
   if (CS > 0) {
     cudaStream_t ks = fork_skip(P, s);
@@ -1074,11 +1139,12 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
   HBM_T(&P->timer, H_BN_ACT_WRITE, 1, 128.0 * ((double)v.h * v.w + (double)(v.h + 2) * (v.w + 2)) * sizeof(float), s,
-        launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, v.P_d1, 128, 1, 1, s));
+        launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, bf ? nullptr : v.P_d1, 128, 1, 1, s, Twin{v.P_d1_16, 128}));
   DIP_CHECK(v.d2.run_fprop(prec, P->params[v.d2.p_b], s));
   HBM_T(&P->timer, H_BN_ACT_WRITE, last ? 0 : 1,
         128.0 * ((double)v.h * v.w + (last ? (double)v.h * v.w : (double)(v.h + 2) * (v.w + 2))) * sizeof(float), s,
-        launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, v.P_d2, 128, last ? 0 : 1, 1, s));
+        launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, (bf && !last && CS != 4) ? nullptr : v.P_d2, 128, last ? 0 : 1, 1, s,
+                            Twin{last ? nullptr : v.P_d2_16, 128}));   // (the 4-channel skip conv of the next level reads the fp32 tensor)
   nl += 4 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
   if (!last) {
     if (deep_on(P) && l + 1 == P->deep_from) {
@@ -1095,10 +1161,10 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   const double cat_in = (128.0 * v.h * v.w + (double)CS * v.H * v.W) * sizeof(float);
   HBM_T(&P->timer, H_CAT_STATS, v.bilinear, cat_in, s, launch_cat_stats(ca, v.bn_cat.fwd, s));
   HBM_T(&P->timer, H_CAT_WRITE, v.bilinear, cat_in + (128.0 + CS) * (v.H + 2) * (v.W + 2) * sizeof(float), s,
-        launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s));
+        launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s, Twin{v.P_cat16, v.cat_ld16}));
   DIP_CHECK(v.up.run_fprop(prec, P->params[v.up.p_b], s));
   HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * 128 * v.H * v.W * sizeof(float), s,
-        launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, v.A_u, 128, 0, 1, s));
+        launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, bf ? nullptr : v.A_u, 128, 0, 1, s, Twin{v.A_u16, 128}));
   DIP_CHECK(v.c11.run_fprop(prec, P->params[v.c11.p_b], s));
   if (l > 0) {
     HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * 128 * v.H * v.W * sizeof(float), s,
@@ -1136,11 +1202,11 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
   if (P->fnoise.on)
     HBM_T(&P->timer, H_NOISE, 1, ((double)v0.Cin_act * v0.H * v0.W + (double)v0.Cin * (v0.H + 2) * (v0.W + 2)) * sizeof(float), s,
           launch_noise_pad(P->fnoise.z0, P->fnoise.sigma, P->fnoise.seed, P->fnoise.offset, P->fnoise.it_dev, v0.Pin, v0.Cin,
-                           v0.H, v0.W, v0.Cin_act, s));
+                           v0.H, v0.W, v0.Cin_act, s, Twin{v0.Pin16, v0.Pin_ld16}));
   else
     HBM_T(&P->timer, H_INPUT_PAD, noise != nullptr,
           ((noise != nullptr ? 2.0 : 1.0) * v0.Cin_act * v0.H * v0.W + (double)v0.Cin * (v0.H + 2) * (v0.W + 2)) * sizeof(float), s,
-          launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act));
+          launch_input_pad(z, noise, sigma, v0.Pin, v0.Cin, v0.H, v0.W, s, v0.Cin_act, Twin{v0.Pin16, v0.Pin_ld16}));
   join_side(P, s);
   nl += 3;
   DIP_CHECK(fwd_level(P, 0, s, nl));
@@ -1155,7 +1221,8 @@ static int plan_forward(dip_plan* P, const float* z, const float* noise, float s
 
 // ------------------------------------------------------------------------------------------------ backward
 static int bn_bwd(dip_plan* P, const float* raw, int ld_raw, BnLayer& b, int act, GradSrc src, int H, int W, float* draw,
-                  float* zs, cudaStream_t s, int& nl) {
+                  float* zs, cudaStream_t s, int& nl, uint16_t* draw16 = nullptr) {
+  if (draw16 != nullptr && zs == nullptr) draw = nullptr;   // bf16 mode: only the tensor-core dgrad / wgrad read this gradient
   BnRef r = bn_ref(P, b);
   // algorithmic bytes: raw + the gradient source as the kernel's contract names it (plain [H][W][C]; fold: the padded
   // dgrad output (+ the 4-channel skip-branch gradient / the plain addend); upsample adjoint: the 2H x 2W gradient; head:
@@ -1167,7 +1234,7 @@ static int bn_bwd(dip_plan* P, const float* raw, int ld_raw, BnLayer& b, int act
   else if (src.kind == 3) gsrc = px * 4 * sizeof(float);
   HBM_T(&P->timer, H_BN_BWD_REDUCE, src.kind, px * C4 + gsrc, s, launch_bn_bwd_reduce(raw, ld_raw, r, act, src, H, W, b.bwd, s));
   HBM_T(&P->timer, H_BN_BWD_APPLY, src.kind + (zs != nullptr ? 4 : 0), px * C4 + gsrc + px * C4 * (zs != nullptr ? 2.0 : 1.0), s,
-        launch_bn_bwd_apply(raw, ld_raw, r, act, src, H, W, b.bwd, draw, zs, b.dbias, s));
+        launch_bn_bwd_apply(raw, ld_raw, r, act, src, H, W, b.bwd, draw, zs, b.dbias, s, Twin{draw16, b.C}));
   nl += 2;
   return 0;
 }
@@ -1221,14 +1288,14 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   const int CS = P->desc.skip_channels;
   const int CC = 128 + CS;
   const bool last = l == (int)P->lv.size() - 1;
-  const int wl = prec == DIP_PRECISION_TF32 ? 1 : 2;   // tensor-core wgrads accumulate in place (no per-conv reduction launch)
+  const int wl = is_tc(prec) ? 1 : 2;   // tensor-core wgrads accumulate in place (no per-conv reduction launch)
   // 1x1 conv + BN + LReLU
-  DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl));
+  DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl, v.dRaw_v16));
   if (l == defer_level()) DIP_CHECK(flush_deferred(P, prec, s));
   DIP_CHECK(conv_backward(P, v.c11, true, prec, s, l));
   nl += wl + 1;
   // up conv + BN + LReLU
-  DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl));
+  DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl, v.dRaw_u16));
   if (CS == 128) {
     cudaStream_t ws = fork_side(P, s);
     DIP_CHECK(v.up_a.run_dgrad(prec, s));
@@ -1252,7 +1319,7 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   HBM_T(&P->timer, H_UPADJ, v.bilinear, 128.0 * ((double)v.H * v.W + (double)v.h * v.w) * sizeof(float), s,
         launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp, s));
   nl += 3;
-  if (CS > 0) DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl));
+  if (CS > 0) DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl, v.dRaw_s16));
   if (CS == 0) {
     // no skip branch (models/skip.py:50-53 with num_channels_skip = 0)
   } else if (CS == 128) {
@@ -1285,12 +1352,12 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   } else {
     src_d2 = src_plain(v.dUp, 128, 0);
   }
-  DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl));
+  DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl, v.dRaw_d2_16));
   DIP_CHECK(conv_backward(P, v.d2, true, prec, s));
   nl += wl + 1;
   const bool d1_dgrad = l > 0 || P->desc.input_grad != 0;
   DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1,
-                   (d1_dgrad && !v.d1.dg_s2) ? v.ZS : nullptr, s, nl));
+                   (d1_dgrad && !v.d1.dg_s2) ? v.ZS : nullptr, s, nl, v.dRaw_d1_16));
   DIP_CHECK(conv_backward(P, v.d1, d1_dgrad, prec, s));
   nl += wl + (d1_dgrad ? 1 : 0);
   DIP_CUDA(cudaGetLastError());
@@ -1885,21 +1952,45 @@ int dip_plan_num_launches(const dip_plan* plan, int* fwd, int* bwd) {
 // ---------------------------------------------------------------------------------------------- single-op entry points
 size_t dip_op_scratch_bytes(void) { return (size_t)96 << 20; }
 
+// scratch layout of the single-op entry points: [fprop pack | dgrad pack | one PackEntry (64 floats) | wgrad accumulator |
+// bf16 copies of the operands (precision bf16)]
+static float* op_partial(ConvOp& op, float* scratch) {
+  return scratch + ((op.wp_f_elems() + 63) & ~size_t(63)) + ((op.wp_d_elems() + 63) & ~size_t(63)) + 64;
+}
 static int op_common(ConvOp& op, int N, int C, int k, int stride, int rot, float* scratch, const float* w, cudaStream_t s,
-                     int max_c = 160) {
+                     int max_c = 160, int prec = DIP_PRECISION_TF32) {
   if (N != 128) return fail("dip_op_conv_*: N must be 128");
   if (C % 4 != 0 || C > max_c) return fail("dip_op_conv_*: C must be a multiple of 4 and <= " + std::to_string(max_c));
   op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;
+  op.bf16 = prec == DIP_PRECISION_BF16;
   op.set_shapes();
   op.wp_f = scratch;
   op.wp_d = scratch + ((op.wp_f_elems() + 63) & ~size_t(63));
-  launch_pack_fprop(w, N, C, k, k, rot, op.wp_f, N, op.c_pad, s);
-  launch_pack_dgrad(w, N, C, k, k, rot, op.wp_d, op.crows, 128, s);
+  if (op.bf16) {
+    // bf16 packs come from the table kernel (one entry, staged in the scratch area)
+    PackEntry e{};
+    e.w = w; e.dst_f = op.wp_f; e.dst_d = op.wp_d; e.N = N; e.C = C; e.k = k; e.rot = rot; e.n_rows = N;
+    e.c_pad = op.c_pad; e.c_rows = op.crows; e.Ctot = C; e.coff = 0; e.s2 = 0; e.bf16 = 1; e.c_pad16 = op.c_pad16;
+    PackEntry* d_e = reinterpret_cast<PackEntry*>(op_partial(op, scratch) - 64);
+    DIP_CUDA(cudaMemcpyAsync(d_e, &e, sizeof e, cudaMemcpyHostToDevice, s));
+    launch_k(k_pack_table, dim3(64, 1), dim3(256), 0, s, 1, (const PackEntry*)d_e);
+  } else {
+    launch_pack_fprop(w, N, C, k, k, rot, op.wp_f, N, op.c_pad, s);
+    launch_pack_dgrad(w, N, C, k, k, rot, op.wp_d, op.crows, 128, s);
+  }
   DIP_CUDA(cudaGetLastError());
   return 0;
 }
-static float* op_partial(ConvOp& op, float* scratch) {
-  return scratch + ((op.wp_f_elems() + 63) & ~size_t(63)) + ((op.wp_d_elems() + 63) & ~size_t(63));
+// precision bf16: bf16 copy of an NHWC fp32 operand [npix][ld] in the scratch area behind *area (advanced)
+static const uint16_t* op_cast(const void* x, int ld, long long npix, uint16_t** area, int* ld16, cudaStream_t s) {
+  *ld16 = round_up(ld, 8);
+  uint16_t* dst = *area;
+  *area += ((size_t)npix * *ld16 + 127) & ~size_t(127);
+  launch_cast_bf16((const float*)x, ld, ld, npix, Twin{dst, *ld16}, s);
+  return dst;
+}
+static uint16_t* op_cast_area(ConvOp& op, float* partial) {
+  return reinterpret_cast<uint16_t*>(partial + ((op.wacc_elems() + 63) & ~size_t(63)));
 }
 
 int dip_op_conv_fprop(const void* a, int a_h, int a_w, int a_c, const void* w, const void* bias, int N, int C, int k, int stride,
@@ -1908,12 +1999,17 @@ int dip_op_conv_fprop(const void* a, int a_h, int a_w, int a_c, const void* w, c
   DIP_CHECK(engine_init());
   cudaStream_t s = (cudaStream_t)stream;
   ConvOp op;
-  DIP_CHECK(op_common(op, N, C, k, stride, rot, (float*)scratch, (const float*)w, s, 256));
+  DIP_CHECK(op_common(op, N, C, k, stride, rot, (float*)scratch, (const float*)w, s, 256, precision));
   op.in = (const float*)a; op.in_rows = a_h; op.in_cols = a_w; op.in_ld = a_c; op.offx = offx; op.offy = offy;
   op.out = (float*)d; op.out_h = d_h; op.out_w = d_w; op.stats = stats;
   op.has_dgrad = false;
   op.wg_dy = (const float*)d; op.wg_h = d_h; op.wg_w = d_w;  // placeholders so that build_tc can encode maps
-  if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
+  if (op.bf16) {
+    uint16_t* area = op_cast_area(op, op_partial(op, (float*)scratch));
+    op.in16 = op_cast(a, a_c, (long long)a_h * a_w, &area, &op.in_ld16, s);
+    op.do_wgrad = false;
+  }
+  if (is_tc(precision)) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
   return op.run_fprop(precision, (const float*)bias, s);
 }
 int dip_op_conv_dgrad(const void* dy, int dy_h, int dy_w, const void* w, int N, int C, int k, int rot, void* dx, int dx_h, int dx_w,
@@ -1921,39 +2017,51 @@ int dip_op_conv_dgrad(const void* dy, int dy_h, int dy_w, const void* w, int N, 
   DIP_CHECK(engine_init());
   cudaStream_t s = (cudaStream_t)stream;
   ConvOp op;
-  DIP_CHECK(op_common(op, N, C, k, 1, rot, (float*)scratch, (const float*)w, s));
+  DIP_CHECK(op_common(op, N, C, k, 1, rot, (float*)scratch, (const float*)w, s, 160, precision));
   // fprop/wgrad placeholders (valid maps over the same buffers; not launched)
   op.in = (const float*)dx; op.in_rows = dx_h; op.in_cols = dx_w; op.in_ld = C; op.out = (float*)const_cast<void*>(dy);
   op.out_h = dy_h; op.out_w = dy_w; op.wg_dy = (const float*)dy; op.wg_h = dy_h; op.wg_w = dy_w;
   op.has_dgrad = true;
   op.dg_in = (const float*)dy; op.dg_in_h = dy_h; op.dg_in_w = dy_w;
   op.dg_out = (float*)dx; op.dg_out_h = dx_h; op.dg_out_w = dx_w; op.dg_off = -(k - 1);
-  if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
+  if (op.bf16) {
+    uint16_t* area = op_cast_area(op, op_partial(op, (float*)scratch));
+    int ld16 = 0;
+    op.dg_in16 = op_cast(dy, 128, (long long)dy_h * dy_w, &area, &ld16, s);
+    op.do_fprop = false; op.do_wgrad = false;
+  }
+  if (is_tc(precision)) DIP_CHECK(op.build_tc(op_partial(op, (float*)scratch)));
   return op.run_dgrad(precision, s);
 }
 int dip_op_conv_dgrad_s2(const void* dy, int dy_h, int dy_w, const void* w, int N, int C, int rot, void* dx, int precision,
                          void* scratch, dip_stream_t stream) {
   DIP_CHECK(engine_init());
-  if (precision != DIP_PRECISION_TF32) return fail("dip_op_conv_dgrad_s2: tensor-core path only (the exact-fp32 mode zero-stuffs)");
+  if (!is_tc(precision)) return fail("dip_op_conv_dgrad_s2: tensor-core path only (the exact-fp32 mode zero-stuffs)");
   cudaStream_t s = (cudaStream_t)stream;
   ConvOp op;
   if (N != 128) return fail("dip_op_conv_dgrad_s2: N must be 128");
   if (C % 4 != 0 || C > 160) return fail("dip_op_conv_dgrad_s2: C must be a multiple of 4 and <= 160");
   op.N = N; op.C = C; op.k = 3; op.stride = 2; op.rot = rot;
+  op.bf16 = precision == DIP_PRECISION_BF16;
   op.set_shapes();
   op.wp_f = (float*)scratch;
   op.wp_d = (float*)scratch + ((op.wp_f_elems() + 63) & ~size_t(63));
   // one-entry pack table in the scratch area behind the packed weights
   PackEntry e{};
   e.w = (const float*)w; e.dst_f = nullptr; e.dst_d = op.wp_d; e.N = N; e.C = C; e.k = 3; e.rot = rot; e.n_rows = N;
-  e.c_pad = op.c_pad; e.c_rows = op.crows; e.Ctot = C; e.coff = 0; e.s2 = 1;
-  PackEntry* d_e = reinterpret_cast<PackEntry*>(op.wp_d + ((op.wp_d_elems() + 63) & ~size_t(63)));
+  e.c_pad = op.c_pad; e.c_rows = op.crows; e.Ctot = C; e.coff = 0; e.s2 = 1; e.bf16 = op.bf16 ? 1 : 0; e.c_pad16 = op.c_pad16;
+  PackEntry* d_e = reinterpret_cast<PackEntry*>(op_partial(op, (float*)scratch) - 64);
   DIP_CUDA(cudaMemcpyAsync(d_e, &e, sizeof e, cudaMemcpyHostToDevice, s));
   launch_k(k_pack_table, dim3(64, 1), dim3(256), 0, s, 1, (const PackEntry*)d_e);
   op.do_fprop = false; op.do_wgrad = false;
   op.has_dgrad = true; op.dg_s2 = true;
   op.dg_in = (const float*)dy; op.dg_in_h = dy_h; op.dg_in_w = dy_w;
   op.dg_out = (float*)dx; op.dg_out_h = 2 * dy_h + 2; op.dg_out_w = 2 * dy_w + 2; op.dg_off = -2;
+  if (op.bf16) {
+    uint16_t* area = op_cast_area(op, op_partial(op, (float*)scratch));
+    int ld16 = 0;
+    op.dg_in16 = op_cast(dy, 128, (long long)dy_h * dy_w, &area, &ld16, s);
+  }
   DIP_CHECK(op.build_tc(nullptr));
   return op.run_dgrad(precision, s);
 }
@@ -1965,6 +2073,7 @@ int dip_op_conv_wgrad(const void* dy, int dy_h, int dy_w, const void* a, int a_h
   // weights are not needed for wgrad; pack from dw is skipped
   if (N != 128) return fail("dip_op_conv_wgrad: N must be 128");
   op.N = N; op.C = C; op.k = k; op.stride = stride; op.rot = rot;
+  op.bf16 = precision == DIP_PRECISION_BF16;
   op.set_shapes();
   op.wp_f = (float*)scratch;
   op.wp_d = nullptr;
@@ -1974,7 +2083,15 @@ int dip_op_conv_wgrad(const void* dy, int dy_h, int dy_w, const void* a, int a_h
   op.wg_dy = (const float*)dy; op.wg_h = dy_h; op.wg_w = dy_w;
   op.simt_ksplits = dy_h < 64 ? dy_h : 64;
   float* partial = (float*)scratch + ((op.wp_f_elems() + 63) & ~size_t(63));
-  if (precision == DIP_PRECISION_TF32) DIP_CHECK(op.build_tc(partial));
+  if (op.bf16) {
+    uint16_t* area = op_cast_area(op, partial);
+    int ld16 = 0;
+    op.wg_dy16 = op_cast(dy, 128, (long long)dy_h * dy_w, &area, &ld16, s);
+    op.in16 = op_cast(a, a_c, (long long)a_h * a_w, &area, &op.in_ld16, s);
+    op.do_fprop = false;
+    if ((uint8_t*)area > (uint8_t*)scratch + dip_op_scratch_bytes()) return fail("dip_op_conv_wgrad: operands too large for the scratch area (bf16 copies)");
+  }
+  if (is_tc(precision)) DIP_CHECK(op.build_tc(partial));
   return op.run_wgrad(precision, partial, (float*)dw, s);
 }
 

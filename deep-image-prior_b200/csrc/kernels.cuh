@@ -66,6 +66,17 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Optional bf16 twin of an NHWC fp32 output (precision mode bf16: the tensor-core kernels read their operands from these).
+// Same pixel order as the fp32 tensor; ld = channel stride in bf16 elements (a multiple of 8: TMA needs 16-byte pitches;
+// channels between the tensor's depth and ld are never written nor read).  p == nullptr: no twin.
+struct Twin {
+  uint16_t* p;
+  int ld;
+};
+static constexpr Twin kNoTwin = {nullptr, 0};
+// plain NHWC fp32 [npix][ld] (c valid channels, c % 4 == 0) -> bf16 [npix][t.ld]   (single-op entry points)
+void launch_cast_bf16(const float* x, int ld, int c, long long npix, Twin t, cudaStream_t s);
+
 // Statistics of one BatchNorm layer: fp64 accumulators, zeroed once per iteration.
 //   fwd[0..C)   sum x          fwd[C..2C)   sum x^2
 //   bwd[0..C)   sum dz         bwd[C..2C)   sum dz * xhat          (dz = grad wrt BN output)
@@ -91,14 +102,15 @@ struct HeadRef {
 // z (NCHW, C x H x W) [+ sigma * noise (NCHW)] -> reflection-padded NHWC [(H+2)][(W+2)][C]
 // C = stored depth of dst; c_src (0: C) = depth of z / noise, the remaining channels are written as zeros
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
-                      cudaStream_t s, int c_src = 0);
+                      cudaStream_t s, int c_src = 0, Twin t16 = kNoTwin);
 
 // generic per-channel sum / sum^2 of a plain NHWC tensor (SIMT-conv path and skinny convs)
 void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, cudaStream_t s);
 
 // y = lrelu(bn(x)) written plain [H][W][ld_out] or reflection padded [(H+2)][(W+2)][ld_out]
+// dst may be null when a bf16 twin is given (the tensor is then only read by tensor-core kernels)
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
-                         int act, cudaStream_t s);
+                         int act, cudaStream_t s, Twin t16 = kNoTwin);
 // y = lrelu(bn(x)) consumed on the fly by the RGB head (C must be 128); y itself is not materialised
 void launch_bn_act_head(const float* raw, BnRef bn, int H, int W, HeadRef head, cudaStream_t s);
 
@@ -112,7 +124,7 @@ struct CatArgs {
 };
 void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s);
 // dst = bn_cat(cat) with reflection pad: [(H+2)][(W+2)][Cu+Cs]
-void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s);
+void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s, Twin t16 = kNoTwin);
 
 // Gradient sources for the BN backward kernels
 struct GradSrc {
@@ -148,8 +160,9 @@ void launch_input_grad(const float* gp, const float* ds, int ld, int C, int H, i
 //        optionally a zero-stuffed copy zs [2H][2W][C] (only even positions written); dbias[c] += sum dx.
 void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W, double* bwd,
                           cudaStream_t s);
+// draw may be null when a bf16 twin is given
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
-                         const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s);
+                         const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s, Twin t16 = kNoTwin);
 
 // Concat-BN backward (no activation). pcat = the stored BN output (padded [(H+2)][(W+2)][ld], ld = bn_cat.C), from which
 // xhat is recovered; gradient = fold of the padded dgrad output gp [(H+2)][(W+2)][ld]; dcat plain [H][W][C].
@@ -185,7 +198,7 @@ void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_
 // runner input in one pass: dst (reflection-padded NHWC [(H+2)][(W+2)][C]) = pad(z0 + sigma * N(0,1)), the same Philox stream
 // as launch_noise (W % 4 == 0); channels >= c_src of the stored depth C are written as zeros
 void launch_noise_pad(const float* z0, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, float* dst, int C, int H,
-                      int W, int c_src, cudaStream_t s);
+                      int W, int c_src, cudaStream_t s, Twin t16 = kNoTwin);
 // it_dev[0] += 1, it_dev[1] += 1 (step / iteration counters of the graph-captured runner)
 void launch_advance(int* it_dev, cudaStream_t s);
 

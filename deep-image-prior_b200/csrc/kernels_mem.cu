@@ -12,6 +12,7 @@
 //   mse / adam / noise: torch.nn.MSELoss, torch.optim.Adam.step, noise.normal_()  (common_utils.py:225-230)
 #include "kernels.cuh"
 
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -50,6 +51,18 @@ __device__ __forceinline__ float4 f4fma(float w, float4 a, float4 acc) {
 __device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 f4mla(float4 a, float4 b, float4 acc) {
   return make_float4(fmaf(a.x, b.x, acc.x), fmaf(a.y, b.y, acc.y), fmaf(a.z, b.z, acc.z), fmaf(a.w, b.w, acc.w));
+}
+// 4 consecutive channels as bf16 (round to nearest even), one 8-byte store
+__device__ __forceinline__ void st4_bf16(uint16_t* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float x) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  return *reinterpret_cast<const uint16_t*>(&h);
 }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
@@ -208,7 +221,7 @@ static void fit_grid(VecGeom& g, Kern kernel, size_t smem) {
 
 // ------------------------------------------------------------------------------------------------ input_pad
 __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict__ noise, float sigma,
-                            float* __restrict__ dst, int C, int H, int W, int Cs) {
+                            float* __restrict__ dst, int C, int H, int W, int Cs, Twin t16) {
   pdl_enter();
   __shared__ float tile[32][33];
   const int Wp = W + 2;
@@ -232,15 +245,35 @@ __global__ void k_input_pad(const float* __restrict__ z, const float* __restrict
     for (int k = 0; k < 4; ++k) {
       const int xo = blockIdx.x * 32 + ty + 8 * k;
       const int c = c0 + tx;
-      if (xo < Wp && c < C) dst[(static_cast<size_t>(yy) * Wp + xo) * C + c] = tile[tx][ty + 8 * k];
+      if (xo < Wp && c < C) {
+        dst[(static_cast<size_t>(yy) * Wp + xo) * C + c] = tile[tx][ty + 8 * k];
+        if (t16.p != nullptr) t16.p[(static_cast<size_t>(yy) * Wp + xo) * t16.ld + c] = bf16_bits(tile[tx][ty + 8 * k]);
+      }
     }
     __syncthreads();
   }
 }
 void launch_input_pad(const float* z, const float* noise, float sigma, float* dst, int C, int H, int W,
-                      cudaStream_t s, int c_src) {
+                      cudaStream_t s, int c_src, Twin t16) {
   dim3 grid((W + 2 + 31) / 32, H + 2), block(32, 8);
-  launch_k(k_input_pad, dim3(grid), dim3(block), 0, s, 1, z, noise, sigma, dst, C, H, W, c_src > 0 ? c_src : C);
+  launch_k(k_input_pad, dim3(grid), dim3(block), 0, s, 1, z, noise, sigma, dst, C, H, W, c_src > 0 ? c_src : C, t16);
+}
+
+// ------------------------------------------------------------------------------------------------ cast (single ops)
+__global__ void __launch_bounds__(256) k_cast_bf16(const float* __restrict__ x, int ld, int c4, long long n4, Twin t) {
+  pdl_enter();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / c4;
+    const int v = static_cast<int>(i - p * c4);
+    st4_bf16(t.p + p * t.ld + 4 * v, ld4(x + p * ld + 4 * v));
+  }
+}
+void launch_cast_bf16(const float* x, int ld, int c, long long npix, Twin t, cudaStream_t s) {
+  const long long n4 = npix * (c / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  launch_k(k_cast_bf16, dim3((unsigned)blocks), dim3(256), 0, s, 1, x, ld, c / 4, n4, t);
 }
 
 // ------------------------------------------------------------------------------------------------ item loop
@@ -288,7 +321,7 @@ void launch_channel_stats(const float* x, int ld, int C, int npix, double* fwd, 
 // ------------------------------------------------------------------------------------------------ bn_act_write
 __device__ __forceinline__ void d_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
                                                       float* __restrict__ dst, int ld_out, int pad, int act, int VL,
-                                                      int PPB) {
+                                                      int PPB, Twin t16 = kNoTwin) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
@@ -302,20 +335,21 @@ __device__ __forceinline__ void d_bn_act_write(const float* __restrict__ raw, in
                [&](int p, float4 x) {
                  float4 y = bn_apply(cf, x);
                  if (act) y = lrelu4(y);
-                 st4(dst + static_cast<size_t>(p) * ld_out + 4 * v, y);
+                 if (dst != nullptr) st4(dst + static_cast<size_t>(p) * ld_out + 4 * v, y);
+                 if (t16.p != nullptr) st4_bf16(t16.p + static_cast<size_t>(p) * t16.ld + 4 * v, y);
                });
 }
 __global__ void __launch_bounds__(256) k_bn_act_write(const float* __restrict__ raw, int ld_in, BnRef bn, int H, int W,
                                                       float* __restrict__ dst, int ld_out, int pad, int act, int VL,
-                                                      int PPB) {
+                                                      int PPB, Twin t16) {
   pdl_enter();
-  d_bn_act_write(raw, ld_in, bn, H, W, dst, ld_out, pad, act, VL, PPB);
+  d_bn_act_write(raw, ld_in, bn, H, W, dst, ld_out, pad, act, VL, PPB, t16);
 }
 void launch_bn_act_write(const float* raw, int ld_in, BnRef bn, int H, int W, float* dst, int ld_out, int pad,
-                         int act, cudaStream_t s) {
+                         int act, cudaStream_t s, Twin t16) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H + 2 * pad) * (W + 2 * pad));
   fit_grid(g, k_bn_act_write, 0);
-  launch_k(k_bn_act_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, raw, ld_in, bn, H, W, dst, ld_out, pad, act, g.VL, g.PPB);
+  launch_k(k_bn_act_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, raw, ld_in, bn, H, W, dst, ld_out, pad, act, g.VL, g.PPB, t16);
 }
 
 // BN + LeakyReLU + RGB head + sigmoid: one warp per pixel (C = 128 -> 32 lanes x float4), nothing but out is written.
@@ -439,7 +473,8 @@ void launch_cat_stats(CatArgs a, double* fwd_cat, cudaStream_t s) {
 }
 
 // store the value of interior pixel (i, j) at its padded position and at every halo position that mirrors it
-__device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld, int H, int W, int i, int j, int v, float4 val) {
+__device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld, int H, int W, int i, int j, int v, float4 val,
+                                                Twin t16 = kNoTwin) {
   int rows[3], cols[3];
   int nr = 0, nc = 0;
   rows[nr++] = i + 1;
@@ -450,10 +485,13 @@ __device__ __forceinline__ void store_with_halo(float* __restrict__ dst, int ld,
   if (j == W - 2) cols[nc++] = W + 1;
   const int Wp = W + 2;
   for (int r = 0; r < nr; ++r)
-    for (int c = 0; c < nc; ++c) st4(dst + (static_cast<size_t>(rows[r]) * Wp + cols[c]) * ld + 4 * v, val);
+    for (int c = 0; c < nc; ++c) {
+      st4(dst + (static_cast<size_t>(rows[r]) * Wp + cols[c]) * ld + 4 * v, val);
+      if (t16.p != nullptr) st4_bf16(t16.p + (static_cast<size_t>(rows[r]) * Wp + cols[c]) * t16.ld + 4 * v, val);
+    }
 }
 
-__device__ __forceinline__ void d_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
+__device__ __forceinline__ void d_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB, Twin t16 = kNoTwin) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const CatLane l = cat_lane(a, v);
   const Bn4 cf = bn_coef<0>(bn_cat, v);
@@ -465,17 +503,17 @@ __device__ __forceinline__ void d_cat_write(CatArgs a, BnRef bn_cat, float* __re
     cat_quad(a, l, si, sj, v, q);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]));
+      store_with_halo(dst, ld, a.H, a.W, 2 * si + (e >> 1), 2 * sj + (e & 1), v, bn_apply(cf, q[e]), t16);
   }
 }
-__global__ void __launch_bounds__(256, DIP_CAT_MINBLOCKS) k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB) {
+__global__ void __launch_bounds__(256, DIP_CAT_MINBLOCKS) k_cat_write(CatArgs a, BnRef bn_cat, float* __restrict__ dst, int VL, int PPB, Twin t16) {
   pdl_enter();
-  d_cat_write(a, bn_cat, dst, VL, PPB);
+  d_cat_write(a, bn_cat, dst, VL, PPB, t16);
 }
-void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s) {
+void launch_cat_write(CatArgs a, BnRef bn_cat, float* dst, cudaStream_t s, Twin t16) {
   VecGeom g = vec_geom(a.Cu + a.Cs, static_cast<long long>(a.H / 2) * (a.W / 2));
   fit_grid(g, k_cat_write, 0);
-  launch_k(k_cat_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, a, bn_cat, dst, g.VL, g.PPB);
+  launch_k(k_cat_write, dim3(g.blocks), dim3(g.threads), 0, s, 1, a, bn_cat, dst, g.VL, g.PPB, t16);
 }
 
 // ------------------------------------------------------------------------------------------------ gradient sources
@@ -775,7 +813,8 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
 template <int KIND>
 __device__ __forceinline__ void d_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                       int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
-                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
+                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB,
+                                                      Twin t16 = kNoTwin) {
   const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
   const Bn4 cf = bn_coef<0>(bn, v);
   const SrcRegs sr = src_regs<KIND>(src, bn.C, v);
@@ -799,7 +838,8 @@ __device__ __forceinline__ void d_bn_bwd_apply(const float* __restrict__ raw, in
                            dx.y = cf.scale.y * (dz.y - m1.y - xh.y * m2.y);
                            dx.z = cf.scale.z * (dz.z - m1.z - xh.z * m2.z);
                            dx.w = cf.scale.w * (dz.w - m1.w - xh.w * m2.w);
-                           st4(draw + (static_cast<size_t>(i) * W + j) * C + 4 * v, dx);
+                           if (draw != nullptr) st4(draw + (static_cast<size_t>(i) * W + j) * C + 4 * v, dx);
+                           if (t16.p != nullptr) st4_bf16(t16.p + (static_cast<size_t>(i) * W + j) * t16.ld + 4 * v, dx);
                            if (zs != nullptr) st4(zs + (static_cast<size_t>(2 * i) * (2 * W) + 2 * j) * C + 4 * v, dx);
                            acc[0] = f4add(acc[0], dx);
                          });
@@ -832,7 +872,8 @@ __device__ __forceinline__ void d_bn_bwd_apply(const float* __restrict__ raw, in
         dx.y = cf.scale.y * (dz.y - m1.y - xh.y * m2.y);
         dx.z = cf.scale.z * (dz.z - m1.z - xh.z * m2.z);
         dx.w = cf.scale.w * (dz.w - m1.w - xh.w * m2.w);
-        st4(draw + static_cast<size_t>(p) * C + 4 * v, dx);
+        if (draw != nullptr) st4(draw + static_cast<size_t>(p) * C + 4 * v, dx);
+        if (t16.p != nullptr) st4_bf16(t16.p + static_cast<size_t>(p) * t16.ld + 4 * v, dx);
         if (zs != nullptr) {
           const int i = p / W, j = p - i * W;
           st4(zs + (static_cast<size_t>(2 * i) * (2 * W) + 2 * j) * C + 4 * v, dx);
@@ -854,21 +895,21 @@ __device__ __forceinline__ void d_bn_bwd_apply(const float* __restrict__ raw, in
 template <int KIND>
 __global__ void __launch_bounds__(256, KIND == 2 ? 3 : 2) k_bn_bwd_apply(const float* __restrict__ raw, int ld_raw, BnRef bn, int act, GradSrc src,
                                                       int H, int W, const double* __restrict__ bwd, float* __restrict__ draw,
-                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB) {
+                                                      float* __restrict__ zs, double* __restrict__ dbias, int VL, int PPB, Twin t16) {
   pdl_enter();
-  d_bn_bwd_apply<KIND>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, VL, PPB);
+  d_bn_bwd_apply<KIND>(raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, VL, PPB, t16);
 }
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
-                         const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s) {
+                         const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s, Twin t16) {
   VecGeom g = vec_geom(bn.C, static_cast<long long>(H) * W);
   if (src.kind == 0) fit_grid(g, k_bn_bwd_apply<0>, red_bytes(g, 1));
   else if (src.kind == 1) fit_grid(g, k_bn_bwd_apply<1>, red_bytes(g, 1));
   else if (src.kind == 2) fit_grid(g, k_bn_bwd_apply<2>, red_bytes(g, 1));
   else fit_grid(g, k_bn_bwd_apply<3>, red_bytes(g, 6));
-  if (src.kind == 0) launch_red(k_bn_bwd_apply<0>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else if (src.kind == 1) launch_red(k_bn_bwd_apply<1>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else if (src.kind == 2) launch_red(k_bn_bwd_apply<2>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
-  else launch_red(k_bn_bwd_apply<3>, g.blocks, g.threads, red_bytes(g, 6), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB);
+  if (src.kind == 0) launch_red(k_bn_bwd_apply<0>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, t16);
+  else if (src.kind == 1) launch_red(k_bn_bwd_apply<1>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, t16);
+  else if (src.kind == 2) launch_red(k_bn_bwd_apply<2>, g.blocks, g.threads, red_bytes(g, 1), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, t16);
+  else launch_red(k_bn_bwd_apply<3>, g.blocks, g.threads, red_bytes(g, 6), s, raw, ld_raw, bn, act, src, H, W, bwd, draw, zs, dbias, g.VL, g.PPB, t16);
 }
 
 // ------------------------------------------------------------------------------------------------ concat-BN backward
@@ -1298,7 +1339,7 @@ void launch_noise(const float* z0, float* z, float sigma, uint64_t seed, uint64_
 // position that mirrors it (ReflectionPad2d(1): padded row 0 <- source row 1, row H+1 <- row H-2, same for columns).
 __global__ void __launch_bounds__(256) k_noise_pad(const float* __restrict__ z0, float sigma, uint64_t seed, uint64_t offset,
                                                    const int* __restrict__ it_dev, float* __restrict__ dst, int C, int H, int W,
-                                                   int Cs) {
+                                                   int Cs, Twin t16) {
   pdl_enter();
   __shared__ float tile[32][33];   // [pixel][channel]
   if (it_dev != nullptr) offset += static_cast<uint64_t>(*it_dev);
@@ -1354,16 +1395,19 @@ __global__ void __launch_bounds__(256) k_noise_pad(const float* __restrict__ z0,
         if (sx == 1) cols[nc++] = 0;
         if (sx == W - 2) cols[nc++] = W + 1;
         for (int a = 0; a < nr; ++a)
-          for (int b = 0; b < nc; ++b) dst[(static_cast<size_t>(rows[a]) * Wp + cols[b]) * C + c0 + tx] = o;
+          for (int b = 0; b < nc; ++b) {
+            dst[(static_cast<size_t>(rows[a]) * Wp + cols[b]) * C + c0 + tx] = o;
+            if (t16.p != nullptr) t16.p[(static_cast<size_t>(rows[a]) * Wp + cols[b]) * t16.ld + c0 + tx] = bf16_bits(o);
+          }
       }
     }
     __syncthreads();
   }
 }
 void launch_noise_pad(const float* z0, float sigma, uint64_t seed, uint64_t offset, const int* it_dev, float* dst, int C, int H,
-                      int W, int c_src, cudaStream_t s) {
+                      int W, int c_src, cudaStream_t s, Twin t16) {
   dim3 grid((W + 31) / 32, H);
-  launch_k(k_noise_pad, dim3(grid), dim3(256), 0, s, 1, z0, sigma, seed, offset, it_dev, dst, C, H, W, c_src > 0 ? c_src : C);
+  launch_k(k_noise_pad, dim3(grid), dim3(256), 0, s, 1, z0, sigma, seed, offset, it_dev, dst, C, H, W, c_src > 0 ? c_src : C, t16);
 }
 __global__ void k_advance(int* it) {
   pdl_enter(); it[0] += 1; it[1] += 1; }  // {global Adam step, iteration index of this call}

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("DIP_LIB") or os.path.join(_HERE, "libdip.so")  # DIP_
 
 PRECISION_TF32 = 0
 PRECISION_FP32 = 1
+PRECISION_BF16 = 2
 
 
 class NetDesc(ctypes.Structure):

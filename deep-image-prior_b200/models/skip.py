@@ -72,7 +72,9 @@ class SkipNet(nn.Sequential):
         self._dip_anchor = None
         self._dip_generation = 0     # bumped by every engine forward (guards backward against stale activations)
         self._dip_active_plan = None
-        self.precision = 'tf32'      # 'tf32' (tcgen05 tensor cores, default) | 'fp32' (exact CUDA-core parity mode)
+        # 'tf32' (tcgen05 kind::tf32, default) | 'fp32' (exact CUDA-core parity mode) | 'bf16' (tcgen05 kind::f16 on bf16
+        # operands, fp32 accumulate / master weights / BatchNorm / Adam: BASELINE.json configs[2])
+        self.precision = 'tf32'
 
     # ---- engine plumbing -------------------------------------------------------------------------------------
     def _apply(self, fn, *args, **kwargs):
@@ -85,7 +87,10 @@ class SkipNet(nn.Sequential):
         re-validated cheaply (storage of the first / last parameter and of one BatchNorm buffer): after the per-step
         loss read-back of a notebook closure the GPU idles until this returns, so it must cost microseconds."""
         import dip_engine as de
-        prec = de.PRECISION_TF32 if self.precision == 'tf32' else de.PRECISION_FP32
+        try:
+            prec = {'tf32': de.PRECISION_TF32, 'fp32': de.PRECISION_FP32, 'bf16': de.PRECISION_BF16}[self.precision]
+        except KeyError:
+            raise ValueError("dip-b200: net.precision must be 'tf32', 'fp32' or 'bf16', not %r" % (self.precision,))
         key = (int(z.shape[2]), int(z.shape[3]), z.device, prec, bool(want_dz))
         c = getattr(self, '_dip_cache', None)
         if c is not None and c['key'] == key:

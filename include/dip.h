@@ -24,7 +24,10 @@ typedef struct dip_adam dip_adam;
 typedef void* dip_stream_t; /* cudaStream_t */
 
 enum { DIP_PRECISION_TF32 = 0, /* tcgen05 kind::tf32 convolutions, fp32 accumulate (cuDNN's default fp32 mode) */
-       DIP_PRECISION_FP32 = 1  /* exact-fp32 CUDA-core convolutions (parity mode) */ };
+       DIP_PRECISION_FP32 = 1, /* exact-fp32 CUDA-core convolutions (parity mode) */
+       DIP_PRECISION_BF16 = 2  /* tcgen05 kind::f16 convolutions on bf16 operands (activations, gradients and weights rounded
+                                  to bf16 where a convolution reads them), fp32 accumulate; fp32 master weights, BatchNorm,
+                                  loss and Adam (BASELINE.json configs[2]: "super-resolution ... bf16") */ };
 
 /* Arguments of models.skip(...) that the engine supports (reference: models/skip.py:5-11, models/__init__.py:12-17). */
 typedef struct {
