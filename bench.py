@@ -469,6 +469,14 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    # ---- 6. BASELINE configs[2]: super-resolution x4 (1024^2 net output -> 256^2 through the Lanczos-2 operator), runner,
+    #         in the default tf32 mode and in bf16 (tcgen05 kind::f16 on bf16 operands) -- single GPU, rank 0 only
+    sr_cfg = None
+    if rank == 0 and world == 1:
+        del fast
+        torch.cuda.empty_cache()
+        sr_cfg = bench_sr_config(torch, de, models, peaks, dev)
+
     # ---- result record per rank (the only data collective of the job)
     recs = mg.gather_records([psnr_img, float(img_hist[-1].item()), ITERS_PER_IMAGE / (img_ms / 1000.0)], device=dev)
     sampler.stop()
@@ -569,6 +577,7 @@ def run_ours(args):
                                      lambda r: r[0] == 16 + 8 * 8 and r[1] == hbm_big,
                                      {"traffic": TRAFFIC.get("bn_bwd_apply_l0")}),
             "step_tflops": ALG_GFLOP_PER_ITER / 1000.0 / (step_ms / 1000.0),
+            "config3_sr_x4_1024": sr_cfg,
             "per_rank": [{"psnr_gt_after_image": r[0], "final_loss": r[1], "it_per_s_image": r[2]} for r in recs],
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -584,6 +593,78 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+SR_ALG_GFLOP_PER_ITER = 1840.3   # the same network at 1024x1024 (4 x the 512x512 count), DESIGN.md section 3
+
+
+def bench_sr_config(torch, de, models, peaks, dev, iters=100):
+    """BASELINE.json configs[2] ("super-resolution x4 zebra 256->1024, skip net + Lanczos downsampler, bf16") on the runner:
+    noise + forward + Lanczos-2 x4 operator + MSE on the 256^2 target + the operator's adjoint + backward + Adam per step.
+    Timed in both tensor-core modes; the bf16 mode also gets a per-launch pass (CUDA events around every tensor-core launch
+    of an eager step) for its roofline against the measured bf16 peak."""
+    HS = WS = 1024
+    gen = torch.Generator().manual_seed(7)
+    z0 = (torch.rand(1, IN_CH, HS, WS, generator=gen) * 0.1).to(dev)
+    target = torch.rand(1, OUT_CH, HS // 4, WS // 4, generator=gen).to(dev)
+    down = models.Downsampler(n_planes=3, factor=4, kernel_type="lanczos2", phase=0.5, preserve_size=True)
+    out = {"workload": "super-resolution x4: skip[128x5] in32 out3 bilinear at 1024x1024, Lanczos-2 operator to 256x256 in the loss, "
+                       "noise+fwd+operator+MSE+adjoint+bwd+Adam per step (BASELINE.json configs[2]); synthetic target",
+           "algorithmic_gflop_per_step": SR_ALG_GFLOP_PER_ITER}
+    for prec_name, prec in (("tf32", de.PRECISION_TF32), ("bf16", de.PRECISION_BF16)):
+        torch.manual_seed(0)
+        net = models.get_net(IN_CH, "skip", "reflection", skip_n33d=128, skip_n33u=128, skip_n11=4, num_scales=5,
+                             upsample_mode="bilinear").type(torch.cuda.FloatTensor)
+        params = [p for p in net.parameters()]
+        grads = [torch.zeros_like(p) for p in params]
+        plan = de.Plan(IN_CH, OUT_CH, 5, 128, 4, True, HS, WS, precision=prec, device=dev)
+        plan.bind(params, grads)
+        for p_, g_ in zip(params, grads):
+            p_.grad = g_
+        opt = de.FusedAdam(params, lr=LR)
+        opt._bind(grads)
+        plan.set_downsampler(down.kernel, 4, down.pad)
+        obuf = torch.empty(1, OUT_CH, HS, WS, device=dev)
+        hist = torch.zeros(iters, dtype=torch.float64, device=dev)
+        de.run_iterations(plan, opt, z0, target, None, 0.03, 99, 5, LR, out=obuf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        de.run_iterations(plan, opt, z0, target, None, 0.03, 99, iters, LR, out=obuf, loss_hist=hist)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        rec = {"it_per_s": 1000.0 / ms, "ms_per_step": ms, "steps": iters, "step_tflops": SR_ALG_GFLOP_PER_ITER / ms,
+               "loss_first": float(hist[0].item()), "loss_last": float(hist[-1].item())}
+        # per-launch pass
+        os.environ["DIP_NO_SIDE"] = "1"
+        plan.set_timing(True)
+        de.run_iterations(plan, opt, z0, target, None, 0.03, 99, 3, LR, out=obuf)
+        torch.cuda.synchronize()
+        records = plan.get_timing_records()
+        plan.set_timing(False)
+        os.environ.pop("DIP_NO_SIDE", None)
+        peak = peaks["bf16_tflops"] * (1.0 if prec_name == "bf16" else 0.5)
+        for nm, classes in (("conv_fprop_dgrad", (0, 1)), ("wgrad", (2,))):
+            sel = [r for r in records if r[0] in classes]
+            ms_, fl_ = sum(r[2] for r in sel), sum(r[1] for r in sel)
+            ach = fl_ / (ms_ / 1000.0) / 1e12 if ms_ > 0 else 0.0
+            rec["roofline_" + nm] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                     "launches_per_step": len(sel) // 3, "ms_per_step": ms_ / 3.0}
+        fp = [r for r in records if r[0] == 0]
+        big = max(fp, key=lambda r: r[1])
+        rec["roofline_dominant_launch"] = {"kernel": "level-0 3x3 conv 132->128 @1024x1024 fprop", "bound": "tensor",
+                                           "achieved": big[1] / (big[2] / 1000.0) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                           "frac": big[1] / (big[2] / 1000.0) / 1e12 / peak}
+        hb = [r for r in records if r[0] >= 16]
+        ms_, by_ = sum(r[2] for r in hb), sum(r[1] for r in hb)
+        rec["hbm_kernels"] = {"ms_per_step": ms_ / 3.0, "algorithmic_GB_per_s_fp32_bytes": by_ / (ms_ / 1000.0) / 1e9 if ms_ > 0 else 0.0}
+        rec["peak_note"] = "peak = measured burst cuBLAS bf16 rate (MEASURED_PEAKS.json)" + ("" if prec_name == "bf16" else " / 2 (tf32)")
+        out[prec_name] = rec
+        del plan, opt, net, params, grads
+        torch.cuda.empty_cache()
+    out["bf16_speedup"] = out["bf16"]["it_per_s"] / out["tf32"]["it_per_s"]
+    return out
 
 
 def main():

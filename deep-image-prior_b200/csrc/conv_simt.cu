@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(160) k_simt_wgrad(SimtWgradArgs a) {
       if (ix < 0 || ix >= a.x_w) continue;
       float xv = 0.f;
       if (c < a.x_c) xv = a.X[(static_cast<long long>(iy) * a.x_w + ix) * a.x_ld + c];
-      const float4* gp = reinterpret_cast<const float4*>(a.dY + (static_cast<long long>(y) * a.w + x) * 128 + ng * 8);
+      const float4* gp = reinterpret_cast<const float4*>(a.dY + (static_cast<long long>(y) * a.w + x) * (a.dy_ld > 0 ? a.dy_ld : 128) + ng * 8);
       const float4 g0 = gp[0], g1 = gp[1];
       acc[0] = fmaf(g0.x, xv, acc[0]); acc[1] = fmaf(g0.y, xv, acc[1]);
       acc[2] = fmaf(g0.z, xv, acc[2]); acc[3] = fmaf(g0.w, xv, acc[3]);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(160) k_simt_wgrad(SimtWgradArgs a) {
   }
 }
 void launch_simt_wgrad(SimtWgradArgs a, cudaStream_t s) {
-  dim3 grid(a.kh * a.kw, 16, a.ksplits);
+  dim3 grid(a.kh * a.kw, a.n > 0 ? (a.n + 7) / 8 : 16, a.ksplits);   // output channels in groups of 8 (widths are multiples of 8)
   launch_k(k_simt_wgrad, dim3(grid), dim3(160), 0, s, 1, a);
 }
 

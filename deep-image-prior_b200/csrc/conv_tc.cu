@@ -126,7 +126,8 @@ __device__ __forceinline__ void tc_conv_body(const TcConvParams& p, const TcConv
   }
   if (!DEEP) pdl_wait();  // everything above is independent of the previous kernel's results
   if (warp == 3) {
-    for (int i = lane; i < 160; i += 32) ctl->bias[i] = (p.bias != nullptr && i < p.n_mma) ? p.bias[n_off + i] : 0.f;
+    for (int i = lane; i < 160; i += 32)
+      ctl->bias[i] = (p.bias != nullptr && i < p.n_mma && (p.n_valid == 0 || n_off + i < p.n_valid)) ? p.bias[n_off + i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();

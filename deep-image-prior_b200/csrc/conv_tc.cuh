@@ -43,7 +43,8 @@ struct TcConvParams {
   int vgrid;               // deep-level kernel only: number of CTAs that work on this conv (= grid of the stand-alone launch)
   int nphase;
   struct Phase { int kh, kw, offx, offy, tap0, opx, opy; } phs[4];   // tap0: first packed weight tap of the phase
-  const float* bias;       // [n_mma] or nullptr
+  int n_valid;             // output channels that exist (bias / statistics are only read / written below it); 0: all n_mma * n_split
+  const float* bias;       // [n_valid] or nullptr
   double* stats;           // [2][stats_ld] per-channel sum / sum of squares (fp64 atomics) or nullptr
   int stats_ld;
   int dbg_shift;           // experiment: start the A descriptor `dbg_shift` 128-byte rows into the stage

@@ -207,8 +207,12 @@ static void fit_stages(TcConvParams& p, size_t budget = 232448) {
 }
 struct ConvOp {
   Timer* timer = nullptr;
-  double alg_flops() const { return 2.0 * out_h * out_w * 128.0 * C * k * k; }
+  double alg_flops() const { return 2.0 * out_h * out_w * (double)N * C * k * k; }
+  // N output channels (a multiple of 8, <= 128: num_channels_down / num_channels_up of the level), C input channels
   int N = 128, C = 0, k = 1, stride = 1, rot = 0;
+  int Np = 128;      // fprop UMMA N: N rounded up to 16 (rows per tap of the fprop pack; rows >= N are zero)
+  int n_pad = 128;   // dgrad K extent per tap: N rounded up to 32 (columns of the dgrad pack), n_pad16: to 64 (bf16)
+  int n_pad16 = 128;
   // An op may cover a SLICE [coff, coff + C) of the (engine-order) input channels of a wider convolution whose weight has
   // Ctot input channels (the 256-channel up conv of the skip=128 configuration: fprop runs as one op with 8 K blocks,
   // dgrad / wgrad as two 128-channel halves -- TMEM holds 512 accumulator columns).  Ctot == 0: the op is the whole conv.
@@ -247,11 +251,12 @@ struct ConvOp {
     c_pad = round_up(C, 32);
     c_pad16 = round_up(C, 64);
     crows = round_up(C, 16);
+    Np = round_up(N, 16); n_pad = round_up(N, 32); n_pad16 = round_up(N, 64);
     if (Ctot == 0) Ctot = C;
     if (dg_ld == 0) dg_ld = C;
   }
-  size_t wp_f_elems() const { return (size_t)k * k * N * c_pad; }
-  size_t wp_d_elems() const { return (size_t)k * k * crows * 128; }
+  size_t wp_f_elems() const { return (size_t)k * k * Np * c_pad; }
+  size_t wp_d_elems() const { return (size_t)k * k * crows * n_pad; }
   size_t wacc_elems() const { return (size_t)k * k * 128 * c_pad; }
   // pixels per K block of the weight-gradient GEMM (TMA box width).  bf16 halves the bytes per pixel and doubles K per MMA:
   // 64-pixel blocks keep 12 MMAs per barrier round
@@ -284,7 +289,7 @@ struct ConvOp {
       // patch mode: tile 8 wide x 16 tall, one 10 x 18 input patch per 32-channel block feeds all nine taps
       bw = 8; bh = 16;
       fp.patch = 1; fp.pw = bw + 2; fp.ph = bh + 2;
-      fp.pair = pick_pair((out_w + bw - 1) / bw, (out_h + bh - 1) / bh, N);
+      fp.pair = pick_pair((out_w + bw - 1) / bw, (out_h + bh - 1) / bh, Np);
       if (fp.pair) fp.ph = 2 * bh + 2;
       DIP_CHECK(bf16 ? map_act5(&fp.tmA, in16, in_rows, in_cols, in_ld16, C, 1, fp.pw, fp.ph, false, true)
                      : map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, 1, fp.pw, fp.ph));
@@ -293,10 +298,10 @@ struct ConvOp {
                      : map_act5(&fp.tmA, in, in_rows, in_cols, in_ld, C, stride, bw, bh));
     }
     if (do_fprop) {
-    fp.csize = fp.pair ? 1 : pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N);
+    fp.csize = fp.pair ? 1 : pick_csize(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), Np);
     fp.tps = (fp.patch && fp.csize == 1) ? pick_tps() : 1;
-    fp.n_split = fp.pair ? 1 : fp.csize == 1 ? pick_nsplit(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), N) : 1;
-    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * N, bf16 ? c_pad16 : c_pad, N / fp.csize / fp.n_split, bf16));
+    fp.n_split = fp.pair ? 1 : fp.csize == 1 ? pick_nsplit(((out_w + bw - 1) / bw) * ((out_h + bh - 1) / bh), Np) : 1;
+    DIP_CHECK(map_w2(&fp.tmB, wp_f, k * k * Np, bf16 ? c_pad16 : c_pad, Np / fp.csize / fp.n_split, bf16));
     DIP_CHECK(map_act3(&fp.tmD, out, out_h, out_w, N, N, bw, bh));
     fp.tiles_x = (out_w + bw - 1) / bw; fp.tiles_y = (out_h + bh - 1) / bh;
     fp.bw = bw; fp.bh = bh; fp.out_w = out_w; fp.out_h = out_h;
@@ -304,7 +309,8 @@ struct ConvOp {
     fp.bf16 = bf16 ? 1 : 0;
     fp.kblocks = bf16 ? c_pad16 / 64 : c_pad / 32;
     fp.tail_mmas = bf16 ? ((C % 64 == 0) ? 4 : (C % 64 + 15) / 16) : ((C % 32 == 0) ? 4 : (C % 32 + 7) / 8);
-    fp.n_mma = N / fp.n_split; fp.n_chunks = fp.n_mma / 32;
+    fp.n_mma = Np / fp.n_split; fp.n_chunks = (fp.n_mma + 31) / 32;
+    fp.n_valid = N;
     fp.bias = nullptr; fp.stats = stats; fp.stats_ld = N;
     fit_stages(fp);
     }
@@ -314,11 +320,11 @@ struct ConvOp {
       const int gh = dg_out_h / 2, gw = dg_out_w / 2;
       pick_tile(gw, gh, &bw, &bh);
       dg = TcConvParams{};
-      DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, 128, 128, 1, bw, bh, false, true)
-                     : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+      DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, N, N, 1, bw, bh, false, true)
+                     : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, N, N, 1, bw, bh));
       dg.csize = 1; dg.tps = 1;
       dg.n_split = pick_nsplit(4 * ((gw + bw - 1) / bw) * ((gh + bh - 1) / bh), crows);
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.n_split, bf16));
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, bf16 ? n_pad16 : n_pad, crows / dg.n_split, bf16));
       DIP_CHECK(map_act5(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, 2, bw, bh));   // parity view of the padded gradient
       dg.tiles_x = (gw + bw - 1) / bw; dg.tiles_y = (gh + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = gw; dg.out_h = gh;
@@ -332,7 +338,8 @@ struct ConvOp {
           t0 += q.kh * q.kw;
         }
       dg.bf16 = bf16 ? 1 : 0;
-      dg.kblocks = bf16 ? 2 : 4; dg.tail_mmas = 4;
+      dg.kblocks = bf16 ? n_pad16 / 64 : n_pad / 32;   // K = the N channels of dY
+      dg.tail_mmas = bf16 ? ((N % 64 == 0) ? 4 : (N % 64 + 15) / 16) : ((N % 32 == 0) ? 4 : (N % 32 + 7) / 8);
       dg.n_mma = crows / dg.n_split; dg.n_chunks = (dg.n_mma + 31) / 32;
       dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
       fit_stages(dg);
@@ -344,22 +351,23 @@ struct ConvOp {
         dg.patch = 1; dg.pw = bw + 2; dg.ph = bh + 2;
         dg.pair = pick_pair((dg_out_w + bw - 1) / bw, (dg_out_h + bh - 1) / bh, crows);
         if (dg.pair) dg.ph = 2 * bh + 2;
-        DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, 128, 128, 1, dg.pw, dg.ph, false, true)
-                       : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, dg.pw, dg.ph));
+        DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, N, N, 1, dg.pw, dg.ph, false, true)
+                       : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, N, N, 1, dg.pw, dg.ph));
       } else {
-        DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, 128, 128, 1, bw, bh, false, true)
-                       : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, 128, 128, 1, bw, bh));
+        DIP_CHECK(bf16 ? map_act5(&dg.tmA, dg_in16, dg_in_h, dg_in_w, N, N, 1, bw, bh, false, true)
+                       : map_act5(&dg.tmA, dg_in, dg_in_h, dg_in_w, N, N, 1, bw, bh));
       }
       dg.csize = dg.pair ? 1 : pick_csize(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows);
       dg.tps = (dg.patch && dg.csize == 1) ? pick_tps() : 1;
       dg.n_split = dg.pair ? 1 : dg.csize == 1 ? pick_nsplit(((dg_out_w + bw - 1) / bw) * ((dg_out_h + bh - 1) / bh), crows) : 1;
-      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, 128, crows / dg.csize / dg.n_split, bf16));
+      DIP_CHECK(map_w2(&dg.tmB, wp_d, k * k * crows, bf16 ? n_pad16 : n_pad, crows / dg.csize / dg.n_split, bf16));
       DIP_CHECK(map_act3(&dg.tmD, dg_out, dg_out_h, dg_out_w, dg_ld, C, bw, bh));
       dg.tiles_x = (dg_out_w + bw - 1) / bw; dg.tiles_y = (dg_out_h + bh - 1) / bh;
       dg.bw = bw; dg.bh = bh; dg.out_w = dg_out_w; dg.out_h = dg_out_h;
       dg.kh = dg.kw = k; dg.stride = 1; dg.offx = dg.offy = dg_off;
       dg.bf16 = bf16 ? 1 : 0;
-      dg.kblocks = bf16 ? 2 : 4; dg.tail_mmas = 4;
+      dg.kblocks = bf16 ? n_pad16 / 64 : n_pad / 32;   // K = the N channels of dY
+      dg.tail_mmas = bf16 ? ((N % 64 == 0) ? 4 : (N % 64 + 15) / 16) : ((N % 32 == 0) ? 4 : (N % 32 + 7) / 8);
       dg.n_mma = crows / dg.n_split; dg.n_chunks = (dg.n_mma + 31) / 32;
       dg.bias = nullptr; dg.stats = nullptr; dg.stats_ld = 0;
       fit_stages(dg);
@@ -371,10 +379,10 @@ struct ConvOp {
     wg.bf16 = bf16 ? 1 : 0;
     wg.xshare = (stride == 1 && k == 3 && getenv("DIP_NO_XSHARE") == nullptr) ? 1 : 0;
     if (bf16) {
-      DIP_CHECK(map_act3(&wg.tmY, wg_dy16, wg_h, wg_w, 128, 128, wg.kp, 1, false, true));
+      DIP_CHECK(map_act3(&wg.tmY, wg_dy16, wg_h, wg_w, N, N, wg.kp, 1, false, true));
       DIP_CHECK(map_act5(&wg.tmX, in16, in_rows, in_cols, in_ld16, C, stride, wg.xshare ? wg.kp + k - 1 : wg.kp, 1, false, true));
     } else {
-      DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, 128, 128, wg.kp, 1, true));
+      DIP_CHECK(map_act3(&wg.tmY, wg_dy, wg_h, wg_w, N, N, wg.kp, 1, true));
       DIP_CHECK(map_act5(&wg.tmX, in, in_rows, in_cols, in_ld, C, stride, wg.xshare ? wg.kp + k - 1 : wg.kp, 1, true));
     }
     wg.partial = partial;
@@ -404,7 +412,7 @@ struct ConvOp {
     } else {
       SimtConvArgs a{};
       a.A = in; a.a_h = in_rows; a.a_w = in_cols; a.a_ld = in_ld; a.a_c = C;
-      a.Wp = wp_f; a.n_rows = N; a.c_pad = c_pad;
+      a.Wp = wp_f; a.n_rows = Np; a.c_pad = c_pad;
       a.D = out; a.d_h = out_h; a.d_w = out_w; a.d_ld = N; a.d_c = N;
       a.kh = a.kw = k; a.stride = stride; a.offx = offx; a.offy = offy; a.bias = bias;
       launch_simt_conv(a, s);
@@ -419,8 +427,8 @@ struct ConvOp {
       DIP_CUDA(tc_conv_launch(dg, g_num_sms, s));
     } else {
       SimtConvArgs a{};
-      a.A = dg_in; a.a_h = dg_in_h; a.a_w = dg_in_w; a.a_ld = 128; a.a_c = 128;
-      a.Wp = wp_d; a.n_rows = crows; a.c_pad = 128;
+      a.A = dg_in; a.a_h = dg_in_h; a.a_w = dg_in_w; a.a_ld = N; a.a_c = N;
+      a.Wp = wp_d; a.n_rows = crows; a.c_pad = n_pad;
       a.D = dg_out; a.d_h = dg_out_h; a.d_w = dg_out_w; a.d_ld = dg_ld; a.d_c = C;
       a.kh = a.kw = k; a.stride = 1; a.offx = a.offy = dg_off; a.bias = nullptr;
       launch_simt_conv(a, s);
@@ -450,7 +458,7 @@ struct ConvOp {
       return 0;
     } else {
       SimtWgradArgs a{};
-      a.dY = wg_dy; a.h = wg_h; a.w = wg_w;
+      a.dY = wg_dy; a.h = wg_h; a.w = wg_w; a.dy_ld = N; a.n = N;
       a.X = in; a.x_h = in_rows; a.x_w = in_cols; a.x_ld = in_ld; a.x_c = C;
       a.kh = a.kw = k; a.stride = stride; a.offx = offx; a.offy = offy;
       a.partial = partial; a.c_pad = c_pad; a.ksplits = ks = simt_ksplits;
@@ -471,6 +479,7 @@ struct PackEntry {
   int s2;           // dgrad pack of a stride-2 3x3 conv: taps in sub-pixel phase order (kS2Taps), not flipped
   int bf16;         // packs hold bf16 (same buffers); the fprop pack then has rows of c_pad16 (multiple of 64) channels
   int c_pad16;
+  int n_pad;        // columns of the dgrad pack: N rounded up to 32 (bf16: to 64)
 };
 // packed tap t of the 4-phase stride-2 dgrad -> filter tap r * 3 + s.  Phase (a, b) = parity of the padded gradient pixel;
 // its taps are r in {2, 0} (a = 0: dY rows i-1, i) or {1} (a = 1), same for s.  Phases in the order (0,0) (0,1) (1,0) (1,1).
@@ -486,7 +495,8 @@ __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
   __nv_bfloat16* const f16 = reinterpret_cast<__nv_bfloat16*>(e.dst_f);
   __nv_bfloat16* const d16 = reinterpret_cast<__nv_bfloat16*>(e.dst_d);
   const long long nf = e.dst_f != nullptr ? (long long)taps * e.n_rows * c_pad : 0;
-  const long long nd = e.dst_d != nullptr ? (long long)taps * e.c_rows * 128 : 0;
+  const int n_pad = e.n_pad > 0 ? e.n_pad : 128;
+  const long long nd = e.dst_d != nullptr ? (long long)taps * e.c_rows * n_pad : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (long long)gridDim.x * blockDim.x) {
     if (i < nf) {
       const int c = (int)(i % c_pad), n = (int)((i / c_pad) % e.n_rows), tap = (int)(i / ((long long)c_pad * e.n_rows));
@@ -495,7 +505,7 @@ __global__ void k_pack_table(const PackEntry* __restrict__ tab) {
       if (e.bf16) f16[i] = __float2bfloat16_rn(v); else e.dst_f[i] = v;
     } else {
       const long long j = i - nf;
-      const int n = (int)(j % 128), c = (int)((j / 128) % e.c_rows), tapf = (int)(j / (128LL * e.c_rows));
+      const int n = (int)(j % n_pad), c = (int)((j / n_pad) % e.c_rows), tapf = (int)(j / ((long long)n_pad * e.c_rows));
       const int tap = e.s2 ? kS2Taps[tapf] : taps - 1 - tapf;
       float v = 0.f;
       if (n < e.N && c < e.C) v = e.w[((long long)n * e.Ctot + (c + e.coff + e.rot) % e.Ctot) * taps + tap];
@@ -575,6 +585,10 @@ struct Level {
   int H, W, h, w, Cin;   // Cin: stored depth of the level input (power of two >= 4)
   int Cin_act;           // depth of the conv weights that read it (differs at level 0 for input depths like 3)
   int bilinear;          // x2 upsampling into this level: 1 bilinear, 0 nearest (skip.py:81, upsample_mode[i])
+  // channel widths (models/skip.py:5-7): nd = num_channels_down[l] (both down convs), nu = num_channels_up[l] (up conv and 1x1),
+  // ns = num_channels_skip[l], cu = depth of the tensor upsampled into this level's concat (nu of the level below, or nd at
+  // the deepest level).  128 / 128 / {0, 4, 128} / 128 in every BASELINE configuration.
+  int nd = 128, nu = 128, ns = 0, cu = 128;
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
   // bf16 twins (precision mode bf16; ld = the fp32 tensor's depth rounded up to 8)
   uint16_t *Pin16 = nullptr, *P_d1_16 = nullptr, *P_d2_16 = nullptr, *P_cat16 = nullptr, *A_u16 = nullptr;
@@ -685,19 +699,38 @@ static BnRef bn_ref(const dip_plan* P, const BnLayer& b) {
 
 static int build_plan(dip_plan* P, Arena& A) {
   const dip_net_desc& d = P->desc;
-  const int L = d.num_scales, CH = d.channels, CS = d.skip_channels;
-  if (CH != 128) return fail("dip-b200: only num_channels_down == num_channels_up == 128 is supported by the engine");
-  if (CS != 0 && CS != 4 && CS != 128) return fail("dip-b200: num_channels_skip must be 0, 4 or 128");
-  const int ps = CS > 0 ? 4 : 0;   // parameters of the skip branch (conv w, b, BN gamma, beta): absent for num_channels_skip = 0
-                                   // (inpainting.ipynb c14:11-16 "vase": models/skip.py:50-53 then adds `deeper` alone, no Concat)
-  const bool wide = CS == 128;   // skip branch on the tensor cores, 256-channel concat
+  const int L = d.num_scales;
+  if (L < 1 || L > 8) return fail("dip-b200: 1..8 scales supported");
+  // widths: one value for every scale (channels / skip_channels), or per scale (channels == 0: channels_down / channels_up /
+  // channels_skip, denoising.ipynb c8:17-23 "snail": [8, 16, 32, 64, 128] with skips [0, 0, 0, 4, 4])
+  std::vector<int> ND(L), NU(L), NS(L);
+  for (int l = 0; l < L; ++l) {
+    ND[l] = d.channels > 0 ? d.channels : d.channels_down[l];
+    NU[l] = d.channels > 0 ? d.channels : d.channels_up[l];
+    NS[l] = d.channels > 0 ? d.skip_channels : d.channels_skip[l];
+    for (int w : {ND[l], NU[l]})
+      if (w < 8 || w > 128 || w % 8 != 0)
+        return fail("dip-b200: num_channels_down / num_channels_up must be multiples of 8 in [8, 128] (128 in the BASELINE configurations)");
+  }
+  bool wide = true, uniform = true;
+  for (int l = 0; l < L; ++l) {
+    wide = wide && NS[l] == 128 && ND[l] == 128 && NU[l] == 128;
+    uniform = uniform && ND[l] == 128 && NU[l] == 128 && NS[l] == NS[0];
+  }
+  for (int l = 0; l < L; ++l)
+    if (!(wide || NS[l] == 0 || NS[l] == 4))
+      return fail("dip-b200: num_channels_skip must be 0 or 4 per scale, or 128 at every scale of a 128-wide network");
+  const int CS = NS[0];   // the uniform skip width where the code below asks for it (wide: 128)
+  // parameters of the skip branch (conv w, b, BN gamma, beta): absent where num_channels_skip[l] = 0
+  // (inpainting.ipynb c14:11-16 "vase": models/skip.py:50-53 then adds `deeper` alone, no Concat)
+  auto psl = [&](int l) { return NS[l] > 0 ? 4 : 0; };
+  // wide: skip branch on the tensor cores, 256-channel concat (all widths 128, all skips 128)
   if (d.in_channels < 1 || d.in_channels > 128) return fail("dip-b200: input depth must be in [1,128]");
   // level-0 activations are stored with the input depth rounded up to a power of two >= 4 (zero channels); the conv
   // weights keep their real depth (TMA zero-fills the missing channels, the 1x1 skip conv reads its rows by element)
   int cin_eng = 4;
   while (cin_eng < d.in_channels) cin_eng *= 2;
   if (d.out_channels < 1 || d.out_channels > 4) return fail("dip-b200: num_output_channels must be <= 4");
-  if (L < 1 || L > 8) return fail("dip-b200: 1..8 scales supported");
   if (P->H % (1 << L) || P->W % (1 << L)) return fail("dip-b200: H and W must be divisible by 2^num_scales");
   if ((P->H >> L) < 2 || (P->W >> L) < 2)
     return fail("dip-b200: H and W must be at least 2 * 2^num_scales (ReflectionPad2d(1) in front of the deepest 3x3 conv needs 2 "
@@ -711,7 +744,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   std::vector<int> pre(L), post(L);
   {
     int idx = 0;
-    for (int l = 0; l < L; ++l) { pre[l] = idx; idx += 8 + ps; }
+    for (int l = 0; l < L; ++l) { pre[l] = idx; idx += 8 + psl(l); }
     for (int l = L - 1; l >= 0; --l) { post[l] = idx; idx += 10; }
     P->p_head_w = idx; P->p_head_b = idx + 1;
     pidx = idx + 2;
@@ -727,8 +760,10 @@ static int build_plan(dip_plan* P, Arena& A) {
   for (int l = 0; l < L; ++l) {
     Level& v = P->lv[l];
     v.H = P->H >> l; v.W = P->W >> l; v.h = v.H / 2; v.w = v.W / 2;
-    v.Cin = l == 0 ? cin_eng : CH;
-    v.Cin_act = l == 0 ? d.in_channels : CH;
+    v.nd = ND[l]; v.nu = NU[l]; v.ns = NS[l]; v.cu = l == L - 1 ? ND[l] : NU[l + 1];
+    const int CS = v.ns, ps = psl(l);   // (shadow the network-wide values inside the level loop)
+    v.Cin = l == 0 ? cin_eng : ND[l - 1];
+    v.Cin_act = l == 0 ? d.in_channels : ND[l - 1];
     v.bilinear = d.upsample_bilinear < 0 ? (d.upsample_mask >> l) & 1 : (d.upsample_bilinear != 0);
     const int b0 = pre[l], b1 = post[l];
     // skip conv 1x1 Cin -> CS
@@ -741,17 +776,17 @@ static int build_plan(dip_plan* P, Arena& A) {
       v.bn_s = BnLayer{};
     }
     // down1 3x3 s2
-    v.d1.C = v.Cin_act; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + ps; v.d1.p_b = b0 + ps + 1;
-    P->numel[b0 + ps] = 128LL * v.Cin_act * 9; P->numel[b0 + ps + 1] = 128;
-    bn_init(v.bn_d1, 128, 0, v.h * v.w, b0 + ps + 2, b0 + ps + 1);
+    v.d1.N = v.nd; v.d1.C = v.Cin_act; v.d1.k = 3; v.d1.stride = 2; v.d1.p_w = b0 + ps; v.d1.p_b = b0 + ps + 1;
+    P->numel[b0 + ps] = (long long)v.nd * v.Cin_act * 9; P->numel[b0 + ps + 1] = v.nd;
+    bn_init(v.bn_d1, v.nd, 0, v.h * v.w, b0 + ps + 2, b0 + ps + 1);
     // down2 3x3
-    v.d2.C = 128; v.d2.k = 3; v.d2.stride = 1; v.d2.p_w = b0 + ps + 4; v.d2.p_b = b0 + ps + 5;
-    P->numel[b0 + ps + 4] = 128LL * 128 * 9; P->numel[b0 + ps + 5] = 128;
-    bn_init(v.bn_d2, 128, 0, v.h * v.w, b0 + ps + 6, b0 + ps + 5);
+    v.d2.N = v.nd; v.d2.C = v.nd; v.d2.k = 3; v.d2.stride = 1; v.d2.p_w = b0 + ps + 4; v.d2.p_b = b0 + ps + 5;
+    P->numel[b0 + ps + 4] = (long long)v.nd * v.nd * 9; P->numel[b0 + ps + 5] = v.nd;
+    bn_init(v.bn_d2, v.nd, 0, v.h * v.w, b0 + ps + 6, b0 + ps + 5);
     // concat BN (torch channel order [skip | up], engine order [up | skip])
-    bn_init(v.bn_cat, 128 + CS, CS, v.H * v.W, b1 + 0, -1);
-    // up 3x3 (128+CS) -> 128
-    v.up.C = 128 + CS; v.up.k = 3; v.up.stride = 1; v.up.rot = CS; v.up.p_w = b1 + 2; v.up.p_b = b1 + 3;
+    bn_init(v.bn_cat, v.cu + CS, CS, v.H * v.W, b1 + 0, -1);
+    // up 3x3 (cu+CS) -> nu
+    v.up.N = v.nu; v.up.C = v.cu + CS; v.up.k = 3; v.up.stride = 1; v.up.rot = CS; v.up.p_w = b1 + 2; v.up.p_b = b1 + 3;
     if (wide) {
       v.up.do_wgrad = false;
       v.sk.C = v.Cin_act; v.sk.k = 1; v.sk.stride = 1; v.sk.p_w = b0; v.sk.p_b = b0 + 1;
@@ -761,27 +796,28 @@ static int build_plan(dip_plan* P, Arena& A) {
       }
       v.up_b.coff = 128;
     }
-    P->numel[b1 + 2] = 128LL * (128 + CS) * 9; P->numel[b1 + 3] = 128;
-    bn_init(v.bn_u, 128, 0, v.H * v.W, b1 + 4, b1 + 3);
-    // 1x1 128 -> 128
-    v.c11.C = 128; v.c11.k = 1; v.c11.stride = 1; v.c11.p_w = b1 + 6; v.c11.p_b = b1 + 7;
-    P->numel[b1 + 6] = 128LL * 128; P->numel[b1 + 7] = 128;
-    bn_init(v.bn_v, 128, 0, v.H * v.W, b1 + 8, b1 + 7);
+    P->numel[b1 + 2] = (long long)v.nu * (v.cu + CS) * 9; P->numel[b1 + 3] = v.nu;
+    bn_init(v.bn_u, v.nu, 0, v.H * v.W, b1 + 4, b1 + 3);
+    // 1x1 nu -> nu
+    v.c11.N = v.nu; v.c11.C = v.nu; v.c11.k = 1; v.c11.stride = 1; v.c11.p_w = b1 + 6; v.c11.p_b = b1 + 7;
+    P->numel[b1 + 6] = (long long)v.nu * v.nu; P->numel[b1 + 7] = v.nu;
+    bn_init(v.bn_v, v.nu, 0, v.H * v.W, b1 + 8, b1 + 7);
   }
-  P->numel[P->p_head_w] = (long long)d.out_channels * 128;
+  const int NH = NU[0];   // depth of the tensor the RGB head reads
+  P->numel[P->p_head_w] = (long long)d.out_channels * NH;
   P->numel[P->p_head_b] = d.out_channels;
   // BN order (running-stat table) follows state_dict order: skip, d1, d2, <deeper>, cat, up, 1x1
   {
     std::vector<BnLayer*> a, b;
-    for (int l = 0; l < L; ++l) { if (CS > 0) a.push_back(&P->lv[l].bn_s); a.push_back(&P->lv[l].bn_d1); a.push_back(&P->lv[l].bn_d2); }
+    for (int l = 0; l < L; ++l) { if (NS[l] > 0) a.push_back(&P->lv[l].bn_s); a.push_back(&P->lv[l].bn_d1); a.push_back(&P->lv[l].bn_d2); }
     for (int l = L - 1; l >= 0; --l) { a.push_back(&P->lv[l].bn_cat); a.push_back(&P->lv[l].bn_u); a.push_back(&P->lv[l].bn_v); }
     P->bns = a;
     for (size_t i = 0; i < P->bns.size(); ++i) P->bns[i]->idx = (int)i;
   }
   // ---- accumulators
   size_t skinny_acc = 0;
-  for (int l = 0; l < L; ++l) skinny_acc += (size_t)CS * P->lv[l].Cin;
-  skinny_acc += (size_t)d.out_channels * 128 + 8;
+  for (int l = 0; l < L; ++l) skinny_acc += (size_t)NS[l] * P->lv[l].Cin;
+  skinny_acc += (size_t)d.out_channels * NH + 8;
   P->acc_fwd_n = acc_f * kAccS;
   P->acc_bwd_n = (acc_b + skinny_acc) * kAccS;
   P->acc_fwd = A.get<double>(P->acc_fwd_n);
@@ -792,8 +828,8 @@ static int build_plan(dip_plan* P, Arena& A) {
       bn->fwd = f; f = f ? f + 2 * bn->C * kAccS : nullptr;
       bn->bwd = b; bn->dbias = b ? b + 2 * bn->C * kAccS : nullptr; b = b ? b + 3 * bn->C * kAccS : nullptr;
     }
-    for (int l = 0; l < L; ++l) { P->lv[l].dw_s = b; b = b ? b + (size_t)CS * P->lv[l].Cin * kAccS : nullptr; }
-    P->dw_head = b; b = b ? b + (size_t)d.out_channels * 128 * kAccS : nullptr;
+    for (int l = 0; l < L; ++l) { P->lv[l].dw_s = b; b = b ? b + (size_t)NS[l] * P->lv[l].Cin * kAccS : nullptr; }
+    P->dw_head = b; b = b ? b + (size_t)d.out_channels * NH * kAccS : nullptr;
     P->db_head = b;
     P->db_scratch = b ? b + 4 * kAccS : nullptr;
   }
@@ -805,67 +841,80 @@ static int build_plan(dip_plan* P, Arena& A) {
     const size_t HW = (size_t)v.H * v.W, hw = (size_t)v.h * v.w;
     const size_t HWp = (size_t)(v.H + 2) * (v.W + 2), hwp = (size_t)(v.h + 2) * (v.w + 2);
     const bool last = l == L - 1;
+    const int CS = v.ns, nd = v.nd, nu = v.nu, CC = v.cu + v.ns;
     if (l == 0) v.Pin = A.get<float>(HWp * v.Cin); else v.Pin = P->lv[l - 1].P_d2;
     v.raw_s = A.get<float>(HW * CS);
-    v.raw_d1 = A.get<float>(hw * 128);
-    v.P_d1 = A.get<float>(hwp * 128);
-    v.raw_d2 = A.get<float>(hw * 128);
-    v.P_d2 = A.get<float>(last ? hw * 128 : hwp * 128);
-    v.P_cat = A.get<float>(HWp * (128 + CS));
-    v.raw_u = A.get<float>(HW * 128);
-    v.A_u = A.get<float>(HW * 128);
-    v.raw_v = A.get<float>(HW * 128);
-    v.U = l > 0 ? A.get<float>(HW * 128) : nullptr;  // level 0 feeds the fused RGB head instead
-    v.dRaw_v = A.get<float>(HW * 128);
-    v.dA_u = A.get<float>(HW * 128);
-    v.dRaw_u = A.get<float>(HW * 128);
-    v.dP_cat = A.get<float>(HWp * (128 + CS));
-    v.dCat = A.get<float>(HW * (128 + CS));
+    v.raw_d1 = A.get<float>(hw * nd);
+    v.P_d1 = A.get<float>(hwp * nd);
+    v.raw_d2 = A.get<float>(hw * nd);
+    v.P_d2 = A.get<float>(last ? hw * nd : hwp * nd);
+    v.P_cat = A.get<float>(HWp * CC);
+    v.raw_u = A.get<float>(HW * nu);
+    v.A_u = A.get<float>(HW * nu);
+    v.raw_v = A.get<float>(HW * nu);
+    v.U = (l > 0 || nu != 128) ? A.get<float>(HW * nu) : nullptr;  // a 128-deep level 0 feeds the fused RGB head instead
+    v.dRaw_v = A.get<float>(HW * nu);
+    v.dA_u = A.get<float>(HW * nu);
+    v.dRaw_u = A.get<float>(HW * nu);
+    v.dP_cat = A.get<float>(HWp * CC);
+    v.dCat = A.get<float>(HW * CC);
     v.dRaw_s = A.get<float>(HW * CS);
-    v.dUp = A.get<float>(hw * 128);
-    v.dRaw_d2 = A.get<float>(hw * 128);
-    v.dP_d1 = A.get<float>(hwp * 128);
-    v.dRaw_d1 = A.get<float>(hw * 128);
+    v.dUp = A.get<float>(hw * v.cu);
+    v.dRaw_d2 = A.get<float>(hw * nd);
+    v.dP_d1 = A.get<float>(hwp * nd);
+    v.dRaw_d1 = A.get<float>(hw * nd);
     const bool in_grad = d.input_grad != 0;   // level 0 then also needs its input gradient
-    v.ZS = (l > 0 || in_grad) ? A.get<float>(HW * 128) : nullptr;
+    v.ZS = (l > 0 || in_grad) ? A.get<float>(HW * nd) : nullptr;
     v.dS = ((wide && l > 0) || (in_grad && l == 0)) ? A.get<float>(HW * v.Cin) : nullptr;
     v.dPin = (l > 0 || in_grad) ? A.get<float>(HWp * v.Cin) : nullptr;
     if (bf) {
-      v.Pin_ld16 = round_up(v.Cin, 8); v.cat_ld16 = round_up(128 + CS, 8);
+      v.Pin_ld16 = round_up(v.Cin, 8); v.cat_ld16 = round_up(CC, 8);
       if (l == 0) v.Pin16 = A.get<uint16_t>(HWp * v.Pin_ld16); else v.Pin16 = P->lv[l - 1].P_d2_16;
-      v.P_d1_16 = A.get<uint16_t>(hwp * 128);
-      v.P_d2_16 = last ? nullptr : A.get<uint16_t>(hwp * 128);
+      v.P_d1_16 = A.get<uint16_t>(hwp * nd);
+      v.P_d2_16 = last ? nullptr : A.get<uint16_t>(hwp * nd);
       v.P_cat16 = A.get<uint16_t>(HWp * v.cat_ld16);
-      v.A_u16 = A.get<uint16_t>(HW * 128);
-      v.dRaw_v16 = A.get<uint16_t>(HW * 128);
-      v.dRaw_u16 = A.get<uint16_t>(HW * 128);
-      v.dRaw_d2_16 = A.get<uint16_t>(hw * 128);
-      v.dRaw_d1_16 = A.get<uint16_t>(hw * 128);
+      v.A_u16 = A.get<uint16_t>(HW * nu);
+      v.dRaw_v16 = A.get<uint16_t>(HW * nu);
+      v.dRaw_u16 = A.get<uint16_t>(HW * nu);
+      v.dRaw_d2_16 = A.get<uint16_t>(hw * nd);
+      v.dRaw_d1_16 = A.get<uint16_t>(hw * nd);
       v.dRaw_s16 = wide ? A.get<uint16_t>(HW * 128) : nullptr;
     }
     reg(pf + "Pin", v.Pin, v.H + 2, v.W + 2, v.Cin, v.Cin);
     reg(pf + "raw_s", v.raw_s, v.H, v.W, CS, CS);
-    reg(pf + "raw_d1", v.raw_d1, v.h, v.w, 128, 128);
-    reg(pf + "P_d1", v.P_d1, v.h + 2, v.w + 2, 128, 128);
-    reg(pf + "raw_d2", v.raw_d2, v.h, v.w, 128, 128);
-    if (last) reg(pf + "P_d2", v.P_d2, v.h, v.w, 128, 128); else reg(pf + "P_d2", v.P_d2, v.h + 2, v.w + 2, 128, 128);
-    reg(pf + "P_cat", v.P_cat, v.H + 2, v.W + 2, 128 + CS, 128 + CS);
-    reg(pf + "raw_u", v.raw_u, v.H, v.W, 128, 128);
-    reg(pf + "A_u", v.A_u, v.H, v.W, 128, 128);
-    reg(pf + "raw_v", v.raw_v, v.H, v.W, 128, 128);
-    if (l > 0) reg(pf + "U", v.U, v.H, v.W, 128, 128);
-    reg(pf + "dRaw_v", v.dRaw_v, v.H, v.W, 128, 128);
-    reg(pf + "dA_u", v.dA_u, v.H, v.W, 128, 128);
-    reg(pf + "dRaw_u", v.dRaw_u, v.H, v.W, 128, 128);
-    reg(pf + "dP_cat", v.dP_cat, v.H + 2, v.W + 2, 128 + CS, 128 + CS);
-    reg(pf + "dCat", v.dCat, v.H, v.W, 128 + CS, 128 + CS);
+    reg(pf + "raw_d1", v.raw_d1, v.h, v.w, nd, nd);
+    reg(pf + "P_d1", v.P_d1, v.h + 2, v.w + 2, nd, nd);
+    reg(pf + "raw_d2", v.raw_d2, v.h, v.w, nd, nd);
+    if (last) reg(pf + "P_d2", v.P_d2, v.h, v.w, nd, nd); else reg(pf + "P_d2", v.P_d2, v.h + 2, v.w + 2, nd, nd);
+    reg(pf + "P_cat", v.P_cat, v.H + 2, v.W + 2, CC, CC);
+    reg(pf + "raw_u", v.raw_u, v.H, v.W, nu, nu);
+    reg(pf + "A_u", v.A_u, v.H, v.W, nu, nu);
+    reg(pf + "raw_v", v.raw_v, v.H, v.W, nu, nu);
+    if (v.U != nullptr) reg(pf + "U", v.U, v.H, v.W, nu, nu);
+    reg(pf + "dRaw_v", v.dRaw_v, v.H, v.W, nu, nu);
+    reg(pf + "dA_u", v.dA_u, v.H, v.W, nu, nu);
+    reg(pf + "dRaw_u", v.dRaw_u, v.H, v.W, nu, nu);
+    reg(pf + "dP_cat", v.dP_cat, v.H + 2, v.W + 2, CC, CC);
+    reg(pf + "dCat", v.dCat, v.H, v.W, CC, CC);
     reg(pf + "dRaw_s", v.dRaw_s, v.H, v.W, CS, CS);
-    reg(pf + "dRaw_d2", v.dRaw_d2, v.h, v.w, 128, 128);
-    reg(pf + "dP_d1", v.dP_d1, v.h + 2, v.w + 2, 128, 128);
-    reg(pf + "dRaw_d1", v.dRaw_d1, v.h, v.w, 128, 128);
+    reg(pf + "dRaw_d2", v.dRaw_d2, v.h, v.w, nd, nd);
+    reg(pf + "dP_d1", v.dP_d1, v.h + 2, v.w + 2, nd, nd);
+    reg(pf + "dRaw_d1", v.dRaw_d1, v.h, v.w, nd, nd);
+    if (bf) {   // bf16 twins of the conv operands (names end in "16": the host side views them as bf16)
+      reg(pf + "Pin16", v.Pin16, v.H + 2, v.W + 2, v.Pin_ld16, v.Cin);
+      reg(pf + "P_d1_16", v.P_d1_16, v.h + 2, v.w + 2, nd, nd);
+      if (!last) reg(pf + "P_d2_16", v.P_d2_16, v.h + 2, v.w + 2, nd, nd);
+      reg(pf + "P_cat16", v.P_cat16, v.H + 2, v.W + 2, v.cat_ld16, CC);
+      reg(pf + "A_u16", v.A_u16, v.H, v.W, nu, nu);
+      reg(pf + "dRaw_v16", v.dRaw_v16, v.H, v.W, nu, nu);
+      reg(pf + "dRaw_u16", v.dRaw_u16, v.H, v.W, nu, nu);
+      reg(pf + "dRaw_d2_16", v.dRaw_d2_16, v.h, v.w, nd, nd);
+      reg(pf + "dRaw_d1_16", v.dRaw_d1_16, v.h, v.w, nd, nd);
+      if (wide) reg(pf + "dRaw_s16", v.dRaw_s16, v.H, v.W, 128, 128);
+    }
     if (l > 0) {
-      reg(pf + "ZS", v.ZS, v.H, v.W, 128, 128);
-      reg(pf + "dPin", v.dPin, v.H + 2, v.W + 2, 128, 128);
+      reg(pf + "ZS", v.ZS, v.H, v.W, nd, nd);
+      reg(pf + "dPin", v.dPin, v.H + 2, v.W + 2, v.Cin, v.Cin);
     }
   }
   P->out_saved = A.get<float>((size_t)P->H * P->W * d.out_channels);
@@ -898,16 +947,16 @@ static int build_plan(dip_plan* P, Arena& A) {
     // down2: P_d1 -> raw_d2
     ConvOp& b = v.d2;
     b.set_shapes();
-    b.in = v.P_d1; b.in_rows = v.h + 2; b.in_cols = v.w + 2; b.in_ld = 128; b.offx = b.offy = 0;
+    b.in = v.P_d1; b.in_rows = v.h + 2; b.in_cols = v.w + 2; b.in_ld = v.nd; b.offx = b.offy = 0;
     b.out = v.raw_d2; b.out_h = v.h; b.out_w = v.w; b.stats = v.bn_d2.fwd;
     b.has_dgrad = true;
     b.dg_in = v.dRaw_d2; b.dg_in_h = v.h; b.dg_in_w = v.w; b.dg_out = v.dP_d1; b.dg_out_h = v.h + 2; b.dg_out_w = v.w + 2; b.dg_off = -2;
     b.wg_dy = v.dRaw_d2; b.wg_h = v.h; b.wg_w = v.w;
-    b.in16 = v.P_d1_16; b.in_ld16 = 128; b.dg_in16 = v.dRaw_d2_16; b.wg_dy16 = v.dRaw_d2_16;
+    b.in16 = v.P_d1_16; b.in_ld16 = v.nd; b.dg_in16 = v.dRaw_d2_16; b.wg_dy16 = v.dRaw_d2_16;
     // up: P_cat -> raw_u
     ConvOp& c = v.up;
     c.set_shapes();
-    c.in = v.P_cat; c.in_rows = v.H + 2; c.in_cols = v.W + 2; c.in_ld = 128 + CS; c.offx = c.offy = 0;
+    c.in = v.P_cat; c.in_rows = v.H + 2; c.in_cols = v.W + 2; c.in_ld = v.cu + v.ns; c.offx = c.offy = 0;
     c.out = v.raw_u; c.out_h = v.H; c.out_w = v.W; c.stats = v.bn_u.fwd;
     c.has_dgrad = !wide;
     c.dg_in = v.dRaw_u; c.dg_in_h = v.H; c.dg_in_w = v.W; c.dg_out = v.dP_cat; c.dg_out_h = v.H + 2; c.dg_out_w = v.W + 2; c.dg_off = -2;
@@ -916,12 +965,12 @@ static int build_plan(dip_plan* P, Arena& A) {
     // 1x1: A_u -> raw_v
     ConvOp& e = v.c11;
     e.set_shapes();
-    e.in = v.A_u; e.in_rows = v.H; e.in_cols = v.W; e.in_ld = 128; e.offx = e.offy = 0;
+    e.in = v.A_u; e.in_rows = v.H; e.in_cols = v.W; e.in_ld = v.nu; e.offx = e.offy = 0;
     e.out = v.raw_v; e.out_h = v.H; e.out_w = v.W; e.stats = v.bn_v.fwd;
     e.has_dgrad = true;
     e.dg_in = v.dRaw_v; e.dg_in_h = v.H; e.dg_in_w = v.W; e.dg_out = v.dA_u; e.dg_out_h = v.H; e.dg_out_w = v.W; e.dg_off = 0;
     e.wg_dy = v.dRaw_v; e.wg_h = v.H; e.wg_w = v.W;
-    e.in16 = v.A_u16; e.in_ld16 = 128; e.dg_in16 = v.dRaw_v16; e.wg_dy16 = v.dRaw_v16;
+    e.in16 = v.A_u16; e.in_ld16 = v.nu; e.dg_in16 = v.dRaw_v16; e.wg_dy16 = v.dRaw_v16;
     std::vector<ConvOp*> ops = {&a, &b, &c, &e};
     if (wide) {
       // skip conv 1x1 on the interior of the padded level input
@@ -993,7 +1042,7 @@ static int build_plan(dip_plan* P, Arena& A) {
   }
   // The zero-stuffed buffers are written at even positions only: clear them once.
   for (int l = 0; l < L; ++l)
-    if (P->lv[l].ZS != nullptr) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * 128 * sizeof(float)));
+    if (P->lv[l].ZS != nullptr) DIP_CUDA(cudaMemset(P->lv[l].ZS, 0, (size_t)P->lv[l].H * P->lv[l].W * P->lv[l].nd * sizeof(float)));
   if (is_tc(prec))
     for (ConvOp* op : P->convs) DIP_CHECK(op->build_tc(P->partial));
   P->pack_max = 0;
@@ -1009,9 +1058,9 @@ static int upload_tables(dip_plan* P) {
   for (ConvOp* op : P->convs) {
     PackEntry e{};
     e.w = P->params[op->p_w]; e.dst_f = op->do_fprop ? op->wp_f : nullptr; e.dst_d = op->has_dgrad ? op->wp_d : nullptr;
-    e.N = op->N; e.C = op->C; e.k = op->k; e.rot = op->rot; e.n_rows = op->N; e.c_pad = op->c_pad; e.c_rows = op->crows;
+    e.N = op->N; e.C = op->C; e.k = op->k; e.rot = op->rot; e.n_rows = op->Np; e.c_pad = op->c_pad; e.c_rows = op->crows;
     e.Ctot = op->Ctot; e.coff = op->coff; e.s2 = op->dg_s2 ? 1 : 0;
-    e.bf16 = op->bf16 ? 1 : 0; e.c_pad16 = op->c_pad16;
+    e.bf16 = op->bf16 ? 1 : 0; e.c_pad16 = op->c_pad16; e.n_pad = op->bf16 ? op->n_pad16 : op->n_pad;
     pk.push_back(e);
   }
   DIP_CUDA(cudaMemcpy(P->d_pack, pk.data(), pk.size() * sizeof(PackEntry), cudaMemcpyHostToDevice));
@@ -1033,7 +1082,7 @@ static int upload_tables(dip_plan* P) {
   }
   for (size_t l = 0; l < P->lv.size(); ++l) {
     // skip=128: the skip conv's weight gradient comes from the tensor-core wgrad, not from fp64 accumulators
-    if (P->desc.skip_channels == 128 || P->desc.skip_channels == 0) cv.push_back(CvtEntry{P->lv[l].dw_s, nullptr, 0, 0});
+    if (P->lv[l].ns == 128 || P->lv[l].ns == 0) cv.push_back(CvtEntry{P->lv[l].dw_s, nullptr, 0, 0});
     else cv.push_back(CvtEntry{P->lv[l].dw_s, P->grads[P->lv[l].p_skip_w], (int)P->numel[P->lv[l].p_skip_w], 0,
                                P->lv[l].Cin_act, P->lv[l].Cin});   // accumulator rows hold the stored depth
   }
@@ -1094,9 +1143,9 @@ static void join_skip(dip_plan* P, cudaStream_t s) {
 static CatArgs cat_args(const dip_plan* P, const Level& v, const float* Usrc) {
   CatArgs a;
   a.U = Usrc; a.raw_s = v.raw_s;
-  if (P->desc.skip_channels > 0) a.bn_s = bn_ref(P, v.bn_s);
+  if (v.ns > 0) a.bn_s = bn_ref(P, v.bn_s);
   else a.bn_s = BnRef{nullptr, nullptr, nullptr, 0, 0, 0.f};   // num_channels_skip = 0: the "concat" is the upsampled tensor alone
-  a.Cu = 128; a.Cs = P->desc.skip_channels; a.H = v.H; a.W = v.W; a.bilinear = v.bilinear;
+  a.Cu = v.cu; a.Cs = v.ns; a.H = v.H; a.W = v.W; a.bilinear = v.bilinear;
   return a;
 }
 static const float* level_usrc(const dip_plan* P, int l) {
@@ -1118,7 +1167,7 @@ static bool deep_on(const dip_plan* P) {
 static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   Level& v = P->lv[l];
   const int prec = P->desc.precision;
-  const int CS = P->desc.skip_channels;
+  const int CS = v.ns, nd = v.nd, nu = v.nu;
   const bool last = l == (int)P->lv.size() - 1;
   const float* pin_interior = v.Pin + ((size_t)(v.W + 2) + 1) * v.Cin;
   // precision mode bf16: conv inputs are written as bf16 twins; the fp32 tensor is dropped where only convolutions read it
@@ -1138,13 +1187,13 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   }
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
-  HBM_T(&P->timer, H_BN_ACT_WRITE, 1, 128.0 * ((double)v.h * v.w + (double)(v.h + 2) * (v.w + 2)) * sizeof(float), s,
-        launch_bn_act_write(v.raw_d1, 128, bn_ref(P, v.bn_d1), v.h, v.w, bf ? nullptr : v.P_d1, 128, 1, 1, s, Twin{v.P_d1_16, 128}));
+  HBM_T(&P->timer, H_BN_ACT_WRITE, 1, (double)nd * ((double)v.h * v.w + (double)(v.h + 2) * (v.w + 2)) * sizeof(float), s,
+        launch_bn_act_write(v.raw_d1, nd, bn_ref(P, v.bn_d1), v.h, v.w, bf ? nullptr : v.P_d1, nd, 1, 1, s, Twin{v.P_d1_16, nd}));
   DIP_CHECK(v.d2.run_fprop(prec, P->params[v.d2.p_b], s));
   HBM_T(&P->timer, H_BN_ACT_WRITE, last ? 0 : 1,
-        128.0 * ((double)v.h * v.w + (last ? (double)v.h * v.w : (double)(v.h + 2) * (v.w + 2))) * sizeof(float), s,
-        launch_bn_act_write(v.raw_d2, 128, bn_ref(P, v.bn_d2), v.h, v.w, (bf && !last && CS != 4) ? nullptr : v.P_d2, 128, last ? 0 : 1, 1, s,
-                            Twin{last ? nullptr : v.P_d2_16, 128}));   // (the 4-channel skip conv of the next level reads the fp32 tensor)
+        (double)nd * ((double)v.h * v.w + (last ? (double)v.h * v.w : (double)(v.h + 2) * (v.w + 2))) * sizeof(float), s,
+        launch_bn_act_write(v.raw_d2, nd, bn_ref(P, v.bn_d2), v.h, v.w, (bf && !last && P->lv[l + 1].ns != 4) ? nullptr : v.P_d2, nd, last ? 0 : 1, 1, s,
+                            Twin{last ? nullptr : v.P_d2_16, nd}));   // (the 4-channel skip conv of the next level reads the fp32 tensor)
   nl += 4 + (prec == DIP_PRECISION_FP32 ? 2 : 0);
   if (!last) {
     if (deep_on(P) && l + 1 == P->deep_from) {
@@ -1158,17 +1207,25 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   // upsample + concat + BN + pad
   if (CS > 0) join_skip(P, s);
   CatArgs ca = cat_args(P, v, level_usrc(P, l));
-  const double cat_in = (128.0 * v.h * v.w + (double)CS * v.H * v.W) * sizeof(float);
+  const double cat_in = ((double)v.cu * v.h * v.w + (double)CS * v.H * v.W) * sizeof(float);
   HBM_T(&P->timer, H_CAT_STATS, v.bilinear, cat_in, s, launch_cat_stats(ca, v.bn_cat.fwd, s));
-  HBM_T(&P->timer, H_CAT_WRITE, v.bilinear, cat_in + (128.0 + CS) * (v.H + 2) * (v.W + 2) * sizeof(float), s,
+  HBM_T(&P->timer, H_CAT_WRITE, v.bilinear, cat_in + ((double)v.cu + CS) * (v.H + 2) * (v.W + 2) * sizeof(float), s,
         launch_cat_write(ca, bn_ref(P, v.bn_cat), v.P_cat, s, Twin{v.P_cat16, v.cat_ld16}));
   DIP_CHECK(v.up.run_fprop(prec, P->params[v.up.p_b], s));
-  HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * 128 * v.H * v.W * sizeof(float), s,
-        launch_bn_act_write(v.raw_u, 128, bn_ref(P, v.bn_u), v.H, v.W, bf ? nullptr : v.A_u, 128, 0, 1, s, Twin{v.A_u16, 128}));
+  HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * nu * v.H * v.W * sizeof(float), s,
+        launch_bn_act_write(v.raw_u, nu, bn_ref(P, v.bn_u), v.H, v.W, bf ? nullptr : v.A_u, nu, 0, 1, s, Twin{v.A_u16, nu}));
   DIP_CHECK(v.c11.run_fprop(prec, P->params[v.c11.p_b], s));
-  if (l > 0) {
-    HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * 128 * v.H * v.W * sizeof(float), s,
-          launch_bn_act_write(v.raw_v, 128, bn_ref(P, v.bn_v), v.H, v.W, v.U, 128, 0, 1, s));
+  if (l > 0 || nu != 128) {
+    HBM_T(&P->timer, H_BN_ACT_WRITE, 0, 2.0 * nu * v.H * v.W * sizeof(float), s,
+          launch_bn_act_write(v.raw_v, nu, bn_ref(P, v.bn_v), v.H, v.W, v.U, nu, 0, 1, s));
+    if (l == 0) {
+      // level 0 narrower than 128 channels: the RGB head (models/skip.py:95-98) as a skinny 1x1 conv over the materialised
+      // activation (the fused BN + head kernel is specialised for 128 channels = one warp per pixel)
+      HBM_T(&P->timer, H_SKINNY_FWD, 1, ((double)nu + P->desc.out_channels) * v.H * v.W * sizeof(float), s,
+            launch_skinny_fwd(v.U, nu, v.W, P->params[P->p_head_w], P->params[P->p_head_b], nu, P->desc.out_channels, v.H, v.W,
+                              P->out_saved, P->desc.need_sigmoid != 0 ? 1 : 2, nullptr, s));
+      nl += 1;
+    }
   } else {
     // top level: BN + LeakyReLU + RGB head + sigmoid in one pass; the 128-channel activation is never materialised
     HeadRef hd{P->params[P->p_head_w], P->params[P->p_head_b], P->desc.out_channels, P->out_saved, P->desc.need_sigmoid != 0};
@@ -1285,17 +1342,17 @@ static int conv_backward(dip_plan* P, ConvOp& op, bool dgrad, int prec, cudaStre
 static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl) {
   Level& v = P->lv[l];
   const int prec = P->desc.precision;
-  const int CS = P->desc.skip_channels;
-  const int CC = 128 + CS;
+  const int CS = v.ns, nd = v.nd, nu = v.nu;
+  const int CC = v.cu + CS;
   const bool last = l == (int)P->lv.size() - 1;
   const int wl = is_tc(prec) ? 1 : 2;   // tensor-core wgrads accumulate in place (no per-conv reduction launch)
   // 1x1 conv + BN + LReLU
-  DIP_CHECK(bn_bwd(P, v.raw_v, 128, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl, v.dRaw_v16));
+  DIP_CHECK(bn_bwd(P, v.raw_v, nu, v.bn_v, 1, src_v, v.H, v.W, v.dRaw_v, nullptr, s, nl, v.dRaw_v16));
   if (l == defer_level()) DIP_CHECK(flush_deferred(P, prec, s));
   DIP_CHECK(conv_backward(P, v.c11, true, prec, s, l));
   nl += wl + 1;
   // up conv + BN + LReLU
-  DIP_CHECK(bn_bwd(P, v.raw_u, 128, v.bn_u, 1, src_plain(v.dA_u, 128, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl, v.dRaw_u16));
+  DIP_CHECK(bn_bwd(P, v.raw_u, nu, v.bn_u, 1, src_plain(v.dA_u, nu, 0), v.H, v.W, v.dRaw_u, nullptr, s, nl, v.dRaw_u16));
   if (CS == 128) {
     cudaStream_t ws = fork_side(P, s);
     DIP_CHECK(v.up_a.run_dgrad(prec, s));
@@ -1316,10 +1373,10 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   // skip branch (on the skip stream: independent of the deeper levels; the level above joins before it reads dRaw_s / dS)
   cudaStream_t ks = fork_skip(P, s);
   // gradient w.r.t. the low-resolution tensor that was upsampled into this concat (adjoint of x2 upsampling), once
-  HBM_T(&P->timer, H_UPADJ, v.bilinear, 128.0 * ((double)v.H * v.W + (double)v.h * v.w) * sizeof(float), s,
-        launch_upadj(v.dCat, CC, 0, v.h, v.w, 128, v.bilinear, v.dUp, s));
+  HBM_T(&P->timer, H_UPADJ, v.bilinear, (double)v.cu * ((double)v.H * v.W + (double)v.h * v.w) * sizeof(float), s,
+        launch_upadj(v.dCat, CC, 0, v.h, v.w, v.cu, v.bilinear, v.dUp, s));
   nl += 3;
-  if (CS > 0) DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, 128), v.H, v.W, v.dRaw_s, nullptr, ks, nl, v.dRaw_s16));
+  if (CS > 0) DIP_CHECK(bn_bwd(P, v.raw_s, CS, v.bn_s, 1, src_plain(v.dCat, CC, v.cu), v.H, v.W, v.dRaw_s, nullptr, ks, nl, v.dRaw_s16));
   if (CS == 0) {
     // no skip branch (models/skip.py:50-53 with num_channels_skip = 0)
   } else if (CS == 128) {
@@ -1342,21 +1399,21 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
       DIP_CUDA(launch_deep(P->d_deep_bwd, P->n_deep_bwd, P->deep_bar + 16, P->deep_grid, s));
       nl += 2;
     } else {
-      DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, 128, 0), s, nl));
+      DIP_CHECK(bwd_level(P, l + 1, src_plain(v.dUp, v.cu, 0), s, nl));
     }
     join_skip(P, s);   // the next level's skip-branch gradients (dRaw_s / dS) feed the BN backward below
-    Level& n = P->lv[l + 1];
-    if (CS == 128) { src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = 128; }
-    else if (CS == 0) src_d2 = src_fold(n.dPin, 128, nullptr, nullptr, 0);
-    else src_d2 = src_fold(n.dPin, 128, n.dRaw_s, P->params[n.p_skip_w], CS);
+    Level& n = P->lv[l + 1];   // (its input depth n.Cin == nd)
+    if (n.ns == 128) { src_d2 = src_fold(n.dPin, nd, nullptr, nullptr, 0); src_d2.add = n.dS; src_d2.ld_add = nd; }
+    else if (n.ns == 0) src_d2 = src_fold(n.dPin, nd, nullptr, nullptr, 0);
+    else src_d2 = src_fold(n.dPin, nd, n.dRaw_s, P->params[n.p_skip_w], n.ns);
   } else {
-    src_d2 = src_plain(v.dUp, 128, 0);
+    src_d2 = src_plain(v.dUp, v.cu, 0);
   }
-  DIP_CHECK(bn_bwd(P, v.raw_d2, 128, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl, v.dRaw_d2_16));
+  DIP_CHECK(bn_bwd(P, v.raw_d2, nd, v.bn_d2, 1, src_d2, v.h, v.w, v.dRaw_d2, nullptr, s, nl, v.dRaw_d2_16));
   DIP_CHECK(conv_backward(P, v.d2, true, prec, s));
   nl += wl + 1;
   const bool d1_dgrad = l > 0 || P->desc.input_grad != 0;
-  DIP_CHECK(bn_bwd(P, v.raw_d1, 128, v.bn_d1, 1, src_fold(v.dP_d1, 128, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1,
+  DIP_CHECK(bn_bwd(P, v.raw_d1, nd, v.bn_d1, 1, src_fold(v.dP_d1, nd, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1,
                    (d1_dgrad && !v.d1.dg_s2) ? v.ZS : nullptr, s, nl, v.dRaw_d1_16));
   DIP_CHECK(conv_backward(P, v.d1, d1_dgrad, prec, s));
   nl += wl + (d1_dgrad ? 1 : 0);
@@ -1512,7 +1569,9 @@ static void deep_bwd_level(dip_plan* P, int l, GradSrc src_v, std::vector<DeepOp
 static int build_deep_ops(dip_plan* P) {
   P->n_deep_fwd = P->n_deep_bwd = 0;
   P->deep_grid = 128 < g_num_sms ? 128 : g_num_sms;
-  if (P->desc.precision != DIP_PRECISION_TF32 || (int)P->lv.size() <= P->deep_from || P->desc.skip_channels == 0) return 0;
+  if (P->desc.precision != DIP_PRECISION_TF32 || (int)P->lv.size() <= P->deep_from) return 0;
+  for (const Level& v : P->lv)   // the op lists below are written for the 128-wide network with a skip branch at every scale
+    if (v.nd != 128 || v.nu != 128 || v.ns == 0 || v.ns != P->lv[0].ns) return 0;
   std::vector<DeepOp> fwd;
   deep_fwd_level(P, P->deep_from, fwd);
   if ((int)fwd.size() > dip_plan::kDeepMaxOps) return fail("internal: deep forward op list too long");
@@ -1902,7 +1961,7 @@ int dip_run_iterations(dip_plan* P, dip_adam* adam, const void* z0, const void* 
 int dip_input_grad(dip_plan* P, void* dz, dip_stream_t stream) {
   if (!P->desc.input_grad) return fail("dip_input_grad: the plan was created without input_grad");
   Level& v = P->lv[0];
-  launch_input_grad(v.dPin, P->desc.skip_channels > 0 ? v.dS : nullptr, v.Cin, v.Cin_act, v.H, v.W, (float*)dz, (cudaStream_t)stream);
+  launch_input_grad(v.dPin, v.ns > 0 ? v.dS : nullptr, v.Cin, v.Cin_act, v.H, v.W, (float*)dz, (cudaStream_t)stream);
   DIP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -251,7 +251,8 @@ struct SimtConvArgs {
 };
 void launch_simt_conv(SimtConvArgs a, cudaStream_t s);
 struct SimtWgradArgs {
-  const float* dY; int h, w;                     // [h][w][128]
+  const float* dY; int h, w;                     // [h][w][dy_ld], n output channels (0 / 0: 128 / 128)
+  int dy_ld, n;
   const float* X; int x_h, x_w, x_ld, x_c;
   int kh, kw, stride, offx, offy;
   float* partial; int c_pad;                     // [ksplits][tap][128][c_pad]

@@ -30,6 +30,9 @@ class NetDesc(ctypes.Structure):
         ("precision", ctypes.c_int),
         ("upsample_mask", ctypes.c_int),
         ("input_grad", ctypes.c_int),
+        ("channels_down", ctypes.c_int * 8),
+        ("channels_up", ctypes.c_int * 8),
+        ("channels_skip", ctypes.c_int * 8),
     ]
 
 
@@ -137,8 +140,16 @@ class Plan:
     """A compiled schedule for one skip network at one input size (dip_plan in include/dip.h)."""
 
     def __init__(self, in_channels, out_channels, num_scales, channels, skip_channels, bilinear, H, W,
-                 precision=PRECISION_TF32, device=None, need_sigmoid=True, input_grad=False):
+                 precision=PRECISION_TF32, device=None, need_sigmoid=True, input_grad=False, channels_up=None):
+        """channels / skip_channels: one width for every scale, or per-scale sequences (num_channels_down / num_channels_skip
+        of models.skip; channels_up = num_channels_up, default = channels)."""
         L = lib()
+        per_scale = None
+        if isinstance(channels, (list, tuple)) or isinstance(skip_channels, (list, tuple)) or channels_up is not None:
+            as_list = lambda x: list(x) if isinstance(x, (list, tuple)) else [x] * num_scales   # noqa: E731
+            per_scale = (as_list(channels), as_list(channels if channels_up is None else channels_up), as_list(skip_channels))
+            assert all(len(x) == num_scales for x in per_scale) and num_scales <= 8
+            channels, skip_channels = 0, 0
         if not torch.cuda.is_available():
             raise RuntimeError("dip-b200 needs a CUDA device (sm_100a); none is visible")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -151,6 +162,11 @@ class Plan:
         else:
             self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, int(bool(bilinear)),
                                 int(bool(need_sigmoid)), precision, 0, int(bool(input_grad)))
+        if per_scale is not None:
+            for name, vals in zip(("channels_down", "channels_up", "channels_skip"), per_scale):
+                arr = getattr(self.desc, name)
+                for i, x in enumerate(vals):
+                    arr[i] = int(x)
         self.H, self.W = H, W
         nbytes = L.dip_plan_workspace_bytes(ctypes.byref(self.desc), H, W)
         if nbytes == 0:
@@ -232,7 +248,10 @@ class Plan:
         check(lib().dip_plan_buffer(self.h, name.encode(), ctypes.byref(p), dims))
         rows, cols, ld, c = dims[0], dims[1], dims[2], dims[3]
         off = p.value - self.workspace.data_ptr()
-        flat = self.workspace[off:off + rows * cols * ld * 4].view(torch.float32)
+        if name.endswith("16"):   # bf16 twin of a conv operand (precision mode bf16)
+            flat = self.workspace[off:off + rows * cols * ld * 2].view(torch.bfloat16)
+        else:
+            flat = self.workspace[off:off + rows * cols * ld * 4].view(torch.float32)
         return flat.view(rows, cols, ld)[:, :, :c].clone()
 
     def set_timing(self, enable):

@@ -109,7 +109,7 @@ class SkipNet(nn.Sequential):
         if plan is None:
             plan = de.Plan(spec['in_channels'], spec['out_channels'], spec['num_scales'], spec['channels'],
                            spec['skip_channels'], spec['bilinear'], H, W, precision=prec, device=z.device,
-                           need_sigmoid=spec['need_sigmoid'], input_grad=key[4])
+                           need_sigmoid=spec['need_sigmoid'], input_grad=key[4], channels_up=spec.get('channels_up'))
             self._dip_plans[pkey] = plan
         params = list(self.parameters())
         for p in params:
@@ -254,10 +254,10 @@ def skip(num_input_channels=2, num_output_channels=3,
     # 3) is this one of the configurations the engine executes?
     why = None
     chans = set(num_channels_down) | set(num_channels_up)
-    if chans != {128}:
-        why = 'num_channels_down/up must all be 128'
-    elif set(num_channels_skip) not in ({0}, {4}, {128}):
-        why = 'num_channels_skip must all be 0, all be 4 or all be 128'
+    if any(c % 8 != 0 or not 8 <= c <= 128 for c in chans):
+        why = 'num_channels_down/up must be multiples of 8 in [8, 128]'
+    elif not (set(num_channels_skip) <= {0, 4} or (set(num_channels_skip) == {128} and chans == {128})):
+        why = 'num_channels_skip must be 0 or 4 per scale (or 128 at every scale of a 128-wide network)'
     elif set(filter_size_down) != {3} or set(filter_size_up) != {3} or filter_skip_size != 1:
         why = 'filter sizes must be 3/3/1'
     elif pad != 'reflection':
@@ -273,8 +273,12 @@ def skip(num_input_channels=2, num_output_channels=3,
     elif not (1 <= num_output_channels <= 4 and 1 <= num_input_channels <= 128):
         why = 'num_output_channels in 1..4 and num_input_channels in 1..128'
     if why is None:
+        uniform = chans == {128} and len(set(num_channels_skip)) == 1
         net._dip_spec = dict(in_channels=num_input_channels, out_channels=num_output_channels, num_scales=n,
-                             channels=128, skip_channels=num_channels_skip[0], need_sigmoid=bool(need_sigmoid),
+                             channels=128 if uniform else list(num_channels_down),
+                             channels_up=None if uniform else list(num_channels_up),
+                             skip_channels=num_channels_skip[0] if uniform else list(num_channels_skip),
+                             need_sigmoid=bool(need_sigmoid),
                              bilinear=(upsample_mode[0] == 'bilinear' if len(set(upsample_mode)) == 1
                                        else [m == 'bilinear' for m in upsample_mode]))
     else:

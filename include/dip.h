@@ -34,8 +34,9 @@ typedef struct {
   int in_channels;       /* num_input_channels, 1..128 (32 in every BASELINE config; 3 in flash-no-flash)  */
   int out_channels;      /* num_output_channels (<= 4; 3)                                               */
   int num_scales;        /* len(num_channels_down)                                                      */
-  int channels;          /* num_channels_down[i] == num_channels_up[i] == 128                           */
-  int skip_channels;     /* num_channels_skip[i]: 4, or 128 (inpainting.ipynb kate)                     */
+  int channels;          /* num_channels_down[i] == num_channels_up[i] (128 in every BASELINE configuration);
+                            0: per-scale widths in channels_down / channels_up / channels_skip below     */
+  int skip_channels;     /* num_channels_skip[i]: 0, 4, or 128 (inpainting.ipynb kate; 128-wide networks only) */
   int upsample_bilinear; /* upsample_mode: 1 'bilinear', 0 'nearest', -1: per scale, see upsample_mask  */
   int need_sigmoid;      /* 1: nn.Sigmoid behind the head (models/skip.py:97-98), 0: none                */
   int precision;         /* DIP_PRECISION_*                                                             */
@@ -43,6 +44,11 @@ typedef struct {
                             (flash-no-flash.ipynb c8: ['nearest','nearest','bilinear','bilinear','bilinear']) */
   int input_grad;        /* 1: dip_backward also prepares dL/d(net_input) for dip_input_grad
                             (OPT_OVER = 'net,input', utils/common_utils.py:47-49); costs two extra level-0 launches */
+  /* channels == 0: widths per scale (index 0 = outermost), multiples of 8 in [8, 128]; skips 0 or 4 per scale
+     (denoising.ipynb c8:17-23 "snail": down = up = [8, 16, 32, 64, 128], skip = [0, 0, 0, 4, 4])           */
+  int channels_down[8];  /* num_channels_down (models/skip.py:6)                                        */
+  int channels_up[8];    /* num_channels_up   (models/skip.py:6)                                        */
+  int channels_skip[8];  /* num_channels_skip (models/skip.py:7)                                        */
 } dip_net_desc;
 
 const char* dip_last_error(void);

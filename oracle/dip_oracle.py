@@ -41,13 +41,33 @@ class SkipConfig:
         self.upsample_mode = upsample_mode
         self.need_sigmoid = need_sigmoid
 
+    # per-scale widths (models/skip.py:6-7): `channels` / `skip_channels` may be one int for every scale or a sequence
+    # (num_channels_down = num_channels_up = channels unless channels_up is set: denoising.ipynb c8:17-23 "snail")
+    channels_up = None
+
+    def nd(self, l):
+        return self.channels[l] if isinstance(self.channels, (list, tuple)) else self.channels
+
+    def nu(self, l):
+        if self.channels_up is not None:
+            return self.channels_up[l]
+        return self.nd(l)
+
+    def ns(self, l):
+        return self.skip_channels[l] if isinstance(self.skip_channels, (list, tuple)) else self.skip_channels
+
+    def cu(self, l):
+        """depth of the tensor upsampled into scale l's concat (models/skip.py:48-55)"""
+        return self.nu(l + 1) if l < self.num_scales - 1 else self.nd(l)
+
 
 def param_layout(cfg):
     """[(name, shape)] in net.parameters() order of the reference (depth-first over the module tree)."""
-    L, C, S = cfg.num_scales, cfg.channels, cfg.skip_channels
+    L = cfg.num_scales
     pre, post = [], []
     for l in range(L):
-        cin = cfg.in_channels if l == 0 else C
+        C, S = cfg.nd(l), cfg.ns(l)
+        cin = cfg.in_channels if l == 0 else cfg.nd(l - 1)
         sk = [("L%d.skip.w" % l, (S, cin, 1, 1)), ("L%d.skip.b" % l, (S,)),
               ("L%d.skip_bn.g" % l, (S,)), ("L%d.skip_bn.b" % l, (S,))] if S > 0 else []   # num_channels_skip = 0: no skip branch
         pre.append(sk + [
@@ -55,17 +75,18 @@ def param_layout(cfg):
                     ("L%d.d1_bn.g" % l, (C,)), ("L%d.d1_bn.b" % l, (C,)),
                     ("L%d.d2.w" % l, (C, C, 3, 3)), ("L%d.d2.b" % l, (C,)),
                     ("L%d.d2_bn.g" % l, (C,)), ("L%d.d2_bn.b" % l, (C,))])
-        post.append([("L%d.cat_bn.g" % l, (C + S,)), ("L%d.cat_bn.b" % l, (C + S,)),
-                     ("L%d.up.w" % l, (C, C + S, 3, 3)), ("L%d.up.b" % l, (C,)),
-                     ("L%d.up_bn.g" % l, (C,)), ("L%d.up_bn.b" % l, (C,)),
-                     ("L%d.c11.w" % l, (C, C, 1, 1)), ("L%d.c11.b" % l, (C,)),
-                     ("L%d.c11_bn.g" % l, (C,)), ("L%d.c11_bn.b" % l, (C,))])
+        U, K = cfg.nu(l), cfg.cu(l) + S
+        post.append([("L%d.cat_bn.g" % l, (K,)), ("L%d.cat_bn.b" % l, (K,)),
+                     ("L%d.up.w" % l, (U, K, 3, 3)), ("L%d.up.b" % l, (U,)),
+                     ("L%d.up_bn.g" % l, (U,)), ("L%d.up_bn.b" % l, (U,)),
+                     ("L%d.c11.w" % l, (U, U, 1, 1)), ("L%d.c11.b" % l, (U,)),
+                     ("L%d.c11_bn.g" % l, (U,)), ("L%d.c11_bn.b" % l, (U,))])
     out = []
     for l in range(L):
         out += pre[l]
     for l in reversed(range(L)):
         out += post[l]
-    out += [("head.w", (cfg.out_channels, C, 1, 1)), ("head.b", (cfg.out_channels,))]
+    out += [("head.w", (cfg.out_channels, cfg.nu(0), 1, 1)), ("head.b", (cfg.out_channels,))]
     return out
 
 
@@ -74,18 +95,19 @@ def init_params(cfg, seed=None, dtype=torch.float32):
     are constructed skip, down1, down2, up3x3, up1x1; levels top-down; head last; BatchNorm draws nothing)."""
     if seed is not None:
         torch.manual_seed(seed)
-    L, C, S = cfg.num_scales, cfg.channels, cfg.skip_channels
+    L = cfg.num_scales
     vals = {}
     for l in range(L):
-        cin = cfg.in_channels if l == 0 else C
-        for name, (o, i, k) in (("skip", (S, cin, 1)), ("d1", (C, cin, 3)), ("d2", (C, C, 3)), ("up", (C, C + S, 3)),
-                                ("c11", (C, C, 1))):
+        C, U, S = cfg.nd(l), cfg.nu(l), cfg.ns(l)
+        cin = cfg.in_channels if l == 0 else cfg.nd(l - 1)
+        for name, (o, i, k) in (("skip", (S, cin, 1)), ("d1", (C, cin, 3)), ("d2", (C, C, 3)), ("up", (U, cfg.cu(l) + S, 3)),
+                                ("c11", (U, U, 1))):
             if o == 0:
                 continue   # models/skip.py:57-60: the skip conv is only constructed (and only draws from the RNG) when it has channels
             m = nn.Conv2d(i, o, k)  # torch default init: kaiming_uniform(a=sqrt(5)) + bias U(+-1/sqrt(fan_in))
             vals["L%d.%s.w" % (l, name)] = m.weight.detach()
             vals["L%d.%s.b" % (l, name)] = m.bias.detach()
-    m = nn.Conv2d(C, cfg.out_channels, 1)
+    m = nn.Conv2d(cfg.nu(0), cfg.out_channels, 1)
     vals["head.w"], vals["head.b"] = m.weight.detach(), m.bias.detach()
     params = []
     for name, shape in param_layout(cfg):
@@ -99,10 +121,58 @@ def init_params(cfg, seed=None, dtype=torch.float32):
     return params
 
 
+# ---- bf16-operand emulation (the checker of the engine's precision mode 'bf16', BASELINE.json configs[2]) -------------
+# The reference has no bf16 path of its own (its GPU path is fp32 / cuDNN-TF32; "bf16" is BASELINE.json's wording for the
+# super-resolution configuration).  The engine's definition: every convolution that runs on the tensor cores -- the wide
+# convs, 8 or more output channels -- reads its input, its weight and, in the backward pass, the incoming gradient
+# ROUNDED TO BF16 (round to nearest even), multiplies exactly and accumulates in fp32; biases, BatchNorm, activations,
+# up-sampling, the skinny skip convs, the head, the loss and Adam stay fp32.  `with operand_rounding('bf16'):` makes
+# _conv evaluate exactly that definition on the CPU (in whatever dtype the parameters have, fp64 included).
+_OPERAND_ROUND = None
+_MIN_TENSOR_CORE_WIDTH = 8   # the skinny skip convs (4 outputs) and the head (<= 4) run in fp32 on the CUDA cores
+
+
+class operand_rounding:
+    def __init__(self, kind):
+        assert kind in (None, "bf16")
+        self.kind = kind
+
+    def __enter__(self):
+        global _OPERAND_ROUND
+        self.prev, _OPERAND_ROUND = _OPERAND_ROUND, self.kind
+
+    def __exit__(self, *a):
+        global _OPERAND_ROUND
+        _OPERAND_ROUND = self.prev
+
+
+def _round_bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _ConvBf16Operands(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride):
+        xr, wr = _round_bf16(x), _round_bf16(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.stride = stride
+        return F.conv2d(xr, wr, b, stride=stride)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, wr = ctx.saved_tensors
+        dyr = _round_bf16(dy)
+        dx = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, stride=ctx.stride)
+        dw = torch.nn.grad.conv2d_weight(xr, wr.shape, dyr, stride=ctx.stride)
+        return dx, dw, dy.sum((0, 2, 3)), None
+
+
 def _conv(x, w, b, stride=1):
     k = w.shape[-1]
     if k > 1:
         x = F.pad(x, (k // 2,) * 4, mode="reflect")  # nn.ReflectionPad2d, models/common.py:116-118
+    if _OPERAND_ROUND == "bf16" and w.shape[0] >= _MIN_TENSOR_CORE_WIDTH:
+        return _ConvBf16Operands.apply(x, w, b, stride)
     return F.conv2d(x, w, b, stride=stride)
 
 
@@ -122,7 +192,7 @@ def skip_forward(params, z, cfg, tape=None):
     def rec(l, x):
         pre = "L%d." % l
         s = None
-        if cfg.skip_channels > 0:
+        if cfg.ns(l) > 0:
             s = _conv(x, P[pre + "skip.w"], P[pre + "skip.b"])
             if tape is not None:
                 tape[pre + "raw_s"] = s

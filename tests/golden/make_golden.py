@@ -62,14 +62,17 @@ def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtyp
 
 
 def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.01, masked=False, dtype=torch.float32,
-                threads=8, skip_ch=4, meshgrid=False):
+                threads=8, skip_ch=4, meshgrid=False, chans=None, skips=None):
     """Skip-net variants of the other notebooks that use the 128-wide network: flash-no-flash.ipynb c8 (image as input,
     per-scale upsampling modes) and restoration.ipynb c7 barbara (n_channels=1, masked loss)."""
     torch.set_num_threads(threads)
     with ref_harness.reference_modules() as ref:
         torch.manual_seed(0)
-        net = ref.models.skip(in_depth, out_ch, num_channels_down=[128] * 5, num_channels_up=[128] * 5,
-                              num_channels_skip=[skip_ch] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True,
+        chans = list(chans) if chans is not None else [128] * 5      # per-scale widths: denoising.ipynb c8:17-23 "snail"
+        skips = list(skips) if skips is not None else [skip_ch] * 5
+        skip_ch = skips[0]
+        net = ref.models.skip(in_depth, out_ch, num_channels_down=chans, num_channels_up=chans,
+                              num_channels_skip=skips, upsample_mode=modes, need_sigmoid=True, need_bias=True,
                               pad='reflection').type(dtype)
         g = torch.Generator().manual_seed(2)
         z0 = torch.rand(1, in_depth, H, W, generator=g).type(dtype)          # an image (or noise) as the network input
@@ -98,7 +101,8 @@ def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.0
     np.savez_compressed(os.path.join(HERE, name + '.npz'), H=H, W=W, in_depth=in_depth, out_ch=out_ch,
                         modes=np.array(modes if isinstance(modes, list) else [modes] * 5), iters=iters, sigma=sigma, lr=lr,
                         masked=masked, losses=np.array(losses), out0=out0.numpy(), gnorm0=gnorm0, g_skip0_w=g_first[0],
-                        g_d1_0_w=g_first[1], dtype=str(dtype), state_keys=np.array(keys), skip_ch=skip_ch, z0=z0.numpy())
+                        g_d1_0_w=g_first[1], dtype=str(dtype), state_keys=np.array(keys), skip_ch=skip_ch, z0=z0.numpy(),
+                        chans=np.array(chans), skips=np.array(skips))
     print(name, 'losses', losses)
 
 
@@ -299,6 +303,11 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'vase':   # inpainting.ipynb "vase": num_channels_skip = 0, meshgrid input, nearest
         for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
             run_variant('vase64x96_in2_skip0_masked_' + tag, 64, 96, 2, 3, 'nearest', masked=True, dtype=dt, skip_ch=0, meshgrid=True)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'snail':   # denoising.ipynb c8:13-23 "snail": per-scale widths and skips, 3-channel noise input
+        for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
+            run_variant('snail64x96_in3_w8to128_' + tag, 64, 96, 3, 3, 'bilinear', sigma=1. / 30, dtype=dt,
+                        chans=[8, 16, 32, 64, 128], skips=[0, 0, 0, 4, 4])
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sr':   # only the super-resolution fixtures
         run_downsampler_cases()

@@ -25,7 +25,7 @@ def test_workspace_query_needs_no_gpu():
     desc = de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0)
     n = de.lib().dip_plan_workspace_bytes(ctypes.byref(desc), 512, 512)
     assert 2 ** 30 < n < 12 * 2 ** 30
-    bad = de.NetDesc(32, 3, 5, 64, 4, 1, 1, 0)
+    bad = de.NetDesc(32, 3, 5, 60, 4, 1, 1, 0)   # widths must be multiples of 8
     assert de.lib().dip_plan_workspace_bytes(ctypes.byref(bad), 512, 512) == 0
     assert b"128" in de.lib().dip_last_error()
 
@@ -83,11 +83,13 @@ def test_integration_md_stub_matches_the_header_struct():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hdr = open(os.path.join(root, "include", "dip.h")).read()
     body = re.search(r"typedef struct \{(.*?)\} dip_net_desc;", hdr, re.S).group(1)
-    header_fields = re.findall(r"^\s*int\s+(\w+);", body, re.M)
+    header_fields = re.findall(r"^\s*int\s+(\w+)(?:\[8\])?;", body, re.M)
+    header_arrays = re.findall(r"^\s*int\s+(\w+)\[8\];", body, re.M)
     doc = open(os.path.join(root, "INTEGRATION.md")).read()
     stub = re.search(r"class NetDesc\(ctypes.Structure\):.*?_fields_ = \[(.*?)\]\n", doc, re.S).group(1)
     stub_fields = re.findall(r'"(\w+)"', stub)
     import dip_engine as de
-    assert header_fields == stub_fields == [n for n, _ in de.NetDesc._fields_] and len(header_fields) == 10
+    assert header_fields == stub_fields == [n for n, _ in de.NetDesc._fields_] and len(header_fields) == 13
+    assert header_arrays == header_fields[10:] == [n for n, t in de.NetDesc._fields_ if t is not ctypes.c_int]
     ctor = re.search(r"desc = NetDesc\((.*?)\)\s+#", doc).group(1)
-    assert len([x for x in ctor.split(",") if x.strip()]) == len(header_fields)
+    assert len([x for x in ctor.split(",") if x.strip()]) == len(header_fields) - len(header_arrays)   # the arrays stay zero

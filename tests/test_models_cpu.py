@@ -58,8 +58,12 @@ def test_no_silent_cpu_fallback():
 
 def test_unsupported_config_raises_not_falls_back():
     net = models.skip(3, 3, num_channels_down=[8, 16], num_channels_up=[8, 16], num_channels_skip=[0, 4],
-                      upsample_mode="bilinear", pad="reflection")
-    assert net._dip_spec is None
+                      upsample_mode="bilinear", pad="reflection", downsample_mode="avg")   # restoration.ipynb kate's in-net pooling
+    assert net._dip_spec is None and "downsample_mode" in net._dip_why
+    # per-scale widths alone (denoising.ipynb c8 "snail") ARE accelerated
+    ok = models.skip(3, 3, num_channels_down=[8, 16], num_channels_up=[8, 16], num_channels_skip=[0, 4],
+                     upsample_mode="bilinear", pad="reflection")
+    assert ok._dip_spec is not None and ok._dip_spec["channels"] == [8, 16] and ok._dip_spec["skip_channels"] == [0, 4]
     with pytest.raises(NotImplementedError):
         net(torch.zeros(1, 3, 32, 32))
 

@@ -52,6 +52,23 @@ def test_denoising_notebook_runs_unchanged():
 
 
 @needs_ref
+def test_denoising_notebook_snail_branch_runs_unchanged():
+    """denoising.ipynb with the "deJPEG" image selected (the user edit of cell 4: fname = 'data/denoising/snail.jpg'): the
+    narrow network of c8:13-23 -- skip(3, 3, num_channels_down = num_channels_up = [8, 16, 32, 64, 128], num_channels_skip =
+    [0, 0, 0, 4, 4]) -- per-scale widths on the engine; no ground truth (PSNR_gt is measured against the noisy image)."""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    ns = run_notebook(os.path.join(REF, "denoising.ipynb"), dict(PLOT=False, num_iter=60, fname="data/denoising/snail.jpg"))
+    _assert_engine_net(ns["net"])
+    spec = ns["net"]._dip_spec
+    assert spec["channels"] == [8, 16, 32, 64, 128] and spec["skip_channels"] == [0, 0, 0, 4, 4] and spec["in_channels"] == 3
+    assert ns["i"] == 60 and ns["out_np"].shape == ns["img_np"].shape and np.isfinite(ns["out_np"]).all()
+    loss = _losses(ns["__stdout__"], r"Loss ([0-9.]+)")
+    assert len(loss) == 60 and loss[-1] < 0.5 * loss[0]
+    assert len(ns["last_net"]) == 100          # parameter tensors of the narrow network (snapshot of the c10 closure)
+
+
+@needs_ref
 def test_super_resolution_notebook_runs_unchanged():
     torch.manual_seed(0)
     ns = run_notebook(os.path.join(REF, "super-resolution.ipynb"), dict(PLOT=False, num_iter=40))

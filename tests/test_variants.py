@@ -11,17 +11,33 @@ import torch
 from oracle import dip_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["flash64x96_in3_mixed", "restore64_out1_masked", "vase64x96_in2_skip0_masked"]
+CASES = ["flash64x96_in3_mixed", "restore64_out1_masked", "vase64x96_in2_skip0_masked", "snail64x96_in3_w8to128"]
+# snail: denoising.ipynb c8:13-23 -- per-scale widths [8, 16, 32, 64, 128], skips [0, 0, 0, 4, 4], 3-channel noise input
 
 
 def skip_ch(g):
     return int(g["skip_ch"]) if "skip_ch" in g else 4
 
 
+def widths(g):
+    """(num_channels_down = num_channels_up, num_channels_skip) of the fixture, per scale"""
+    if "chans" in g:
+        return [int(x) for x in g["chans"]], [int(x) for x in g["skips"]]
+    return [128] * 5, [skip_ch(g)] * 5
+
+
+def oracle_cfg(g, modes):
+    chans, skips = widths(g)
+    if set(chans) == {128} and len(set(skips)) == 1:
+        return O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skips[0])
+    return O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, channels=chans,
+                        skip_channels=skips)
+
+
 def setup(g, dtype):
     H, W = int(g["H"]), int(g["W"])
     modes = [str(m) for m in g["modes"]]
-    cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skip_ch(g))
+    cfg = oracle_cfg(g, modes)
     gen = torch.Generator().manual_seed(2)
     z0 = torch.rand(1, cfg.in_channels, H, W, generator=gen).to(dtype)
     if "z0" in g:   # the vase fixture's meshgrid input (the generator draws above stay, so target / mask match the fixture's)
@@ -60,15 +76,16 @@ def test_module_tree_matches_reference_and_is_accelerated(case):
     g = np.load(os.path.join(GOLD, case + "_fp32.npz"))
     modes = [str(m) for m in g["modes"]]
     torch.manual_seed(0)
-    net = models.skip(int(g["in_depth"]), int(g["out_ch"]), num_channels_down=[128] * 5, num_channels_up=[128] * 5,
-                      num_channels_skip=[skip_ch(g)] * 5, upsample_mode=modes, need_sigmoid=True, need_bias=True, pad="reflection")
+    chans, skips = widths(g)
+    net = models.skip(int(g["in_depth"]), int(g["out_ch"]), num_channels_down=chans, num_channels_up=chans,
+                      num_channels_skip=skips, upsample_mode=modes, need_sigmoid=True, need_bias=True, pad="reflection")
     assert list(net.state_dict().keys()) == [str(k) for k in g["state_keys"]]
     spec = net._dip_spec
     assert spec is not None and spec["in_channels"] == int(g["in_depth"]) and spec["out_channels"] == int(g["out_ch"])
     if len(set(modes)) > 1:
         assert spec["bilinear"] == [m == "bilinear" for m in modes]
-    cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skip_ch(g))
-    assert spec["skip_channels"] == skip_ch(g)
+    cfg = oracle_cfg(g, modes)
+    assert spec["skip_channels"] == (skip_ch(g) if set(chans) == {128} else skips)
     for a, b in zip(net.parameters(), O.init_params(cfg, seed=0)):
         assert a.shape == b.shape and torch.equal(a.detach(), b.detach())
 
@@ -84,8 +101,9 @@ def test_engine_matches_reference_golden(case, prec):
     cfg, z0, target, mask, noises = setup(g, torch.float32)
     dtype = torch.cuda.FloatTensor
     torch.manual_seed(0)
-    net = models.skip(cfg.in_channels, cfg.out_channels, num_channels_down=[128] * 5, num_channels_up=[128] * 5,
-                      num_channels_skip=[cfg.skip_channels] * 5, upsample_mode=list(cfg.upsample_mode), need_sigmoid=True,
+    chans, skips = widths(g)
+    net = models.skip(cfg.in_channels, cfg.out_channels, num_channels_down=chans, num_channels_up=chans,
+                      num_channels_skip=skips, upsample_mode=list(cfg.upsample_mode), need_sigmoid=True,
                       need_bias=True, pad="reflection").type(dtype)
     net.precision = prec
     z0d, tgt = z0.type(dtype), target.type(dtype)
@@ -119,9 +137,9 @@ def test_engine_matches_reference_golden(case, prec):
     # (tf32 tier, 64 x 96: the deepest BatchNorms normalise over 2 x 3 pixels, so TF32 rounding moves the first layer's gradient by
     # tens of percent -- for cuDNN-TF32 as well, tests/test_engine_gpu.py; without skip connections every path to the first layer
     # crosses all five levels, hence the wider bound for the vase configuration)
-    tol1 = 3e-2 if prec == "fp32" else (0.3 if cfg.skip_channels else 0.6)
+    tol1 = 3e-2 if prec == "fp32" else (0.3 if skips[0] else 0.6)
     assert rel(params[0].grad, g["g_skip0_w"]) < tol1
-    assert rel(params[4 if cfg.skip_channels else 0].grad, g["g_d1_0_w"]) < tol1
+    assert rel(params[4 if skips[0] else 0].grad, g["g_d1_0_w"]) < tol1
     optimize("adam", params, closure, float(g["lr"]), 2)
     assert np.isfinite(losses).all() and abs(losses[1] - float(g["losses"][1])) < 2e-2
 
