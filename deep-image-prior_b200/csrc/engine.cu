@@ -589,6 +589,10 @@ struct Level {
   // ns = num_channels_skip[l], cu = depth of the tensor upsampled into this level's concat (nu of the level below, or nd at
   // the deepest level).  128 / 128 / {0, 4, 128} / 128 in every BASELINE configuration.
   int nd = 128, nu = 128, ns = 0, cu = 128;
+  // downsample_mode 'avg': the first down conv runs at stride 1 into rawF [H][W][nd], raw_d1 = AvgPool2d(2, 2)(rawF);
+  // dRawF [H][W][nd] = the pooling adjoint of dRaw_d1 (input of that conv's dgrad / wgrad)
+  float *rawF = nullptr, *dRawF = nullptr;
+  uint16_t* dRawF16 = nullptr;
   float *Pin, *raw_s, *raw_d1, *P_d1, *raw_d2, *P_d2, *P_cat, *raw_u, *A_u, *raw_v, *U;
   // bf16 twins (precision mode bf16; ld = the fp32 tensor's depth rounded up to 8)
   uint16_t *Pin16 = nullptr, *P_d1_16 = nullptr, *P_d2_16 = nullptr, *P_cat16 = nullptr, *A_u16 = nullptr;
@@ -721,6 +725,8 @@ static int build_plan(dip_plan* P, Arena& A) {
     if (!(wide || NS[l] == 0 || NS[l] == 4))
       return fail("dip-b200: num_channels_skip must be 0 or 4 per scale, or 128 at every scale of a 128-wide network");
   const int CS = NS[0];   // the uniform skip width where the code below asks for it (wide: 128)
+  if (d.downsample_mode != 0 && d.downsample_mode != 1) return fail("dip-b200: downsample_mode must be 'stride' (0) or 'avg' (1)");
+  const bool avg = d.downsample_mode == 1;
   // parameters of the skip branch (conv w, b, BN gamma, beta): absent where num_channels_skip[l] = 0
   // (inpainting.ipynb c14:11-16 "vase": models/skip.py:50-53 then adds `deeper` alone, no Concat)
   auto psl = [&](int l) { return NS[l] > 0 ? 4 : 0; };
@@ -864,6 +870,11 @@ static int build_plan(dip_plan* P, Arena& A) {
     v.dP_d1 = A.get<float>(hwp * nd);
     v.dRaw_d1 = A.get<float>(hw * nd);
     const bool in_grad = d.input_grad != 0;   // level 0 then also needs its input gradient
+    if (avg) {
+      v.rawF = A.get<float>(HW * nd);
+      v.dRawF = A.get<float>(HW * nd);
+      if (bf) v.dRawF16 = A.get<uint16_t>(HW * nd);
+    }
     v.ZS = (l > 0 || in_grad) ? A.get<float>(HW * nd) : nullptr;
     v.dS = ((wide && l > 0) || (in_grad && l == 0)) ? A.get<float>(HW * v.Cin) : nullptr;
     v.dPin = (l > 0 || in_grad) ? A.get<float>(HWp * v.Cin) : nullptr;
@@ -944,6 +955,12 @@ static int build_plan(dip_plan* P, Arena& A) {
     a.dg_out = v.dPin; a.dg_out_h = v.H + 2; a.dg_out_w = v.W + 2; a.dg_off = -2;
     a.wg_dy = v.dRaw_d1; a.wg_h = v.h; a.wg_w = v.w;
     a.in16 = v.Pin16; a.in_ld16 = v.Pin_ld16; a.dg_in16 = v.dRaw_d1_16; a.wg_dy16 = v.dRaw_d1_16;
+    if (avg) {   // stride-1 conv at the level's full resolution; pooling is a separate pass (fwd_level / bwd_level)
+      a.stride = 1; a.out = v.rawF; a.out_h = v.H; a.out_w = v.W; a.stats = nullptr;
+      a.dg_s2 = false; a.dg_in = v.dRawF; a.dg_in_h = v.H; a.dg_in_w = v.W;
+      a.wg_dy = v.dRawF; a.wg_h = v.H; a.wg_w = v.W;
+      a.dg_in16 = v.dRawF16; a.wg_dy16 = v.dRawF16;
+    }
     // down2: P_d1 -> raw_d2
     ConvOp& b = v.d2;
     b.set_shapes();
@@ -1187,6 +1204,11 @@ static int fwd_level(dip_plan* P, int l, cudaStream_t s, int& nl) {
   }
   // deeper branch
   DIP_CHECK(v.d1.run_fprop(prec, P->params[v.d1.p_b], s));
+  if (v.rawF != nullptr) {   // downsample_mode 'avg': pool the stride-1 conv output, then the statistics of the pooled tensor
+    launch_avgpool2(v.rawF, v.h, v.w, nd, v.raw_d1, s);
+    launch_channel_stats(v.raw_d1, nd, nd, v.h * v.w, v.bn_d1.fwd, s);
+    nl += 2;
+  }
   HBM_T(&P->timer, H_BN_ACT_WRITE, 1, (double)nd * ((double)v.h * v.w + (double)(v.h + 2) * (v.w + 2)) * sizeof(float), s,
         launch_bn_act_write(v.raw_d1, nd, bn_ref(P, v.bn_d1), v.h, v.w, bf ? nullptr : v.P_d1, nd, 1, 1, s, Twin{v.P_d1_16, nd}));
   DIP_CHECK(v.d2.run_fprop(prec, P->params[v.d2.p_b], s));
@@ -1413,8 +1435,13 @@ static int bwd_level(dip_plan* P, int l, GradSrc src_v, cudaStream_t s, int& nl)
   DIP_CHECK(conv_backward(P, v.d2, true, prec, s));
   nl += wl + 1;
   const bool d1_dgrad = l > 0 || P->desc.input_grad != 0;
+  const bool avg = v.rawF != nullptr;
   DIP_CHECK(bn_bwd(P, v.raw_d1, nd, v.bn_d1, 1, src_fold(v.dP_d1, nd, nullptr, nullptr, 0), v.h, v.w, v.dRaw_d1,
-                   (d1_dgrad && !v.d1.dg_s2) ? v.ZS : nullptr, s, nl, v.dRaw_d1_16));
+                   (d1_dgrad && !v.d1.dg_s2 && !avg) ? v.ZS : nullptr, s, nl, avg ? nullptr : v.dRaw_d1_16));
+  if (avg) {   // adjoint of AvgPool2d(2, 2): the conv's dY at full resolution
+    launch_avgpool2_bwd(v.dRaw_d1, v.h, v.w, nd, prec == DIP_PRECISION_BF16 ? nullptr : v.dRawF, s, Twin{v.dRawF16, nd});
+    nl += 1;
+  }
   DIP_CHECK(conv_backward(P, v.d1, d1_dgrad, prec, s));
   nl += wl + (d1_dgrad ? 1 : 0);
   DIP_CUDA(cudaGetLastError());

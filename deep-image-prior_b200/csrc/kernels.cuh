@@ -164,6 +164,11 @@ void launch_bn_bwd_reduce(const float* raw, int ld_raw, BnRef bn, int act, GradS
 void launch_bn_bwd_apply(const float* raw, int ld_raw, BnRef bn, int act, GradSrc src, int H, int W,
                          const double* bwd, float* draw, float* zs, double* dbias, cudaStream_t s, Twin t16 = kNoTwin);
 
+// In-net 'avg' downsampling (models/common.py:101-105: conv stride 1 + nn.AvgPool2d(2, 2)): y[i][j][c] = mean of the 2 x 2 block
+// of x [2h][2w][C]; its adjoint spreads 0.25 * dy to the four positions (optionally also as a bf16 twin; dx may be null then)
+void launch_avgpool2(const float* x, int h, int w, int C, float* y, cudaStream_t s);
+void launch_avgpool2_bwd(const float* dy, int h, int w, int C, float* dx, cudaStream_t s, Twin t16 = kNoTwin);
+
 // Concat-BN backward (no activation). pcat = the stored BN output (padded [(H+2)][(W+2)][ld], ld = bn_cat.C), from which
 // xhat is recovered; gradient = fold of the padded dgrad output gp [(H+2)][(W+2)][ld]; dcat plain [H][W][C].
 void launch_cat_bwd_reduce(const float* pcat, BnRef bn_cat, const float* gp, int ld, int H, int W, double* bwd,

@@ -1039,6 +1039,49 @@ void launch_upadj(const float* D, int ld, int coff, int h, int w, int C, int bil
   launch_k(k_upadj, dim3(g.blocks), dim3(g.threads), 0, s, 1, D, ld, coff, h, w, C, bilinear, dst, g.VL, g.PPB);
 }
 
+// ------------------------------------------------------------------------------------------------ 2 x 2 average pooling
+__global__ void __launch_bounds__(256) k_avgpool2(const float* __restrict__ x, int h, int w, int C, float* __restrict__ y, int VL, int PPB) {
+  pdl_enter();
+  const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
+  const int W2 = 2 * w;
+  item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, h * w,
+               [&](int p) {
+                 const int i = p / w, j = p - i * w;
+                 const float* b = x + (static_cast<size_t>(2 * i) * W2 + 2 * j) * C + 4 * v;
+                 const float4 a0 = ld4(b), a1 = ld4(b + C), a2 = ld4(b + static_cast<size_t>(W2) * C), a3 = ld4(b + static_cast<size_t>(W2 + 1) * C);
+                 return f4add(f4add(a0, a1), f4add(a2, a3));
+               },
+               [&](int p, float4 t) { st4(y + static_cast<size_t>(p) * C + 4 * v, make_float4(0.25f * t.x, 0.25f * t.y, 0.25f * t.z, 0.25f * t.w)); });
+}
+void launch_avgpool2(const float* x, int h, int w, int C, float* y, cudaStream_t s) {
+  VecGeom g = vec_geom(C, static_cast<long long>(h) * w);
+  fit_grid(g, k_avgpool2, 0);
+  launch_k(k_avgpool2, dim3(g.blocks), dim3(g.threads), 0, s, 1, x, h, w, C, y, g.VL, g.PPB);
+}
+__global__ void __launch_bounds__(256) k_avgpool2_bwd(const float* __restrict__ dy, int h, int w, int C, float* __restrict__ dx, int VL,
+                                                      int PPB, Twin t16) {
+  pdl_enter();
+  const int v = threadIdx.x % VL, slot = threadIdx.x / VL;
+  const int W2 = 2 * w;
+  item_loop<2>(blockIdx.x * PPB + slot, gridDim.x * PPB, h * w,
+               [&](int p) { return ld4(dy + static_cast<size_t>(p) * C + 4 * v); },
+               [&](int p, float4 t) {
+                 const int i = p / w, j = p - i * w;
+                 const float4 q = make_float4(0.25f * t.x, 0.25f * t.y, 0.25f * t.z, 0.25f * t.w);
+#pragma unroll
+                 for (int a = 0; a < 4; ++a) {
+                   const size_t o = static_cast<size_t>(2 * i + (a >> 1)) * W2 + 2 * j + (a & 1);
+                   if (dx != nullptr) st4(dx + o * C + 4 * v, q);
+                   if (t16.p != nullptr) st4_bf16(t16.p + o * t16.ld + 4 * v, q);
+                 }
+               });
+}
+void launch_avgpool2_bwd(const float* dy, int h, int w, int C, float* dx, cudaStream_t s, Twin t16) {
+  VecGeom g = vec_geom(C, static_cast<long long>(h) * w);
+  fit_grid(g, k_avgpool2_bwd, 0);
+  launch_k(k_avgpool2_bwd, dim3(g.blocks), dim3(g.threads), 0, s, 1, dy, h, w, C, dx, g.VL, g.PPB, t16);
+}
+
 // weight row n of a skinny conv for lanes 4v..4v+3: rows are cw long (cw < C when the stored depth is zero-padded)
 __device__ __forceinline__ float4 skinny_wrow(const float* __restrict__ w, int n, int cw, int v) {
   if ((cw & 3) == 0) return 4 * v < cw ? ld4(w + n * cw + 4 * v) : f4zero();

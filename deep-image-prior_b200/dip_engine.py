@@ -33,6 +33,7 @@ class NetDesc(ctypes.Structure):
         ("channels_down", ctypes.c_int * 8),
         ("channels_up", ctypes.c_int * 8),
         ("channels_skip", ctypes.c_int * 8),
+        ("downsample_mode", ctypes.c_int),
     ]
 
 
@@ -140,7 +141,8 @@ class Plan:
     """A compiled schedule for one skip network at one input size (dip_plan in include/dip.h)."""
 
     def __init__(self, in_channels, out_channels, num_scales, channels, skip_channels, bilinear, H, W,
-                 precision=PRECISION_TF32, device=None, need_sigmoid=True, input_grad=False, channels_up=None):
+                 precision=PRECISION_TF32, device=None, need_sigmoid=True, input_grad=False, channels_up=None,
+                 downsample_mode="stride"):
         """channels / skip_channels: one width for every scale, or per-scale sequences (num_channels_down / num_channels_skip
         of models.skip; channels_up = num_channels_up, default = channels)."""
         L = lib()
@@ -162,6 +164,7 @@ class Plan:
         else:
             self.desc = NetDesc(in_channels, out_channels, num_scales, channels, skip_channels, int(bool(bilinear)),
                                 int(bool(need_sigmoid)), precision, 0, int(bool(input_grad)))
+        self.desc.downsample_mode = {"stride": 0, "avg": 1}[downsample_mode]
         if per_scale is not None:
             for name, vals in zip(("channels_down", "channels_up", "channels_skip"), per_scale):
                 arr = getattr(self.desc, name)

@@ -109,7 +109,8 @@ class SkipNet(nn.Sequential):
         if plan is None:
             plan = de.Plan(spec['in_channels'], spec['out_channels'], spec['num_scales'], spec['channels'],
                            spec['skip_channels'], spec['bilinear'], H, W, precision=prec, device=z.device,
-                           need_sigmoid=spec['need_sigmoid'], input_grad=key[4], channels_up=spec.get('channels_up'))
+                           need_sigmoid=spec['need_sigmoid'], input_grad=key[4], channels_up=spec.get('channels_up'),
+                           downsample_mode=spec.get('downsample_mode', 'stride'))
             self._dip_plans[pkey] = plan
         params = list(self.parameters())
         for p in params:
@@ -262,8 +263,8 @@ def skip(num_input_channels=2, num_output_channels=3,
         why = 'filter sizes must be 3/3/1'
     elif pad != 'reflection':
         why = "pad must be 'reflection'"
-    elif set(downsample_mode) != {'stride'}:
-        why = "downsample_mode must be 'stride'"
+    elif set(downsample_mode) not in ({'stride'}, {'avg'}):
+        why = "downsample_mode must be 'stride' or 'avg' (at every scale)"
     elif act_fun != 'LeakyReLU':
         why = "act_fun must be 'LeakyReLU'"
     elif not (need_bias and need1x1_up):
@@ -278,7 +279,7 @@ def skip(num_input_channels=2, num_output_channels=3,
                              channels=128 if uniform else list(num_channels_down),
                              channels_up=None if uniform else list(num_channels_up),
                              skip_channels=num_channels_skip[0] if uniform else list(num_channels_skip),
-                             need_sigmoid=bool(need_sigmoid),
+                             need_sigmoid=bool(need_sigmoid), downsample_mode=downsample_mode[0],
                              bilinear=(upsample_mode[0] == 'bilinear' if len(set(upsample_mode)) == 1
                                        else [m == 'bilinear' for m in upsample_mode]))
     else:

@@ -49,6 +49,8 @@ typedef struct {
   int channels_down[8];  /* num_channels_down (models/skip.py:6)                                        */
   int channels_up[8];    /* num_channels_up   (models/skip.py:6)                                        */
   int channels_skip[8];  /* num_channels_skip (models/skip.py:7)                                        */
+  int downsample_mode;   /* 0: 'stride' (stride-2 conv); 1: 'avg' (stride-1 conv + AvgPool2d(2, 2), models/common.py:101-105,
+                            restoration.ipynb c7:28-36 kate)                                            */
 } dip_net_desc;
 
 const char* dip_last_error(void);

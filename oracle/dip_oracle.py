@@ -44,6 +44,9 @@ class SkipConfig:
     # per-scale widths (models/skip.py:6-7): `channels` / `skip_channels` may be one int for every scale or a sequence
     # (num_channels_down = num_channels_up = channels unless channels_up is set: denoising.ipynb c8:17-23 "snail")
     channels_up = None
+    # in-net downsampling of the first down conv (models/common.py:101-113): 'stride' (stride-2 conv) or 'avg'
+    # (stride-1 conv + nn.AvgPool2d(2, 2): restoration.ipynb c7:28-36 kate)
+    downsample_mode = "stride"
 
     def nd(self, l):
         return self.channels[l] if isinstance(self.channels, (list, tuple)) else self.channels
@@ -197,7 +200,10 @@ def skip_forward(params, z, cfg, tape=None):
             if tape is not None:
                 tape[pre + "raw_s"] = s
             s = _act(_bn(s, P[pre + "skip_bn.g"], P[pre + "skip_bn.b"]))
-        d = _conv(x, P[pre + "d1.w"], P[pre + "d1.b"], stride=2)
+        if cfg.downsample_mode == "avg":
+            d = F.avg_pool2d(_conv(x, P[pre + "d1.w"], P[pre + "d1.b"], stride=1), 2, 2)
+        else:
+            d = _conv(x, P[pre + "d1.w"], P[pre + "d1.b"], stride=2)
         if tape is not None:
             tape[pre + "raw_d1"] = d
         d = _act(_bn(d, P[pre + "d1_bn.g"], P[pre + "d1_bn.b"]))

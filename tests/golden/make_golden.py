@@ -62,7 +62,7 @@ def run_case(name, H, W, mode, iters, sigma=1. / 30, lr=0.01, masked=False, dtyp
 
 
 def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.01, masked=False, dtype=torch.float32,
-                threads=8, skip_ch=4, meshgrid=False, chans=None, skips=None):
+                threads=8, skip_ch=4, meshgrid=False, chans=None, skips=None, downsample_mode='stride'):
     """Skip-net variants of the other notebooks that use the 128-wide network: flash-no-flash.ipynb c8 (image as input,
     per-scale upsampling modes) and restoration.ipynb c7 barbara (n_channels=1, masked loss)."""
     torch.set_num_threads(threads)
@@ -73,7 +73,7 @@ def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.0
         skip_ch = skips[0]
         net = ref.models.skip(in_depth, out_ch, num_channels_down=chans, num_channels_up=chans,
                               num_channels_skip=skips, upsample_mode=modes, need_sigmoid=True, need_bias=True,
-                              pad='reflection').type(dtype)
+                              pad='reflection', downsample_mode=downsample_mode).type(dtype)
         g = torch.Generator().manual_seed(2)
         z0 = torch.rand(1, in_depth, H, W, generator=g).type(dtype)          # an image (or noise) as the network input
         if meshgrid:   # inpainting.ipynb c14:1-16 (vase): INPUT = 'meshgrid', input_depth = 2 (utils/common_utils.py:145-149)
@@ -102,7 +102,7 @@ def run_variant(name, H, W, in_depth, out_ch, modes, iters=3, sigma=0.03, lr=0.0
                         modes=np.array(modes if isinstance(modes, list) else [modes] * 5), iters=iters, sigma=sigma, lr=lr,
                         masked=masked, losses=np.array(losses), out0=out0.numpy(), gnorm0=gnorm0, g_skip0_w=g_first[0],
                         g_d1_0_w=g_first[1], dtype=str(dtype), state_keys=np.array(keys), skip_ch=skip_ch, z0=z0.numpy(),
-                        chans=np.array(chans), skips=np.array(skips))
+                        chans=np.array(chans), skips=np.array(skips), downsample_mode=downsample_mode)
     print(name, 'losses', losses)
 
 
@@ -308,6 +308,11 @@ if __name__ == '__main__':
         for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
             run_variant('snail64x96_in3_w8to128_' + tag, 64, 96, 3, 3, 'bilinear', sigma=1. / 30, dtype=dt,
                         chans=[8, 16, 32, 64, 128], skips=[0, 0, 0, 4, 4])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'kate_restore':   # restoration.ipynb c7:28-36 kate: widths 16..128, no skips, 'avg' downsampling, masked
+        for dt, tag in ((torch.float64, 'fp64'), (torch.float32, 'fp32')):
+            run_variant('restorekate64x96_avg_w16to128_' + tag, 64, 96, 32, 3, 'bilinear', sigma=0.0, masked=True, dtype=dt,
+                        chans=[16, 32, 64, 128, 128], skips=[0, 0, 0, 0, 0], downsample_mode='avg')
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sr':   # only the super-resolution fixtures
         run_downsampler_cases()

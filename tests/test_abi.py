@@ -89,7 +89,7 @@ def test_integration_md_stub_matches_the_header_struct():
     stub = re.search(r"class NetDesc\(ctypes.Structure\):.*?_fields_ = \[(.*?)\]\n", doc, re.S).group(1)
     stub_fields = re.findall(r'"(\w+)"', stub)
     import dip_engine as de
-    assert header_fields == stub_fields == [n for n, _ in de.NetDesc._fields_] and len(header_fields) == 13
-    assert header_arrays == header_fields[10:] == [n for n, t in de.NetDesc._fields_ if t is not ctypes.c_int]
+    assert header_fields == stub_fields == [n for n, _ in de.NetDesc._fields_] and len(header_fields) == 14
+    assert header_arrays == header_fields[10:13] == [n for n, t in de.NetDesc._fields_ if t is not ctypes.c_int]
     ctor = re.search(r"desc = NetDesc\((.*?)\)\s+#", doc).group(1)
-    assert len([x for x in ctor.split(",") if x.strip()]) == len(header_fields) - len(header_arrays)   # the arrays stay zero
+    assert len([x for x in ctor.split(",") if x.strip()]) == 10   # the per-scale arrays and downsample_mode stay zero

@@ -58,7 +58,7 @@ def test_no_silent_cpu_fallback():
 
 def test_unsupported_config_raises_not_falls_back():
     net = models.skip(3, 3, num_channels_down=[8, 16], num_channels_up=[8, 16], num_channels_skip=[0, 4],
-                      upsample_mode="bilinear", pad="reflection", downsample_mode="avg")   # restoration.ipynb kate's in-net pooling
+                      upsample_mode="bilinear", pad="reflection", downsample_mode="max")   # in-net max pooling (models/common.py:106-107)
     assert net._dip_spec is None and "downsample_mode" in net._dip_why
     # per-scale widths alone (denoising.ipynb c8 "snail") ARE accelerated
     ok = models.skip(3, 3, num_channels_down=[8, 16], num_channels_up=[8, 16], num_channels_skip=[0, 4],

@@ -11,8 +11,14 @@ import torch
 from oracle import dip_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["flash64x96_in3_mixed", "restore64_out1_masked", "vase64x96_in2_skip0_masked", "snail64x96_in3_w8to128"]
+CASES = ["flash64x96_in3_mixed", "restore64_out1_masked", "vase64x96_in2_skip0_masked", "snail64x96_in3_w8to128",
+         "restorekate64x96_avg_w16to128"]
 # snail: denoising.ipynb c8:13-23 -- per-scale widths [8, 16, 32, 64, 128], skips [0, 0, 0, 4, 4], 3-channel noise input
+# restorekate: restoration.ipynb c7:28-36 -- widths [16, 32, 64, 128, 128], no skips, downsample_mode='avg', masked loss
+
+
+def dmode(g):
+    return str(g["downsample_mode"]) if "downsample_mode" in g else "stride"
 
 
 def skip_ch(g):
@@ -29,9 +35,12 @@ def widths(g):
 def oracle_cfg(g, modes):
     chans, skips = widths(g)
     if set(chans) == {128} and len(set(skips)) == 1:
-        return O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skips[0])
-    return O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, channels=chans,
-                        skip_channels=skips)
+        cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, skip_channels=skips[0])
+    else:
+        cfg = O.SkipConfig(in_channels=int(g["in_depth"]), out_channels=int(g["out_ch"]), upsample_mode=modes, channels=chans,
+                           skip_channels=skips)
+    cfg.downsample_mode = dmode(g)
+    return cfg
 
 
 def setup(g, dtype):
@@ -78,7 +87,8 @@ def test_module_tree_matches_reference_and_is_accelerated(case):
     torch.manual_seed(0)
     chans, skips = widths(g)
     net = models.skip(int(g["in_depth"]), int(g["out_ch"]), num_channels_down=chans, num_channels_up=chans,
-                      num_channels_skip=skips, upsample_mode=modes, need_sigmoid=True, need_bias=True, pad="reflection")
+                      num_channels_skip=skips, upsample_mode=modes, need_sigmoid=True, need_bias=True, pad="reflection",
+                      downsample_mode=dmode(g))
     assert list(net.state_dict().keys()) == [str(k) for k in g["state_keys"]]
     spec = net._dip_spec
     assert spec is not None and spec["in_channels"] == int(g["in_depth"]) and spec["out_channels"] == int(g["out_ch"])
@@ -104,7 +114,7 @@ def test_engine_matches_reference_golden(case, prec):
     chans, skips = widths(g)
     net = models.skip(cfg.in_channels, cfg.out_channels, num_channels_down=chans, num_channels_up=chans,
                       num_channels_skip=skips, upsample_mode=list(cfg.upsample_mode), need_sigmoid=True,
-                      need_bias=True, pad="reflection").type(dtype)
+                      need_bias=True, pad="reflection", downsample_mode=dmode(g)).type(dtype)
     net.precision = prec
     z0d, tgt = z0.type(dtype), target.type(dtype)
     md = mask.type(dtype) if mask is not None else None
