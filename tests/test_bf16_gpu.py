@@ -38,8 +38,8 @@ def dead(name):
 
 def make_plan(cfg, params, H, W):
     import dip_engine as de
-    plan = de.Plan(32, 3, cfg.num_scales, 128, cfg.skip_channels, cfg.upsample_mode == "bilinear", H, W,
-                   precision=de.PRECISION_BF16)
+    plan = de.Plan(cfg.in_channels, cfg.out_channels, cfg.num_scales, cfg.channels, cfg.skip_channels, cfg.upsample_mode == "bilinear", H, W,
+                   precision=de.PRECISION_BF16, downsample_mode=cfg.downsample_mode)
     dparams = [p.detach().cuda().contiguous() for p in params]
     dgrads = [torch.zeros_like(p) for p in dparams]
     plan.bind(dparams, dgrads)
@@ -59,7 +59,8 @@ def check_layers(tag, cfg, plan, params, dgrads):
     P = {n: p.detach().bfloat16().double() for n, p in zip(names, params)}     # weights as the kernels read them
     B = {n: p.detach().double() for n, p in zip(names, params)}
     G = {n: g.double().cpu() for n, g in zip(names, dgrads)}
-    cs, L = cfg.skip_channels, cfg.num_scales
+    L = cfg.num_scales
+    avg = cfg.downsample_mode == "avg"
     worst = {"fprop": ("", 0.0), "dgrad": ("", 0.0), "wgrad": ("", 0.0)}
 
     def upd(kind, key, got, ref):
@@ -68,6 +69,8 @@ def check_layers(tag, cfg, plan, params, dgrads):
 
     for l in range(L):
         pf = "L%d." % l
+        cs = cfg.ns(l)
+        nd, nu, cc = cfg.nd(l), cfg.nu(l), cfg.cu(l) + cs
         pin = chw(plan.buffer(pf + "Pin16"))
         cin = P[pf + "d1.w"].shape[1]
         pin = pin[:cin]
@@ -78,7 +81,11 @@ def check_layers(tag, cfg, plan, params, dgrads):
         if l == 0 or cs == 4:
             assert torch.equal(plan.buffer(pf + "Pin16")[:, :, :cin], plan.buffer(pf + "Pin")[:, :, :cin].bfloat16()), pf + "Pin16"
         # forward
-        upd("fprop", pf + "raw_d1", chw(plan.buffer(pf + "raw_d1")), F.conv2d(pin[None], P[pf + "d1.w"], B[pf + "d1.b"], stride=2)[0])
+        if avg:   # stride-1 conv + AvgPool2d(2, 2) (models/common.py:101-105)
+            upd("fprop", pf + "raw_d1", chw(plan.buffer(pf + "raw_d1")),
+                F.avg_pool2d(F.conv2d(pin[None], P[pf + "d1.w"], B[pf + "d1.b"]), 2, 2)[0])
+        else:
+            upd("fprop", pf + "raw_d1", chw(plan.buffer(pf + "raw_d1")), F.conv2d(pin[None], P[pf + "d1.w"], B[pf + "d1.b"], stride=2)[0])
         upd("fprop", pf + "raw_d2", chw(plan.buffer(pf + "raw_d2")), F.conv2d(x_d2[None], P[pf + "d2.w"], B[pf + "d2.b"])[0])
         upd("fprop", pf + "raw_u", chw(plan.buffer(pf + "raw_u")), F.conv2d(x_up_t[None], P[pf + "up.w"], B[pf + "up.b"])[0])
         upd("fprop", pf + "raw_v", chw(plan.buffer(pf + "raw_v")), F.conv2d(x_11[None], P[pf + "c11.w"], B[pf + "c11.b"])[0])
@@ -100,20 +107,27 @@ def check_layers(tag, cfg, plan, params, dgrads):
             assert (diff > 0).sum().item() <= 1e-2 * diff.numel() + 8 and (diff <= 2.0 ** -7 * yb.abs() + 1e-5).all(), raw_key
         # backward: dY twins -> input gradients and weight gradients
         dy_v, dy_u = chw(plan.buffer(pf + "dRaw_v16")), chw(plan.buffer(pf + "dRaw_u16"))
-        dy_d2, dy_d1 = chw(plan.buffer(pf + "dRaw_d2_16")), chw(plan.buffer(pf + "dRaw_d1_16"))
+        dy_d2 = chw(plan.buffer(pf + "dRaw_d2_16"))
+        if avg:   # the conv's dY = pooling adjoint of the (fp32) pooled gradient, rounded to bf16 where the kernels read it
+            dy_d1 = (0.25 * plan.buffer(pf + "dRaw_d1")).bfloat16().permute(2, 0, 1).double().cpu()
+            dy_d1 = dy_d1.repeat_interleave(2, 1).repeat_interleave(2, 2)
+        else:
+            dy_d1 = chw(plan.buffer(pf + "dRaw_d1_16"))
         upd("dgrad", pf + "dA_u", chw(plan.buffer(pf + "dA_u")), F.conv_transpose2d(dy_v[None], P[pf + "c11.w"])[0])
         upd("dgrad", pf + "dP_cat", chw(plan.buffer(pf + "dP_cat")), torch.roll(F.conv_transpose2d(dy_u[None], P[pf + "up.w"])[0], -cs, 0))
         upd("dgrad", pf + "dP_d1", chw(plan.buffer(pf + "dP_d1")), F.conv_transpose2d(dy_d2[None], P[pf + "d2.w"])[0])
-        if l > 0:
+        if l > 0 and avg:
+            upd("dgrad", pf + "dPin", chw(plan.buffer(pf + "dPin")), F.conv_transpose2d(dy_d1[None], P[pf + "d1.w"])[0])
+        elif l > 0:
             got = chw(plan.buffer(pf + "dPin"))
             ref = F.conv_transpose2d(dy_d1[None], P[pf + "d1.w"], stride=2)[0]
             upd("dgrad", pf + "dPin", got[:, :-1, :-1], ref)
             assert got[:, -1, :].abs().max() == 0 and got[:, :, -1].abs().max() == 0
         wg = torch.nn.grad.conv2d_weight
-        upd("wgrad", pf + "c11.w", G[pf + "c11.w"], wg(x_11[None], (128, 128, 1, 1), dy_v[None]))
-        upd("wgrad", pf + "up.w", G[pf + "up.w"], wg(x_up_t[None], (128, 128 + cs, 3, 3), dy_u[None]))
-        upd("wgrad", pf + "d2.w", G[pf + "d2.w"], wg(x_d2[None], (128, 128, 3, 3), dy_d2[None]))
-        upd("wgrad", pf + "d1.w", G[pf + "d1.w"], wg(pin[None], (128, cin, 3, 3), dy_d1[None], stride=2)[:, :, :3, :3])
+        upd("wgrad", pf + "c11.w", G[pf + "c11.w"], wg(x_11[None], (nu, nu, 1, 1), dy_v[None]))
+        upd("wgrad", pf + "up.w", G[pf + "up.w"], wg(x_up_t[None], (nu, cc, 3, 3), dy_u[None]))
+        upd("wgrad", pf + "d2.w", G[pf + "d2.w"], wg(x_d2[None], (nd, nd, 3, 3), dy_d2[None]))
+        upd("wgrad", pf + "d1.w", G[pf + "d1.w"], wg(pin[None], (nd, cin, 3, 3), dy_d1[None], stride=1 if avg else 2)[:, :, :3, :3])
         if cs == 128:
             dy_s = chw(plan.buffer(pf + "dRaw_s16"))
             upd("wgrad", pf + "skip.w", G[pf + "skip.w"], wg(pin[None, :, 1:-1, 1:-1], (128, cin, 1, 1), dy_s[None]))
@@ -122,6 +136,30 @@ def check_layers(tag, cfg, plan, params, dgrads):
     assert worst["fprop"][1] < LOCAL_TOL, worst["fprop"]
     assert worst["dgrad"][1] < LOCAL_TOL, worst["dgrad"]
     assert worst["wgrad"][1] < WGRAD_TOL, worst["wgrad"]
+
+
+@pytest.mark.parametrize("kind", ["snail", "restoration_kate"])
+def test_bf16_layers_per_scale_widths(kind):
+    """The bf16 kernels on per-scale widths (K blocks with 8 / 16 / 32 valid channels of 64, UMMA N = 16 .. 128) and, for
+    restoration.ipynb's kate network, the stride-1 first down conv behind downsample_mode='avg': layer-local, exact-level."""
+    if kind == "snail":      # denoising.ipynb c8:13-23
+        cfg = O.SkipConfig(in_channels=3, channels=[8, 16, 32, 64, 128], skip_channels=[0, 0, 0, 4, 4])
+    else:                    # restoration.ipynb c7:28-36
+        cfg = O.SkipConfig(in_channels=32, channels=[16, 32, 64, 128, 128], skip_channels=[0, 0, 0, 0, 0])
+        cfg.downsample_mode = "avg"
+    H, W = 64, 96
+    params = O.init_params(cfg, seed=0)
+    z0 = O.get_noise(cfg.in_channels, (H, W), seed=1)
+    target = torch.rand(1, 3, H, W, generator=torch.Generator().manual_seed(2))
+    plan, dparams, dgrads = make_plan(cfg, params, H, W)
+    out = plan.forward(z0.cuda())
+    plan.backward((2.0 * (out - target.cuda()) / out.numel()).contiguous())
+    torch.cuda.synchronize()
+    check_layers(kind, cfg, plan, params, dgrads)
+    # and the whole step lands where the bf16-operand oracle does (floor-level agreement, see above)
+    with O.operand_rounding("bf16"):
+        ref = O.skip_forward(params, z0, cfg).detach()
+    assert (out.cpu() - ref).abs().max().item() < 0.1
 
 
 def net_errors(cfg, raw_get, out, grads, tape_ref, out_ref, grads_ref, raws):
