@@ -660,8 +660,41 @@ def bench_sr_config(torch, de, models, peaks, dev, iters=100):
         ms_, by_ = sum(r[2] for r in hb), sum(r[1] for r in hb)
         rec["hbm_kernels"] = {"ms_per_step": ms_ / 3.0, "algorithmic_GB_per_s_fp32_bytes": by_ / (ms_ / 1000.0) / 1e9 if ms_ > 0 else 0.0}
         rec["peak_note"] = "peak = measured burst cuBLAS bf16 rate (MEASURED_PEAKS.json)" + ("" if prec_name == "bf16" else " / 2 (tf32)")
+        del plan, opt
+        # the same configuration end to end through the notebook-facing API (super-resolution.ipynb c10 without the logging):
+        # net(net_input + noise) -> Downsampler -> MSELoss -> backward() -> optimize('adam', ...), loss read back every step
+        from utils.common_utils import get_params
+        from utils.common_utils import optimize as _opt
+        import contextlib
+        import io
+        net.precision = prec_name
+        for p_ in params:
+            p_.grad = None
+        dmod = down.type(torch.cuda.FloatTensor)
+        mse = torch.nn.MSELoss().type(torch.cuda.FloatTensor)
+        noise = z0.detach().clone()
+        last = [0.0]
+
+        def closure():
+            out_hr = net(z0 + noise.normal_() * 0.03)
+            total_loss = mse(dmod(out_hr), target)
+            total_loss.backward()
+            last[0] = total_loss.item()
+            return total_loss
+
+        def run(n):
+            with contextlib.redirect_stdout(io.StringIO()):
+                _opt("adam", get_params("net", net, z0), closure, LR, n)
+        run(5)
+        torch.cuda.synchronize()
+        e0.record()
+        run(50)
+        e1.record()
+        torch.cuda.synchronize()
+        rec["e2e_it_per_s"] = 50.0 / (e0.elapsed_time(e1) / 1000.0)
+        rec["e2e_api"] = "models.get_net(...).type(cuda) with net.precision = '%s', models.Downsampler, utils.optimize('adam', ...), loss.item() every step" % prec_name
         out[prec_name] = rec
-        del plan, opt, net, params, grads
+        del net, params, grads, dmod
         torch.cuda.empty_cache()
     out["bf16_speedup"] = out["bf16"]["it_per_s"] / out["tf32"]["it_per_s"]
     return out

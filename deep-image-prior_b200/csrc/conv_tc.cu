@@ -10,6 +10,8 @@
 //                       warps 4-7  epilogue: tcgen05.ld -> +bias -> swizzled smem -> per-channel BN statistics
 //                                  -> TMA store
 //   tc_wgrad_kernel : weight gradient, both operands MN-major straight from NHWC activations, split-K over CTAs.
+//   Both are templated on the operand type: kind::tf32 on fp32 tensors (tc_conv_kernel / tc_wgrad_kernel) and kind::f16 on
+//   bf16 twins (tc_conv_kernel_bf16 / tc_wgrad_kernel_bf16, precision mode bf16); accumulators and outputs are fp32 in both.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 #include "kernels.cuh"

@@ -7,10 +7,10 @@
 namespace dip {
 
 // Implicit-GEMM forward/dgrad conv:  D[pixel][n] = sum_{tap, c} A[pixel (+) tap][c] * Wp[tap][n][c]  (+ bias[n])
-//   A  : NHWC fp32 activation seen through a 5-D tensor map (C, px, X, py, Y)   (parity dims px/py have extent 1
-//        for stride-1 convs and 2 for stride-2 convs; out-of-bounds coordinates read as zero)
-//   Wp : packed weights [tap][n_rows][c_pad] fp32, K-major, through a 2-D map (c_pad, taps*n_rows)
-//   D  : NHWC fp32 output through a 3-D map (C_out, W_out, H_out); partial tiles are clipped by TMA.
+//   A  : NHWC activation (fp32, or its bf16 twin when bf16 = 1) seen through a 5-D tensor map (C, px, X, py, Y)   (parity
+//        dims px/py have extent 1 for stride-1 convs and 2 for stride-2 convs; out-of-bounds coordinates read as zero)
+//   Wp : packed weights [tap][n_rows][c_pad] (fp32 or bf16), K-major, through a 2-D map (c_pad, taps*n_rows)
+//   D  : NHWC fp32 output through a 3-D map (C_out, W_out, H_out); partial tiles and channels >= C_out are clipped by TMA.
 struct TcConvParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
@@ -54,7 +54,7 @@ struct TcConvParams {
 };
 
 // Weight-gradient GEMM:  dW[tap][n][c] = sum_{pixels} dY[pixel][n] * X[pixel (+) tap][c]
-//   dY : NHWC fp32 [H][W][128] through a 3-D map (128, W, H)
+//   dY : NHWC [H][W][N] (fp32 or bf16 twin; N <= 128 output channels, channels >= N read as zero) through a 3-D map (N, W, H)
 //   X  : conv input through the same 5-D view as in TcConvParams
 //   out: atomic = 1 (engine): every split-K CTA adds its tile into ONE fp32 accumulator [tap][128][c_pad] with vector
 //        reductions at the L2 (red.global.add.v4.f32; the 0.6 MB accumulator never leaves the L2) -- no partials in

@@ -1,5 +1,6 @@
 // Launch wrappers of the HBM-bound kernels of the dip-b200 engine (kernels_mem.cu, conv_simt.cu).
-// All activations are fp32 NHWC; "ld" is the channel stride of a buffer in floats.
+// All activations are fp32 NHWC; "ld" is the channel stride of a buffer in floats.  Precision mode bf16 adds bf16 twins (Twin) of
+// the tensors the tensor-core kernels read; everything these kernels compute with stays fp32.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -20,7 +20,8 @@ REF = os.environ.get("DIP_REFERENCE_DIR", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
-NOTEBOOKS = ["denoising.ipynb", "super-resolution.ipynb", "inpainting.ipynb", "restoration.ipynb", "flash-no-flash.ipynb"]
+NOTEBOOKS = ["denoising.ipynb", "super-resolution.ipynb", "inpainting.ipynb", "restoration.ipynb", "flash-no-flash.ipynb",
+             "sr_prior_effect.ipynb"]
 DATA_DIRS = ["denoising", "sr", "inpainting", "restoration", "flash_no_flash"]
 
 

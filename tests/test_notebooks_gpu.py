@@ -115,6 +115,21 @@ def test_inpainting_notebook_vase_branch_runs_unchanged():
 
 
 @needs_ref
+def test_sr_prior_effect_notebook_runs_unchanged():
+    """sr_prior_effect.ipynb: three optimisations of the same x4 problem -- no prior and TV prior (net = nn.Sequential(), i.e. the
+    identity: OPT_OVER = 'input' optimises the image itself through the engine's Downsampler autograd node, utils.sr_utils.tv_loss),
+    then the deep prior (the 128-wide skip network on a 3-channel noise input, c17)."""
+    torch.manual_seed(0)
+    ns = run_notebook(os.path.join(REF, "sr_prior_effect.ipynb"), dict(PLOT=False, num_iter=25))
+    _assert_engine_net(ns["net"])
+    assert ns["net"]._dip_spec["in_channels"] == 3 and ns["OPT_OVER"] == "net"
+    for key in ("psnr_history_direct", "psnr_history_tv", "psnr_history_deep_prior"):
+        hist = np.array(ns[key])
+        assert hist.shape == (25, 2) and np.isfinite(hist).all() and hist[-1, 0] > hist[0, 0], key   # PSNR_LR rises in all three
+    assert ns["result_deep_prior"].shape == ns["result_no_prior"].shape == ns["result_tv_prior"].shape
+
+
+@needs_ref
 def test_super_resolution_notebook_factor_8():
     """super-resolution.ipynb with the user edit `factor = 8` of cell 3 (c7:16-18: num_iter 4000, reg_noise_std 0.05): the
     32 x 32 Lanczos-2 downsampler (models/downsampler.py:14-17) in the loss, LR target 72 x 48."""
