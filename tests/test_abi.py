@@ -65,6 +65,26 @@ def test_workspace_query_rejects_unsupported_configurations_with_a_reason():
     assert nosig == base
     ingrad, _ = q(de.NetDesc(32, 3, 5, 128, 4, 1, 1, 0, 0, 1))
     assert ingrad > base
+    # per-scale widths (channels == 0: the arrays), precision bf16, downsample_mode 'avg'
+    def per_scale(down, skip, in_ch=3, prec=0, dmode=0, up=None):
+        d = de.NetDesc(in_ch, 3, len(down), 0, 0, 1, 1, prec)
+        for i, (a, b, c) in enumerate(zip(down, up or down, skip)):
+            d.channels_down[i], d.channels_up[i], d.channels_skip[i] = a, b, c
+        d.downsample_mode = dmode
+        return d
+    snail, _ = q(per_scale([8, 16, 32, 64, 128], [0, 0, 0, 4, 4]))                       # denoising.ipynb c8:17-23
+    assert 0 < snail < 0.25 * base
+    kate, _ = q(per_scale([16, 32, 64, 128, 128], [0] * 5, in_ch=32, dmode=1))           # restoration.ipynb c7:28-36
+    assert snail < kate < base
+    bf16, _ = q(de.NetDesc(32, 3, 5, 128, 4, 1, 1, 2))                                   # + the bf16 twins
+    assert base < bf16 < 1.35 * base
+    for desc, word in [(per_scale([8, 12, 32, 64, 128], [0] * 5), "multiples of 8"),
+                       (per_scale([8, 16, 32, 64, 128], [0, 0, 0, 128, 128]), "num_channels_skip"),
+                       (per_scale([8, 16, 32, 64, 256], [0] * 5), "multiples of 8"),
+                       (per_scale([16, 32, 64, 128, 128], [0] * 5, dmode=2), "downsample_mode"),
+                       (de.NetDesc(32, 3, 5, 128, 4, 1, 1, 3), "precision")]:
+        n, err = q(desc)
+        assert n == 0 and word in err, (n, err)
 
 
 def test_downsampler_output_size_matches_torch_conv_arithmetic():
