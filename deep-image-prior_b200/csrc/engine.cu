@@ -258,9 +258,14 @@ struct ConvOp {
   size_t wp_f_elems() const { return (size_t)k * k * Np * c_pad; }
   size_t wp_d_elems() const { return (size_t)k * k * crows * n_pad; }
   size_t wacc_elems() const { return (size_t)k * k * 128 * c_pad; }
-  // pixels per K block of the weight-gradient GEMM (TMA box width).  bf16 halves the bytes per pixel and doubles K per MMA:
-  // 64-pixel blocks keep 12 MMAs per barrier round
-  int wg_kp() const { return (bf16 && wg_w % 64 == 0) ? 64 : (wg_w % 32 == 0) ? 32 : 16; }
+  // pixels per K block of the weight-gradient GEMM (TMA box width): 64 where the row length allows it -- half the barrier
+  // rounds per FLOP (bf16: 12 MMAs per round instead of 6; tf32: 24 instead of 12).  Measured (profiles/r02_wgrad_kp_ab.txt):
+  // 512^2 denoise 376.6 -> 377.7 it/s, SR 1024^2 122.0 -> 122.6 (tf32) / 150.2 -> 150.7 (bf16).  DIP_WGRAD_KP=32|64: A/B switch.
+  int wg_kp() const {
+    static const int forced = getenv("DIP_WGRAD_KP") ? atoi(getenv("DIP_WGRAD_KP")) : 0;
+    const bool want64 = forced ? forced == 64 : true;
+    return (want64 && wg_w % 64 == 0) ? 64 : (wg_w % 32 == 0) ? 32 : 16;
+  }
   int tc_ksplits() const {
     const int kp = wg_kp();
     const int blocks = wg_h * ((wg_w + kp - 1) / kp);
