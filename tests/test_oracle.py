@@ -109,3 +109,33 @@ def test_oracle_matches_reference_fixture_at_baseline_shape(kind):
     from baseline_cases import oracle_step
     c = oracle_step(kind)
     assert np.isfinite(c["loss"])
+
+
+def test_bf16_operand_mode_of_the_oracle_is_a_faithful_conv_when_rounding_is_the_identity(monkeypatch):
+    """The checker of the engine's bf16 mode (`with O.operand_rounding('bf16')`) swaps the wide convolutions for a custom
+    autograd function (operands rounded in forward AND backward).  With the rounding replaced by the identity it must
+    reproduce the plain oracle exactly -- output and every gradient -- on a per-scale-width network with skip branches;
+    with real rounding it must change the wide convolutions only (the 4-output skip convs and the head stay fp32)."""
+    cfg = O.SkipConfig(in_channels=3, num_scales=3, channels=[8, 16, 32], skip_channels=[0, 4, 4])
+    params = O.init_params(cfg, seed=0, dtype=torch.float64)
+    z = O.get_noise(3, (32, 48), seed=1).double()
+    target = torch.rand(1, 3, 32, 48, generator=torch.Generator().manual_seed(2)).double()
+    out0 = O.skip_forward(params, z, cfg)
+    g0 = torch.autograd.grad(O.mse_loss(out0, target), params)
+    monkeypatch.setattr(O, "_round_bf16", lambda t: t)
+    with O.operand_rounding("bf16"):
+        out1 = O.skip_forward(params, z, cfg)
+        g1 = torch.autograd.grad(O.mse_loss(out1, target), params)
+    assert torch.allclose(out0, out1, atol=1e-13)
+    for a, b in zip(g0, g1):
+        assert torch.allclose(a, b, rtol=1e-9, atol=1e-14)
+    monkeypatch.undo()
+    # real rounding: a lone wide conv sees bf16 operands, a 4-output conv does not
+    x = torch.randn(1, 8, 6, 6, dtype=torch.float64)
+    w_wide, w_skinny = torch.randn(16, 8, 1, 1, dtype=torch.float64), torch.randn(4, 8, 1, 1, dtype=torch.float64)
+    with O.operand_rounding("bf16"):
+        y_wide, y_skinny = O._conv(x, w_wide, None), O._conv(x, w_skinny, None)
+    assert torch.equal(y_skinny, torch.nn.functional.conv2d(x, w_skinny))
+    assert torch.equal(y_wide, torch.nn.functional.conv2d(x.bfloat16().double(), w_wide.bfloat16().double()))
+    assert not torch.equal(y_wide, torch.nn.functional.conv2d(x, w_wide))
+    assert O._OPERAND_ROUND is None
