@@ -475,7 +475,10 @@ def run_ours(args):
     if rank == 0 and world == 1:
         del fast
         torch.cuda.empty_cache()
-        sr_cfg = bench_sr_config(torch, de, models, peaks, dev)
+        try:
+            sr_cfg = bench_sr_config(torch, de, models, peaks, dev)
+        except Exception as e:      # the headline line must still come out
+            sr_cfg = {"error": repr(e)[:300]}
 
     # ---- result record per rank (the only data collective of the job)
     recs = mg.gather_records([psnr_img, float(img_hist[-1].item()), ITERS_PER_IMAGE / (img_ms / 1000.0)], device=dev)
